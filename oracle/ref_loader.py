@@ -1,0 +1,55 @@
+"""Import the UNMODIFIED reference modules from /root/reference (this container only).
+
+TEST INFRASTRUCTURE ONLY -- used by ``oracle/make_golden.py`` and by the ``not gpu`` tests that pin
+the oracle restatement against the real reference classes.  /root/reference does not exist on the
+GPU box; nothing reachable from ``-m gpu`` tests, ``smoke()`` or ``bench.py`` may call this.
+"""
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("VIAI_REFERENCE_ROOT", "/root/reference")
+_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "networks"))
+
+
+def load(normlayer=None, cin_channels=None):
+    """Returns a namespace of reference modules.  ``normlayer``/``cin_channels`` patch the shim config
+    *before* import because the reference evaluates them as default arguments at import time
+    (/root/reference/networks/New_Inpainting_Networks.py:49)."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    for p in (_SHIMS, REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    # the reference imports two loader modules it never uses on this path
+    for name in ("Data_loaders.mel_loader", "Data_loaders.AV_loader"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    import Options_inpainting
+    if normlayer is not None:
+        Options_inpainting.Inpainting_Config.normlayer = normlayer
+    if cin_channels is not None:
+        Options_inpainting.Inpainting_Config.cin_channels = cin_channels
+    ns = types.SimpleNamespace()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ns.Inpainting_Networks = importlib.import_module("networks.Inpainting_Networks")
+        ns.New_Inpainting_Networks = importlib.import_module("networks.New_Inpainting_Networks")
+        ns.Discriminator_Networks = importlib.import_module("networks.Discriminator_Networks")
+        ns.loss_functions = importlib.import_module("loss_functions")
+        ns.wavenet = importlib.import_module("wavenet_vocoder.wavenet")
+        ns.mixture = importlib.import_module("wavenet_vocoder.mixture")
+        ns.lrschedule = importlib.import_module("utils.lrschedule")
+        try:
+            ns.Image_Embedding = importlib.import_module("networks.Image_Embedding")
+        except Exception as e:  # cv2 missing etc.
+            ns.Image_Embedding = None
+            ns.Image_Embedding_error = e
+    ns.Options_inpainting = Options_inpainting
+    return ns

@@ -1,0 +1,178 @@
+"""Shared helpers for the parity tests (build reference-keyed state dicts without the reference)."""
+import math
+import os
+
+import torch
+
+from oracle import fixtures as FX
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def relerr(a, b):
+    """max |a-b| / max |b| -- the normwise relative error used for every fp32 tolerance in tests/."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def _bn(sd, p, c, norm, affine):
+    if norm == "bn":
+        sd[p + ".weight"] = torch.ones(c)
+        sd[p + ".bias"] = torch.zeros(c)
+        sd[p + ".running_mean"] = torch.zeros(c)
+        sd[p + ".running_var"] = torch.ones(c)
+        sd[p + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+    elif affine:
+        sd[p + ".weight"] = torch.ones(c)
+        sd[p + ".bias"] = torch.zeros(c)
+
+
+def encoder_sd(norm="bn"):
+    """Key/shape layout of MelEncoder.state_dict() (/root/reference/networks/Inpainting_Networks.py:55-64)."""
+    sd = {}
+    ch = [1, 32, 64, 128, 256, 256]
+    for i in range(5):
+        sd["conv%d.weight" % (i + 1)] = torch.zeros(ch[i + 1], ch[i], 3, 3)
+        if norm == "in":
+            sd["conv%d.bias" % (i + 1)] = torch.zeros(ch[i + 1])
+        _bn(sd, "bn%d" % (i + 1), ch[i + 1], norm, True)
+    return sd
+
+
+def decoder_sd(norm="bn", variant="MelDecoder"):
+    """MelDecoder*/MelDecoder_old.state_dict() layout (/root/reference/networks/New_Inpainting_Networks.py:49-68 etc.)."""
+    sd = {}
+
+    def ct(name, cin, cout, bias=True):
+        sd[name + ".weight"] = torch.zeros(cin, cout, 3, 3)
+        if bias:
+            sd[name + ".bias"] = torch.zeros(cout)
+
+    def block(idx, cin, cout, nums):
+        for i in range(nums):
+            k = "convblock%d.conv%d_%d" % (idx, idx, i)
+            ct(k, cin, cout, norm == "in")
+            _bn(sd, k + "_bn", cout, norm, False)
+            cin = cout
+
+    ct("deconv1_1", 256, 256)
+    _bn(sd, "deconv1_1_bn", 256, norm, False)
+    if "Image" in variant:
+        ct("deconv1_1_1", 512, 256)
+        _bn(sd, "deconv1_1_1_bn", 256, norm, False)
+    ct("deconv1_2", 256, 256)
+    _bn(sd, "deconv1_2_bn", 256, norm, False)
+    if variant in ("MelDecoder", "MelDecoder_old"):
+        block(1, 256, 256, 2)
+    block(2, 256, 128, 3)
+    block(3, 128, 64, 3)
+    if variant in ("MelDecoder", "MelDecoderImage"):
+        block(4, 128, 32, 3)
+        block(5, 32, 32, 4)
+    else:
+        block(4, 64, 32, 3)
+        block(5, 64, 32, 2)
+    ct("conv6_1", 32, 32)
+    ct("conv6_2", 32, 1)
+    _bn(sd, "conv6_1_bn", 32, norm, False)
+    return sd
+
+
+def discriminator_sd(norm="bn"):
+    """MelDiscriminator.state_dict() layout (/root/reference/networks/Discriminator_Networks.py:17-33)."""
+    sd = {}
+
+    def cv(name, cout, cin, kh, kw):
+        sd[name + ".weight"] = torch.zeros(cout, cin, kh, kw)
+        if norm == "in":
+            sd[name + ".bias"] = torch.zeros(cout)
+
+    cv("conv1", 64, 1, 1, 4)
+    _bn(sd, "bn1", 64, norm, False)
+    cv("conv2_1", 128, 64, 3, 3)
+    _bn(sd, "norm_1", 128, norm, False)
+    cv("conv2_2", 256, 128, 3, 3)
+    _bn(sd, "norm_2", 256, norm, False)
+    cv("conv3", 512, 256, 3, 3)
+    _bn(sd, "norm3", 512, norm, False)
+    cv("conv4", 1, 512, 3, 3)
+    return sd
+
+
+def wavenet_sd(layers=24, residual_channels=512, gate_channels=512, skip_out_channels=256, cin_channels=80,
+               out_channels=30, upsample_scales=(4, 4, 10), kernel_size=3, freq_axis_kernel_size=3, **_):
+    """WaveNet.state_dict() layout with weight norm (weight_g / weight_v), wavenet_vocoder/wavenet.py:119-166."""
+    sd = {}
+
+    def wn(name, cout, cin, k):
+        sd[name + ".bias"] = torch.zeros(cout)
+        sd[name + ".weight_g"] = torch.zeros(cout, 1, 1)
+        sd[name + ".weight_v"] = torch.zeros(cout, cin, k)
+
+    wn("first_conv", residual_channels, 1, 1)
+    for l in range(layers):
+        p = "conv_layers.%d." % l
+        wn(p + "conv", gate_channels, residual_channels, kernel_size)
+        wn(p + "conv1x1c", gate_channels, cin_channels, 1)
+        wn(p + "conv1x1_out", residual_channels, gate_channels // 2, 1)
+        wn(p + "conv1x1_skip", skip_out_channels, gate_channels // 2, 1)
+    wn("last_conv_layers.1", skip_out_channels, skip_out_channels, 1)
+    wn("last_conv_layers.3", out_channels, skip_out_channels, 1)
+    for i, s in enumerate(upsample_scales):
+        k = "upsample_conv.%d" % (2 * i)
+        sd[k + ".bias"] = torch.zeros(1)
+        sd[k + ".weight_g"] = torch.zeros(1, 1, 1, 1)
+        sd[k + ".weight_v"] = torch.zeros(1, 1, freq_axis_kernel_size, s)
+    return sd
+
+
+def resnet18_sd(channel_size=3, length_feature=256, prefix=""):
+    sd = {}
+
+    def bn(p, c):
+        _bn(sd, prefix + p, c, "bn", False)
+
+    sd[prefix + "conv1.weight"] = torch.zeros(64, channel_size, 7, 7)
+    bn("bn1", 64)
+    inpl = 64
+    for li, planes in enumerate([64, 128, 256, 512], start=1):
+        for bi in range(2):
+            p = "layer%d.%d." % (li, bi)
+            stride = 2 if (li > 1 and bi == 0) else 1
+            sd[prefix + p + "conv1.weight"] = torch.zeros(planes, inpl, 3, 3)
+            bn(p + "bn1", planes)
+            sd[prefix + p + "conv2.weight"] = torch.zeros(planes, planes, 3, 3)
+            bn(p + "bn2", planes)
+            if stride != 1 or inpl != planes:
+                sd[prefix + p + "downsample.0.weight"] = torch.zeros(planes, inpl, 1, 1)
+                bn(p + "downsample.1", planes)
+            inpl = planes
+    sd[prefix + "fc.weight"] = torch.zeros(length_feature, 512)
+    sd[prefix + "fc.bias"] = torch.zeros(length_feature)
+    return sd
+
+
+def image_embedding_sd(length_feature=256):
+    sd = {}
+    sd.update(resnet18_sd(3, length_feature, "image_single_model."))
+    sd.update(resnet18_sd(2, length_feature, "flow_single_model."))
+    sd["conv_1.weight"] = torch.zeros(2 * length_feature, 2 * length_feature, 3)
+    _bn(sd, "bn_1", 2 * length_feature, "bn", False)
+    sd["conv_2.weight"] = torch.zeros(length_feature, 2 * length_feature, 3)
+    _bn(sd, "bn_2", length_feature, "bn", False)
+    return sd
+
+
+def filled(sd, salt=0):
+    return FX.deterministic_fill(sd, salt)
+
+
+def center_mask(shape):
+    W = shape[-1]
+    m = torch.ones(shape)
+    m[..., W // 4:W // 4 + W // 2] = 0
+    return m
