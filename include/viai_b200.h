@@ -1,0 +1,146 @@
+/*
+ * viai_b200.h -- C ABI of libviai_b200.so: the sm_100a kernels behind the VIAI hot path.
+ *
+ * The reference (Hangz-nju-cuhk/Vision-Infused-Audio-Inpainter-VIAI) is pure Python; its seam for this
+ * path is the nn.Module API.  There is no FFI to mirror, so every entry point below names
+ * the ATen operator call site in the reference that it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - All tensors are dense, fp32 unless stated, activation layout is NHWC ("rows x C").
+ *   - The caller owns every buffer; kernels borrow raw device pointers for the stream-ordered call.
+ *     Nothing is allocated inside the library; workspaces are arguments.
+ *   - Every function returns 0 on success, a negative viai_status otherwise; viai_last_error() returns a
+ *     thread-local human-readable message.  No function synchronises the device.
+ *   - `stream` is a cudaStream_t passed as void*.  All entry points are re-entrant (no global mutable
+ *     state besides the thread-local error string) and capturable into CUDA graphs.
+ */
+#ifndef VIAI_B200_H
+#define VIAI_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* viai_stream_t;
+
+enum viai_status { VIAI_OK = 0, VIAI_ERR_ARG = -1, VIAI_ERR_CUDA = -2, VIAI_ERR_UNSUPPORTED = -3 };
+enum viai_act { VIAI_ACT_NONE = 0, VIAI_ACT_RELU = 1, VIAI_ACT_LRELU = 2, VIAI_ACT_SIGMOID = 3 };
+
+const char* viai_last_error(void);
+int viai_version(void);
+/* number of kernel launches issued through this library by the calling process (for bench.py gpu_launches) */
+long long viai_launch_count(void);
+
+/* Geometry of one implicit-GEMM convolution.
+ *   out[n, y, x, o] = bias[o] + sum_{r,s,i} in[n, Y, X, i] * wp[o][r][s][i]
+ *   mode 0 (forward gather):     Y = y*stride_h - pad_h + r,            X likewise
+ *   mode 1 (transposed gather):  Y = (y + pad_h - r) / stride_h  when divisible, else the tap is skipped
+ * mode 0 is nn.Conv2d forward (networks/Inpainting_Networks.py:55-63, networks/Discriminator_Networks.py:17-33,
+ * networks/Image_Embedding.py:18, networks/ResNet.py:22) and the data-gradient of a stride-1 ConvTranspose2d;
+ * mode 1 is nn.ConvTranspose2d forward (networks/New_Inpainting_Networks.py:24,53-63) and the data-gradient
+ * (`convolution_backward`) of nn.Conv2d. */
+typedef struct {
+  int32_t N, Hin, Win, Cin;   /* gathered tensor */
+  int32_t Hout, Wout, Cout;   /* produced tensor */
+  int32_t R, S;               /* filter taps */
+  int32_t stride_h, stride_w, pad_h, pad_w;
+  int32_t mode;
+} viai_conv_geom;
+
+/* dst[o][r'][s'][i] = src[o*so + i*si + r*sr + s*ss];  r' = flip ? R-1-r : r, s' likewise.
+ * Re-lays a parameter stored in the reference's state_dict layout ((Cout,Cin,kh,kw) for Conv2d,
+ * (Cin,Cout,kh,kw) for ConvTranspose2d) into the [O][R][S][I] operand the kernels read. */
+int viai_pack_weight(const float* src, float* dst, int O, int I, int R, int S, int64_t so, int64_t si,
+                     int64_t sr, int64_t ss, int flip, viai_stream_t stream);
+
+/* CUDA-core fp32 implicit-GEMM convolution (exact-fp32 path; also the on-device validator of the
+ * tensor-core path).  bias may be NULL. */
+int viai_conv2d_simt(const viai_conv_geom* g, const float* in, const float* wp, const float* bias, float* out,
+                     viai_stream_t stream);
+
+/* Weight gradient.  dw[a*sa + b*sb + r*sr + s*ss] (+)= sum_{n,y,x} U[n,y,x,a] * G[n, y*stride-pad+r, x*stride-pad+s, b]
+ * U is (N,Hout,Wout,Cout=A), G is (N,Hin,Win,Cin=B) in the geometry struct (mode ignored).
+ * For nn.Conv2d: U = dOut, G = input.  For stride-1 nn.ConvTranspose2d: U = input, G = dOut.
+ * The destination is zeroed first unless accumulate != 0.  (`convolution_backward` weight branch.) */
+int viai_conv2d_wgrad_simt(const viai_conv_geom* g, const float* U, const float* G, float* dw, int64_t sa,
+                           int64_t sb, int64_t sr, int64_t ss, int accumulate, viai_stream_t stream);
+
+/* Per-(group,channel) sum and sum of squares over rows of an NHWC tensor: groups = 1 is BatchNorm2d's
+ * batch statistics, groups = N is InstanceNorm2d's (rows_per_group = H*W).  sum/sumsq are double[groups*C],
+ * zeroed by the call.  sumsq may be NULL (plain channel sum: the bias gradient). */
+int viai_channel_stats(const float* y, int64_t rows_per_group, int groups, int C, double* sum, double* sumsq,
+                       viai_stream_t stream);
+
+/* mean/invstd (float[groups*C]) from the sums; if running_mean != NULL also performs BatchNorm's running
+ * update (momentum, unbiased variance) and increments *num_batches_tracked (int64, may be NULL).
+ * Replaces native_batch_norm / instance_norm statistics (networks/Inpainting_Networks.py:56-64 etc.). */
+int viai_norm_finalize(const double* sum, const double* sumsq, int64_t rows_per_group, int groups, int C, float eps,
+                       float* mean, float* invstd, float* running_mean, float* running_var, float momentum,
+                       int64_t* num_batches_tracked, viai_stream_t stream);
+
+/* out = act(((y - mean) * invstd) * gamma + beta).  mean/invstd NULL => no normalisation; gamma/beta NULL => 1/0.
+ * stat index = (row / rows_per_group) * C + c  (groups = 1: per channel).  In-place allowed. */
+int viai_norm_act_fwd(const float* y, int64_t rows_per_group, int groups, int C, const float* mean,
+                      const float* invstd, const float* gamma, const float* beta, int act, float slope, float* out,
+                      viai_stream_t stream);
+
+/* Backward of viai_norm_act_fwd in two passes.  g = dz * act'(.);  s1 = sum g, s2 = sum g*xhat per (group,channel).
+ * s1/s2: double[groups*C], zeroed by the call. */
+int viai_norm_act_bwd_reduce(const float* dz, const float* y, int64_t rows_per_group, int groups, int C,
+                             const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
+                             float slope, double* s1, double* s2, viai_stream_t stream);
+/* dy = gamma*invstd*(g - s1/cnt - xhat*s2/cnt)   (training-mode statistics);  with mean == NULL: dy = g.
+ * dgamma/dbeta (float[C], may be NULL) receive sum_groups s2 / s1. */
+int viai_norm_act_bwd_apply(const float* dz, const float* y, int64_t rows_per_group, int groups, int C,
+                            const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
+                            float slope, const double* s1, const double* s2, float* dy, float* dgamma, float* dbeta,
+                            viai_stream_t stream);
+/* out[c] (+)= sum_g sums[g*C+c]  -- double -> float fold used for bias gradients. */
+int viai_fold_groups(const double* sums, int groups, int C, float* out, int accumulate, viai_stream_t stream);
+
+/* F.interpolate(mode='bilinear', align_corners=True) (networks/New_Inpainting_Networks.py:78,83) written into the
+ * channel slice [coff, coff+C) of an NHWC tensor with Ctot channels (this is how torch.cat :81 is made copy-free). */
+int viai_bilinear_fwd(const float* in, int N, int Hin, int Win, int C, float* out, int Hout, int Wout, int Ctot,
+                      int coff, viai_stream_t stream);
+int viai_bilinear_bwd(const float* dout, int N, int Hin, int Win, int C, float* din, int Hout, int Wout, int Ctot,
+                      int coff, viai_stream_t stream);
+/* dst[row][doff + c] = src[row][soff + c], c < C   (torch.cat / its backward slice) */
+int viai_copy_channels(const float* src, int64_t rows, int Csrc, int soff, float* dst, int Cdst, int doff, int C,
+                       viai_stream_t stream);
+/* nn.AvgPool2d((kh,1)) on NHWC (networks/Inpainting_Networks.py:65,77) */
+int viai_avgpool_h_fwd(const float* in, int N, int H, int W, int C, int kh, float* out, viai_stream_t stream);
+int viai_avgpool_h_bwd(const float* dout, int N, int H, int W, int C, int kh, float* din, viai_stream_t stream);
+/* nn.MaxPool2d(3, 2, 1) (networks/Image_Embedding.py:21) forward/backward, NHWC */
+int viai_maxpool3s2_fwd(const float* in, int N, int H, int W, int C, float* out, int Ho, int Wo, viai_stream_t stream);
+int viai_maxpool3s2_bwd(const float* in, const float* dout, int N, int H, int W, int C, float* din, int Ho, int Wo,
+                        viai_stream_t stream);
+/* out = a * b  (mask application, bit exact), out = a + b, out = relu(a + b) and its backward */
+int viai_mul(const float* a, const float* b, float* out, int64_t n, viai_stream_t stream);
+int viai_add_act(const float* a, const float* b, float* out, int64_t n, int act, viai_stream_t stream);
+int viai_add_act_bwd(const float* out, const float* dout, float* din, int64_t n, int act, viai_stream_t stream);
+
+/* Losses (loss_functions.py:79-104 GANLoss = MSELoss / BCELoss against an expanded scalar; nn.L1Loss).
+ * kind 0: mean (p-t)^2   1: BCE(p, t)   2: mean |p - q|  (q = other tensor).  acc: double[1] workspace.
+ * loss_out: float[1] on device. */
+int viai_loss_fwd(int kind, const float* p, const float* q, float target, int64_t n, double* acc, float* loss_out,
+                  viai_stream_t stream);
+/* dp = (*gout) * dloss/dp;  gout: float[1] on device (upstream scalar gradient). */
+int viai_loss_bwd(int kind, const float* p, const float* q, float target, int64_t n, const float* gout, float* dp,
+                  viai_stream_t stream);
+
+/* Fused Adam over one flat buffer (torch.optim.Adam semantics, no weight decay / amsgrad).
+ * step_dev: float[1] device counter, incremented first when tick != 0; lr_dev: float[1] device learning rate (so
+ * schedules work under CUDA graphs); grad_scale multiplies g (1/world_size after a sum all-reduce). */
+int viai_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, double beta1,
+                   double beta2, double eps, float* step_dev, int tick, float grad_scale, viai_stream_t stream);
+/* out[0] = wa * a[0] + wb * b[0]   (b may be NULL) -- scalar loss arithmetic kept on the device */
+int viai_lincomb2(const float* a, float wa, const float* b, float wb, float* out, viai_stream_t stream);
+int viai_fill(float* p, int64_t n, float value, viai_stream_t stream);
+/* out[i] = 1/sqrt(var[i] + eps)  (eval-mode BatchNorm uses running_var) */
+int viai_rsqrt_eps(const float* var, int n, float eps, float* out, viai_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIAI_B200_H */

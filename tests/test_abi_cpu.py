@@ -1,0 +1,78 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol declared in include/viai_b200.h; the
+product modules expose the reference's constructor signatures and state_dict layouts; host logic that needs no GPU."""
+import inspect
+import os
+import re
+
+import pytest
+import torch
+import torch.nn as nn
+
+import viai_test_helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from viai_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "viai_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(viai_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    L = lib.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), "libviai_b200.so does not export %s" % name
+    bound = set(lib.SIGNATURES) | {"viai_last_error", "viai_version", "viai_launch_count"}
+    assert declared == bound, declared ^ bound
+    assert L.viai_version() >= 100
+
+
+def test_no_cpu_fallback(lib):
+    from viai_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.conv2d(torch.zeros(1, 4, 4, 2), torch.zeros(3, 2, 3, 3))
+    from viai_b200.networks.Inpainting_Networks import MelEncoder
+    with pytest.raises(RuntimeError):
+        MelEncoder()(torch.rand(1, 80, 64))
+
+
+@pytest.mark.parametrize("norm", ["bn", "in"])
+def test_state_dict_layouts_match_reference(lib, norm):
+    from viai_b200.networks import Discriminator_Networks as DN, Inpainting_Networks as IN, New_Inpainting_Networks as NN
+    nl = nn.BatchNorm2d if norm == "bn" else nn.InstanceNorm2d
+    pairs = [(IN.MelEncoder(norm_layer=nl), H.encoder_sd(norm)), (DN.MelDiscriminator(norm_layer=nl), H.discriminator_sd(norm))]
+    for v in ("MelDecoder", "MelDecoderImage", "MelDecoderImage2", "MelDecoder_old"):
+        pairs.append((getattr(NN, v)(norm_layer=nl), H.decoder_sd(norm, v)))
+    for m, want in pairs:
+        got = {k: tuple(t.shape) for k, t in m.state_dict().items()}
+        assert got == {k: tuple(t.shape) for k, t in want.items()}, type(m).__name__
+    n = lambda m: sum(p.numel() for p in m.parameters())
+    if norm == "bn":     # SURVEY 8c KAT (7)
+        assert (n(pairs[0][0]), n(pairs[2][0]), n(pairs[1][0])) == (978656, 3202497, 1555072)
+    else:
+        assert (n(pairs[0][0]), n(pairs[2][0]), n(pairs[1][0])) == (979392, 3200097, 1554113)
+
+
+def test_constructor_signatures(lib):
+    from viai_b200.networks import Discriminator_Networks as DN, Inpainting_Networks as IN, New_Inpainting_Networks as NN
+    from viai_b200.loss_functions import GANLoss
+    assert list(inspect.signature(IN.MelEncoder.__init__).parameters) == ["self", "hparams", "norm_layer"]
+    assert list(inspect.signature(NN.MelDecoder.__init__).parameters) == ["self", "hparams", "norm_layer"]
+    assert list(inspect.signature(NN.MelDecoderImage.forward).parameters) == ["self", "net", "x_size", "video_net"]
+    assert list(inspect.signature(NN.TransConvBlock.__init__).parameters) == [
+        "self", "inplanes", "outplanes", "name", "nums", "kernel_size", "padding", "stride", "norm_layer"]
+    assert list(inspect.signature(DN.MelDiscriminator.__init__).parameters) == [
+        "self", "input_nc", "ndf", "n_layers", "norm_layer", "use_sigmoid"]
+    assert list(inspect.signature(GANLoss.__init__).parameters) == [
+        "self", "use_lsgan", "device", "target_real_label", "target_fake_label"]
+    with pytest.raises(Exception, match="name should be str"):
+        NN.TransConvBlock(4, 4, 1)
+    g = GANLoss()
+    assert set(dict(g.named_buffers())) == {"real_label", "fake_label"}

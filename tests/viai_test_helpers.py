@@ -19,6 +19,13 @@ def relerr(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
 
 
+def relerr_l2(a, b):
+    """||a-b||_2 / ||b||_2 -- used where a handful of sign flips (Adam's first step is +-lr per element) would make the
+    max-norm meaningless."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
 def _bn(sd, p, c, norm, affine):
     if norm == "bn":
         sd[p + ".weight"] = torch.ones(c)

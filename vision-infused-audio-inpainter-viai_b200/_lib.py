@@ -1,0 +1,88 @@
+"""ctypes binding of libviai_b200.so (the C ABI declared in include/viai_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libviai_b200.so")
+_lib = None
+
+c_p = ctypes.c_void_p
+c_i = ctypes.c_int
+c_l = ctypes.c_int64
+c_f = ctypes.c_float
+c_d = ctypes.c_double
+
+
+class ConvGeom(ctypes.Structure):
+    """Mirror of ``viai_conv_geom``."""
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "N", "Hin", "Win", "Cin", "Hout", "Wout", "Cout", "R", "S", "stride_h", "stride_w", "pad_h", "pad_w", "mode")]
+
+
+_GP = ctypes.POINTER(ConvGeom)
+
+# name -> argtypes (return type is always int)
+SIGNATURES = {
+    "viai_pack_weight": [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_l, c_l, c_i, c_p],
+    "viai_conv2d_simt": [_GP, c_p, c_p, c_p, c_p, c_p],
+    "viai_conv2d_wgrad_simt": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p],
+    "viai_channel_stats": [c_p, c_l, c_i, c_i, c_p, c_p, c_p],
+    "viai_norm_finalize": [c_p, c_p, c_l, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
+    "viai_norm_act_fwd": [c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_f, c_p, c_p],
+    "viai_norm_act_bwd_reduce": [c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_f, c_p, c_p, c_p],
+    "viai_norm_act_bwd_apply": [c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p],
+    "viai_fold_groups": [c_p, c_i, c_i, c_p, c_i, c_p],
+    "viai_rsqrt_eps": [c_p, c_i, c_f, c_p, c_p],
+    "viai_bilinear_fwd": [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p],
+    "viai_bilinear_bwd": [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p],
+    "viai_copy_channels": [c_p, c_l, c_i, c_i, c_p, c_i, c_i, c_i, c_p],
+    "viai_avgpool_h_fwd": [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
+    "viai_avgpool_h_bwd": [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
+    "viai_maxpool3s2_fwd": [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p],
+    "viai_maxpool3s2_bwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p],
+    "viai_mul": [c_p, c_p, c_p, c_l, c_p],
+    "viai_add_act": [c_p, c_p, c_p, c_l, c_i, c_p],
+    "viai_add_act_bwd": [c_p, c_p, c_p, c_l, c_i, c_p],
+    "viai_loss_fwd": [c_i, c_p, c_p, c_f, c_l, c_p, c_p, c_p],
+    "viai_loss_bwd": [c_i, c_p, c_p, c_f, c_l, c_p, c_p, c_p],
+    "viai_adam_step": [c_p, c_p, c_p, c_p, c_l, c_p, c_d, c_d, c_d, c_p, c_i, c_f, c_p],
+    "viai_lincomb2": [c_p, c_f, c_p, c_f, c_p, c_p],
+    "viai_fill": [c_p, c_l, c_f, c_p],
+}
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    """Loads the shared library once.  Raises if it has not been built (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libviai_b200.so not found at %s -- build it with __graft_entry__.build(); "
+                               "there is no CPU or PyTorch fallback for the VIAI hot path" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.viai_last_error.restype = ctypes.c_char_p
+        L.viai_last_error.argtypes = []
+        L.viai_version.restype = c_i
+        L.viai_launch_count.restype = ctypes.c_longlong
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = c_i
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().viai_last_error().decode("utf-8", "replace")
+        raise RuntimeError("libviai_b200 %s failed (%d): %s" % (what, rc, msg))
+
+
+def launch_count():
+    return int(lib().viai_launch_count())

@@ -1,0 +1,372 @@
+// Batch / instance normalisation statistics, fused normalise+activation, and its two-pass backward (NHWC fp32).
+#include "common.cuh"
+using namespace viai;
+
+namespace {
+
+constexpr int THREADS = 256;
+constexpr int ROWS_PER_BLOCK = 2048;
+
+// thread -> (channel vector cv, row lane rl).  VEC channels per thread; cvec = C/VEC <= THREADS.
+struct Lanes {
+  int cvec, lanes;
+};
+__host__ __device__ inline Lanes make_lanes(int C, int VEC) {
+  Lanes l;
+  l.cvec = C / VEC;
+  l.lanes = THREADS / l.cvec;
+  if (l.lanes < 1) l.lanes = 1;
+  return l;
+}
+
+// Reduces `NV` per-thread double values across the row lanes that share a channel vector, then atomically adds
+// lane 0's totals to global double accumulators.
+template <int NV>
+__device__ __forceinline__ void block_reduce_lanes(double (&v)[NV], int cv, int rl, Lanes L, double* smem) {
+  // smem: [lanes][cvec][NV]
+  for (int k = 0; k < NV; ++k) smem[(rl * L.cvec + cv) * NV + k] = v[k];
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 0; k < NV; ++k) {
+      double t = 0.0;
+      for (int l = 0; l < L.lanes; ++l) t += smem[(l * L.cvec + cv) * NV + k];
+      v[k] = t;
+    }
+  }
+}
+
+template <int VEC, bool SQ>
+__global__ void __launch_bounds__(THREADS)
+stats_kernel(const float* __restrict__ y, int64_t rows_per_group, int C, double* __restrict__ sum, double* __restrict__ sumsq) {
+  extern __shared__ double sred[];
+  const Lanes L = make_lanes(C, VEC);
+  const int tid = threadIdx.x;
+  const int cv = tid % L.cvec, rl = tid / L.cvec;
+  const int g = blockIdx.y;
+  const bool active = rl < L.lanes;
+  const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK;
+  const int64_t r1 = imin64(r0 + ROWS_PER_BLOCK, rows_per_group);
+  float s[VEC], q[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { s[k] = 0.f; q[k] = 0.f; }
+  if (active) {
+    const float* base = y + ((int64_t)g * rows_per_group) * C + cv * VEC;
+    for (int64_t r = r0 + rl; r < r1; r += L.lanes) {
+      if (VEC == 4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(base + r * C));
+        s[0] += v.x; s[1 % VEC] += v.y; s[2 % VEC] += v.z; s[3 % VEC] += v.w;
+        if (SQ) { q[0] += v.x * v.x; q[1 % VEC] += v.y * v.y; q[2 % VEC] += v.z * v.z; q[3 % VEC] += v.w * v.w; }
+      } else {
+        float v = __ldg(base + r * C);
+        s[0] += v;
+        if (SQ) q[0] += v * v;
+      }
+    }
+  }
+  double v[2 * VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { v[k] = s[k]; v[VEC + k] = q[k]; }
+  if (active) {
+    for (int k = 0; k < 2 * VEC; ++k) sred[(rl * L.cvec + cv) * 2 * VEC + k] = v[k];
+  }
+  __syncthreads();
+  if (active && rl == 0) {
+    for (int k = 0; k < 2 * VEC; ++k) {
+      double t = 0.0;
+      for (int l = 0; l < L.lanes; ++l) t += sred[(l * L.cvec + cv) * 2 * VEC + k];
+      v[k] = t;
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      atomicAdd(sum + (int64_t)g * C + cv * VEC + k, v[k]);
+      if (SQ) atomicAdd(sumsq + (int64_t)g * C + cv * VEC + k, v[VEC + k]);
+    }
+  }
+}
+
+__global__ void finalize_kernel(const double* sum, const double* sumsq, int64_t cnt, int groups, int C, float eps,
+                                float* mean, float* invstd, float* running_mean, float* running_var, float momentum,
+                                int64_t* nbt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && nbt) *nbt += 1;
+  if (i >= groups * C) return;
+  double m = sum[i] / (double)cnt;
+  double var = sumsq[i] / (double)cnt - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[i] = (float)m;
+  invstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean && groups == 1) {
+    double unb = cnt > 1 ? var * (double)cnt / (double)(cnt - 1) : var;
+    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * (float)m;
+    running_var[i] = (1.f - momentum) * running_var[i] + momentum * (float)unb;
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(THREADS)
+apply_kernel(const float* __restrict__ y, int64_t total_vec, int64_t rows_per_group, int C, const float* __restrict__ mean,
+             const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+             float slope, float* __restrict__ out) {
+  const int cvec = C / VEC;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = i / cvec;
+    int c0 = (int)(i - row * cvec) * VEC;
+    int64_t sbase = mean ? (row / rows_per_group) * C : 0;
+    float v[VEC];
+    if (VEC == 4) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(y) + i);
+      v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+    } else {
+      v[0] = __ldg(y + i);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      int c = c0 + k;
+      float x = v[k];
+      if (mean) x = (x - __ldg(mean + sbase + c)) * __ldg(invstd + sbase + c);
+      if (gamma) x = x * __ldg(gamma + c);
+      if (beta) x = x + __ldg(beta + c);
+      v[k] = act_fwd(x, act, slope);
+    }
+    if (VEC == 4) reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+    else out[i] = v[0];
+  }
+}
+
+// g = dz * act'(pre), xhat; shared by both backward passes
+__device__ __forceinline__ void bwd_terms(float dz, float yv, float mu, float is, float ga, float be, bool has_norm, int act,
+                                          float slope, float& gout, float& xhat) {
+  xhat = has_norm ? (yv - mu) * is : yv;
+  float pre = xhat * ga + be;
+  gout = dz * act_grad(pre, act, slope);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(THREADS)
+bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y, int64_t rows_per_group, int C,
+                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, int act, float slope, double* __restrict__ s1, double* __restrict__ s2) {
+  extern __shared__ double sred[];
+  const Lanes L = make_lanes(C, VEC);
+  const int tid = threadIdx.x;
+  const int cv = tid % L.cvec, rl = tid / L.cvec;
+  const int g = blockIdx.y;
+  const bool active = rl < L.lanes;
+  const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK;
+  const int64_t r1 = imin64(r0 + ROWS_PER_BLOCK, rows_per_group);
+  float a1[VEC], a2[VEC], mu[VEC], is[VEC], ga[VEC], be[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    a1[k] = 0.f; a2[k] = 0.f;
+    int c = cv * VEC + k;
+    bool ok = active && c < C;
+    mu[k] = (ok && mean) ? mean[(int64_t)g * C + c] : 0.f;
+    is[k] = (ok && mean) ? invstd[(int64_t)g * C + c] : 1.f;
+    ga[k] = (ok && gamma) ? gamma[c] : 1.f;
+    be[k] = (ok && beta) ? beta[c] : 0.f;
+  }
+  if (active) {
+    const int64_t off = ((int64_t)g * rows_per_group) * C + cv * VEC;
+    for (int64_t r = r0 + rl; r < r1; r += L.lanes) {
+      float d[VEC], yv[VEC];
+      if (VEC == 4) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(dz + off + r * C));
+        float4 u = __ldg(reinterpret_cast<const float4*>(y + off + r * C));
+        d[0] = t.x; d[1 % VEC] = t.y; d[2 % VEC] = t.z; d[3 % VEC] = t.w;
+        yv[0] = u.x; yv[1 % VEC] = u.y; yv[2 % VEC] = u.z; yv[3 % VEC] = u.w;
+      } else {
+        d[0] = __ldg(dz + off + r * C);
+        yv[0] = __ldg(y + off + r * C);
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        float gg, xh;
+        bwd_terms(d[k], yv[k], mu[k], is[k], ga[k], be[k], mean != nullptr, act, slope, gg, xh);
+        a1[k] += gg;
+        a2[k] += gg * xh;
+      }
+    }
+  }
+  double v[2 * VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { v[k] = a1[k]; v[VEC + k] = a2[k]; }
+  if (active)
+    for (int k = 0; k < 2 * VEC; ++k) sred[(rl * L.cvec + cv) * 2 * VEC + k] = v[k];
+  __syncthreads();
+  if (active && rl == 0) {
+    for (int k = 0; k < 2 * VEC; ++k) {
+      double t = 0.0;
+      for (int l = 0; l < L.lanes; ++l) t += sred[(l * L.cvec + cv) * 2 * VEC + k];
+      v[k] = t;
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      atomicAdd(s1 + (int64_t)g * C + cv * VEC + k, v[k]);
+      atomicAdd(s2 + (int64_t)g * C + cv * VEC + k, v[VEC + k]);
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(THREADS)
+bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, int64_t total_vec, int64_t rows_per_group, int C,
+                 const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, int act, float slope, const double* __restrict__ s1,
+                 const double* __restrict__ s2, float* __restrict__ dy) {
+  const int cvec = C / VEC;
+  const float inv_cnt = 1.f / (float)rows_per_group;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = i / cvec;
+    int c0 = (int)(i - row * cvec) * VEC;
+    int64_t sbase = (row / rows_per_group) * C;
+    float d[VEC], yv[VEC], o[VEC];
+    if (VEC == 4) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(dz) + i);
+      float4 u = __ldg(reinterpret_cast<const float4*>(y) + i);
+      d[0] = t.x; d[1 % VEC] = t.y; d[2 % VEC] = t.z; d[3 % VEC] = t.w;
+      yv[0] = u.x; yv[1 % VEC] = u.y; yv[2 % VEC] = u.z; yv[3 % VEC] = u.w;
+    } else {
+      d[0] = __ldg(dz + i);
+      yv[0] = __ldg(y + i);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      int c = c0 + k;
+      float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
+      if (mean) {
+        float mu = __ldg(mean + sbase + c), is = __ldg(invstd + sbase + c);
+        float gg, xh;
+        bwd_terms(d[k], yv[k], mu, is, ga, be, true, act, slope, gg, xh);
+        float m1 = (float)(s1[sbase + c]) * inv_cnt, m2 = (float)(s2[sbase + c]) * inv_cnt;
+        o[k] = ga * is * (gg - m1 - xh * m2);
+      } else {
+        float gg, xh;
+        bwd_terms(d[k], yv[k], 0.f, 1.f, ga, be, false, act, slope, gg, xh);
+        o[k] = gg * ga;
+      }
+    }
+    if (VEC == 4) reinterpret_cast<float4*>(dy)[i] = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+    else dy[i] = o[0];
+  }
+}
+
+__global__ void fold_kernel(const double* sums, int groups, int C, float* out, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double t = 0.0;
+  for (int g = 0; g < groups; ++g) t += sums[(int64_t)g * C + c];
+  out[c] = (accumulate ? out[c] : 0.f) + (float)t;
+}
+
+__global__ void rsqrt_eps_kernel(const float* var, int n, float eps, float* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)(1.0 / sqrt((double)var[i] + (double)eps));
+}
+
+int pick_vec(int C, const void* p0, const void* p1 = nullptr) {
+  bool aligned = (reinterpret_cast<uintptr_t>(p0) % 16 == 0) && (p1 == nullptr || reinterpret_cast<uintptr_t>(p1) % 16 == 0);
+  return (C % 4 == 0 && aligned) ? 4 : 1;
+}
+
+}  // namespace
+
+extern "C" int viai_channel_stats(const float* y, int64_t rows_per_group, int groups, int C, double* sum, double* sumsq,
+                                  viai_stream_t stream) {
+  VIAI_REQUIRE(y && sum && rows_per_group > 0 && groups > 0 && C > 0, "viai_channel_stats: bad arguments");
+  cudaStream_t st = STR(stream);
+  VIAI_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * groups * C, st));
+  if (sumsq) VIAI_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * groups * C, st));
+  const int VEC = pick_vec(C, y);
+  VIAI_REQUIRE(C / VEC <= THREADS, "viai_channel_stats: C=%d too large", C);
+  dim3 grid((unsigned)cdiv(rows_per_group, ROWS_PER_BLOCK), (unsigned)groups);
+  size_t smem = sizeof(double) * THREADS * 2 * VEC;
+  if (VEC == 4) {
+    if (sumsq) stats_kernel<4, true><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq);
+    else stats_kernel<4, false><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq);
+  } else {
+    if (sumsq) stats_kernel<1, true><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq);
+    else stats_kernel<1, false><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq);
+  }
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_norm_finalize(const double* sum, const double* sumsq, int64_t rows_per_group, int groups, int C,
+                                  float eps, float* mean, float* invstd, float* running_mean, float* running_var,
+                                  float momentum, int64_t* num_batches_tracked, viai_stream_t stream) {
+  VIAI_REQUIRE(sum && sumsq && mean && invstd && groups > 0 && C > 0, "viai_norm_finalize: bad arguments");
+  int n = groups * C;
+  finalize_kernel<<<(n + 255) / 256, 256, 0, STR(stream)>>>(sum, sumsq, rows_per_group, groups, C, eps, mean, invstd,
+                                                          running_mean, running_var, momentum, num_batches_tracked);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_norm_act_fwd(const float* y, int64_t rows_per_group, int groups, int C, const float* mean,
+                                 const float* invstd, const float* gamma, const float* beta, int act, float slope,
+                                 float* out, viai_stream_t stream) {
+  VIAI_REQUIRE(y && out && rows_per_group > 0 && groups > 0 && C > 0, "viai_norm_act_fwd: bad arguments");
+  VIAI_REQUIRE((mean == nullptr) == (invstd == nullptr), "viai_norm_act_fwd: mean/invstd must both be set or NULL");
+  const int VEC = pick_vec(C, y, out);
+  int64_t total = rows_per_group * groups * C / VEC;
+  int blocks = (int)imin64(cdiv(total, THREADS), 16 * kNumSMs);
+  if (VEC == 4) apply_kernel<4><<<blocks, THREADS, 0, STR(stream)>>>(y, total, rows_per_group, C, mean, invstd, gamma, beta, act, slope, out);
+  else apply_kernel<1><<<blocks, THREADS, 0, STR(stream)>>>(y, total, rows_per_group, C, mean, invstd, gamma, beta, act, slope, out);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_norm_act_bwd_reduce(const float* dz, const float* y, int64_t rows_per_group, int groups, int C,
+                                        const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                        int act, float slope, double* s1, double* s2, viai_stream_t stream) {
+  VIAI_REQUIRE(dz && y && s1 && s2 && rows_per_group > 0 && groups > 0 && C > 0, "viai_norm_act_bwd_reduce: bad arguments");
+  cudaStream_t st = STR(stream);
+  VIAI_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * groups * C, st));
+  VIAI_CUDA(cudaMemsetAsync(s2, 0, sizeof(double) * groups * C, st));
+  const int VEC = pick_vec(C, dz, y);
+  VIAI_REQUIRE(C / VEC <= THREADS, "viai_norm_act_bwd_reduce: C=%d too large", C);
+  dim3 grid((unsigned)cdiv(rows_per_group, ROWS_PER_BLOCK), (unsigned)groups);
+  size_t smem = sizeof(double) * THREADS * 2 * VEC;
+  if (VEC == 4) bwd_reduce_kernel<4><<<grid, THREADS, smem, st>>>(dz, y, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2);
+  else bwd_reduce_kernel<1><<<grid, THREADS, smem, st>>>(dz, y, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_norm_act_bwd_apply(const float* dz, const float* y, int64_t rows_per_group, int groups, int C,
+                                       const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                       int act, float slope, const double* s1, const double* s2, float* dy, float* dgamma,
+                                       float* dbeta, viai_stream_t stream) {
+  VIAI_REQUIRE(dz && y && dy && rows_per_group > 0 && groups > 0 && C > 0, "viai_norm_act_bwd_apply: bad arguments");
+  VIAI_REQUIRE(mean == nullptr || (s1 && s2 && invstd), "viai_norm_act_bwd_apply: statistics missing");
+  cudaStream_t st = STR(stream);
+  const int VEC = pick_vec(C, dz, y) == 4 && pick_vec(C, dy) == 4 ? 4 : 1;
+  int64_t total = rows_per_group * groups * C / VEC;
+  int blocks = (int)imin64(cdiv(total, THREADS), 16 * kNumSMs);
+  if (VEC == 4) bwd_apply_kernel<4><<<blocks, THREADS, 0, st>>>(dz, y, total, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy);
+  else bwd_apply_kernel<1><<<blocks, THREADS, 0, st>>>(dz, y, total, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy);
+  VIAI_LAUNCHED();
+  if (dgamma && s2) {
+    fold_kernel<<<(C + 255) / 256, 256, 0, st>>>(s2, groups, C, dgamma, 0);
+    VIAI_LAUNCHED();
+  }
+  if (dbeta && s1) {
+    fold_kernel<<<(C + 255) / 256, 256, 0, st>>>(s1, groups, C, dbeta, 0);
+    VIAI_LAUNCHED();
+  }
+  return VIAI_OK;
+}
+
+extern "C" int viai_fold_groups(const double* sums, int groups, int C, float* out, int accumulate, viai_stream_t stream) {
+  VIAI_REQUIRE(sums && out && groups > 0 && C > 0, "viai_fold_groups: bad arguments");
+  fold_kernel<<<(C + 255) / 256, 256, 0, STR(stream)>>>(sums, groups, C, out, accumulate);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_rsqrt_eps(const float* var, int n, float eps, float* out, viai_stream_t stream) {
+  VIAI_REQUIRE(var && out && n > 0, "viai_rsqrt_eps: bad arguments");
+  rsqrt_eps_kernel<<<(n + 255) / 256, 256, 0, STR(stream)>>>(var, n, eps, out);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}

@@ -1,0 +1,310 @@
+// Bilinear (align_corners=True) resize into a channel slice, channel-slice copy, pooling and small elementwise ops (NHWC fp32).
+#include "common.cuh"
+using namespace viai;
+
+namespace {
+
+constexpr int THREADS = 256;
+
+// Same float arithmetic as ATen's upsample_bilinear2d (align_corners=True): ratio = (in-1)/(out-1) in float,
+// src = ratio*dst, i0 = (int)src, lambda1 = src - i0, i1 = i0 + (i0 < in-1).
+__device__ __forceinline__ float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+__device__ __forceinline__ void src_index(float scale, int dst, int in, int& i0, int& i1, float& l0, float& l1) {
+  float src = scale * (float)dst;
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f);
+  l0 = 1.f - l1;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(THREADS)
+bilinear_fwd_kernel(const float* __restrict__ in, int N, int Hin, int Win, int C, float* __restrict__ out, int Hout,
+                    int Wout, int Ctot, int coff) {
+  const int cvec = C / VEC;
+  const int64_t total = (int64_t)N * Hout * Wout * cvec;
+  const float sh = ac_scale(Hin, Hout), sw = ac_scale(Win, Wout);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % cvec);
+    int64_t t = i / cvec;
+    int x = (int)(t % Wout); t /= Wout;
+    int y = (int)(t % Hout);
+    int n = (int)(t / Hout);
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    src_index(sh, y, Hin, y0, y1, ly0, ly1);
+    src_index(sw, x, Win, x0, x1, lx0, lx1);
+    const float* b = in + (int64_t)n * Hin * Win * C + cv * VEC;
+    float* o = out + (((int64_t)n * Hout + y) * Wout + x) * Ctot + coff + cv * VEC;
+    if (VEC == 4) {
+      float4 a = __ldg(reinterpret_cast<const float4*>(b + ((int64_t)y0 * Win + x0) * C));
+      float4 bb = __ldg(reinterpret_cast<const float4*>(b + ((int64_t)y0 * Win + x1) * C));
+      float4 c = __ldg(reinterpret_cast<const float4*>(b + ((int64_t)y1 * Win + x0) * C));
+      float4 d = __ldg(reinterpret_cast<const float4*>(b + ((int64_t)y1 * Win + x1) * C));
+      float4 r;
+      r.x = ly0 * (lx0 * a.x + lx1 * bb.x) + ly1 * (lx0 * c.x + lx1 * d.x);
+      r.y = ly0 * (lx0 * a.y + lx1 * bb.y) + ly1 * (lx0 * c.y + lx1 * d.y);
+      r.z = ly0 * (lx0 * a.z + lx1 * bb.z) + ly1 * (lx0 * c.z + lx1 * d.z);
+      r.w = ly0 * (lx0 * a.w + lx1 * bb.w) + ly1 * (lx0 * c.w + lx1 * d.w);
+      *reinterpret_cast<float4*>(o) = r;
+    } else {
+      float a = __ldg(b + ((int64_t)y0 * Win + x0) * C), bb = __ldg(b + ((int64_t)y0 * Win + x1) * C);
+      float c = __ldg(b + ((int64_t)y1 * Win + x0) * C), d = __ldg(b + ((int64_t)y1 * Win + x1) * C);
+      *o = ly0 * (lx0 * a + lx1 * bb) + ly1 * (lx0 * c + lx1 * d);
+    }
+  }
+}
+
+// Gather-form backward (deterministic, no atomics): for every input pixel, visit the output pixels whose
+// forward footprint touches it.  Candidate range is widened by one and each candidate re-evaluates the
+// forward index computation, so float rounding cannot desynchronise the two directions.
+__device__ __forceinline__ void cand_range(float scale, int i, int in, int out, int& lo, int& hi) {
+  if (scale <= 0.f) { lo = 0; hi = out - 1; return; }
+  float inv = 1.f / scale;
+  lo = (int)floorf((float)(i - 1) * inv) - 1;
+  hi = (int)ceilf((float)(i + 1) * inv) + 1;
+  if (lo < 0) lo = 0;
+  if (hi > out - 1) hi = out - 1;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(THREADS)
+bilinear_bwd_kernel(const float* __restrict__ dout, int N, int Hin, int Win, int C, float* __restrict__ din, int Hout,
+                    int Wout, int Ctot, int coff) {
+  const int cvec = C / VEC;
+  const int64_t total = (int64_t)N * Hin * Win * cvec;
+  const float sh = ac_scale(Hin, Hout), sw = ac_scale(Win, Wout);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % cvec);
+    int64_t t = i / cvec;
+    int ix = (int)(t % Win); t /= Win;
+    int iy = (int)(t % Hin);
+    int n = (int)(t / Hin);
+    int ylo, yhi, xlo, xhi;
+    cand_range(sh, iy, Hin, Hout, ylo, yhi);
+    cand_range(sw, ix, Win, Wout, xlo, xhi);
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int y = ylo; y <= yhi; ++y) {
+      int y0, y1; float ly0, ly1;
+      src_index(sh, y, Hin, y0, y1, ly0, ly1);
+      float wy = (y0 == iy ? ly0 : 0.f) + (y1 == iy ? ly1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int x = xlo; x <= xhi; ++x) {
+        int x0, x1; float lx0, lx1;
+        src_index(sw, x, Win, x0, x1, lx0, lx1);
+        float wx = (x0 == ix ? lx0 : 0.f) + (x1 == ix ? lx1 : 0.f);
+        if (wx == 0.f) continue;
+        const float* d = dout + (((int64_t)n * Hout + y) * Wout + x) * Ctot + coff + cv * VEC;
+        float w = wy * wx;
+        if (VEC == 4) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(d));
+          acc[0] += w * v.x; acc[1 % VEC] += w * v.y; acc[2 % VEC] += w * v.z; acc[3 % VEC] += w * v.w;
+        } else {
+          acc[0] += w * __ldg(d);
+        }
+      }
+    }
+    float* o = din + i * VEC;
+    if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+    else *o = acc[0];
+  }
+}
+
+__global__ void copy_channels_kernel(const float* __restrict__ src, int64_t rows, int Csrc, int soff, float* __restrict__ dst,
+                                     int Cdst, int doff, int C) {
+  const int64_t total = rows * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = i / C;
+    int c = (int)(i - row * C);
+    dst[row * Cdst + doff + c] = __ldg(src + row * Csrc + soff + c);
+  }
+}
+
+__global__ void avgpool_h_fwd_kernel(const float* __restrict__ in, int N, int H, int W, int C, int kh, float* __restrict__ out) {
+  const int Ho = H / kh;
+  const int64_t total = (int64_t)N * Ho * W * C;
+  const float inv = 1.f / (float)kh;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t wc = i % ((int64_t)W * C);
+    int64_t t = i / ((int64_t)W * C);
+    int yo = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    float s = 0.f;
+    for (int k = 0; k < kh; ++k) s += __ldg(in + ((int64_t)n * H + yo * kh + k) * W * C + wc);
+    out[i] = s * inv;
+  }
+}
+
+__global__ void avgpool_h_bwd_kernel(const float* __restrict__ dout, int N, int H, int W, int C, int kh, float* __restrict__ din) {
+  const int Ho = H / kh;
+  const int64_t total = (int64_t)N * H * W * C;
+  const float inv = 1.f / (float)kh;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t wc = i % ((int64_t)W * C);
+    int64_t t = i / ((int64_t)W * C);
+    int y = (int)(t % H);
+    int n = (int)(t / H);
+    int yo = y / kh;
+    din[i] = yo < Ho ? __ldg(dout + ((int64_t)n * Ho + yo) * W * C + wc) * inv : 0.f;
+  }
+}
+
+__global__ void maxpool_fwd_kernel(const float* __restrict__ in, int N, int H, int W, int C, float* __restrict__ out, int Ho, int Wo) {
+  const int64_t total = (int64_t)N * Ho * Wo * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int xo = (int)(t % Wo); t /= Wo;
+    int yo = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    float m = -INFINITY;
+    for (int r = 0; r < 3; ++r) {
+      int y = yo * 2 - 1 + r;
+      if (y < 0 || y >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        int x = xo * 2 - 1 + s;
+        if (x < 0 || x >= W) continue;
+        m = fmaxf(m, __ldg(in + (((int64_t)n * H + y) * W + x) * C + c));
+      }
+    }
+    out[i] = m;
+  }
+}
+
+// Gather-form backward: an input pixel collects the gradient of every window in which it is the FIRST maximum
+// (row-major scan order, which is ATen's tie-breaking rule).
+__global__ void maxpool_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout, int N, int H, int W, int C,
+                                   float* __restrict__ din, int Ho, int Wo) {
+  const int64_t total = (int64_t)N * H * W * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int x = (int)(t % W); t /= W;
+    int y = (int)(t % H);
+    int n = (int)(t / H);
+    const float v = __ldg(in + i);
+    float acc = 0.f;
+    for (int yo = (y + 1) / 2 - 1; yo <= (y + 1) / 2; ++yo) {
+      if (yo < 0 || yo >= Ho || yo * 2 - 1 > y || yo * 2 + 1 < y) continue;
+      for (int xo = (x + 1) / 2 - 1; xo <= (x + 1) / 2; ++xo) {
+        if (xo < 0 || xo >= Wo || xo * 2 - 1 > x || xo * 2 + 1 < x) continue;
+        // is (y,x) the first max of window (yo,xo)?
+        bool first = true;
+        for (int r = 0; r < 3 && first; ++r) {
+          int yy = yo * 2 - 1 + r;
+          if (yy < 0 || yy >= H) continue;
+          for (int s = 0; s < 3; ++s) {
+            int xx = xo * 2 - 1 + s;
+            if (xx < 0 || xx >= W) continue;
+            float u = __ldg(in + (((int64_t)n * H + yy) * W + xx) * C + c);
+            bool before = (yy < y) || (yy == y && xx < x);
+            if (u > v || (before && u == v)) { first = false; break; }
+          }
+        }
+        if (first) acc += __ldg(dout + (((int64_t)n * Ho + yo) * Wo + xo) * C + c);
+      }
+    }
+    din[i] = acc;
+  }
+}
+
+__global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = a[i] * b[i];
+}
+__global__ void add_act_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n, int act) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = act_fwd(a[i] + b[i], act, 0.f);
+}
+__global__ void add_act_bwd_kernel(const float* __restrict__ out, const float* __restrict__ dout, float* __restrict__ din, int64_t n, int act) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    din[i] = (act == VIAI_ACT_RELU && !(out[i] > 0.f)) ? 0.f : dout[i];
+}
+
+inline int grid_for(int64_t total) { return (int)imin64(cdiv(total, THREADS), 16 * kNumSMs); }
+
+}  // namespace
+
+extern "C" int viai_bilinear_fwd(const float* in, int N, int Hin, int Win, int C, float* out, int Hout, int Wout,
+                                 int Ctot, int coff, viai_stream_t stream) {
+  VIAI_REQUIRE(in && out && N > 0 && Hin > 0 && Win > 0 && C > 0 && Hout > 0 && Wout > 0 && coff >= 0 && coff + C <= Ctot,
+               "viai_bilinear_fwd: bad arguments");
+  bool v4 = C % 4 == 0 && Ctot % 4 == 0 && coff % 4 == 0 &&
+            (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
+  int64_t total = (int64_t)N * Hout * Wout * (C / (v4 ? 4 : 1));
+  if (v4) bilinear_fwd_kernel<4><<<grid_for(total), THREADS, 0, STR(stream)>>>(in, N, Hin, Win, C, out, Hout, Wout, Ctot, coff);
+  else bilinear_fwd_kernel<1><<<grid_for(total), THREADS, 0, STR(stream)>>>(in, N, Hin, Win, C, out, Hout, Wout, Ctot, coff);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_bilinear_bwd(const float* dout, int N, int Hin, int Win, int C, float* din, int Hout, int Wout,
+                                 int Ctot, int coff, viai_stream_t stream) {
+  VIAI_REQUIRE(dout && din && N > 0 && Hin > 0 && Win > 0 && C > 0 && Hout > 0 && Wout > 0 && coff >= 0 && coff + C <= Ctot,
+               "viai_bilinear_bwd: bad arguments");
+  bool v4 = C % 4 == 0 && Ctot % 4 == 0 && coff % 4 == 0 &&
+            (reinterpret_cast<uintptr_t>(din) | reinterpret_cast<uintptr_t>(dout)) % 16 == 0;
+  int64_t total = (int64_t)N * Hin * Win * (C / (v4 ? 4 : 1));
+  if (v4) bilinear_bwd_kernel<4><<<grid_for(total), THREADS, 0, STR(stream)>>>(dout, N, Hin, Win, C, din, Hout, Wout, Ctot, coff);
+  else bilinear_bwd_kernel<1><<<grid_for(total), THREADS, 0, STR(stream)>>>(dout, N, Hin, Win, C, din, Hout, Wout, Ctot, coff);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_copy_channels(const float* src, int64_t rows, int Csrc, int soff, float* dst, int Cdst, int doff,
+                                  int C, viai_stream_t stream) {
+  VIAI_REQUIRE(src && dst && rows > 0 && C > 0 && soff >= 0 && doff >= 0 && soff + C <= Csrc && doff + C <= Cdst,
+               "viai_copy_channels: bad arguments");
+  copy_channels_kernel<<<grid_for(rows * C), THREADS, 0, STR(stream)>>>(src, rows, Csrc, soff, dst, Cdst, doff, C);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_avgpool_h_fwd(const float* in, int N, int H, int W, int C, int kh, float* out, viai_stream_t stream) {
+  VIAI_REQUIRE(in && out && N > 0 && W > 0 && C > 0 && kh > 0 && H >= kh, "viai_avgpool_h_fwd: bad arguments (H=%d, kh=%d)", H, kh);
+  avgpool_h_fwd_kernel<<<grid_for((int64_t)N * (H / kh) * W * C), THREADS, 0, STR(stream)>>>(in, N, H, W, C, kh, out);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+extern "C" int viai_avgpool_h_bwd(const float* dout, int N, int H, int W, int C, int kh, float* din, viai_stream_t stream) {
+  VIAI_REQUIRE(dout && din && N > 0 && W > 0 && C > 0 && kh > 0 && H >= kh, "viai_avgpool_h_bwd: bad arguments");
+  avgpool_h_bwd_kernel<<<grid_for((int64_t)N * H * W * C), THREADS, 0, STR(stream)>>>(dout, N, H, W, C, kh, din);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+extern "C" int viai_maxpool3s2_fwd(const float* in, int N, int H, int W, int C, float* out, int Ho, int Wo, viai_stream_t stream) {
+  VIAI_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1,
+               "viai_maxpool3s2_fwd: bad arguments");
+  maxpool_fwd_kernel<<<grid_for((int64_t)N * Ho * Wo * C), THREADS, 0, STR(stream)>>>(in, N, H, W, C, out, Ho, Wo);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+extern "C" int viai_maxpool3s2_bwd(const float* in, const float* dout, int N, int H, int W, int C, float* din, int Ho,
+                                   int Wo, viai_stream_t stream) {
+  VIAI_REQUIRE(in && dout && din && N > 0 && H > 0 && W > 0 && C > 0 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1,
+               "viai_maxpool3s2_bwd: bad arguments");
+  maxpool_bwd_kernel<<<grid_for((int64_t)N * H * W * C), THREADS, 0, STR(stream)>>>(in, dout, N, H, W, C, din, Ho, Wo);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+extern "C" int viai_mul(const float* a, const float* b, float* out, int64_t n, viai_stream_t stream) {
+  VIAI_REQUIRE(a && b && out && n > 0, "viai_mul: bad arguments");
+  mul_kernel<<<grid_for(n), THREADS, 0, STR(stream)>>>(a, b, out, n);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+extern "C" int viai_add_act(const float* a, const float* b, float* out, int64_t n, int act, viai_stream_t stream) {
+  VIAI_REQUIRE(a && b && out && n > 0, "viai_add_act: bad arguments");
+  add_act_kernel<<<grid_for(n), THREADS, 0, STR(stream)>>>(a, b, out, n, act);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+extern "C" int viai_add_act_bwd(const float* out, const float* dout, float* din, int64_t n, int act, viai_stream_t stream) {
+  VIAI_REQUIRE(out && dout && din && n > 0, "viai_add_act_bwd: bad arguments");
+  add_act_bwd_kernel<<<grid_for(n), THREADS, 0, STR(stream)>>>(out, dout, din, n, act);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}

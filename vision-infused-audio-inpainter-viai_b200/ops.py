@@ -1,0 +1,490 @@
+"""Autograd operators of the VIAI hot path.  Every op launches kernels of libviai_b200.so through the C ABI;
+PyTorch only owns memory, streams and the autograd tape.  Activations are NHWC fp32 CUDA tensors of shape
+(N, H, W, C)."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvGeom
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise RuntimeError("VIAI ops need float32 CUDA tensors (got %s on %s); there is no CPU path" % (t.dtype, t.device))
+
+
+def grad_target(param):
+    """Gradient-bucket view installed by viai_b200.optim.GradBucket (fused wgrad accumulation), else None."""
+    return None if param is None else getattr(param, "_viai_grad", None)
+
+
+def _geom(N, Hin, Win, Cin, Hout, Wout, Cout, R, S, stride, pad, mode):
+    return ConvGeom(N, Hin, Win, Cin, Hout, Wout, Cout, R, S, stride[0], stride[1], pad[0], pad[1], mode)
+
+
+def _pack(weight, O_dim, I_dim, flip=False):
+    """[O][R][S][I] operand from a (d0, d1, kh, kw) parameter; O_dim/I_dim say which of d0/d1 is O/I."""
+    L = _lib.lib()
+    O, I = weight.size(O_dim), weight.size(I_dim)
+    R, S = weight.size(2), weight.size(3)
+    out = torch.empty((O, R, S, I), device=weight.device, dtype=torch.float32)
+    _lib.check(L.viai_pack_weight(_p(weight), _p(out), O, I, R, S, weight.stride(O_dim), weight.stride(I_dim),
+                                  weight.stride(2), weight.stride(3), int(flip), _stream()), "pack_weight")
+    return out
+
+
+def _conv_out_size(H, k, s, p, transposed):
+    return (H - 1) * s - 2 * p + k if transposed else (H + 2 * p - k) // s + 1
+
+
+class _ConvFn(torch.autograd.Function):
+    """nn.Conv2d / nn.ConvTranspose2d forward + convolution_backward (see include/viai_b200.h for the site list)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, transposed):
+        _require_cuda(x, weight, bias)
+        x = x.contiguous()
+        L = _lib.lib()
+        N, H, W, C = x.shape
+        R, S = weight.size(2), weight.size(3)
+        if not transposed:
+            Cout = weight.size(0)
+            assert weight.size(1) == C, "conv: weight expects %d input channels, got %d" % (weight.size(1), C)
+            wp = _pack(weight, 0, 1)
+            mode = 0
+        else:
+            Cout = weight.size(1)
+            assert weight.size(0) == C, "convT: weight expects %d input channels, got %d" % (weight.size(0), C)
+            wp = _pack(weight, 1, 0)
+            mode = 1
+        Ho = _conv_out_size(H, R, stride[0], padding[0], transposed)
+        Wo = _conv_out_size(W, S, stride[1], padding[1], transposed)
+        if Ho <= 0 or Wo <= 0:
+            raise RuntimeError("conv output size is non-positive: (%d, %d)" % (Ho, Wo))
+        y = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+        g = _geom(N, H, W, C, Ho, Wo, Cout, R, S, stride, padding, mode)
+        _lib.check(L.viai_conv2d_simt(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _stream()), "conv2d")
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (stride, padding, transposed, bias is not None)
+        ctx.targets = (grad_target(weight), grad_target(bias))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        stride, padding, transposed, has_bias = ctx.cfg
+        L = _lib.lib()
+        dy = dy.contiguous()
+        N, H, W, C = x.shape
+        _, Ho, Wo, Cout = dy.shape
+        R, S = weight.size(2), weight.size(3)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            if not transposed:       # dgrad of Conv2d: transposed gather with wp[o=ci][r][s][i=co]
+                wp = _pack(weight, 1, 0)
+                g = _geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 1)
+            else:                    # dgrad of ConvTranspose2d: forward gather with wp[o=ci][r][s][i=co]
+                wp = _pack(weight, 0, 1)
+                g = _geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0)
+            _lib.check(L.viai_conv2d_simt(ctypes.byref(g), _p(dy), _p(wp), None, _p(dx), _stream()), "conv2d dgrad")
+        wt, bt = ctx.targets
+        if ctx.needs_input_grad[1]:
+            dw = wt if wt is not None else torch.empty_like(weight, memory_format=torch.contiguous_format)
+            if not transposed:       # U = dOut (A = Cout), G = x (B = Cin)
+                g = _geom(N, H, W, C, Ho, Wo, Cout, R, S, stride, padding, 0)
+                U, G = dy, x
+            else:                    # U = x (A = Cin_t), G = dOut (B = Cout_t)
+                g = _geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0)
+                U, G = x, dy
+            _lib.check(L.viai_conv2d_wgrad_simt(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1),
+                                                dw.stride(2), dw.stride(3), int(wt is not None), _stream()), "conv2d wgrad")
+            if wt is not None:
+                dw = None            # accumulated straight into the gradient bucket
+        if has_bias and ctx.needs_input_grad[2]:
+            rows = N * Ho * Wo
+            acc = torch.empty(Cout, device=dy.device, dtype=torch.float64)
+            db = bt if bt is not None else torch.empty(Cout, device=dy.device, dtype=torch.float32)
+            _lib.check(L.viai_channel_stats(_p(dy), rows, 1, Cout, _p(acc), None, _stream()), "bias grad")
+            _lib.check(L.viai_fold_groups(_p(acc), 1, Cout, _p(db), int(bt is not None), _stream()), "bias grad fold")
+            if bt is not None:
+                db = None
+        return dx, dw, db, None, None, None
+
+
+def conv2d(x, weight, bias=None, stride=(1, 1), padding=(0, 0), transposed=False):
+    return _ConvFn.apply(x, weight, bias, tuple(stride), tuple(padding), transposed)
+
+
+class _NormActFn(torch.autograd.Function):
+    """norm in {'bn','in','none'} followed by an activation.  Replaces native_batch_norm / instance_norm +
+    leaky_relu / relu / sigmoid (networks/Inpainting_Networks.py:72-76, networks/New_Inpainting_Networks.py:31-33,
+    networks/Discriminator_Networks.py:38-49)."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, nbt, norm, training, act, slope, eps, momentum):
+        _require_cuda(y, gamma, beta)
+        L = _lib.lib()
+        y = y.contiguous()
+        N, H, W, C = y.shape
+        dev = y.device
+        mean = invstd = None
+        groups, rpg = 1, N * H * W
+        if norm == "in":
+            groups, rpg = N, H * W
+        if norm in ("bn", "in"):
+            use_batch = training or norm == "in" or running_mean is None
+            if use_batch:
+                s = torch.empty((2, groups * C), device=dev, dtype=torch.float64)
+                mean = torch.empty(groups * C, device=dev, dtype=torch.float32)
+                invstd = torch.empty(groups * C, device=dev, dtype=torch.float32)
+                _lib.check(L.viai_channel_stats(_p(y), rpg, groups, C, _p(s[0]), _p(s[1]), _stream()), "channel_stats")
+                upd = norm == "bn" and training and running_mean is not None
+                _lib.check(L.viai_norm_finalize(_p(s[0]), _p(s[1]), rpg, groups, C, eps, _p(mean), _p(invstd),
+                                                _p(running_mean) if upd else None, _p(running_var) if upd else None,
+                                                momentum, _p(nbt) if upd else None, _stream()), "norm_finalize")
+            else:
+                mean = running_mean
+                invstd = torch.empty(C, device=dev, dtype=torch.float32)
+                _lib.check(L.viai_rsqrt_eps(_p(running_var), C, eps, _p(invstd), _stream()), "rsqrt_eps")
+        out = torch.empty_like(y)
+        _lib.check(L.viai_norm_act_fwd(_p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta), act, slope,
+                                       _p(out), _stream()), "norm_act_fwd")
+        ctx.save_for_backward(y, mean, invstd, gamma, beta)
+        ctx.cfg = (norm, groups, rpg, act, slope, training or norm != "bn")
+        ctx.targets = (grad_target(gamma), grad_target(beta))
+        return out
+
+    @staticmethod
+    def backward(ctx, dz):
+        y, mean, invstd, gamma, beta = ctx.saved_tensors
+        norm, groups, rpg, act, slope, batch_stats = ctx.cfg
+        if norm == "bn" and not batch_stats:
+            raise RuntimeError("backward through eval-mode BatchNorm is not part of the VIAI hot path")
+        L = _lib.lib()
+        dz = dz.contiguous()
+        C = y.size(3)
+        dy = torch.empty_like(y)
+        gt, bt = ctx.targets
+        s = None
+        if mean is not None:
+            s = torch.empty((2, groups * C), device=y.device, dtype=torch.float64)
+            _lib.check(L.viai_norm_act_bwd_reduce(_p(dz), _p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta),
+                                                  act, slope, _p(s[0]), _p(s[1]), _stream()), "norm_act_bwd_reduce")
+        _lib.check(L.viai_norm_act_bwd_apply(_p(dz), _p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta), act,
+                                             slope, _p(s[0]) if s is not None else None, _p(s[1]) if s is not None else None,
+                                             _p(dy), None, None, _stream()), "norm_act_bwd_apply")
+        dgamma = dbeta = None
+        if s is not None and gamma is not None and ctx.needs_input_grad[1]:
+            dgamma = gt if gt is not None else torch.empty_like(gamma)
+            _lib.check(L.viai_fold_groups(_p(s[1]), groups, C, _p(dgamma), int(gt is not None), _stream()), "dgamma")
+            dgamma = None if gt is not None else dgamma
+        if s is not None and beta is not None and ctx.needs_input_grad[2]:
+            dbeta = bt if bt is not None else torch.empty_like(beta)
+            _lib.check(L.viai_fold_groups(_p(s[0]), groups, C, _p(dbeta), int(bt is not None), _stream()), "dbeta")
+            dbeta = None if bt is not None else dbeta
+        return dy, dgamma, dbeta, None, None, None, None, None, None, None, None, None
+
+
+def norm_act(y, norm_module, norm, act, slope=0.0):
+    """``norm_module`` is the nn.BatchNorm2d / nn.InstanceNorm2d parameter container (or None)."""
+    if norm == "none" or norm_module is None:
+        return _NormActFn.apply(y, None, None, None, None, None, "none", False, act, slope, 0.0, 0.0)
+    gamma = getattr(norm_module, "weight", None)
+    beta = getattr(norm_module, "bias", None)
+    rm = getattr(norm_module, "running_mean", None)
+    rv = getattr(norm_module, "running_var", None)
+    nbt = getattr(norm_module, "num_batches_tracked", None)
+    mom = norm_module.momentum if norm_module.momentum is not None else 0.1
+    return _NormActFn.apply(y, gamma, beta, rm, rv, nbt, norm, norm_module.training, act, slope, norm_module.eps, mom)
+
+
+class _BilinearCatFn(torch.autograd.Function):
+    """F.interpolate(bilinear, align_corners=True) [+ torch.cat((out, skip), 1)] written straight into the
+    concatenated buffer (networks/New_Inpainting_Networks.py:78-83)."""
+
+    @staticmethod
+    def forward(ctx, x, skip, Hout, Wout):
+        _require_cuda(x, skip)
+        L = _lib.lib()
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        Cs = 0 if skip is None else skip.size(3)
+        out = torch.empty((N, Hout, Wout, C + Cs), device=x.device, dtype=torch.float32)
+        _lib.check(L.viai_bilinear_fwd(_p(x), N, H, W, C, _p(out), Hout, Wout, C + Cs, 0, _stream()), "bilinear_fwd")
+        if skip is not None:
+            skip = skip.contiguous()
+            assert skip.shape[:3] == (N, Hout, Wout), "cat: spatial sizes differ"
+            _lib.check(L.viai_copy_channels(_p(skip), N * Hout * Wout, Cs, 0, _p(out), C + Cs, C, Cs, _stream()), "cat")
+        ctx.shape = (N, H, W, C, Hout, Wout, Cs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        N, H, W, C, Hout, Wout, Cs = ctx.shape
+        L = _lib.lib()
+        dout = dout.contiguous()
+        dx = dskip = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((N, H, W, C), device=dout.device, dtype=torch.float32)
+            _lib.check(L.viai_bilinear_bwd(_p(dout), N, H, W, C, _p(dx), Hout, Wout, C + Cs, 0, _stream()), "bilinear_bwd")
+        if Cs and ctx.needs_input_grad[1]:
+            dskip = torch.empty((N, Hout, Wout, Cs), device=dout.device, dtype=torch.float32)
+            _lib.check(L.viai_copy_channels(_p(dout), N * Hout * Wout, C + Cs, C, _p(dskip), Cs, 0, Cs, _stream()), "cat bwd")
+        return dx, dskip, None, None
+
+
+def bilinear_cat(x, size, skip=None):
+    return _BilinearCatFn.apply(x, skip, int(size[0]), int(size[1]))
+
+
+class _CatFn(torch.autograd.Function):
+    """torch.cat along channels for NHWC tensors (networks/New_Inpainting_Networks.py:120)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        _require_cuda(a, b)
+        L = _lib.lib()
+        a, b = a.contiguous(), b.contiguous()
+        N, H, W, Ca = a.shape
+        Cb = b.size(3)
+        out = torch.empty((N, H, W, Ca + Cb), device=a.device, dtype=torch.float32)
+        rows = N * H * W
+        _lib.check(L.viai_copy_channels(_p(a), rows, Ca, 0, _p(out), Ca + Cb, 0, Ca, _stream()), "cat a")
+        _lib.check(L.viai_copy_channels(_p(b), rows, Cb, 0, _p(out), Ca + Cb, Ca, Cb, _stream()), "cat b")
+        ctx.shape = (N, H, W, Ca, Cb)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        N, H, W, Ca, Cb = ctx.shape
+        L = _lib.lib()
+        dout = dout.contiguous()
+        rows = N * H * W
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty((N, H, W, Ca), device=dout.device, dtype=torch.float32)
+            _lib.check(L.viai_copy_channels(_p(dout), rows, Ca + Cb, 0, _p(da), Ca, 0, Ca, _stream()), "cat bwd a")
+        if ctx.needs_input_grad[1]:
+            db = torch.empty((N, H, W, Cb), device=dout.device, dtype=torch.float32)
+            _lib.check(L.viai_copy_channels(_p(dout), rows, Ca + Cb, Ca, _p(db), Cb, 0, Cb, _stream()), "cat bwd b")
+        return da, db
+
+
+def cat_channels(a, b):
+    return _CatFn.apply(a, b)
+
+
+class _AvgPoolHFn(torch.autograd.Function):
+    """nn.AvgPool2d((kh, 1)) (networks/Inpainting_Networks.py:65,77)."""
+
+    @staticmethod
+    def forward(ctx, x, kh):
+        _require_cuda(x)
+        L = _lib.lib()
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        if H < kh:
+            raise RuntimeError("Given input size: (%dx%dx%d). Calculated output size: (%dx0x%d). Output size is too small"
+                               % (C, H, W, C, W))
+        out = torch.empty((N, H // kh, W, C), device=x.device, dtype=torch.float32)
+        _lib.check(L.viai_avgpool_h_fwd(_p(x), N, H, W, C, kh, _p(out), _stream()), "avgpool_h_fwd")
+        ctx.shape = (N, H, W, C, kh)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        N, H, W, C, kh = ctx.shape
+        L = _lib.lib()
+        dout = dout.contiguous()
+        dx = torch.empty((N, H, W, C), device=dout.device, dtype=torch.float32)
+        _lib.check(L.viai_avgpool_h_bwd(_p(dout), N, H, W, C, kh, _p(dx), _stream()), "avgpool_h_bwd")
+        return dx, None
+
+
+def avgpool_h(x, kh):
+    return _AvgPoolHFn.apply(x, kh)
+
+
+class _MaxPoolFn(torch.autograd.Function):
+    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (networks/Image_Embedding.py:21)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        L = _lib.lib()
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        out = torch.empty((N, Ho, Wo, C), device=x.device, dtype=torch.float32)
+        _lib.check(L.viai_maxpool3s2_fwd(_p(x), N, H, W, C, _p(out), Ho, Wo, _stream()), "maxpool fwd")
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        L = _lib.lib()
+        dout = dout.contiguous()
+        N, H, W, C = x.shape
+        dx = torch.empty_like(x)
+        _lib.check(L.viai_maxpool3s2_bwd(_p(x), _p(dout), N, H, W, C, _p(dx), dout.size(1), dout.size(2), _stream()), "maxpool bwd")
+        return dx
+
+
+def maxpool3s2(x):
+    return _MaxPoolFn.apply(x)
+
+
+class _AddActFn(torch.autograd.Function):
+    """``out += residual; relu(out)`` (networks/ResNet.py:52-53)."""
+
+    @staticmethod
+    def forward(ctx, a, b, act):
+        _require_cuda(a, b)
+        L = _lib.lib()
+        a, b = a.contiguous(), b.contiguous()
+        out = torch.empty_like(a)
+        _lib.check(L.viai_add_act(_p(a), _p(b), _p(out), a.numel(), act, _stream()), "add_act")
+        ctx.save_for_backward(out)
+        ctx.act = act
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        L = _lib.lib()
+        dout = dout.contiguous()
+        d = torch.empty_like(out)
+        _lib.check(L.viai_add_act_bwd(_p(out), _p(dout), _p(d), out.numel(), ctx.act, _stream()), "add_act_bwd")
+        return d, d, None
+
+
+def add_act(a, b, act=ACT_RELU):
+    return _AddActFn.apply(a, b, act)
+
+
+class _MulFn(torch.autograd.Function):
+    """mel * mask (bit exact: one IEEE multiply per element)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        _require_cuda(a, b)
+        L = _lib.lib()
+        a, b = a.contiguous(), b.contiguous()
+        assert a.shape == b.shape
+        out = torch.empty_like(a)
+        _lib.check(L.viai_mul(_p(a), _p(b), _p(out), a.numel(), _stream()), "mul")
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a, b = ctx.saved_tensors
+        L = _lib.lib()
+        dout = dout.contiguous()
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty_like(a)
+            _lib.check(L.viai_mul(_p(dout), _p(b), _p(da), a.numel(), _stream()), "mul bwd")
+        if ctx.needs_input_grad[1]:
+            db = torch.empty_like(b)
+            _lib.check(L.viai_mul(_p(dout), _p(a), _p(db), a.numel(), _stream()), "mul bwd")
+        return da, db
+
+
+def mul(a, b):
+    return _MulFn.apply(a, b)
+
+
+class _LossFn(torch.autograd.Function):
+    """kind 0: MSE vs scalar, 1: BCE vs scalar (loss_functions.py:86-104), 2: L1 between two tensors."""
+
+    @staticmethod
+    def forward(ctx, p, q, kind, target):
+        _require_cuda(p, q)
+        L = _lib.lib()
+        p = p.contiguous()
+        q = q.contiguous() if q is not None else None
+        acc = torch.empty(1, device=p.device, dtype=torch.float64)
+        out = torch.empty((), device=p.device, dtype=torch.float32)
+        _lib.check(L.viai_loss_fwd(kind, _p(p), _p(q), float(target), p.numel(), _p(acc), _p(out), _stream()), "loss_fwd")
+        ctx.save_for_backward(p, q)
+        ctx.cfg = (kind, float(target))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        p, q = ctx.saved_tensors
+        kind, target = ctx.cfg
+        L = _lib.lib()
+        gout = gout.contiguous().float()
+        dp = torch.empty_like(p)
+        _lib.check(L.viai_loss_bwd(kind, _p(p), _p(q), target, p.numel(), _p(gout), _p(dp), _stream()), "loss_bwd")
+        dq = None
+        if q is not None and ctx.needs_input_grad[1]:
+            dq = -dp
+        return dp, dq, None, None
+
+
+def mse_scalar(p, target):
+    return _LossFn.apply(p, None, 0, target)
+
+
+def bce_scalar(p, target):
+    return _LossFn.apply(p, None, 1, target)
+
+
+def l1_loss(p, q):
+    return _LossFn.apply(p, q, 2, 0.0)
+
+
+class _LinComb2Fn(torch.autograd.Function):
+    """wa * a + wb * b for 0-dim device scalars (loss weighting without leaving the library)."""
+
+    @staticmethod
+    def forward(ctx, a, b, wa, wb):
+        L = _lib.lib()
+        out = torch.empty((), device=a.device, dtype=torch.float32)
+        _lib.check(L.viai_lincomb2(_p(a), wa, _p(b), wb, _p(out), _stream()), "lincomb2")
+        ctx.w = (wa, wb, b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        wa, wb, has_b = ctx.w
+        L = _lib.lib()
+        g = g.contiguous()
+        da = torch.empty_like(g)
+        _lib.check(L.viai_lincomb2(_p(g), wa, None, 0.0, _p(da), _stream()), "lincomb2 bwd")
+        db = None
+        if has_b:
+            db = torch.empty_like(g)
+            _lib.check(L.viai_lincomb2(_p(g), wb, None, 0.0, _p(db), _stream()), "lincomb2 bwd")
+        return da, db, None, None
+
+
+def lincomb2(a, wa, b=None, wb=0.0):
+    return _LinComb2Fn.apply(a, b, float(wa), float(wb))
+
+
+def to_nhwc(t):
+    """(N,C,H,W) logical tensor -> contiguous (N,H,W,C).  Free when the tensor is already channels-last or C == 1."""
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def to_nchw(t):
+    """(N,H,W,C) -> (N,C,H,W) view (channels-last strides; no copy)."""
+    return t.permute(0, 3, 1, 2)

@@ -1,0 +1,98 @@
+"""Flat parameter / gradient buckets and the fused Adam that steps them with one kernel launch.
+
+The bucket is the B200-native replacement for what ``torch.nn.DataParallel`` does in the reference
+(/root/reference/utils/model_util.py:137): gradients of one optimizer live in ONE flat fp32 buffer that the
+weight-gradient kernels accumulate into directly (``param._viai_grad`` views) and that is all-reduced once per
+optimizer step over NCCL."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (no weight decay, no amsgrad).  ``state_dict()`` has the usual per-parameter layout
+    (``step``, ``exp_avg``, ``exp_avg_sq``) so reference-style checkpoints (/root/reference/utils/util.py:149-150)
+    round-trip; internally the three are views of flat buffers."""
+
+    def __init__(self, params, lr=2e-4, betas=(0.5, 0.999), eps=1e-8, world_size=1, process_group=None):
+        params = list(params)
+        super(FusedAdam, self).__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.world_size = world_size
+        self.process_group = process_group
+        plist = [p for g in self.param_groups for p in g["params"]]
+        if len(self.param_groups) != 1:
+            raise ValueError("FusedAdam supports a single param group")
+        dev = plist[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedAdam needs CUDA parameters; there is no CPU path")
+        n = sum(p.numel() for p in plist)
+        self.numel = n
+        self.flat_param = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
+        self._lr_host = float(lr)
+        off = 0
+        for p in plist:
+            k = p.numel()
+            view = self.flat_param[off:off + k].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            gview = self.flat_grad[off:off + k].view(p.shape)
+            p._viai_grad = gview          # weight-gradient kernels accumulate here (ops.grad_target)
+            p.grad = gview
+            self.state[p] = dict(step=self.step_dev[0], exp_avg=self.flat_m[off:off + k].view(p.shape),
+                                 exp_avg_sq=self.flat_v[off:off + k].view(p.shape))
+            off += k
+        self._plist = plist
+
+    def zero_grad(self, set_to_none=False):
+        L = _lib.lib()
+        _lib.check(L.viai_fill(_p(self.flat_grad), self.numel, 0.0, _stream()), "zero_grad")
+        for p in self._plist:             # keep .grad pointing at the bucket
+            if p.grad is None or p.grad.data_ptr() != p._viai_grad.data_ptr():
+                p.grad = p._viai_grad
+
+    def all_reduce_grads(self):
+        """One NCCL all-reduce (sum) over the whole bucket; the 1/world_size is folded into the Adam kernel."""
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.process_group)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        g = self.param_groups[0]
+        lr = float(g["lr"])
+        if lr != self._lr_host:           # LR schedules: refresh the device scalar (outside any captured graph)
+            self.lr_dev.fill_(lr)
+            self._lr_host = lr
+        L = _lib.lib()
+        b1, b2 = g["betas"]
+        _lib.check(L.viai_adam_step(_p(self.flat_param), _p(self.flat_grad), _p(self.flat_m), _p(self.flat_v),
+                                    self.numel, _p(self.lr_dev), float(b1), float(b2), float(g["eps"]),
+                                    _p(self.step_dev), 1, 1.0 / self.world_size, _stream()), "adam_step")
+
+    def load_state_dict(self, state_dict):
+        sd = state_dict["state"]
+        for i, p in enumerate(self._plist):
+            if i in sd:
+                st = sd[i]
+                self.state[p]["exp_avg"].copy_(st["exp_avg"])
+                self.state[p]["exp_avg_sq"].copy_(st["exp_avg_sq"])
+                self.step_dev.fill_(float(st["step"]))
+        pg = state_dict["param_groups"][0]
+        self.param_groups[0]["lr"] = pg["lr"]
+        self.param_groups[0]["betas"] = tuple(pg["betas"])
+        self.param_groups[0]["eps"] = pg["eps"]

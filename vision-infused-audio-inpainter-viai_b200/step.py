@@ -1,0 +1,157 @@
+"""The GAN training step of VIAI (one D update + one G update) on the CUDA path.
+
+The reference's ``Models/Whole_Sync_inpainting_modify.py`` (class ``AudioModel``) is missing from its tree; the step
+follows the call contract of /root/reference/train_whole_sync.py:49-112 and the pix2pix update order restated in
+SURVEY.md 3.1.  ``GanTrainer`` owns the networks, the two optimizers and (optionally) a CUDA graph of the step."""
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .loss_functions import GANLoss, L1Loss
+from .networks.Discriminator_Networks import MelDiscriminator
+from .networks.Inpainting_Networks import MelEncoder
+from .networks import New_Inpainting_Networks as NIN
+from .optim import FusedAdam
+
+
+def set_requires_grad(net, flag):
+    for p in net.parameters():
+        p.requires_grad_(flag)
+
+
+class GanTrainer(object):
+    def __init__(self, hparams, device="cuda", norm_layer_d=nn.BatchNorm2d, norm_layer_e=nn.BatchNorm2d,
+                 decoder="MelDecoder", video_encoder=None, world_size=1, process_group=None):
+        self.hparams = hparams
+        self.device = torch.device(device)
+        self.world_size = world_size
+        self.Mel_Encoder = MelEncoder(hparams, norm_layer=norm_layer_e).to(self.device)
+        self.Mel_Decoder = getattr(NIN, decoder)(hparams, norm_layer=hparams.normlayer).to(self.device)
+        self.netD = MelDiscriminator(norm_layer=norm_layer_d).to(self.device)
+        self.VideoEncoder = video_encoder
+        self.uses_video = decoder in ("MelDecoderImage", "MelDecoderImage2")
+        self.criterionGAN = GANLoss(use_lsgan=getattr(hparams, "use_lsgan", True), device=self.device).to(self.device)
+        self.criterionL1 = L1Loss()
+        lr = getattr(hparams, "lr", 2e-4)
+        b1 = getattr(hparams, "beta1", 0.5)
+        g_params = list(self.Mel_Encoder.parameters()) + list(self.Mel_Decoder.parameters())
+        if self.VideoEncoder is not None:
+            g_params += list(self.VideoEncoder.parameters())
+        self.optimizer_G = FusedAdam(g_params, lr=lr, betas=(b1, 0.999), world_size=world_size, process_group=process_group)
+        self.optimizer_D = FusedAdam(self.netD.parameters(), lr=lr, betas=(b1, 0.999), world_size=world_size,
+                                     process_group=process_group)
+        self.lambda_L1 = float(getattr(hparams, "lambda_L1", 100.0))
+        self._graphs = None
+        self._static = None
+        self.launches_per_step = None
+
+    # ---- the three segments of a step; NCCL all-reduces sit between them -------------------------------------
+    def _seg_forward_and_d_backward(self, mel, mask, video=None, flow=None):
+        B = mel.size(0)
+        H = self.hparams.cin_channels
+        real = mel.reshape(B, 1, H, -1)
+        self.real = real
+        masked = ops.mul(real.reshape(B, H, -1, 1), mask.reshape(B, H, -1, 1)).reshape(real.shape)
+        feats = self.Mel_Encoder(masked)
+        if self.uses_video:
+            vnet = self.VideoEncoder(video, flow)
+            self.fake = self.Mel_Decoder(feats, real.shape, vnet)
+        else:
+            self.fake = self.Mel_Decoder(feats, real.shape)
+        set_requires_grad(self.netD, True)
+        self.optimizer_D.zero_grad()
+        pred_fake = self.netD(self.fake.detach())
+        pred_real = self.netD(real)
+        self.loss_D_fake = self.criterionGAN(pred_fake, False)
+        self.loss_D_real = self.criterionGAN(pred_real, True)
+        self.loss_D = ops.lincomb2(self.loss_D_fake, 0.5, self.loss_D_real, 0.5)
+        self.loss_D.backward()
+
+    def _seg_d_update_and_g_backward(self):
+        self.optimizer_D.step()
+        set_requires_grad(self.netD, False)
+        self.optimizer_G.zero_grad()
+        pred_fake = self.netD(self.fake)
+        self.loss_G_GAN = self.criterionGAN(pred_fake, True)
+        self.loss_L1 = self.criterionL1(self.fake, self.real)
+        self.loss_G = ops.lincomb2(self.loss_G_GAN, 1.0, self.loss_L1, self.lambda_L1)
+        self.loss_G.backward()
+        set_requires_grad(self.netD, True)
+
+    def _seg_g_update(self):
+        self.optimizer_G.step()
+
+    def _outputs(self):
+        return dict(fake=self.fake.detach(), loss_D=self.loss_D.detach(), loss_G_GAN=self.loss_G_GAN.detach(),
+                    loss_L1=self.loss_L1.detach(), loss_G=self.loss_G.detach())
+
+    # ---- eager step -------------------------------------------------------------------------------------------
+    def train_step(self, mel, mask, video=None, flow=None):
+        """mel (B,1,H,W) or (B,H,W) fp32 in [0,1]; mask same shape, {0,1}.  Returns dict of device tensors."""
+        n0 = _lib.launch_count()
+        self._seg_forward_and_d_backward(mel, mask, video, flow)
+        self.optimizer_D.all_reduce_grads()
+        self._seg_d_update_and_g_backward()
+        self.optimizer_G.all_reduce_grads()
+        self._seg_g_update()
+        self.launches_per_step = _lib.launch_count() - n0
+        return self._outputs()
+
+    # ---- CUDA-graph step --------------------------------------------------------------------------------------
+    def capture(self, mel, mask, video=None, flow=None, warmup=2):
+        """Captures the step into CUDA graphs (one graph per segment so that the NCCL all-reduces stay eager when
+        world_size > 1; a single graph otherwise).  ``mel``/``mask`` become the static input buffers."""
+        self._static = dict(mel=mel.clone(), mask=mask.clone(),
+                            video=None if video is None else video.clone(), flow=None if flow is None else flow.clone())
+        st = self._static
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.train_step(st["mel"], st["mask"], st["video"], st["flow"])
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        if self.world_size == 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._seg_forward_and_d_backward(st["mel"], st["mask"], st["video"], st["flow"])
+                self._seg_d_update_and_g_backward()
+                self._seg_g_update()
+                self._static_out = self._outputs()
+            self._graphs = [g]
+        else:
+            pool = torch.cuda.graph_pool_handle()
+            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1, pool=pool):
+                self._seg_forward_and_d_backward(st["mel"], st["mask"], st["video"], st["flow"])
+            self.optimizer_D.all_reduce_grads()
+            with torch.cuda.graph(g2, pool=pool):
+                self._seg_d_update_and_g_backward()
+            self.optimizer_G.all_reduce_grads()
+            with torch.cuda.graph(g3, pool=pool):
+                self._seg_g_update()
+                self._static_out = self._outputs()
+            self._graphs = [g1, g2, g3]
+        self.launches_per_step = _lib.launch_count() - n0
+        return self
+
+    def replay(self, mel=None, mask=None, video=None, flow=None):
+        st = self._static
+        if mel is not None:
+            st["mel"].copy_(mel, non_blocking=True)
+        if mask is not None:
+            st["mask"].copy_(mask, non_blocking=True)
+        if video is not None:
+            st["video"].copy_(video, non_blocking=True)
+        if flow is not None:
+            st["flow"].copy_(flow, non_blocking=True)
+        if len(self._graphs) == 1:
+            self._graphs[0].replay()
+        else:
+            self._graphs[0].replay()
+            self.optimizer_D.all_reduce_grads()
+            self._graphs[1].replay()
+            self.optimizer_G.all_reduce_grads()
+            self._graphs[2].replay()
+        return self._static_out
