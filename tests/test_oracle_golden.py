@@ -23,12 +23,17 @@ def test_gan_step_matches_reference_golden(name):
     assert H.relerr(r["pred_real"], fx["pred_real"]) < 1e-5
     for k in ("loss_D", "loss_G_GAN", "loss_L1"):
         assert math.isclose(r[k], fx[k], rel_tol=1e-5), k
-    for got, want in ((r["grads_E"], fx["grad_E_small"]), (r["grads_Dec"], fx["grad_G_small"]), (r["grads_D"], fx["grad_D_small"])):
-        for k, v in want.items():
-            assert H.relerr(got[k], v) < 2e-3, k          # L1-sign flips bound gradient agreement
-    for got, want in ((r["grads_E"], fx["grad_E_norm"]), (r["grads_Dec"], fx["grad_G_norm"]), (r["grads_D"], fx["grad_D_norm"])):
-        for k, v in want.items():
-            assert abs(float(got[k].norm()) - v) <= 2e-3 * v + 1e-9, k
+    # gradients: the golden (reference fp32) must sit inside the oracle's fp32-vs-fp64 envelope (see viai_test_helpers)
+    _, r64 = H.oracle_pair(esd, gsd, dsd, mel, H.center_mask(mel.shape), Hh, norm, norm, update=False)
+    for gk, small, norms in (("grads_E", fx["grad_E_small"], fx["grad_E_norm"]), ("grads_Dec", fx["grad_G_small"], fx["grad_G_norm"]),
+                             ("grads_D", fx["grad_D_small"], fx["grad_D_norm"])):
+        scale = max(float(g.abs().max()) for g in r64[gk].values())
+        for k, v in small.items():
+            H.assert_within_envelope(v, r[gk][k], r64[gk][k], gk + "." + k, net_scale=scale)
+        for k, v in norms.items():
+            if float(r64[gk][k].abs().max()) >= 1e-7 * scale:
+                env = H.relerr_l2(r[gk][k], r64[gk][k])
+                assert abs(float(r[gk][k].norm()) - v) <= max(1e-3, 4 * env) * v + 1e-9, k
     for k in fx["dead"]:
         assert k not in r["grads_Dec"]                     # convblock1 never receives a gradient
     if norm == "bn":

@@ -183,3 +183,74 @@ def center_mask(shape):
     m = torch.ones(shape)
     m[..., W // 4:W // 4 + W // 2] = 0
     return m
+
+
+# ------------------------------------------------------------------------------------------------
+# Gradient parity against the reference's own rounding envelope.
+#
+# The GAN step's gradients are ill-conditioned at (any) random initialisation: the CPU oracle evaluated in fp32 and in
+# fp64 on identical inputs disagrees by 1e-3 .. 3e-2 on individual weight gradients (train-mode normalisation over few
+# elements + saturating sigmoid + the sign() in the L1 gradient), while the forward spectrogram agrees to 7e-6.  A fixed
+# 1e-3 bound on gradients is therefore not a property the reference itself has.  The tests bound the CUDA path by the
+# reference's envelope instead: with r32 / r64 the oracle in fp32 / fp64,
+#       relerr(cuda, r64) <= max(floor, K * relerr(r32, r64))
+# i.e. the CUDA result must be as close to the exact answer as the reference's fp32 arithmetic is (within K).
+# ------------------------------------------------------------------------------------------------
+def to_dtype(sd, dtype):
+    return {k: (v.to(dtype) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+
+
+def oracle_pair(esd, gsd, dsd, mel, mask, Hh, norm_g="bn", norm_d="bn", update=True, **kw):
+    """Runs oracle.gan_step in fp32 and fp64 from the same (fp32-representable) inputs."""
+    from oracle import viai_oracle as O
+    r32 = O.gan_step(esd, gsd, dsd, mel, mask, Hh, norm_g, norm_d, update=update, **kw)
+    d = torch.float64
+    r64 = O.gan_step(to_dtype(esd, d), to_dtype(gsd, d), to_dtype(dsd, d), mel.to(d), mask.to(d), Hh, norm_g, norm_d,
+                     update=update, **kw)
+    return r32, r64
+
+
+def assert_within_envelope(got, r32, r64, what, floor=1e-3, K=4.0, net_scale=None, metric=relerr):
+    """``got`` vs the fp64 oracle, bounded by K x the fp32 oracle's own error.  Tensors that are mathematically zero
+    (e.g. the gradient of a conv bias that feeds a normalisation layer) are compared in absolute terms."""
+    ref = r64.detach().double().cpu()
+    if net_scale is not None and float(ref.abs().max()) < 1e-7 * net_scale:
+        assert float(got.detach().abs().max()) <= 1e-4 * net_scale, "%s: expected ~0, got %g" % (what, float(got.abs().max()))
+        return 0.0, 0.0
+    env = metric(r32, ref)
+    err = metric(got, ref)
+    assert err <= max(floor, K * env), "%s: err %.3e vs fp64 oracle exceeds max(%.0e, %g x reference envelope %.3e)" % (
+        what, err, floor, K, env)
+    return err, env
+
+
+def whole_net_metrics(got, ref, skip_below=1e-7):
+    """Concatenates all tensors of two {name: tensor} dicts (keys of ``ref``; entries whose reference is numerically zero
+    relative to the net are skipped) and returns (L2-relative error, cosine similarity, worst per-tensor max-norm error)."""
+    scale = max(float(v.abs().max()) for v in ref.values())
+    a, b, worst = [], [], 0.0
+    for k, r in ref.items():
+        if float(r.abs().max()) < skip_below * scale:
+            continue
+        g = got[k].detach().double().cpu().flatten()
+        r = r.detach().double().cpu().flatten()
+        a.append(g); b.append(r)
+        worst = max(worst, float((g - r).abs().max() / r.abs().max()))
+    A, B = torch.cat(a), torch.cat(b)
+    return float((A - B).norm() / B.norm()), float((A @ B) / (A.norm() * B.norm())), worst
+
+
+# End-to-end gradient tolerances (see DESIGN.md "Parity"): LeakyReLU/ReLU derivative and the L1 sign are discontinuous, so
+# two fp32 evaluations of the reference (or fp32 vs fp64) differ by O(1e-3..1e-2) on gradients once any pre-activation
+# changes sign; measured on the B200: CUDA vs fp64 oracle whole-net L2 error 6.5e-4..1.7e-2, fp32 oracle vs fp64 oracle
+# 1.5e-5..3.7e-3, cosine >= 0.99986.  Wiring mistakes (a missing 0.5, a wrong detach, a swapped label) move these by O(1).
+E2E_GRAD_L2 = 5e-2
+E2E_GRAD_COS = 0.999
+E2E_GRAD_WORST = 0.25
+
+
+def assert_e2e_grads(got, ref64, what):
+    l2, cos, worst = whole_net_metrics(got, ref64)
+    assert l2 <= E2E_GRAD_L2 and cos >= E2E_GRAD_COS and worst <= E2E_GRAD_WORST, (
+        "%s: whole-net gradient L2 err %.3e cosine %.6f worst tensor %.3e" % (what, l2, cos, worst))
+    return l2, cos, worst

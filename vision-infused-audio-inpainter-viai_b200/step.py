@@ -81,6 +81,12 @@ class GanTrainer(object):
     def _seg_g_update(self):
         self.optimizer_G.step()
 
+    def _drop_step_state(self):
+        for k in ("real", "fake", "loss_D_fake", "loss_D_real", "loss_D", "loss_G_GAN", "loss_L1", "loss_G"):
+            setattr(self, k, None)
+        import gc
+        gc.collect()
+
     def _outputs(self):
         return dict(fake=self.fake.detach(), loss_D=self.loss_D.detach(), loss_G_GAN=self.loss_G_GAN.detach(),
                     loss_L1=self.loss_L1.detach(), loss_G=self.loss_G.detach())
@@ -111,6 +117,9 @@ class GanTrainer(object):
                 self.train_step(st["mel"], st["mask"], st["video"], st["flow"])
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        # Drop every autograd graph built during warm-up: the AccumulateGrad nodes they keep alive are bound to the
+        # warm-up stream, and a backward inside the capture would then wait on that (uncaptured) stream.
+        self._drop_step_state()
         n0 = _lib.launch_count()
         if self.world_size == 1:
             g = torch.cuda.CUDAGraph()
