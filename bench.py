@@ -112,7 +112,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
             "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: audio-only GAN train step, 256x256 mel, 50% centre time-band mask (CPU arm: B=%d sample)" % batch,
+            "config": {"workload": "C2: audio-only GAN train step, 256x256 mel, 50%% centre time-band mask (CPU arm: B=%d sample)" % batch,
                        "global_batch": batch, "mel_bins": HMEL, "frames": WFR},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -195,7 +195,6 @@ def main():
     else:
         step_dev = lambda: tr.train_step(mel_d, mask_d)
         step_e2e = lambda: tr.train_step(mel_h.cuda(non_blocking=True), mask_h.cuda(non_blocking=True))
-    launches = tr.launches_per_step
 
     def timed(fn, steps, read_loss):
         barrier()
@@ -217,6 +216,7 @@ def main():
 
     for _ in range(args.warmup):
         step_dev()
+    launches = tr.launches_per_step
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
