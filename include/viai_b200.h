@@ -59,6 +59,22 @@ int viai_pack_weight(const float* src, float* dst, int O, int I, int R, int S, i
 int viai_conv2d_simt(const viai_conv_geom* g, const float* in, const float* wp, const float* bias, float* out,
                      viai_stream_t stream);
 
+/* ---- tensor-core (tcgen05, kind::tf32, fp32 accumulate) implicit-GEMM convolution -------------------------------
+ * Same geometry and operand meaning as viai_conv2d_simt; replaces the same ATen call sites.  The weight operand is
+ * pre-packed by viai_pack_weight_tc (arguments as viai_pack_weight; values rounded to tf32) into
+ * viai_tc_packed_size(O, I, R, S) floats.  If stat_sum/stat_sumsq are non-NULL the epilogue also produces the
+ * per-(group, channel) sum and sum of squares of the OUTPUT (double[groups*Cout], zeroed by the call; groups = 1:
+ * BatchNorm2d batch statistics, groups = N: InstanceNorm2d), i.e. viai_channel_stats fused into the convolution.
+ * viai_conv2d_tc_supported() says whether a geometry is handled (Cin, Cout multiples of 4 and >= 16, <= 16 taps,
+ * strides 1 or 2); callers use viai_conv2d_simt otherwise.  flags: debugging switches, pass 0. */
+int viai_tc_bn(int Cout);
+int64_t viai_tc_packed_size(int O, int I, int R, int S);
+int viai_pack_weight_tc(const float* src, float* dst, int O, int I, int R, int S, int64_t so, int64_t si, int64_t sr,
+                        int64_t ss, int flip, viai_stream_t stream);
+int viai_conv2d_tc_supported(const viai_conv_geom* g);
+int viai_conv2d_tc(const viai_conv_geom* g, const float* in, const float* wp_tc, const float* bias, float* out,
+                   double* stat_sum, double* stat_sumsq, int stat_groups, int flags, viai_stream_t stream);
+
 /* Weight gradient.  dw[a*sa + b*sb + r*sr + s*ss] (+)= sum_{n,y,x} U[n,y,x,a] * G[n, y*stride-pad+r, x*stride-pad+s, b]
  * U is (N,Hout,Wout,Cout=A), G is (N,Hin,Win,Cin=B) in the geometry struct (mode ignored).
  * For nn.Conv2d: U = dOut, G = input.  For stride-1 nn.ConvTranspose2d: U = input, G = dOut.

@@ -28,6 +28,10 @@ _GP = ctypes.POINTER(ConvGeom)
 SIGNATURES = {
     "viai_pack_weight": [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_l, c_l, c_i, c_p],
     "viai_conv2d_simt": [_GP, c_p, c_p, c_p, c_p, c_p],
+    "viai_pack_weight_tc": [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_l, c_l, c_i, c_p],
+    "viai_conv2d_tc_supported": [_GP],
+    "viai_conv2d_tc": [_GP, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p],
+    "viai_tc_bn": [c_i],
     "viai_conv2d_wgrad_simt": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p],
     "viai_channel_stats": [c_p, c_l, c_i, c_i, c_p, c_p, c_p],
     "viai_norm_finalize": [c_p, c_p, c_l, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
@@ -70,6 +74,8 @@ def lib():
         L.viai_last_error.argtypes = []
         L.viai_version.restype = c_i
         L.viai_launch_count.restype = ctypes.c_longlong
+        L.viai_tc_packed_size.restype = ctypes.c_int64
+        L.viai_tc_packed_size.argtypes = [c_i, c_i, c_i, c_i]
         for name, args in SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = args

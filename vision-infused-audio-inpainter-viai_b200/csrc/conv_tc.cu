@@ -1,0 +1,575 @@
+// Tensor-core implicit-GEMM convolution for sm_100a: TMA -> shared memory -> tcgen05.mma (kind::tf32, fp32 accumulate in
+// TMEM) -> tcgen05.ld epilogue with fused bias and per-channel sum / sum-of-squares (the statistics of the following
+// BatchNorm2d / InstanceNorm2d).
+//
+// One persistent CTA per SM, 7 warps: warp 0 = activation-patch TMA producer, warp 1 = weight-tile bulk-copy producer,
+// warp 2 = TMEM owner + single-thread MMA issuer, warps 3..6 = epilogue (one TMEM lane quarter each).
+//
+// Work decomposition ("patch-resident implicit GEMM"):
+//   * an M tile is a 16 x 8 patch of output pixels of one image (128 accumulator rows);
+//   * for every 32-channel slab of the input, the (16+kh-1) x (8+kw-1) input patch that all filter taps of the tile read
+//     is loaded ONCE by TMA into shared memory as [8 x 16-byte channel chunk][patch row][patch col][4 floats].  In that
+//     layout 8 horizontally adjacent pixels of one 16-byte chunk are 128 contiguous bytes = one UMMA core matrix, so a
+//     filter tap is nothing but a different start address of the same no-swizzle K-major shared-memory descriptor
+//     (SBO = patch row pitch, LBO = chunk pitch).  Zero padding and ragged edges come from TMA out-of-bounds fill;
+//   * strided convolutions split the input into stride_h x stride_w parity sub-grids (one strided tensor map each), so
+//     every tap is again a unit-stride window of one sub-patch;
+//   * the transposed gather (ConvTranspose2d forward, Conv2d data gradient) runs one launch per output parity class, each
+//     a unit-stride convolution over the tap subset that class touches, writing its outputs with the class stride;
+//   * the weight operand of (tap, slab, cout tile) is one contiguous pre-packed block fetched by a single cp.async.bulk.
+#include "common.cuh"
+#include "tc_common.cuh"
+using namespace viai;
+using namespace viai::tc;
+
+namespace viai {
+namespace tc {
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+int encode_f32_map(CUtensorMap* map, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, int swizzle128) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return -1;
+  }
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]", (int)r, rank,
+              (unsigned long long)d[0], (unsigned long long)d[1], (unsigned long long)d[2], (unsigned long long)(rank > 3 ? d[3] : 0),
+              (unsigned long long)(rank > 4 ? d[4] : 0), b[0], b[1], b[2], rank > 3 ? b[3] : 0, rank > 4 ? b[4] : 0);
+    return -1;
+  }
+  return 0;
+}
+}  // namespace tc
+}  // namespace viai
+
+namespace {
+
+constexpr int TH = 16, TW = 8;          // output pixels per M tile (TW = 8 = rows of one UMMA core matrix)
+constexpr int KC = 32;                  // input channels per slab (8 chunks of 16 bytes)
+constexpr int MAX_SUB = 4, MAX_TAP = 16;
+constexpr int NTHREADS = 224;
+constexpr int EPI_WARP0 = 3;
+
+struct TcSub {
+  int32_t ox, oy;        // sub-grid coordinate of the patch origin relative to the tile origin
+  int32_t pw, ph;        // patch extent
+  uint32_t smem_off;     // byte offset of this sub-patch inside a slab stage
+};
+struct TcTap {
+  uint32_t a_off;        // byte offset inside the slab stage of the tap's first pixel (chunk 0)
+  uint32_t sbo, lbo;     // descriptor strides in bytes (patch row pitch, chunk pitch)
+  uint32_t wtap;         // index of the tap in the packed weight tensor
+};
+struct TcParams {
+  CUtensorMap mapA[MAX_SUB];
+  TcSub sub[MAX_SUB];
+  TcTap tap[MAX_TAP];
+  int32_t nsub, ntap;
+  const float* wp;
+  const float* bias;
+  float* out;
+  double* ssum;
+  double* ssq;
+  int32_t stat_groups;   // 0: no statistics, 1: per channel, N: per (image, channel)
+  int32_t N, Hv, Wv;     // virtual output grid (per image)
+  int32_t tilesX, tilesY, ntilesN, ntiles;
+  int32_t nchunks, BN, Cout;
+  int64_t o_sn, o_sy, o_sx, o_base;   // output element strides of (n, y, x) on the virtual grid, and base offset
+  uint32_t slab_bytes, slab_tx_bytes, btile_bytes;
+  int32_t SA, SB;
+  uint32_t idesc;
+  int32_t a4d;           // 1: sub-patch loaded by 8 rank-4 TMA copies instead of one rank-5 copy
+  int32_t a_sw128;       // 1: activation patch stored as dense 128-byte pixel rows under the 128-byte swizzle (rank-4 TMA)
+  int32_t a_baseoff;     // debug: put (start >> 7) & 7 in the descriptor's base-offset field
+};
+
+__device__ __forceinline__ void transpose_reduce32(float (&v)[32], int lane) {
+  // After the call v[0] of lane l holds sum over lanes of the original v[l].
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      float send = up ? v[j] : v[j + off];
+      float keep = up ? v[j + off] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzled TMA destinations need 1 KB alignment
+  uint8_t* slabA = smem;
+  uint8_t* tileB = slabA + (size_t)p.SA * p.slab_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tileB + (size_t)p.SB * p.btile_bytes);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + p.SA;
+  uint64_t* fullB = emptyA + p.SA;
+  uint64_t* emptyB = fullB + p.SB;
+  uint64_t* tfull = emptyB + p.SB;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  double* stat_acc = reinterpret_cast<double*>(tmem_slot + 2);   // [4 warps][2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = (2 * p.BN <= 32) ? 32u : (2 * p.BN <= 64) ? 64u : (2 * p.BN <= 128) ? 128u : (2 * p.BN <= 256) ? 256u : 512u;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+    for (int i = 0; i < p.nsub; ++i) prefetch_tmap(&p.mapA[i]);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== activation patch producer =====
+    if (lane == 0) {
+      int sa = 0;
+      uint32_t pha = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int rest = tile / p.ntilesN;
+        const int tx = rest % p.tilesX; rest /= p.tilesX;
+        const int ty = rest % p.tilesY;
+        const int n = rest / p.tilesY;
+        const int x0 = tx * TW, y0 = ty * TH;
+        for (int c = 0; c < p.nchunks; ++c) {
+          mbar_wait(&emptyA[sa], pha ^ 1u);
+          mbar_expect_tx(&fullA[sa], p.slab_tx_bytes);
+          uint8_t* dst = slabA + (size_t)sa * p.slab_bytes;
+          for (int s = 0; s < p.nsub; ++s) {
+            const TcSub& sb = p.sub[s];
+            if (p.a_sw128) {
+              tma_load_4d(dst + sb.smem_off, &p.mapA[s], &fullA[sa], c * KC, x0 + sb.ox, y0 + sb.oy, n);
+            } else if (!p.a4d) {
+              tma_load_5d(dst + sb.smem_off, &p.mapA[s], &fullA[sa], 0, x0 + sb.ox, y0 + sb.oy, c * (KC / 4), n);
+            } else {
+              const uint32_t chunk_bytes = ((uint32_t)(sb.pw * sb.ph) * 16u + 127u) & ~127u;
+              for (int j = 0; j < KC / 4; ++j)
+                tma_load_4d(dst + sb.smem_off + j * chunk_bytes, &p.mapA[s], &fullA[sa], c * KC + j * 4, x0 + sb.ox, y0 + sb.oy, n);
+            }
+          }
+          if (++sa == p.SA) { sa = 0; pha ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== weight tile producer =====
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t phb = 0;
+      const size_t btile_floats = p.btile_bytes / 4;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int nt = tile % p.ntilesN;
+        for (int c = 0; c < p.nchunks; ++c) {
+          for (int t = 0; t < p.ntap; ++t) {
+            mbar_wait(&emptyB[sb], phb ^ 1u);
+            mbar_expect_tx(&fullB[sb], p.btile_bytes);
+            const float* src = p.wp + (((size_t)p.tap[t].wtap * p.nchunks + c) * p.ntilesN + nt) * btile_floats;
+            bulk_load(tileB + (size_t)sb * p.btile_bytes, src, p.btile_bytes, &fullB[sb]);
+            if (++sb == p.SB) { sb = 0; phb ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      int it = 0;
+      const uint32_t b_lbo = (uint32_t)p.BN * 16u, b_sbo = 128u;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        uint32_t accumulate = 0;
+        for (int c = 0; c < p.nchunks; ++c) {
+          mbar_wait(&fullA[sa], pha);
+          const uint32_t a_base = smem_u32(slabA + (size_t)sa * p.slab_bytes);
+          for (int t = 0; t < p.ntap; ++t) {
+            mbar_wait(&fullB[sb], phb);
+            tc_fence_after();
+            const TcTap& tp = p.tap[t];
+            const uint32_t b_base = smem_u32(tileB + (size_t)sb * p.btile_bytes);
+#pragma unroll
+            for (int kk = 0; kk < KC / 8; ++kk) {
+              const uint32_t b_addr = b_base + (uint32_t)kk * 2u * b_lbo;
+              uint64_t ad;
+              if (p.a_sw128) {
+                const uint32_t a_addr = a_base + tp.a_off + (uint32_t)kk * 32u;
+                ad = make_desc_sw128(a_addr, tp.sbo, p.a_baseoff ? ((a_base + tp.a_off) >> 7) : 0u);
+              } else {
+                ad = make_desc(a_base + tp.a_off + (uint32_t)kk * 2u * tp.lbo, tp.lbo, tp.sbo);
+              }
+              const uint64_t bd = make_desc(b_addr, b_lbo, b_sbo);
+              mma_tf32(d_tmem, ad, bd, p.idesc, accumulate);
+              accumulate = 1;
+            }
+            mma_commit(&emptyB[sb]);
+            if (++sb == p.SB) { sb = 0; phb ^= 1u; }
+          }
+          mma_commit(&emptyA[sa]);
+          if (++sa == p.SA) { sa = 0; pha ^= 1u; }
+        }
+        mma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> (+bias, statistics) -> global =====
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;                // accumulator row = pixel of the tile
+    const int ly = row >> 3, lx = row & 7;
+    double* my_sum = stat_acc + (size_t)(warp - EPI_WARP0) * 2 * p.BN;
+    double* my_sq = my_sum + p.BN;
+    const bool do_stats = p.stat_groups > 0;
+    if (do_stats)
+      for (int i = lane; i < 2 * p.BN; i += 32) my_sum[i] = 0.0;
+    int cur_group = -1, cur_nt = -1;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int nt = tile % p.ntilesN;
+      int rest = tile / p.ntilesN;
+      const int tx = rest % p.tilesX; rest /= p.tilesX;
+      const int ty = rest % p.tilesY;
+      const int n = rest / p.tilesY;
+      const int y = ty * TH + ly, x = tx * TW + lx;
+      const bool valid = (y < p.Hv) && (x < p.Wv);
+      const int acc = it & 1;
+      if (do_stats) {
+        const int grp = (p.stat_groups > 1) ? n : 0;
+        if ((grp != cur_group || nt != cur_nt) && cur_group >= 0) {
+          // flush the partial sums of the finished (group, cout tile)
+          for (int i = lane; i < p.BN; i += 32) {
+            const int ch = cur_nt * p.BN + i;
+            if (ch < p.Cout) {
+              atomicAdd(&p.ssum[(size_t)cur_group * p.Cout + ch], my_sum[i]);
+              atomicAdd(&p.ssq[(size_t)cur_group * p.Cout + ch], my_sq[i]);
+            }
+            my_sum[i] = 0.0;
+            my_sq[i] = 0.0;
+          }
+        }
+        cur_group = grp;
+        cur_nt = nt;
+      }
+      mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      float* optr = p.out + p.o_base + (int64_t)n * p.o_sn + (int64_t)y * p.o_sy + (int64_t)x * p.o_sx + (int64_t)nt * p.BN;
+      for (int j = 0; j < p.BN / 32; ++j) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + j * 32), v);
+        const int ch0 = nt * p.BN + j * 32;
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (ch0 + i < p.Cout) v[i] += __ldg(&p.bias[ch0 + i]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            if (ch0 + i < p.Cout) *reinterpret_cast<float4*>(optr + j * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        if (do_stats) {
+          float s[32], s2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            s[i] = valid ? v[i] : 0.f;
+            s2[i] = s[i] * s[i];
+          }
+          transpose_reduce32(s, lane);
+          transpose_reduce32(s2, lane);
+          my_sum[j * 32 + lane] += (double)s[0];
+          my_sq[j * 32 + lane] += (double)s2[0];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+    if (do_stats && cur_group >= 0) {
+      __syncwarp();
+      for (int i = lane; i < p.BN; i += 32) {
+        const int ch = cur_nt * p.BN + i;
+        if (ch < p.Cout) {
+          atomicAdd(&p.ssum[(size_t)cur_group * p.Cout + ch], my_sum[i]);
+          atomicAdd(&p.ssq[(size_t)cur_group * p.Cout + ch], my_sq[i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// dst[tap][slab][cout tile][16-byte chunk j][row][4] = tf32(w[o][tap][i]),  i = slab*32 + j*4 + e, o = tile*BN + row
+__global__ void pack_weight_tc_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int R, int S,
+                                      int64_t so, int64_t si, int64_t sr, int64_t ss, int flip, int BN, int nchunks, int ntilesN) {
+  const int64_t total = (int64_t)R * S * nchunks * ntilesN * (KC / 4) * BN * 4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = idx;
+    const int e = t & 3; t >>= 2;
+    const int row = t % BN; t /= BN;
+    const int j = t % (KC / 4); t /= (KC / 4);
+    const int nt = t % ntilesN; t /= ntilesN;
+    const int c = t % nchunks; t /= nchunks;
+    const int tap = (int)t;
+    const int r = tap / S, s = tap % S;
+    const int o = nt * BN + row, i = c * KC + j * 4 + e;
+    float v = 0.f;
+    if (o < O && i < I) {
+      const int rr = flip ? R - 1 - r : r, sw = flip ? S - 1 - s : s;
+      v = to_tf32(src[o * so + i * si + rr * sr + sw * ss]);
+    }
+    dst[idx] = v;
+  }
+}
+
+inline int tc_bn(int Cout) {
+  int bn = ((Cout + 31) / 32) * 32;
+  return bn > 256 ? 256 : bn;
+}
+inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+inline int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
+
+struct TapSpec { int suby, subx, offy, offx, wtap; };
+
+// Builds and launches one "virtual unit-stride convolution" (see the file header).
+int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int inC, int sub_sy, int sub_sx,
+                const TapSpec* taps, int ntap, const float* wp, const float* bias, float* out, int Hv, int Wv, int64_t o_sn,
+                int64_t o_sy, int64_t o_sx, int64_t o_base, int Cout, double* ssum, double* ssq, int stat_groups, int flags,
+                cudaStream_t stream) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  VIAI_REQUIRE(ntap >= 1 && ntap <= MAX_TAP, "conv2d_tc: %d taps (max %d)", ntap, MAX_TAP);
+  p.a4d = (flags & 2) ? 1 : 0;
+  p.a_sw128 = (flags & 4) ? 1 : 0;
+  p.a_baseoff = (flags & 8) ? 1 : 0;
+  if (p.a_sw128) p.a4d = 0;
+  // sub-patches: one per (suby, subx) parity that occurs
+  int sub_id[2][2] = {{-1, -1}, {-1, -1}};
+  int mn_y[MAX_SUB], mx_y[MAX_SUB], mn_x[MAX_SUB], mx_x[MAX_SUB], sy_of[MAX_SUB], sx_of[MAX_SUB];
+  int nsub = 0;
+  for (int t = 0; t < ntap; ++t) {
+    int& id = sub_id[taps[t].suby][taps[t].subx];
+    if (id < 0) {
+      id = nsub++;
+      sy_of[id] = taps[t].suby; sx_of[id] = taps[t].subx;
+      mn_y[id] = mx_y[id] = taps[t].offy;
+      mn_x[id] = mx_x[id] = taps[t].offx;
+    } else {
+      mn_y[id] = taps[t].offy < mn_y[id] ? taps[t].offy : mn_y[id];
+      mx_y[id] = taps[t].offy > mx_y[id] ? taps[t].offy : mx_y[id];
+      mn_x[id] = taps[t].offx < mn_x[id] ? taps[t].offx : mn_x[id];
+      mx_x[id] = taps[t].offx > mx_x[id] ? taps[t].offx : mx_x[id];
+    }
+  }
+  p.nsub = nsub;
+  uint32_t off = 0;
+  for (int s = 0; s < nsub; ++s) {
+    TcSub& sb = p.sub[s];
+    sb.ox = mn_x[s]; sb.oy = mn_y[s];
+    sb.pw = TW + (mx_x[s] - mn_x[s]);
+    sb.ph = TH + (mx_y[s] - mn_y[s]);
+    sb.smem_off = off;
+    if (p.a_sw128) {
+      off = (off + 1023u) & ~1023u;
+      sb.smem_off = off;
+      off += (uint32_t)(sb.pw * sb.ph) * (KC * 4);
+    }
+    const uint32_t chunk_pitch = p.a_sw128 ? 0u : p.a4d ? (((uint32_t)(sb.pw * sb.ph) * 16u + 127u) & ~127u) : (uint32_t)(sb.pw * sb.ph) * 16u;
+    off += chunk_pitch * (KC / 4);
+    VIAI_REQUIRE(sb.pw <= 256 && sb.ph <= 256, "conv2d_tc: patch %dx%d too large", sb.ph, sb.pw);
+    const int subH = (inH - sy_of[s] + sub_sy - 1) / sub_sy, subW = (inW - sx_of[s] + sub_sx - 1) / sub_sx;
+    VIAI_REQUIRE(subH >= 1 && subW >= 1, "conv2d_tc: empty parity sub-grid");
+    const float* base = in + ((int64_t)sy_of[s] * inW + sx_of[s]) * inC;
+    if (p.a_sw128) {
+      uint64_t dims[4] = {(uint64_t)inC, (uint64_t)subW, (uint64_t)subH, (uint64_t)g.N};
+      uint64_t strides[3] = {(uint64_t)sub_sx * inC * 4, (uint64_t)sub_sy * inW * inC * 4, (uint64_t)inH * inW * inC * 4};
+      uint32_t box[4] = {KC, (uint32_t)sb.pw, (uint32_t)sb.ph, 1};
+      if (encode_f32_map(&p.mapA[s], 4, base, dims, strides, box, 1)) return VIAI_ERR_CUDA;
+    } else if (!p.a4d) {
+      uint64_t dims[5] = {4, (uint64_t)subW, (uint64_t)subH, (uint64_t)(inC / 4), (uint64_t)g.N};
+      uint64_t strides[4] = {(uint64_t)sub_sx * inC * 4, (uint64_t)sub_sy * inW * inC * 4, 16, (uint64_t)inH * inW * inC * 4};
+      uint32_t box[5] = {4, (uint32_t)sb.pw, (uint32_t)sb.ph, KC / 4, 1};
+      if (encode_f32_map(&p.mapA[s], 5, base, dims, strides, box)) return VIAI_ERR_CUDA;
+    } else {
+      uint64_t dims[4] = {(uint64_t)inC, (uint64_t)subW, (uint64_t)subH, (uint64_t)g.N};
+      uint64_t strides[3] = {(uint64_t)sub_sx * inC * 4, (uint64_t)sub_sy * inW * inC * 4, (uint64_t)inH * inW * inC * 4};
+      uint32_t box[4] = {4, (uint32_t)sb.pw, (uint32_t)sb.ph, 1};
+      if (encode_f32_map(&p.mapA[s], 4, base, dims, strides, box)) return VIAI_ERR_CUDA;
+    }
+  }
+  if (p.a_sw128) off = (off + 1023u) & ~1023u;
+  p.slab_bytes = off;
+  for (int s = 0; s < nsub; ++s) p.slab_tx_bytes += (uint32_t)(p.sub[s].pw * p.sub[s].ph) * (KC * 4);
+  p.ntap = ntap;
+  for (int t = 0; t < ntap; ++t) {
+    const int s = sub_id[taps[t].suby][taps[t].subx];
+    const TcSub& sb = p.sub[s];
+    TcTap& tp = p.tap[t];
+    const uint32_t pix_pitch = p.a_sw128 ? 128u : 16u;
+    tp.a_off = sb.smem_off + (uint32_t)((taps[t].offy - sb.oy) * sb.pw + (taps[t].offx - sb.ox)) * pix_pitch;
+    tp.sbo = (uint32_t)sb.pw * pix_pitch;
+    tp.lbo = p.a4d ? (((uint32_t)(sb.pw * sb.ph) * 16u + 127u) & ~127u) : (uint32_t)(sb.pw * sb.ph) * 16u;
+    tp.wtap = (uint32_t)taps[t].wtap;
+  }
+  p.wp = wp; p.bias = bias; p.out = out; p.ssum = ssum; p.ssq = ssq;
+  p.stat_groups = (ssum != nullptr) ? stat_groups : 0;
+  p.N = g.N; p.Hv = Hv; p.Wv = Wv;
+  p.tilesX = (Wv + TW - 1) / TW; p.tilesY = (Hv + TH - 1) / TH;
+  p.BN = tc_bn(Cout);
+  p.ntilesN = (Cout + p.BN - 1) / p.BN;
+  p.ntiles = p.N * p.tilesX * p.tilesY * p.ntilesN;
+  p.nchunks = (inC + KC - 1) / KC;
+  p.Cout = Cout;
+  p.o_sn = o_sn; p.o_sy = o_sy; p.o_sx = o_sx; p.o_base = o_base;
+  p.btile_bytes = (uint32_t)p.BN * KC * 4;
+  p.idesc = make_idesc_tf32(128, p.BN, 0, 0);
+  // pipeline depths under the 227 KB shared-memory limit
+  const size_t fixed = 1024 /*alignment slack*/ + 64 * 8 + 16 + (size_t)4 * 2 * p.BN * 8;
+  const size_t budget = 227 * 1024;
+  int SA = 3, SB = 4;
+  auto need = [&](int a, int b) { return fixed + (size_t)a * p.slab_bytes + (size_t)b * p.btile_bytes; };
+  while (need(SA, SB) > budget && SB > 2) --SB;
+  while (need(SA, SB) > budget && SA > 2) --SA;
+  while (need(SA, SB) > budget && SB > 1) --SB;
+  while (need(SA, SB) > budget && SA > 1) --SA;
+  VIAI_REQUIRE(need(SA, SB) <= budget, "conv2d_tc: tile does not fit in shared memory (slab %u B, weight tile %u B)", p.slab_bytes,
+               p.btile_bytes);
+  p.SA = SA; p.SB = SB;
+  size_t smem = need(SA, SB);
+  if (smem < 120 * 1024) smem = 120 * 1024;   // force one CTA per SM (each CTA may allocate up to all 512 TMEM columns)
+  static bool attr_set = false;
+  if (!attr_set) {
+    VIAI_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  if (p.ntiles == 0) return VIAI_OK;
+  const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
+  conv_tc_kernel<<<grid, NTHREADS, smem, stream>>>(p);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+}  // namespace
+
+extern "C" int viai_tc_bn(int Cout) { return tc_bn(Cout); }
+
+extern "C" int64_t viai_tc_packed_size(int O, int I, int R, int S) {
+  const int BN = tc_bn(O);
+  return (int64_t)R * S * ((I + KC - 1) / KC) * ((O + BN - 1) / BN) * BN * KC;
+}
+
+extern "C" int viai_pack_weight_tc(const float* src, float* dst, int O, int I, int R, int S, int64_t so, int64_t si, int64_t sr,
+                                   int64_t ss, int flip, viai_stream_t stream) {
+  VIAI_REQUIRE(src && dst && O > 0 && I > 0 && R > 0 && S > 0, "pack_weight_tc: bad arguments");
+  const int BN = tc_bn(O), nchunks = (I + KC - 1) / KC, ntilesN = (O + BN - 1) / BN;
+  const int64_t total = viai_tc_packed_size(O, I, R, S);
+  const int blocks = (int)imin64(cdiv(total, 256), 4096);
+  pack_weight_tc_kernel<<<blocks, 256, 0, STR(stream)>>>(src, dst, O, I, R, S, so, si, sr, ss, flip, BN, nchunks, ntilesN);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_conv2d_tc_supported(const viai_conv_geom* g) {
+  if (!g) return 0;
+  if (g->Cin % 4 != 0 || g->Cin < 16 || g->Cout % 4 != 0 || g->Cout < 16) return 0;
+  if (g->R * g->S > MAX_TAP || g->stride_h < 1 || g->stride_h > 2 || g->stride_w < 1 || g->stride_w > 2) return 0;
+  if (g->mode != 0 && g->mode != 1) return 0;
+  return 1;
+}
+
+extern "C" int viai_conv2d_tc(const viai_conv_geom* gp, const float* in, const float* wp_tc, const float* bias, float* out,
+                              double* stat_sum, double* stat_sumsq, int stat_groups, int flags, viai_stream_t stream) {
+  VIAI_REQUIRE(gp && in && wp_tc && out, "conv2d_tc: null argument");
+  const viai_conv_geom& g = *gp;
+  VIAI_REQUIRE(viai_conv2d_tc_supported(gp), "conv2d_tc: unsupported geometry (Cin %d Cout %d %dx%d stride %d,%d mode %d)", g.Cin,
+               g.Cout, g.R, g.S, g.stride_h, g.stride_w, g.mode);
+  VIAI_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(wp_tc) & 15) == 0,
+               "conv2d_tc: pointers must be 16-byte aligned");
+  VIAI_REQUIRE((stat_sum == nullptr) == (stat_sumsq == nullptr), "conv2d_tc: stat_sum and stat_sumsq go together");
+  cudaStream_t st = STR(stream);
+  if (stat_sum) {
+    const size_t nb = (size_t)(stat_groups > 1 ? stat_groups : 1) * g.Cout * sizeof(double);
+    VIAI_CUDA(cudaMemsetAsync(stat_sum, 0, nb, st));
+    VIAI_CUDA(cudaMemsetAsync(stat_sumsq, 0, nb, st));
+  }
+  TapSpec taps[MAX_TAP];
+  const int64_t o_row = (int64_t)g.Wout * g.Cout, o_img = (int64_t)g.Hout * o_row;
+  if (g.mode == 0) {
+    int nt = 0;
+    for (int r = 0; r < g.R; ++r)
+      for (int s = 0; s < g.S; ++s) {
+        const int qy = r - g.pad_h, qx = s - g.pad_w;
+        taps[nt++] = TapSpec{posmod(qy, g.stride_h), posmod(qx, g.stride_w), floordiv(qy, g.stride_h), floordiv(qx, g.stride_w),
+                             r * g.S + s};
+      }
+    return launch_plan(g, in, g.Hin, g.Win, g.Cin, g.stride_h, g.stride_w, taps, nt, wp_tc, bias, out, g.Hout, g.Wout, o_img, o_row,
+                       g.Cout, 0, g.Cout, stat_sum, stat_sumsq, stat_groups, flags, st);
+  }
+  // transposed gather: one launch per output parity class
+  auto class_taps = [&](int py, int px, TapSpec* out_taps) {
+    int nt = 0;
+    for (int r = 0; r < g.R; ++r) {
+      if (posmod(py + g.pad_h - r, g.stride_h) != 0) continue;
+      for (int s = 0; s < g.S; ++s) {
+        if (posmod(px + g.pad_w - s, g.stride_w) != 0) continue;
+        out_taps[nt++] = TapSpec{0, 0, floordiv(py + g.pad_h - r, g.stride_h), floordiv(px + g.pad_w - s, g.stride_w), r * g.S + s};
+      }
+    }
+    return nt;
+  };
+  bool any_empty = false;
+  for (int py = 0; py < g.stride_h; ++py)
+    for (int px = 0; px < g.stride_w; ++px)
+      if (class_taps(py, px, taps) == 0) any_empty = true;
+  if (any_empty) {   // classes no filter tap reaches receive no contribution
+    VIAI_REQUIRE(bias == nullptr && stat_sum == nullptr, "conv2d_tc: empty parity class with bias/statistics is unsupported");
+    VIAI_CUDA(cudaMemsetAsync(out, 0, (size_t)g.N * o_img * sizeof(float), st));
+  }
+  for (int py = 0; py < g.stride_h; ++py)
+    for (int px = 0; px < g.stride_w; ++px) {
+      const int Hv = (g.Hout - py + g.stride_h - 1) / g.stride_h, Wv = (g.Wout - px + g.stride_w - 1) / g.stride_w;
+      if (Hv <= 0 || Wv <= 0) continue;
+      const int nt = class_taps(py, px, taps);
+      if (nt == 0) continue;
+      int rc = launch_plan(g, in, g.Hin, g.Win, g.Cin, 1, 1, taps, nt, wp_tc, bias, out, Hv, Wv, o_img, o_row * g.stride_h,
+                           (int64_t)g.Cout * g.stride_w, (int64_t)py * o_row + (int64_t)px * g.Cout, g.Cout, stat_sum, stat_sumsq,
+                           stat_groups, flags, st);
+      if (rc != VIAI_OK) return rc;
+    }
+  return VIAI_OK;
+}
