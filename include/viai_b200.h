@@ -66,14 +66,27 @@ int viai_conv2d_simt(const viai_conv_geom* g, const float* in, const float* wp, 
  * per-(group, channel) sum and sum of squares of the OUTPUT (double[groups*Cout], zeroed by the call; groups = 1:
  * BatchNorm2d batch statistics, groups = N: InstanceNorm2d), i.e. viai_channel_stats fused into the convolution.
  * viai_conv2d_tc_supported() says whether a geometry is handled (Cin, Cout multiples of 4 and >= 16, <= 16 taps,
- * strides 1 or 2); callers use viai_conv2d_simt otherwise.  flags: debugging switches, pass 0. */
+ * strides 1 or 2); callers use viai_conv2d_simt otherwise.
+ * flags: VIAI_TC_X3 (4) = error-compensated 3-term product  x*w ~ hi(x)*hi(w) + hi(x)*lo(w) + lo(x)*hi(w)  with
+ * hi = tf32(.), lo = tf32(. - hi): three tensor-core MMAs per tile instead of one, product error ~2^-19 instead of
+ * ~2^-10 (the precision needed for the north star's 1e-3 end-to-end bound; see DESIGN.md "Precision").  It needs
+ * weights packed with split = 1.  Other bits select alternative shared-memory layouts used as cross-checks. */
+#define VIAI_TC_X3 4
 int viai_tc_bn(int Cout);
-int64_t viai_tc_packed_size(int O, int I, int R, int S);
+int64_t viai_tc_packed_size(int O, int I, int R, int S, int split);
 int viai_pack_weight_tc(const float* src, float* dst, int O, int I, int R, int S, int64_t so, int64_t si, int64_t sr,
-                        int64_t ss, int flip, viai_stream_t stream);
+                        int64_t ss, int flip, int split, viai_stream_t stream);
 int viai_conv2d_tc_supported(const viai_conv_geom* g);
 int viai_conv2d_tc(const viai_conv_geom* g, const float* in, const float* wp_tc, const float* bias, float* out,
                    double* stat_sum, double* stat_sumsq, int stat_groups, int flags, viai_stream_t stream);
+
+/* Tensor-core weight gradient: same meaning as viai_conv2d_wgrad_simt (below).  `workspace` is a caller-owned scratch of
+ * viai_wgrad_tc_workspace(g) floats (the per-tap partial sums are reduced there across CTAs before being scattered into
+ * the gradient layout). */
+int viai_conv2d_wgrad_tc_supported(const viai_conv_geom* g);
+int64_t viai_wgrad_tc_workspace(const viai_conv_geom* g);
+int viai_conv2d_wgrad_tc(const viai_conv_geom* g, const float* U, const float* G, float* dw, int64_t sa, int64_t sb,
+                         int64_t sr, int64_t ss, int accumulate, float* workspace, viai_stream_t stream);
 
 /* Weight gradient.  dw[a*sa + b*sb + r*sr + s*ss] (+)= sum_{n,y,x} U[n,y,x,a] * G[n, y*stride-pad+r, x*stride-pad+s, b]
  * U is (N,Hout,Wout,Cout=A), G is (N,Hin,Win,Cin=B) in the geometry struct (mode ignored).

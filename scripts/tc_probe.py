@@ -48,8 +48,9 @@ def run(name, flags):
         ref = F.conv_transpose2d(x.permute(0, 3, 1, 2), w.permute(3, 0, 1, 2), bias, st, pd).permute(0, 2, 3, 1).contiguous()
     geom = ConvGeom(N, H, W, Ci, Ho, Wo, Co, R, Sx, st[0], st[1], pd[0], pd[1], mode)
     assert L.viai_conv2d_tc_supported(ctypes.byref(geom)), "unsupported"
-    wp = torch.empty(L.viai_tc_packed_size(Co, Ci, R, Sx), device="cuda")
-    _lib.check(L.viai_pack_weight_tc(P(w), P(wp), Co, Ci, R, Sx, w.stride(0), w.stride(3), w.stride(1), w.stride(2), 0, S()), "pack")
+    x3 = 1 if (flags & 4) else 0
+    wp = torch.empty(L.viai_tc_packed_size(Co, Ci, R, Sx, x3), device="cuda")
+    _lib.check(L.viai_pack_weight_tc(P(w), P(wp), Co, Ci, R, Sx, w.stride(0), w.stride(3), w.stride(1), w.stride(2), 0, x3, S()), "pack")
     out = torch.full((N, Ho, Wo, Co), float("nan"), device="cuda")
     ssum = torch.empty(N * Co, device="cuda", dtype=torch.float64)
     ssq = torch.empty(N * Co, device="cuda", dtype=torch.float64)
@@ -82,7 +83,63 @@ def run(name, flags):
     print(msg, flush=True)
 
 
+WCASES = {
+    # name: (N, Hin, Win, Cin, Cout, R, S, stride, pad)
+    "w_s1_32_32": (2, 16, 16, 32, 32, 3, 3, (1, 1), (1, 1)),
+    "w_s1_ragged": (3, 20, 13, 64, 48, 3, 3, (1, 1), (1, 1)),
+    "w_s1_256_512": (2, 16, 16, 256, 512, 3, 3, (1, 1), (1, 1)),
+    "w_s2_64_128": (2, 32, 32, 64, 128, 3, 3, (2, 2), (1, 1)),
+    "w_s21_32_64": (2, 32, 32, 32, 64, 3, 3, (2, 1), (1, 1)),
+    "w_pad21": (2, 2, 16, 64, 64, 3, 3, (1, 1), (2, 1)),
+    "WT_dconv3": (32, 64, 32, 256, 512, 3, 3, (1, 1), (1, 1)),
+    "WT_conv6_1": (32, 256, 256, 32, 32, 3, 3, (1, 1), (1, 1)),
+    "WT_dconv2_2": (32, 128, 64, 128, 256, 3, 3, (2, 2), (1, 1)),
+}
+
+
+def run_w(name):
+    N, H, W, Ci, Co, R, Sx, st, pd = WCASES[name]
+    g = torch.Generator(device="cuda").manual_seed(2)
+    Ho, Wo = (H + 2 * pd[0] - R) // st[0] + 1, (W + 2 * pd[1] - Sx) // st[1] + 1
+    x = torch.randn(N, H, W, Ci, device="cuda", generator=g)
+    dy = torch.randn(N, Ho, Wo, Co, device="cuda", generator=g)
+    ref = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2), (Co, Ci, R, Sx), dy.permute(0, 3, 1, 2), st, pd)   # (Co,Ci,R,S)
+    geom = ConvGeom(N, H, W, Ci, Ho, Wo, Co, R, Sx, st[0], st[1], pd[0], pd[1], 0)
+    assert L.viai_conv2d_wgrad_tc_supported(ctypes.byref(geom)), "unsupported"
+    ws = torch.empty(L.viai_wgrad_tc_workspace(ctypes.byref(geom)), device="cuda")
+    dw = torch.full((Co, Ci, R, Sx), 1.0, device="cuda")
+    call = lambda acc: _lib.check(L.viai_conv2d_wgrad_tc(ctypes.byref(geom), P(dy), P(x), P(dw), dw.stride(0), dw.stride(1),
+                                                         dw.stride(2), dw.stride(3), acc, P(ws), S()), "wgrad_tc")
+    call(0)
+    torch.cuda.synchronize()
+    err = float((dw - ref).abs().max() / ref.abs().max())
+    call(1)
+    torch.cuda.synchronize()
+    err2 = float((dw - 2 * ref).abs().max() / ref.abs().max())
+    msg = "%-18s relerr=%.3e accumulate=%.3e" % (name, err, err2)
+    if name.startswith("WT_"):
+        for _ in range(3):
+            call(0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            call(0)
+        e1.record(); e1.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        msg += "  %.3f ms  %.1f TFLOP/s" % (ms, 2.0 * N * Ho * Wo * Co * Ci * R * Sx / ms / 1e9)
+    print(msg, flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "w":
+        for n in (sys.argv[2:] or list(WCASES)):
+            try:
+                run_w(n)
+            except Exception as e:
+                print("%-18s FAILED: %s" % (n, str(e)[:300]), flush=True)
+                if "CUDA" in str(e) or "cuda" in str(e):
+                    break
+        sys.exit(0)
     flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     names = sys.argv[2:] or list(CASES)
     for n in names:

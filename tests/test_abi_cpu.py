@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib):
     L = lib.lib()
     for name in sorted(declared):
         assert hasattr(L, name), "libviai_b200.so does not export %s" % name
-    bound = set(lib.SIGNATURES) | {"viai_last_error", "viai_version", "viai_launch_count"}
+    bound = set(lib.SIGNATURES) | set(lib.VALUE_FUNCS) | {"viai_last_error", "viai_version", "viai_launch_count"}
     assert declared == bound, declared ^ bound
     assert L.viai_version() >= 100
 

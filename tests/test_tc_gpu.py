@@ -1,0 +1,162 @@
+"""The tcgen05 convolution path: kernels against torch fp64 at every layer geometry of the generator / discriminator, the
+fused normalisation statistics, and the whole GAN step against the oracle.
+
+Tolerances.  tf32 keeps 10 mantissa bits, so a single-product convolution differs from exact fp32 by up to ~1e-3 of the
+tensor's largest value (measured 3-9e-4): 2e-3 per kernel (TC_TOL).  Chained through the 22 normalised layers of G that
+becomes ~1e-2 on the spectrogram (measured here and reproduced on the CPU by truncating operands to tf32), which misses the
+north star's 1e-3 bound -- so the library default "tf32x3" runs every FORWARD convolution as the error-compensated 3-term
+product (hi*hi + hi*lo + lo*hi, ~2^-19 per product; X3_TOL = 5e-5 per kernel) and asserts the 1e-3 spectrogram bound
+directly; gradients keep the single product and the gradient criteria of tests/test_gan_gpu.py."""
+import ctypes
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import viai_test_helpers as H
+from test_layers_gpu import LAYERS
+
+pytestmark = pytest.mark.gpu
+TC_TOL = 2e-3
+X3_TOL = 5e-5
+
+
+def _supported(layer):
+    name, tr, Cin, Cout, kh, kw, stride, pad, Hh, W = layer
+    return Cin >= 16 and Cout >= 16
+
+
+@pytest.mark.parametrize("layer", [l for l in LAYERS if _supported(l)], ids=[l[0] for l in LAYERS if _supported(l)])
+@pytest.mark.parametrize("N", [2, 3])
+@pytest.mark.tf32
+def test_tc_layer_geometry(layer, N):
+    from viai_b200 import ops, _lib
+    assert ops.get_precision() == "tf32"
+    name, tr, Cin, Cout, kh, kw, stride, pad, Hh, W = layer
+    g = torch.Generator().manual_seed(abs(hash(name)) % 100000 + N)
+    x = torch.randn(N, Cin, Hh, W, generator=g, dtype=torch.float64).float().double().requires_grad_(True)
+    wshape = (Cin, Cout, kh, kw) if tr else (Cout, Cin, kh, kw)
+    w = (torch.randn(wshape, generator=g, dtype=torch.float64) / math.sqrt(Cin * kh * kw)).float().double().requires_grad_(True)
+    b = (torch.randn(Cout, generator=g, dtype=torch.float64) * 0.1).float().double().requires_grad_(True)
+    y = F.conv_transpose2d(x, w, b, stride, pad) if tr else F.conv2d(x, w, b, stride, pad)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64).float().double()
+    y.backward(dy)
+    nhwc = lambda t: t.float().permute(0, 2, 3, 1).contiguous().cuda()
+    xg = nhwc(x.detach()).requires_grad_(True)
+    wg = w.detach().float().cuda().requires_grad_(True)
+    bg = b.detach().float().cuda().requires_grad_(True)
+    n0 = _lib.launch_count()
+    yg, stats = ops.conv2d_stats(xg, wg, bg, stride, pad, tr, 1)
+    yg.backward(nhwc(dy))
+    errs = dict(fwd=H.relerr(yg.permute(0, 3, 1, 2), y), dgrad=H.relerr(xg.grad.permute(0, 3, 1, 2), x.grad),
+                wgrad=H.relerr(wg.grad, w.grad), bgrad=H.relerr(bg.grad, b.grad))
+    for k, v in errs.items():
+        assert v < TC_TOL, (name, k, v)
+    # statistics fused into the epilogue: per-channel sum and sum of squares of the output
+    yd = y.detach()
+    assert H.relerr(stats[0], yd.sum((0, 2, 3))) < TC_TOL
+    assert H.relerr(stats[1], (yd * yd).sum((0, 2, 3))) < TC_TOL
+
+
+@pytest.mark.parametrize("layer", [l for l in LAYERS if _supported(l)], ids=[l[0] for l in LAYERS if _supported(l)])
+@pytest.mark.tf32x3
+def test_x3_forward_is_fp32_accurate(layer):
+    """The 3-term product: forward output and fused statistics at fp32-level accuracy."""
+    from viai_b200 import ops
+    assert ops.get_precision() == "tf32x3"
+    name, tr, Cin, Cout, kh, kw, stride, pad, Hh, W = layer
+    g = torch.Generator().manual_seed(abs(hash(name)) % 100000)
+    x = torch.randn(2, Cin, Hh, W, generator=g, dtype=torch.float64).float().double()
+    wshape = (Cin, Cout, kh, kw) if tr else (Cout, Cin, kh, kw)
+    w = (torch.randn(wshape, generator=g, dtype=torch.float64) / math.sqrt(Cin * kh * kw)).float().double()
+    b = (torch.randn(Cout, generator=g, dtype=torch.float64) * 0.1).float().double()
+    y = F.conv_transpose2d(x, w, b, stride, pad) if tr else F.conv2d(x, w, b, stride, pad)
+    with torch.no_grad():
+        yg, stats = ops.conv2d_stats(x.float().permute(0, 2, 3, 1).contiguous().cuda(), w.float().cuda(), b.float().cuda(),
+                                     stride, pad, tr, 1)
+    assert H.relerr(yg.permute(0, 3, 1, 2), y) < X3_TOL, name
+    assert H.relerr(stats[0], y.sum((0, 2, 3))) < X3_TOL and H.relerr(stats[1], (y * y).sum((0, 2, 3))) < X3_TOL
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 8), (2, 17, 9), (3, 5, 21), (1, 1, 1), (2, 33, 7)])
+@pytest.mark.tf32
+def test_tc_ragged_shapes_and_instance_stats(shape):
+    """Tiles that overhang the image (TMA out-of-bounds fill), tiny images, per-image statistics."""
+    from viai_b200 import ops
+    N, Hh, W = shape
+    g = torch.Generator().manual_seed(N * 1000 + Hh * 10 + W)
+    x = torch.randn(N, 32, Hh, W, generator=g, dtype=torch.float64).float().double()
+    w = (torch.randn(48, 32, 3, 3, generator=g, dtype=torch.float64) / 17.0).float().double()
+    y = F.conv2d(x, w, None, 1, 1)
+    yg, stats = ops.conv2d_stats(x.float().permute(0, 2, 3, 1).contiguous().cuda(), w.float().cuda(), None, (1, 1), (1, 1), False, N)
+    assert H.relerr(yg.permute(0, 3, 1, 2), y) < TC_TOL
+    assert H.relerr(stats[0].view(N, 48), y.sum((2, 3))) < TC_TOL
+    assert H.relerr(stats[1].view(N, 48), (y * y).sum((2, 3))) < TC_TOL
+
+
+def test_tc_matches_cuda_core_path_bitwise_shapes_and_unsupported_geometries_fall_back():
+    """Cin = 1 / Cout = 1 layers are not tensor-core shaped: the library must route them to the CUDA-core kernel (and say so)."""
+    from viai_b200 import _lib
+    from viai_b200._lib import ConvGeom
+    L = _lib.lib()
+    ok = ConvGeom(2, 16, 16, 32, 16, 16, 32, 3, 3, 1, 1, 1, 1, 0)
+    assert L.viai_conv2d_tc_supported(ctypes.byref(ok)) == 1 and L.viai_conv2d_wgrad_tc_supported(ctypes.byref(ok)) == 1
+    for bad in (ConvGeom(2, 16, 16, 1, 16, 16, 32, 3, 3, 1, 1, 1, 1, 0), ConvGeom(2, 16, 16, 32, 16, 16, 1, 3, 3, 1, 1, 1, 1, 0),
+                ConvGeom(2, 16, 16, 32, 4, 4, 32, 3, 3, 4, 4, 1, 1, 0), ConvGeom(2, 16, 16, 32, 10, 10, 32, 7, 7, 1, 1, 0, 0, 0)):
+        assert L.viai_conv2d_tc_supported(ctypes.byref(bad)) == 0
+    x = torch.zeros(1, 8, 8, 32, device="cuda")
+    rc = L.viai_conv2d_tc(ctypes.byref(ConvGeom(1, 8, 8, 1, 8, 8, 32, 3, 3, 1, 1, 1, 1, 0)), ctypes.c_void_p(x.data_ptr()),
+                          ctypes.c_void_p(x.data_ptr()), None, ctypes.c_void_p(x.data_ptr()), None, None, 0, 0, None)
+    assert rc != 0 and b"unsupported" in L.viai_last_error()
+
+
+@pytest.mark.parametrize("cfg", [("bn", 1, 80, 64), ("in", 2, 96, 48), ("bn", 2, 128, 128)], ids=["c1", "in96", "s128"])
+@pytest.mark.tf32x3
+def test_tc_train_step_matches_oracle(cfg):
+    """GanTrainer.train_step on the default tensor-core path vs oracle.gan_step (fp32 CPU restatement of the reference)."""
+    from viai_b200 import Options_inpainting as OI, ops
+    assert ops.get_precision() == "tf32x3"
+    from viai_b200.step import GanTrainer
+    from oracle import viai_oracle as O
+    import torch.nn as nn
+    norm, B, Hh, W = cfg
+    nl = nn.BatchNorm2d if norm == "bn" else nn.InstanceNorm2d
+    hp = OI.Inpainting_Config(cin_channels=Hh, normlayer=nl)
+    torch.manual_seed(1234)
+    tr = GanTrainer(hp, "cuda", norm_layer_d=nl, norm_layer_e=nl)
+    cpu = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    esd, gsd, dsd = cpu(tr.Mel_Encoder), cpu(tr.Mel_Decoder), cpu(tr.netD)
+    mel = torch.rand(B, 1, Hh, W)
+    mask = O.time_band_mask(mel.shape, W // 4, W // 2)
+    want, want64 = H.oracle_pair(esd, gsd, dsd, mel, mask, Hh, norm, norm)
+    got = tr.train_step(mel.cuda(), mask.cuda())
+    e_fake = H.relerr(got["fake"], want["fake"])
+    print("tf32 step", cfg, "fake relerr %.3e" % e_fake, {k: (float(got[k]), want[k]) for k in ("loss_D", "loss_G_GAN", "loss_L1")})
+    assert e_fake < 1e-3                                  # north star: <= 1e-3 rel for fp32 spectrograms
+    for k in ("loss_D", "loss_G_GAN", "loss_L1"):
+        assert math.isclose(float(got[k]), want[k], rel_tol=2e-3), k
+    for mod, gk in ((tr.netD, "grads_D"), (tr.Mel_Encoder, "grads_E"), (tr.Mel_Decoder, "grads_Dec")):
+        ps = dict(mod.named_parameters())
+        H.assert_e2e_grads({k: ps[k]._viai_grad for k in want64[gk]}, want64[gk], gk)
+
+
+@pytest.mark.tf32
+def test_single_tf32_step_is_outside_the_parity_bound():
+    """Documents WHY the default is tf32x3: with one tf32 product per convolution (cuDNN's default behaviour on Ampere+) the
+    spectrogram is off by ~1e-2, an order of magnitude above the 1e-3 bound, while staying well inside 5e-2."""
+    from viai_b200 import Options_inpainting as OI
+    from viai_b200.step import GanTrainer
+    from oracle import viai_oracle as O
+    hp = OI.Inpainting_Config(cin_channels=128)
+    torch.manual_seed(1234)
+    tr = GanTrainer(hp, "cuda")
+    cpu = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    esd, gsd, dsd = cpu(tr.Mel_Encoder), cpu(tr.Mel_Decoder), cpu(tr.netD)
+    mel = torch.rand(2, 1, 128, 128)
+    mask = O.time_band_mask(mel.shape, 32, 64)
+    want = O.gan_step(esd, gsd, dsd, mel, mask, 128)
+    got = tr.train_step(mel.cuda(), mask.cuda())
+    e = H.relerr(got["fake"], want["fake"])
+    print("single tf32 spectrogram relerr %.3e" % e)
+    assert 1e-3 < e < 5e-2

@@ -28,10 +28,12 @@ _GP = ctypes.POINTER(ConvGeom)
 SIGNATURES = {
     "viai_pack_weight": [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_l, c_l, c_i, c_p],
     "viai_conv2d_simt": [_GP, c_p, c_p, c_p, c_p, c_p],
-    "viai_pack_weight_tc": [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_l, c_l, c_i, c_p],
+    "viai_pack_weight_tc": [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_l, c_l, c_i, c_i, c_p],
     "viai_conv2d_tc_supported": [_GP],
     "viai_conv2d_tc": [_GP, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p],
     "viai_tc_bn": [c_i],
+    "viai_conv2d_wgrad_tc_supported": [_GP],
+    "viai_conv2d_wgrad_tc": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p, c_p],
     "viai_conv2d_wgrad_simt": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p],
     "viai_channel_stats": [c_p, c_l, c_i, c_i, c_p, c_p, c_p],
     "viai_norm_finalize": [c_p, c_p, c_l, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
@@ -58,6 +60,13 @@ SIGNATURES = {
 }
 
 
+# entry points whose return type is not the int status code: name -> (restype, argtypes)
+VALUE_FUNCS = {
+    "viai_tc_packed_size": (ctypes.c_int64, [c_i, c_i, c_i, c_i, c_i]),
+    "viai_wgrad_tc_workspace": (ctypes.c_int64, [_GP]),
+}
+
+
 def available():
     return os.path.exists(LIB_PATH)
 
@@ -74,8 +83,10 @@ def lib():
         L.viai_last_error.argtypes = []
         L.viai_version.restype = c_i
         L.viai_launch_count.restype = ctypes.c_longlong
-        L.viai_tc_packed_size.restype = ctypes.c_int64
-        L.viai_tc_packed_size.argtypes = [c_i, c_i, c_i, c_i]
+        for name, (res, args) in VALUE_FUNCS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
         for name, args in SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = args

@@ -38,7 +38,7 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 int encode_f32_map(CUtensorMap* map, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, int swizzle128) {
+                   const uint32_t* box, int swizzle) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -49,7 +49,7 @@ int encode_f32_map(CUtensorMap* map, int rank, const void* base, const uint64_t*
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]", (int)r, rank,
@@ -67,8 +67,8 @@ namespace {
 constexpr int TH = 16, TW = 8;          // output pixels per M tile (TW = 8 = rows of one UMMA core matrix)
 constexpr int KC = 32;                  // input channels per slab (8 chunks of 16 bytes)
 constexpr int MAX_SUB = 4, MAX_TAP = 16;
-constexpr int NTHREADS = 224;
-constexpr int EPI_WARP0 = 3;
+constexpr int NTHREADS = 352;          // warps 0-2: producers + MMA, 3-6: epilogue, 7-10: hi/lo split (tf32x3 only)
+constexpr int XF_WARP0 = 7;
 
 struct TcSub {
   int32_t ox, oy;        // sub-grid coordinate of the patch origin relative to the tile origin
@@ -99,8 +99,8 @@ struct TcParams {
   int32_t SA, SB;
   uint32_t idesc;
   int32_t a4d;           // 1: sub-patch loaded by 8 rank-4 TMA copies instead of one rank-5 copy
+  int32_t x3;            // 1: error-compensated 3-term tf32 product (A*Bhi + A*Blo + Alo*Bhi), ~fp32 accuracy
   int32_t a_sw128;       // 1: activation patch stored as dense 128-byte pixel rows under the 128-byte swizzle (rank-4 TMA)
-  int32_t a_baseoff;     // debug: put (start >> 7) & 7 in the descriptor's base-offset field
 };
 
 __device__ __forceinline__ void transpose_reduce32(float (&v)[32], int lane) {
@@ -121,22 +121,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzled TMA destinations need 1 KB alignment
   uint8_t* slabA = smem;
-  uint8_t* tileB = slabA + (size_t)p.SA * p.slab_bytes;
+  const uint32_t a_stage = p.slab_bytes * (p.x3 ? 2u : 1u);     // [raw / hi slab][lo slab]
+  uint8_t* tileB = slabA + (size_t)p.SA * a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tileB + (size_t)p.SB * p.btile_bytes);
   uint64_t* fullA = bars;
   uint64_t* emptyA = fullA + p.SA;
-  uint64_t* fullB = emptyA + p.SA;
+  uint64_t* loA = emptyA + p.SA;
+  uint64_t* fullB = loA + p.SA;
   uint64_t* emptyB = fullB + p.SB;
   uint64_t* tfull = emptyB + p.SB;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  double* stat_acc = reinterpret_cast<double*>(tmem_slot + 2);   // [4 warps][2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = (2 * p.BN <= 32) ? 32u : (2 * p.BN <= 64) ? 64u : (2 * p.BN <= 128) ? 128u : (2 * p.BN <= 256) ? 256u : 512u;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < p.SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); mbar_init(&loA[i], 128); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     fence_barrier_init();
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(&emptyA[sa], pha ^ 1u);
           mbar_expect_tx(&fullA[sa], p.slab_tx_bytes);
-          uint8_t* dst = slabA + (size_t)sa * p.slab_bytes;
+          uint8_t* dst = slabA + (size_t)sa * a_stage;
           for (int s = 0; s < p.nsub; ++s) {
             const TcSub& sb = p.sub[s];
             if (p.a_sw128) {
@@ -213,7 +214,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         uint32_t accumulate = 0;
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(&fullA[sa], pha);
-          const uint32_t a_base = smem_u32(slabA + (size_t)sa * p.slab_bytes);
+          if (p.x3) mbar_wait(&loA[sa], pha);
+          const uint32_t a_base = smem_u32(slabA + (size_t)sa * a_stage);
           for (int t = 0; t < p.ntap; ++t) {
             mbar_wait(&fullB[sb], phb);
             tc_fence_after();
@@ -222,14 +224,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
             for (int kk = 0; kk < KC / 8; ++kk) {
               const uint32_t b_addr = b_base + (uint32_t)kk * 2u * b_lbo;
-              uint64_t ad;
+              uint64_t ad, ad_lo = 0;
               if (p.a_sw128) {
                 const uint32_t a_addr = a_base + tp.a_off + (uint32_t)kk * 32u;
-                ad = make_desc_sw128(a_addr, tp.sbo, p.a_baseoff ? ((a_base + tp.a_off) >> 7) : 0u);
+                ad = make_desc_sw128(a_addr, tp.sbo, 0u);
+                ad_lo = make_desc_sw128(a_addr + p.slab_bytes, tp.sbo, 0u);
               } else {
                 ad = make_desc(a_base + tp.a_off + (uint32_t)kk * 2u * tp.lbo, tp.lbo, tp.sbo);
               }
               const uint64_t bd = make_desc(b_addr, b_lbo, b_sbo);
+              if (p.x3) {   // small terms first, then the leading one
+                mma_tf32(d_tmem, ad_lo, bd, p.idesc, accumulate);
+                mma_tf32(d_tmem, ad, make_desc(b_addr + (uint32_t)p.BN * 128u, b_lbo, b_sbo), p.idesc, 1);
+                accumulate = 1;
+              }
               mma_tf32(d_tmem, ad, bd, p.idesc, accumulate);
               accumulate = 1;
             }
@@ -242,17 +250,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         mma_commit(&tfull[acc]);
       }
     }
+  } else if (warp >= XF_WARP0) {
+    // ===== tf32x3: split every landed slab into hi = trunc_tf32(x) (in place) and lo = x - hi (second slab) =====
+    if (p.x3) {
+      const int tid = threadIdx.x - XF_WARP0 * 32;
+      int sa = 0;
+      uint32_t pha = 0;
+      const uint32_t n16 = p.slab_bytes / 16;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int c = 0; c < p.nchunks; ++c) {
+          mbar_wait(&fullA[sa], pha);
+          float4* hi = reinterpret_cast<float4*>(slabA + (size_t)sa * a_stage);
+          float4* lo = reinterpret_cast<float4*>(slabA + (size_t)sa * a_stage + p.slab_bytes);
+          for (uint32_t i = tid; i < n16; i += 128) {
+            float4 v = hi[i], h;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            hi[i] = h;
+            lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&loA[sa]);
+          if (++sa == p.SA) { sa = 0; pha ^= 1u; }
+        }
+      }
+    }
   } else {
     // ===== epilogue: TMEM -> registers -> (+bias, statistics) -> global =====
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;                // accumulator row = pixel of the tile
     const int ly = row >> 3, lx = row & 7;
-    double* my_sum = stat_acc + (size_t)(warp - EPI_WARP0) * 2 * p.BN;
-    double* my_sq = my_sum + p.BN;
     const bool do_stats = p.stat_groups > 0;
-    if (do_stats)
-      for (int i = lane; i < 2 * p.BN; i += 32) my_sum[i] = 0.0;
+    const int nj = p.BN / 32;
+    float rs[8], rq[8];                           // this lane's running sum / sum of squares of channel j*32 + lane
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rs[j] = rq[j] = 0.f;
     int cur_group = -1, cur_nt = -1;
+    auto flush = [&]() {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ch = cur_nt * p.BN + j * 32 + lane;
+        if (j < nj && ch < p.Cout) {
+          atomicAdd(&p.ssum[(size_t)cur_group * p.Cout + ch], (double)rs[j]);
+          atomicAdd(&p.ssq[(size_t)cur_group * p.Cout + ch], (double)rq[j]);
+        }
+        rs[j] = rq[j] = 0.f;
+      }
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int nt = tile % p.ntilesN;
@@ -265,25 +311,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       const int acc = it & 1;
       if (do_stats) {
         const int grp = (p.stat_groups > 1) ? n : 0;
-        if ((grp != cur_group || nt != cur_nt) && cur_group >= 0) {
-          // flush the partial sums of the finished (group, cout tile)
-          for (int i = lane; i < p.BN; i += 32) {
-            const int ch = cur_nt * p.BN + i;
-            if (ch < p.Cout) {
-              atomicAdd(&p.ssum[(size_t)cur_group * p.Cout + ch], my_sum[i]);
-              atomicAdd(&p.ssq[(size_t)cur_group * p.Cout + ch], my_sq[i]);
-            }
-            my_sum[i] = 0.0;
-            my_sq[i] = 0.0;
-          }
-        }
+        if ((grp != cur_group || nt != cur_nt) && cur_group >= 0) flush();   // finished (group, cout tile)
         cur_group = grp;
         cur_nt = nt;
       }
       mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
       float* optr = p.out + p.o_base + (int64_t)n * p.o_sn + (int64_t)y * p.o_sy + (int64_t)x * p.o_sx + (int64_t)nt * p.BN;
-      for (int j = 0; j < p.BN / 32; ++j) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j >= nj) break;
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + j * 32), v);
         const int ch0 = nt * p.BN + j * 32;
@@ -298,32 +335,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
             if (ch0 + i < p.Cout) *reinterpret_cast<float4*>(optr + j * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
         if (do_stats) {
-          float s[32], s2[32];
+          float s2[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            s[i] = valid ? v[i] : 0.f;
-            s2[i] = s[i] * s[i];
+            v[i] = valid ? v[i] : 0.f;
+            s2[i] = v[i] * v[i];
           }
-          transpose_reduce32(s, lane);
+          transpose_reduce32(v, lane);
           transpose_reduce32(s2, lane);
-          my_sum[j * 32 + lane] += (double)s[0];
-          my_sq[j * 32 + lane] += (double)s2[0];
+          rs[j] += v[0];
+          rq[j] += s2[0];
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
-    if (do_stats && cur_group >= 0) {
-      __syncwarp();
-      for (int i = lane; i < p.BN; i += 32) {
-        const int ch = cur_nt * p.BN + i;
-        if (ch < p.Cout) {
-          atomicAdd(&p.ssum[(size_t)cur_group * p.Cout + ch], my_sum[i]);
-          atomicAdd(&p.ssq[(size_t)cur_group * p.Cout + ch], my_sq[i]);
-        }
-      }
-    }
+    if (do_stats && cur_group >= 0) flush();
   }
   tc_fence_before();
   __syncthreads();
@@ -333,15 +361,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   }
 }
 
-// dst[tap][slab][cout tile][16-byte chunk j][row][4] = tf32(w[o][tap][i]),  i = slab*32 + j*4 + e, o = tile*BN + row
+// dst[tap][slab][cout tile][part][16-byte chunk j][row][4]; part 0 = tf32(w[o][tap][i]), part 1 (split packing only) =
+// tf32(w - part 0);  i = slab*32 + j*4 + e, o = tile*BN + row
 __global__ void pack_weight_tc_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int R, int S,
-                                      int64_t so, int64_t si, int64_t sr, int64_t ss, int flip, int BN, int nchunks, int ntilesN) {
-  const int64_t total = (int64_t)R * S * nchunks * ntilesN * (KC / 4) * BN * 4;
+                                      int64_t so, int64_t si, int64_t sr, int64_t ss, int flip, int BN, int nchunks, int ntilesN,
+                                      int parts) {
+  const int64_t total = (int64_t)R * S * nchunks * ntilesN * parts * (KC / 4) * BN * 4;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t t = idx;
     const int e = t & 3; t >>= 2;
     const int row = t % BN; t /= BN;
     const int j = t % (KC / 4); t /= (KC / 4);
+    const int part = t % parts; t /= parts;
     const int nt = t % ntilesN; t /= ntilesN;
     const int c = t % nchunks; t /= nchunks;
     const int tap = (int)t;
@@ -350,7 +381,9 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ src, float* __re
     float v = 0.f;
     if (o < O && i < I) {
       const int rr = flip ? R - 1 - r : r, sw = flip ? S - 1 - s : s;
-      v = to_tf32(src[o * so + i * si + rr * sr + sw * ss]);
+      const float w = src[o * so + i * si + rr * sr + sw * ss];
+      const float hi = to_tf32(w);
+      v = part == 0 ? hi : to_tf32(w - hi);
     }
     dst[idx] = v;
   }
@@ -373,10 +406,12 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   TcParams p;
   memset(&p, 0, sizeof(p));
   VIAI_REQUIRE(ntap >= 1 && ntap <= MAX_TAP, "conv2d_tc: %d taps (max %d)", ntap, MAX_TAP);
-  p.a4d = (flags & 2) ? 1 : 0;
-  p.a_sw128 = (flags & 4) ? 1 : 0;
-  p.a_baseoff = (flags & 8) ? 1 : 0;
-  if (p.a_sw128) p.a4d = 0;
+  // default: dense 128-byte pixel rows under the 128-byte swizzle.  flags & 1: 16-byte channel chunks, no swizzle (rank-5
+  // TMA); flags & 3 == 3: the same through eight rank-4 copies.  Both alternatives are kept as cross-checks of the layout.
+  p.x3 = (flags & 4) ? 1 : 0;
+  p.a_sw128 = (flags & 1) ? 0 : 1;
+  VIAI_REQUIRE(!p.x3 || p.a_sw128, "conv2d_tc: the 3-term product needs the swizzled activation layout");
+  p.a4d = (!p.a_sw128 && (flags & 2)) ? 1 : 0;
   // sub-patches: one per (suby, subx) parity that occurs
   int sub_id[2][2] = {{-1, -1}, {-1, -1}};
   int mn_y[MAX_SUB], mx_y[MAX_SUB], mn_x[MAX_SUB], mx_x[MAX_SUB], sy_of[MAX_SUB], sx_of[MAX_SUB];
@@ -455,13 +490,14 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   p.nchunks = (inC + KC - 1) / KC;
   p.Cout = Cout;
   p.o_sn = o_sn; p.o_sy = o_sy; p.o_sx = o_sx; p.o_base = o_base;
-  p.btile_bytes = (uint32_t)p.BN * KC * 4;
+  p.btile_bytes = (uint32_t)p.BN * KC * 4 * (p.x3 ? 2u : 1u);
   p.idesc = make_idesc_tf32(128, p.BN, 0, 0);
   // pipeline depths under the 227 KB shared-memory limit
-  const size_t fixed = 1024 /*alignment slack*/ + 64 * 8 + 16 + (size_t)4 * 2 * p.BN * 8;
+  const size_t fixed = 1024 /*alignment slack*/ + 64 * 8 + 16;
   const size_t budget = 227 * 1024;
   int SA = 3, SB = 4;
-  auto need = [&](int a, int b) { return fixed + (size_t)a * p.slab_bytes + (size_t)b * p.btile_bytes; };
+  VIAI_REQUIRE(3 * SA + 2 * SB + 4 <= 64, "conv2d_tc: barrier area");
+  auto need = [&](int a, int b) { return fixed + (size_t)a * p.slab_bytes * (p.x3 ? 2 : 1) + (size_t)b * p.btile_bytes; };
   while (need(SA, SB) > budget && SB > 2) --SB;
   while (need(SA, SB) > budget && SA > 2) --SA;
   while (need(SA, SB) > budget && SB > 1) --SB;
@@ -487,18 +523,18 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
 
 extern "C" int viai_tc_bn(int Cout) { return tc_bn(Cout); }
 
-extern "C" int64_t viai_tc_packed_size(int O, int I, int R, int S) {
+extern "C" int64_t viai_tc_packed_size(int O, int I, int R, int S, int split) {
   const int BN = tc_bn(O);
-  return (int64_t)R * S * ((I + KC - 1) / KC) * ((O + BN - 1) / BN) * BN * KC;
+  return (int64_t)R * S * ((I + KC - 1) / KC) * ((O + BN - 1) / BN) * BN * KC * (split ? 2 : 1);
 }
 
 extern "C" int viai_pack_weight_tc(const float* src, float* dst, int O, int I, int R, int S, int64_t so, int64_t si, int64_t sr,
-                                   int64_t ss, int flip, viai_stream_t stream) {
+                                   int64_t ss, int flip, int split, viai_stream_t stream) {
   VIAI_REQUIRE(src && dst && O > 0 && I > 0 && R > 0 && S > 0, "pack_weight_tc: bad arguments");
   const int BN = tc_bn(O), nchunks = (I + KC - 1) / KC, ntilesN = (O + BN - 1) / BN;
-  const int64_t total = viai_tc_packed_size(O, I, R, S);
+  const int64_t total = viai_tc_packed_size(O, I, R, S, split);
   const int blocks = (int)imin64(cdiv(total, 256), 4096);
-  pack_weight_tc_kernel<<<blocks, 256, 0, STR(stream)>>>(src, dst, O, I, R, S, so, si, sr, ss, flip, BN, nchunks, ntilesN);
+  pack_weight_tc_kernel<<<blocks, 256, 0, STR(stream)>>>(src, dst, O, I, R, S, so, si, sr, ss, flip, BN, nchunks, ntilesN, split ? 2 : 1);
   VIAI_LAUNCHED();
   return VIAI_OK;
 }

@@ -1,0 +1,314 @@
+// Tensor-core weight gradient for sm_100a (tcgen05.mma kind::tf32, fp32 accumulation in TMEM).
+//
+//   dW[a][b][r][s] (+)= sum_{n,y,x} U[n,y,x,a] * G[n, y*stride_h - pad_h + r, x*stride_w - pad_w + s, b]
+//
+// Per filter tap this is a GEMM  D_t[a][b] = U^T (A x pixels) . G_t (pixels x B)  whose reduction runs over pixels, so both
+// operands are "MN-major" in shared memory: a TMA box of (32 channels, 8 columns, TH rows) lands as dense 128-byte pixel rows
+// (128B swizzle with 32B atoms -- the one layout the tensor core accepts for MN-major tf32), i.e. 8 consecutive pixels of 32
+// channels are the two 512-byte atoms of one K step of 8.
+//   * A operand: the U tile (TH x 8 pixels, 128 channels = 4 boxes of 32 channels, LBO = box pitch);
+//   * B operand: the (TH + kh - 1) x (8 + kw - 1) patch of G (32 channels) that ALL taps of the tile read, loaded once; a tap
+//     is a different start row of the descriptor (as in conv_tc.cu), strides become parity sub-grids;
+//   * accumulators: one 128 x 32 fp32 block per tap in TMEM (9 taps -> 288 of the 512 columns), kept for the CTA's whole
+//     pixel range (split-K across CTAs), then added to a packed fp32 workspace with vector reductions (red.global.add.v4.f32);
+//   * a second tiny kernel scatters the workspace into the parameter-gradient layout (overwrite or accumulate).
+// Ragged tiles and zero padding need no masking: TMA fills out-of-bounds elements of either operand with zeros.
+#include "common.cuh"
+#include "tc_common.cuh"
+using namespace viai;
+using namespace viai::tc;
+
+namespace {
+
+constexpr int TW = 8, KC = 32, BM = 128, BNW = 32;
+constexpr int MAX_SUB = 4, MAX_TAP = 16;
+constexpr int NTHREADS = 192;   // warp 0: TMA producer, warp 1: TMEM + MMA issuer, warps 2..5: epilogue
+
+struct WgSub {
+  int32_t ox, oy, pw, ph;
+  uint32_t smem_off;     // inside the G region of a stage
+};
+struct WgTap {
+  uint32_t g_off;        // byte offset (inside the G region) of the tap's first pixel row
+  uint32_t row_pitch;    // bytes between consecutive 8-pixel row segments (pw * 128)
+  uint32_t wtap;
+};
+struct WgParams {
+  CUtensorMap mapU;
+  CUtensorMap mapG[MAX_SUB];
+  WgSub sub[MAX_SUB];
+  WgTap tap[MAX_TAP];
+  int32_t nsub, ntap;
+  float* ws;             // [tap][A][B] fp32 workspace
+  int32_t A, B;
+  int32_t N, tilesX, tilesY, TH;
+  int32_t a_tiles, b_tiles, splits, tiles_per_split, npix_tiles;
+  int32_t u_slices;      // 32-channel boxes of U actually loaded per stage (<= 4)
+  uint32_t u_bytes, u_slice_bytes, g_bytes, g_tx_bytes, stage_bytes;
+  int32_t stages;
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = full + p.stages;
+  uint64_t* done = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 512;
+
+  // work item
+  int item = blockIdx.x;
+  const int bt = item % p.b_tiles; item /= p.b_tiles;
+  const int at = item % p.a_tiles; item /= p.a_tiles;
+  const int split = item;
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(p.npix_tiles, t_begin + p.tiles_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+    prefetch_tmap(&p.mapU);
+    for (int i = 0; i < p.nsub; ++i) prefetch_tmap(&p.mapG[i]);
+  }
+  // U slices that are never loaded (A < 128) must read as zeros
+  if (p.u_slices < 4) {
+    for (int s = 0; s < p.stages; ++s) {
+      uint8_t* u = smem + (size_t)s * p.stage_bytes;
+      for (uint32_t i = p.u_slices * p.u_slice_bytes + threadIdx.x * 16; i < p.u_bytes; i += NTHREADS * 16)
+        *reinterpret_cast<float4*>(u + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        int rest = t;
+        const int tx = rest % p.tilesX; rest /= p.tilesX;
+        const int ty = rest % p.tilesY;
+        const int n = rest / p.tilesY;
+        const int x0 = tx * TW, y0 = ty * p.TH;
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_expect_tx(&full[st], p.u_slices * p.u_slice_bytes + p.g_tx_bytes);
+        uint8_t* u = smem + (size_t)st * p.stage_bytes;
+        uint8_t* g = u + p.u_bytes;
+        for (int s = 0; s < p.u_slices; ++s)
+          tma_load_4d(u + (size_t)s * p.u_slice_bytes, &p.mapU, &full[st], at * BM + s * KC, x0, y0, n);
+        for (int s = 0; s < p.nsub; ++s)
+          tma_load_4d(g + p.sub[s].smem_off, &p.mapG[s], &full[st], bt * BNW, x0 + p.sub[s].ox, y0 + p.sub[s].oy, n);
+        if (++st == p.stages) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t u_base = smem_u32(smem + (size_t)st * p.stage_bytes);
+        const uint32_t g_base = u_base + p.u_bytes;
+        for (int tp = 0; tp < p.ntap; ++tp) {
+          const WgTap& w = p.tap[tp];
+          const uint32_t d_tmem = tmem_base + (uint32_t)(tp * BNW);
+          // A: MN-major, 4 blocks of 32 channels LBO apart; B: MN-major, one block.  SBO (between K groups of 8) is unused
+          // because every MMA covers exactly one group.
+          uint64_t ad = make_desc_sw128x32_mn(u_base, p.u_slice_bytes, 512u);
+          uint64_t bd = make_desc_sw128x32_mn(g_base + w.g_off, 1024u, 512u);
+          const uint64_t a_step = 1024u >> 4, b_step = w.row_pitch >> 4;
+          for (int kk = 0; kk < p.TH; ++kk) {
+            mma_tf32(d_tmem, ad, bd, p.idesc, (t > t_begin || kk > 0) ? 1u : 0u);
+            ad += a_step;
+            bd += b_step;
+          }
+        }
+        mma_commit(&empty[st]);
+        if (++st == p.stages) { st = 0; ph ^= 1u; }
+      }
+      mma_commit(done);
+    }
+  } else {
+    // epilogue: add the CTA's partial D_t blocks into the workspace
+    const int q = warp & 3;
+    const int a = at * BM + q * 32 + lane;
+    if (t_end > t_begin) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      for (int tp = 0; tp < p.ntap; ++tp) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * BNW), v);
+        if (a < p.A) {
+          float* dst = p.ws + ((size_t)p.tap[tp].wtap * p.A + a) * p.B + (size_t)bt * BNW;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            if (bt * BNW + i < p.B) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+__global__ void wgrad_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw, int A, int B, int R, int S, int64_t sa,
+                                    int64_t sb, int64_t sr, int64_t ss, int accumulate) {
+  const int64_t total = (int64_t)R * S * A * B;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int b = idx % B;
+    int64_t t = idx / B;
+    const int a = t % A;
+    const int tap = (int)(t / A);
+    const int r = tap / S, s = tap % S;
+    float* d = dw + a * sa + b * sb + r * sr + s * ss;
+    *d = accumulate ? (*d + ws[idx]) : ws[idx];
+  }
+}
+
+inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+inline int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
+
+}  // namespace
+
+extern "C" int viai_conv2d_wgrad_tc_supported(const viai_conv_geom* g) {
+  if (!g) return 0;
+  if (g->Cin % 4 != 0 || g->Cin < 16 || g->Cout % 4 != 0 || g->Cout < 16) return 0;
+  if (g->R * g->S > MAX_TAP || g->R * g->S * BNW > 512) return 0;
+  if (g->stride_h < 1 || g->stride_h > 2 || g->stride_w < 1 || g->stride_w > 2) return 0;
+  return 1;
+}
+
+extern "C" int64_t viai_wgrad_tc_workspace(const viai_conv_geom* g) {
+  return g ? (int64_t)g->R * g->S * g->Cout * g->Cin : 0;
+}
+
+// U: (N,Hout,Wout,Cout=A), G: (N,Hin,Win,Cin=B) as in viai_conv2d_wgrad_simt.  workspace: viai_wgrad_tc_workspace(g) floats.
+extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, const float* G, float* dw, int64_t sa, int64_t sb,
+                                    int64_t sr, int64_t ss, int accumulate, float* workspace, viai_stream_t stream) {
+  VIAI_REQUIRE(gp && U && G && dw && workspace, "conv2d_wgrad_tc: null argument");
+  const viai_conv_geom& g = *gp;
+  VIAI_REQUIRE(viai_conv2d_wgrad_tc_supported(gp), "conv2d_wgrad_tc: unsupported geometry");
+  VIAI_REQUIRE((reinterpret_cast<uintptr_t>(U) & 15) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+               "conv2d_wgrad_tc: pointers must be 16-byte aligned");
+  cudaStream_t st = STR(stream);
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  const int A = g.Cout, B = g.Cin;
+  p.A = A; p.B = B; p.ws = workspace; p.N = g.N;
+  const bool strided = g.stride_h > 1 || g.stride_w > 1;
+  p.TH = strided ? 8 : 16;
+  // taps and parity sub-patches of G
+  int sub_id[2][2] = {{-1, -1}, {-1, -1}};
+  int mn_y[MAX_SUB], mx_y[MAX_SUB], mn_x[MAX_SUB], mx_x[MAX_SUB], sy_of[MAX_SUB], sx_of[MAX_SUB], t_sub[MAX_TAP], t_oy[MAX_TAP], t_ox[MAX_TAP];
+  int nsub = 0, ntap = 0;
+  for (int r = 0; r < g.R; ++r)
+    for (int s = 0; s < g.S; ++s) {
+      const int qy = r - g.pad_h, qx = s - g.pad_w;
+      const int py = posmod(qy, g.stride_h), px = posmod(qx, g.stride_w), oy = floordiv(qy, g.stride_h), ox = floordiv(qx, g.stride_w);
+      int& id = sub_id[py][px];
+      if (id < 0) {
+        id = nsub++;
+        sy_of[id] = py; sx_of[id] = px;
+        mn_y[id] = mx_y[id] = oy; mn_x[id] = mx_x[id] = ox;
+      } else {
+        mn_y[id] = oy < mn_y[id] ? oy : mn_y[id]; mx_y[id] = oy > mx_y[id] ? oy : mx_y[id];
+        mn_x[id] = ox < mn_x[id] ? ox : mn_x[id]; mx_x[id] = ox > mx_x[id] ? ox : mx_x[id];
+      }
+      t_sub[ntap] = id; t_oy[ntap] = oy; t_ox[ntap] = ox;
+      p.tap[ntap].wtap = (uint32_t)(r * g.S + s);
+      ++ntap;
+    }
+  p.nsub = nsub; p.ntap = ntap;
+  uint32_t off = 0;
+  for (int s = 0; s < nsub; ++s) {
+    WgSub& sb2 = p.sub[s];
+    sb2.ox = mn_x[s]; sb2.oy = mn_y[s];
+    sb2.pw = TW + (mx_x[s] - mn_x[s]);
+    sb2.ph = p.TH + (mx_y[s] - mn_y[s]);
+    sb2.smem_off = off;
+    off += (uint32_t)(sb2.pw * sb2.ph) * 128u;
+    p.g_tx_bytes += (uint32_t)(sb2.pw * sb2.ph) * 128u;
+    off = (off + 1023u) & ~1023u;
+    const int subH = (g.Hin - sy_of[s] + g.stride_h - 1) / g.stride_h, subW = (g.Win - sx_of[s] + g.stride_w - 1) / g.stride_w;
+    VIAI_REQUIRE(subH >= 1 && subW >= 1, "conv2d_wgrad_tc: empty parity sub-grid");
+    const float* base = G + ((int64_t)sy_of[s] * g.Win + sx_of[s]) * B;
+    uint64_t dims[4] = {(uint64_t)B, (uint64_t)subW, (uint64_t)subH, (uint64_t)g.N};
+    uint64_t strides[3] = {(uint64_t)g.stride_w * B * 4, (uint64_t)g.stride_h * g.Win * B * 4, (uint64_t)g.Hin * g.Win * B * 4};
+    uint32_t box[4] = {KC, (uint32_t)sb2.pw, (uint32_t)sb2.ph, 1};
+    if (encode_f32_map(&p.mapG[s], 4, base, dims, strides, box, 2)) return VIAI_ERR_CUDA;
+  }
+  p.g_bytes = off;
+  for (int t = 0; t < ntap; ++t) {
+    const WgSub& sb2 = p.sub[t_sub[t]];
+    p.tap[t].g_off = sb2.smem_off + (uint32_t)((t_oy[t] - sb2.oy) * sb2.pw + (t_ox[t] - sb2.ox)) * 128u;
+    p.tap[t].row_pitch = (uint32_t)sb2.pw * 128u;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)A, (uint64_t)g.Wout, (uint64_t)g.Hout, (uint64_t)g.N};
+    uint64_t strides[3] = {(uint64_t)A * 4, (uint64_t)g.Wout * A * 4, (uint64_t)g.Hout * g.Wout * A * 4};
+    uint32_t box[4] = {KC, TW, (uint32_t)p.TH, 1};
+    if (encode_f32_map(&p.mapU, 4, U, dims, strides, box, 2)) return VIAI_ERR_CUDA;
+  }
+  p.u_slice_bytes = (uint32_t)(p.TH * TW) * 128u;
+  p.u_bytes = 4 * p.u_slice_bytes;
+  p.a_tiles = (A + BM - 1) / BM;
+  p.b_tiles = (B + BNW - 1) / BNW;
+  {
+    const int rem = A - 0;   // slices needed by the widest a-tile; narrower (last) tiles read zero-filled boxes
+    const int need = rem >= BM ? 4 : (rem + KC - 1) / KC;
+    p.u_slices = need;
+  }
+  p.stage_bytes = p.u_bytes + p.g_bytes;
+  p.tilesX = (g.Wout + TW - 1) / TW;
+  p.tilesY = (g.Hout + p.TH - 1) / p.TH;
+  p.npix_tiles = g.N * p.tilesX * p.tilesY;
+  // split the pixel range so that the grid is about two waves of the 148 SMs
+  const int ab = p.a_tiles * p.b_tiles;
+  int splits = (2 * kNumSMs + ab - 1) / ab;
+  if (splits > p.npix_tiles) splits = p.npix_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.npix_tiles + splits - 1) / splits;
+  p.splits = (p.npix_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  const size_t budget = 227 * 1024, fixed = 1024 + 32 * 8 + 16;
+  int stages = 4;
+  while (stages > 1 && fixed + (size_t)stages * p.stage_bytes > budget) --stages;
+  VIAI_REQUIRE(fixed + (size_t)stages * p.stage_bytes <= budget, "conv2d_wgrad_tc: stage of %u bytes does not fit", p.stage_bytes);
+  p.stages = stages;
+  p.idesc = make_idesc_tf32(BM, BNW, 1, 1);
+  size_t smem = fixed + (size_t)stages * p.stage_bytes;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VIAI_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int64_t ws_elems = (int64_t)ntap * A * B;
+  VIAI_CUDA(cudaMemsetAsync(workspace, 0, (size_t)ws_elems * sizeof(float), st));
+  const int grid = p.splits * ab;
+  wgrad_tc_kernel<<<grid, NTHREADS, smem, st>>>(p);
+  VIAI_LAUNCHED();
+  const int blocks = (int)imin64(cdiv(ws_elems, 256), 2048);
+  wgrad_unpack_kernel<<<blocks, 256, 0, st>>>(workspace, dw, A, B, g.R, g.S, sa, sb, sr, ss, accumulate);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}

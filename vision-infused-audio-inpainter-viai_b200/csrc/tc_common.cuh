@@ -96,6 +96,19 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t sbo
   d |= (uint64_t)2 << 61;   // SWIZZLE_128B
   return d;
 }
+// MN-major 32-bit (tf32) operand.  The only layout the tensor core accepts for it is "128B swizzle with 32B atoms"
+// (layout type 1; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 128-byte rows hold 32 consecutive MN elements of one K index,
+// 32-byte chunks of a row are XOR-ed with (row & 3), 4 consecutive rows (K indices) form one 512-byte atom.
+// LBO = byte distance between 32-element MN blocks, SBO = between the two 4-row K atoms of one MMA (K = 8).
+__device__ __forceinline__ uint64_t make_desc_sw128x32_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;   // SWIZZLE_128B_BASE32B
+  return d;
+}
 // Instruction descriptor for kind::tf32 (fp32 accumulate).  a_mn / b_mn: 1 = MN-major operand, 0 = K-major.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
@@ -140,7 +153,7 @@ EncodeTiledFn encode_tiled_fn();   // resolved through cudaGetDriverEntryPoint (
 
 // fp32 tensor map of rank `rank` (<= 5) without swizzle; strides in bytes for dims 1..rank-1.  Returns 0 on success.
 int encode_f32_map(CUtensorMap* map, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, int swizzle128 = 0);
+                   const uint32_t* box, int swizzle = 0);   // swizzle: 0 none, 1 128B, 2 128B with 32B atoms
 
 }  // namespace tc
 }  // namespace viai

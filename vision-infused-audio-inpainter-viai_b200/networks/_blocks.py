@@ -24,7 +24,10 @@ def conv_norm_act(x, conv, norm, act, slope=0.0):
         raise RuntimeError("unsupported ConvTranspose2d configuration on the VIAI hot path")
     if not transposed and (_pair(conv.dilation) != (1, 1) or conv.groups != 1):
         raise RuntimeError("unsupported Conv2d configuration on the VIAI hot path")
-    y = ops.conv2d(x, conv.weight, conv.bias, _pair(conv.stride), _pair(conv.padding), transposed)
     if norm is None:
+        y = ops.conv2d(x, conv.weight, conv.bias, _pair(conv.stride), _pair(conv.padding), transposed)
         return ops.norm_act(y, None, "none", act, slope)
-    return ops.norm_act(y, norm, norm_kind(norm), act, slope)
+    kind = norm_kind(norm)
+    y, stats = ops.conv2d_stats(x, conv.weight, conv.bias, _pair(conv.stride), _pair(conv.padding), transposed,
+                                ops.stat_groups_for(norm, kind, x.size(0)))
+    return ops.norm_act(y, norm, kind, act, slope, pre_stats=stats if stats.numel() else None)

@@ -8,7 +8,38 @@ import torch
 from . import _lib
 from ._lib import ConvGeom
 
+import os
+
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
+
+# Arithmetic of the convolutions (wherever the geometry is tensor-core shaped; CUDA cores otherwise):
+#   "tf32x3" (default): tcgen05 tensor cores; forward convolutions use the error-compensated 3-term tf32 product (~fp32
+#            accuracy: keeps spectrograms within the 1e-3 parity bound), data / weight gradients use one tf32 product;
+#   "tf32":  one tf32 product everywhere (what cuDNN does by default on Ampere+; ~1e-2 end to end on this network);
+#   "fp32":  CUDA-core fp32 everywhere (the exact path, also the on-device validator of the other two).
+_PRECISION = os.environ.get("VIAI_PRECISION", "tf32x3")
+_WS = {}
+
+
+def set_precision(p):
+    global _PRECISION
+    if p not in ("tf32x3", "tf32", "fp32"):
+        raise ValueError("precision must be 'tf32x3', 'tf32' or 'fp32'")
+    prev, _PRECISION = _PRECISION, p
+    return prev
+
+
+def get_precision():
+    return _PRECISION
+
+
+def _workspace(device, n):
+    """Per-device fp32 scratch for the tensor-core weight gradient (grown on demand, reused by every layer)."""
+    w = _WS.get(device)
+    if w is None or w.numel() < n:
+        w = torch.empty(max(n, 1 << 22), device=device, dtype=torch.float32)
+        _WS[device] = w
+    return w
 
 
 def _stream():
@@ -49,11 +80,38 @@ def _conv_out_size(H, k, s, p, transposed):
     return (H - 1) * s - 2 * p + k if transposed else (H + 2 * p - k) // s + 1
 
 
+def _pack_tc(weight, O_dim, I_dim, split):
+    L = _lib.lib()
+    O, I = weight.size(O_dim), weight.size(I_dim)
+    R, S = weight.size(2), weight.size(3)
+    out = torch.empty(L.viai_tc_packed_size(O, I, R, S, split), device=weight.device, dtype=torch.float32)
+    _lib.check(L.viai_pack_weight_tc(_p(weight), _p(out), O, I, R, S, weight.stride(O_dim), weight.stride(I_dim),
+                                     weight.stride(2), weight.stride(3), 0, split, _stream()), "pack_weight_tc")
+    return out
+
+
+def _run_conv(g, x, weight, O_dim, I_dim, bias, y, stats=None, groups=1, forward=False):
+    """One gather convolution (forward or data gradient) on the tensor cores when possible, else on the CUDA cores.
+    Returns True when ``stats`` (2 x groups*C doubles) was filled by the convolution's epilogue."""
+    L = _lib.lib()
+    if _PRECISION != "fp32" and L.viai_conv2d_tc_supported(ctypes.byref(g)):
+        x3 = int(forward and _PRECISION == "tf32x3")
+        wp = _pack_tc(weight, O_dim, I_dim, x3)
+        _lib.check(L.viai_conv2d_tc(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _p(stats[0]) if stats is not None else None,
+                                    _p(stats[1]) if stats is not None else None, groups, 4 * x3, _stream()), "conv2d_tc")
+        return stats is not None
+    wp = _pack(weight, O_dim, I_dim)
+    _lib.check(L.viai_conv2d_simt(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _stream()), "conv2d")
+    return False
+
+
 class _ConvFn(torch.autograd.Function):
-    """nn.Conv2d / nn.ConvTranspose2d forward + convolution_backward (see include/viai_b200.h for the site list)."""
+    """nn.Conv2d / nn.ConvTranspose2d forward + convolution_backward (see include/viai_b200.h for the site list).
+    ``stat_groups`` > 0 asks for the per-(group, channel) sum / sum of squares of the output (what the following norm
+    layer needs): the tensor-core kernel produces them in its epilogue, the CUDA-core path with viai_channel_stats."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, transposed):
+    def forward(ctx, x, weight, bias, stride, padding, transposed, stat_groups):
         _require_cuda(x, weight, bias)
         x = x.contiguous()
         L = _lib.lib()
@@ -62,27 +120,33 @@ class _ConvFn(torch.autograd.Function):
         if not transposed:
             Cout = weight.size(0)
             assert weight.size(1) == C, "conv: weight expects %d input channels, got %d" % (weight.size(1), C)
-            wp = _pack(weight, 0, 1)
-            mode = 0
+            od, idim, mode = 0, 1, 0
         else:
             Cout = weight.size(1)
             assert weight.size(0) == C, "convT: weight expects %d input channels, got %d" % (weight.size(0), C)
-            wp = _pack(weight, 1, 0)
-            mode = 1
+            od, idim, mode = 1, 0, 1
         Ho = _conv_out_size(H, R, stride[0], padding[0], transposed)
         Wo = _conv_out_size(W, S, stride[1], padding[1], transposed)
         if Ho <= 0 or Wo <= 0:
             raise RuntimeError("conv output size is non-positive: (%d, %d)" % (Ho, Wo))
         y = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
         g = _geom(N, H, W, C, Ho, Wo, Cout, R, S, stride, padding, mode)
-        _lib.check(L.viai_conv2d_simt(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _stream()), "conv2d")
+        stats = None
+        if stat_groups > 0:
+            stats = torch.empty((2, stat_groups * Cout), device=x.device, dtype=torch.float64)
+        if not _run_conv(g, x, weight, od, idim, bias, y, stats, stat_groups, forward=True) and stats is not None:
+            _lib.check(L.viai_channel_stats(_p(y), (N * Ho * Wo) // stat_groups, stat_groups, Cout, _p(stats[0]), _p(stats[1]),
+                                            _stream()), "channel_stats")
         ctx.save_for_backward(x, weight)
         ctx.cfg = (stride, padding, transposed, bias is not None)
         ctx.targets = (grad_target(weight), grad_target(bias))
-        return y
+        if stats is None:
+            stats = torch.empty(0, device=x.device, dtype=torch.float64)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dstats):
         x, weight = ctx.saved_tensors
         stride, padding, transposed, has_bias = ctx.cfg
         L = _lib.lib()
@@ -94,12 +158,9 @@ class _ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             if not transposed:       # dgrad of Conv2d: transposed gather with wp[o=ci][r][s][i=co]
-                wp = _pack(weight, 1, 0)
-                g = _geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 1)
+                _run_conv(_geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 1), dy, weight, 1, 0, None, dx)
             else:                    # dgrad of ConvTranspose2d: forward gather with wp[o=ci][r][s][i=co]
-                wp = _pack(weight, 0, 1)
-                g = _geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0)
-            _lib.check(L.viai_conv2d_simt(ctypes.byref(g), _p(dy), _p(wp), None, _p(dx), _stream()), "conv2d dgrad")
+                _run_conv(_geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0), dy, weight, 0, 1, None, dx)
         wt, bt = ctx.targets
         if ctx.needs_input_grad[1]:
             dw = wt if wt is not None else torch.empty_like(weight, memory_format=torch.contiguous_format)
@@ -109,8 +170,13 @@ class _ConvFn(torch.autograd.Function):
             else:                    # U = x (A = Cin_t), G = dOut (B = Cout_t)
                 g = _geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0)
                 U, G = x, dy
-            _lib.check(L.viai_conv2d_wgrad_simt(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1),
-                                                dw.stride(2), dw.stride(3), int(wt is not None), _stream()), "conv2d wgrad")
+            if _PRECISION != "fp32" and L.viai_conv2d_wgrad_tc_supported(ctypes.byref(g)):
+                ws = _workspace(dy.device, L.viai_wgrad_tc_workspace(ctypes.byref(g)))
+                _lib.check(L.viai_conv2d_wgrad_tc(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1), dw.stride(2),
+                                                  dw.stride(3), int(wt is not None), _p(ws), _stream()), "conv2d wgrad_tc")
+            else:
+                _lib.check(L.viai_conv2d_wgrad_simt(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1),
+                                                    dw.stride(2), dw.stride(3), int(wt is not None), _stream()), "conv2d wgrad")
             if wt is not None:
                 dw = None            # accumulated straight into the gradient bucket
         if has_bias and ctx.needs_input_grad[2]:
@@ -121,11 +187,16 @@ class _ConvFn(torch.autograd.Function):
             _lib.check(L.viai_fold_groups(_p(acc), 1, Cout, _p(db), int(bt is not None), _stream()), "bias grad fold")
             if bt is not None:
                 db = None
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 def conv2d(x, weight, bias=None, stride=(1, 1), padding=(0, 0), transposed=False):
-    return _ConvFn.apply(x, weight, bias, tuple(stride), tuple(padding), transposed)
+    return _ConvFn.apply(x, weight, bias, tuple(stride), tuple(padding), transposed, 0)[0]
+
+
+def conv2d_stats(x, weight, bias, stride, padding, transposed, stat_groups):
+    """Convolution that also returns the (2, groups*C) double statistics of its output for the following norm layer."""
+    return _ConvFn.apply(x, weight, bias, tuple(stride), tuple(padding), transposed, int(stat_groups))
 
 
 class _NormActFn(torch.autograd.Function):
@@ -134,7 +205,7 @@ class _NormActFn(torch.autograd.Function):
     networks/Discriminator_Networks.py:38-49)."""
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, running_mean, running_var, nbt, norm, training, act, slope, eps, momentum):
+    def forward(ctx, y, gamma, beta, running_mean, running_var, nbt, norm, training, act, slope, eps, momentum, pre_stats=None):
         _require_cuda(y, gamma, beta)
         L = _lib.lib()
         y = y.contiguous()
@@ -147,10 +218,13 @@ class _NormActFn(torch.autograd.Function):
         if norm in ("bn", "in"):
             use_batch = training or norm == "in" or running_mean is None
             if use_batch:
-                s = torch.empty((2, groups * C), device=dev, dtype=torch.float64)
                 mean = torch.empty(groups * C, device=dev, dtype=torch.float32)
                 invstd = torch.empty(groups * C, device=dev, dtype=torch.float32)
-                _lib.check(L.viai_channel_stats(_p(y), rpg, groups, C, _p(s[0]), _p(s[1]), _stream()), "channel_stats")
+                if pre_stats is not None and pre_stats.numel() == 2 * groups * C:
+                    s = pre_stats          # produced by the convolution's epilogue
+                else:
+                    s = torch.empty((2, groups * C), device=dev, dtype=torch.float64)
+                    _lib.check(L.viai_channel_stats(_p(y), rpg, groups, C, _p(s[0]), _p(s[1]), _stream()), "channel_stats")
                 upd = norm == "bn" and training and running_mean is not None
                 _lib.check(L.viai_norm_finalize(_p(s[0]), _p(s[1]), rpg, groups, C, eps, _p(mean), _p(invstd),
                                                 _p(running_mean) if upd else None, _p(running_var) if upd else None,
@@ -195,20 +269,29 @@ class _NormActFn(torch.autograd.Function):
             dbeta = bt if bt is not None else torch.empty_like(beta)
             _lib.check(L.viai_fold_groups(_p(s[0]), groups, C, _p(dbeta), int(bt is not None), _stream()), "dbeta")
             dbeta = None if bt is not None else dbeta
-        return dy, dgamma, dbeta, None, None, None, None, None, None, None, None, None
+        return dy, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None
 
 
-def norm_act(y, norm_module, norm, act, slope=0.0):
+def stat_groups_for(norm_module, norm, batch):
+    """How many statistic groups the norm layer will want from the producing convolution (0: none)."""
+    if norm_module is None or norm == "none":
+        return 0
+    if norm == "in":
+        return batch
+    return 1 if (norm_module.training or getattr(norm_module, "running_mean", None) is None) else 0
+
+
+def norm_act(y, norm_module, norm, act, slope=0.0, pre_stats=None):
     """``norm_module`` is the nn.BatchNorm2d / nn.InstanceNorm2d parameter container (or None)."""
     if norm == "none" or norm_module is None:
-        return _NormActFn.apply(y, None, None, None, None, None, "none", False, act, slope, 0.0, 0.0)
+        return _NormActFn.apply(y, None, None, None, None, None, "none", False, act, slope, 0.0, 0.0, None)
     gamma = getattr(norm_module, "weight", None)
     beta = getattr(norm_module, "bias", None)
     rm = getattr(norm_module, "running_mean", None)
     rv = getattr(norm_module, "running_var", None)
     nbt = getattr(norm_module, "num_batches_tracked", None)
     mom = norm_module.momentum if norm_module.momentum is not None else 0.1
-    return _NormActFn.apply(y, gamma, beta, rm, rv, nbt, norm, norm_module.training, act, slope, norm_module.eps, mom)
+    return _NormActFn.apply(y, gamma, beta, rm, rv, nbt, norm, norm_module.training, act, slope, norm_module.eps, mom, pre_stats)
 
 
 class _BilinearCatFn(torch.autograd.Function):
