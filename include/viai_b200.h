@@ -95,6 +95,16 @@ int viai_conv2d_wgrad_tc(const viai_conv_geom* g, const float* U, const float* G
 int viai_conv2d_wgrad_simt(const viai_conv_geom* g, const float* U, const float* G, float* dw, int64_t sa,
                            int64_t sb, int64_t sr, int64_t ss, int accumulate, viai_stream_t stream);
 
+/* Convolutions with one input or one output channel (the first / last layers of the generator and the discriminator):
+ * HBM-bound CUDA-core kernels with coalesced 128-bit accesses.  Operands as viai_conv2d_simt / viai_conv2d_wgrad_simt.
+ * viai_conv2d_thin_supported: 1 (Cout == 1), 2 (Cin == 1) or 0;  viai_conv2d_wgrad_thin_supported: A == 1 or B == 1. */
+int viai_conv2d_thin_supported(const viai_conv_geom* g);
+int viai_conv2d_thin(const viai_conv_geom* g, const float* in, const float* wp, const float* bias, float* out,
+                     viai_stream_t stream);
+int viai_conv2d_wgrad_thin_supported(const viai_conv_geom* g);
+int viai_conv2d_wgrad_thin(const viai_conv_geom* g, const float* U, const float* G, float* dw, int64_t sa, int64_t sb,
+                           int64_t sr, int64_t ss, int accumulate, viai_stream_t stream);
+
 /* Per-(group,channel) sum and sum of squares over rows of an NHWC tensor: groups = 1 is BatchNorm2d's
  * batch statistics, groups = N is InstanceNorm2d's (rows_per_group = H*W).  sum/sumsq are double[groups*C],
  * zeroed by the call.  sumsq may be NULL (plain channel sum: the bias gradient). */
@@ -148,6 +158,15 @@ int viai_maxpool3s2_bwd(const float* in, const float* dout, int N, int H, int W,
 int viai_mul(const float* a, const float* b, float* out, int64_t n, viai_stream_t stream);
 int viai_add_act(const float* a, const float* b, float* out, int64_t n, int act, viai_stream_t stream);
 int viai_add_act_bwd(const float* out, const float* dout, float* din, int64_t n, int act, viai_stream_t stream);
+
+/* STFT -> mel front end: utils/audio.py:70-75 melspectrogram (lws framing :90-108, |STFT| -> mel basis :116-120 -> dB :130-132
+ * -> minus ref_level_db :72 -> normalise/clip :139-140) as one kernel.  y: T samples; frame m covers samples
+ * [m*hop - pad_left, m*hop - pad_left + fft_size) with zeros outside [0, T); window: fft_size floats; mel_basis:
+ * (n_mels, fft_size/2+1) row-major; mel_span: int[n_mels][2] = [first, last+1) non-zero bin of each filter;
+ * out: (n_mels, num_frames) in [0,1]; mag_out (optional): |STFT| (fft_size/2+1, num_frames). */
+int viai_stft_mel(const float* y, int64_t T, int fft_size, int hop, int pad_left, int num_frames, const float* window,
+                  const float* mel_basis, const int* mel_span, int n_mels, float min_level_db, float ref_level_db,
+                  float* out, float* mag_out, viai_stream_t stream);
 
 /* Losses (loss_functions.py:79-104 GANLoss = MSELoss / BCELoss against an expanded scalar; nn.L1Loss).
  * kind 0: mean (p-t)^2   1: BCE(p, t)   2: mean |p - q|  (q = other tensor).  acc: double[1] workspace.

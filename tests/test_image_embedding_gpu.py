@@ -1,0 +1,66 @@
+"""ResNet-18 visual encoder (BASELINE config 3) on the CUDA path against the reference golden vector and the oracle."""
+import pytest
+import torch
+
+import viai_test_helpers as H
+from oracle import fixtures as FX
+from oracle import viai_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _module():
+    from viai_b200 import Options_inpainting as OI
+    from viai_b200.networks.Image_Embedding import ImageEmbedding
+    M = ImageEmbedding(OI.Inpainting_Config())
+    M.load_state_dict({k: v.clone() for k, v in H.filled(H.image_embedding_sd()).items()})
+    return M.cuda()
+
+
+def _inputs():
+    v = FX.normal("video", (1, 4, 3, 224, 224)).clamp(-1, 1)
+    f = FX.normal("flow", (1, 4, 2, 224, 224)).clamp(-1, 1)
+    return v, f
+
+
+def test_state_dict_layout_matches_reference():
+    M = _module()
+    want = H.image_embedding_sd()
+    got = M.state_dict()
+    assert set(got) == set(want)
+    for k in want:
+        assert tuple(got[k].shape) == tuple(want[k].shape), k
+
+
+@pytest.mark.parametrize("precision", ["fp32", pytest.param("tf32x3", marks=pytest.mark.tf32x3)])
+def test_forward_matches_reference_golden(precision):
+    from viai_b200 import ops
+    assert ops.get_precision() == precision
+    fx = H.load_golden("image_embedding.pt")
+    M = _module().train()
+    v, f = _inputs()
+    out = M(v.cuda(), f.cuda())
+    assert tuple(out.shape) == tuple(fx["out"].shape) == (1, 256, 1, 1)
+    assert H.relerr(out, fx["out"]) < 1e-3
+    sd = M.state_dict()
+    assert H.relerr(sd["bn_1.running_mean"], fx["bn_1_running_mean"]) < 1e-3          # the discarded relu(bn_1(.)) still updates
+    assert H.relerr(sd["image_single_model.bn1.running_mean"], fx["img_bn1_running_mean"]) < 1e-3
+    assert int(sd["bn_1.num_batches_tracked"]) == 1
+
+
+def test_backward_matches_oracle_autograd():
+    M = _module().train()
+    v, f = _inputs()
+    sd = {k: (t.clone().double().requires_grad_(True) if t.is_floating_point() and "running" not in k else t.clone().double()
+              if t.is_floating_point() else t.clone()) for k, t in H.filled(H.image_embedding_sd()).items()}
+    want = O.image_embedding_forward(sd, v.double(), f.double())
+    dy = FX.normal("ie_dy", tuple(want.shape)).double()
+    want.backward(dy)
+    out = M(v.cuda(), f.cuda())
+    out.backward(dy.float().cuda())
+    ps = dict(M.named_parameters())
+    for k in ("conv_2.weight", "conv_1.weight", "image_single_model.fc.weight", "image_single_model.layer4.1.conv2.weight",
+              "image_single_model.layer2.0.downsample.0.weight", "flow_single_model.conv1.weight", "image_single_model.bn1.weight"):
+        assert H.relerr(ps[k].grad, sd[k].grad) < 2e-3, k
+    for k in ("bn_1.weight", "bn_2.weight"):                       # never reach the output (reference :123 / unused bn_2)
+        assert ps[k].grad is None

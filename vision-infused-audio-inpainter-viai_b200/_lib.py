@@ -34,6 +34,10 @@ SIGNATURES = {
     "viai_tc_bn": [c_i],
     "viai_conv2d_wgrad_tc_supported": [_GP],
     "viai_conv2d_wgrad_tc": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p, c_p],
+    "viai_conv2d_thin_supported": [_GP],
+    "viai_conv2d_thin": [_GP, c_p, c_p, c_p, c_p, c_p],
+    "viai_conv2d_wgrad_thin_supported": [_GP],
+    "viai_conv2d_wgrad_thin": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p],
     "viai_conv2d_wgrad_simt": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p],
     "viai_channel_stats": [c_p, c_l, c_i, c_i, c_p, c_p, c_p],
     "viai_norm_finalize": [c_p, c_p, c_l, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
@@ -52,6 +56,7 @@ SIGNATURES = {
     "viai_mul": [c_p, c_p, c_p, c_l, c_p],
     "viai_add_act": [c_p, c_p, c_p, c_l, c_i, c_p],
     "viai_add_act_bwd": [c_p, c_p, c_p, c_l, c_i, c_p],
+    "viai_stft_mel": [c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_i, c_f, c_f, c_p, c_p, c_p],
     "viai_loss_fwd": [c_i, c_p, c_p, c_f, c_l, c_p, c_p, c_p],
     "viai_loss_bwd": [c_i, c_p, c_p, c_f, c_l, c_p, c_p, c_p],
     "viai_adam_step": [c_p, c_p, c_p, c_p, c_l, c_p, c_d, c_d, c_d, c_p, c_i, c_f, c_p],

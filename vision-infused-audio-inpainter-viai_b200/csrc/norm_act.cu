@@ -5,7 +5,6 @@ using namespace viai;
 namespace {
 
 constexpr int THREADS = 256;
-constexpr int ROWS_PER_BLOCK = 2048;
 
 // thread -> (channel vector cv, row lane rl).  VEC channels per thread; cvec = C/VEC <= THREADS.
 struct Lanes {
@@ -37,15 +36,16 @@ __device__ __forceinline__ void block_reduce_lanes(double (&v)[NV], int cv, int 
 
 template <int VEC, bool SQ>
 __global__ void __launch_bounds__(THREADS)
-stats_kernel(const float* __restrict__ y, int64_t rows_per_group, int C, double* __restrict__ sum, double* __restrict__ sumsq) {
+stats_kernel(const float* __restrict__ y, int64_t rows_per_group, int C, double* __restrict__ sum, double* __restrict__ sumsq,
+             int64_t rows_per_block) {
   extern __shared__ double sred[];
   const Lanes L = make_lanes(C, VEC);
   const int tid = threadIdx.x;
   const int cv = tid % L.cvec, rl = tid / L.cvec;
   const int g = blockIdx.y;
   const bool active = rl < L.lanes;
-  const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK;
-  const int64_t r1 = imin64(r0 + ROWS_PER_BLOCK, rows_per_group);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = imin64(r0 + rows_per_block, rows_per_group);
   float s[VEC], q[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) { s[k] = 0.f; q[k] = 0.f; }
@@ -145,15 +145,16 @@ template <int VEC>
 __global__ void __launch_bounds__(THREADS)
 bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y, int64_t rows_per_group, int C,
                   const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, int act, float slope, double* __restrict__ s1, double* __restrict__ s2) {
+                  const float* __restrict__ beta, int act, float slope, double* __restrict__ s1, double* __restrict__ s2,
+                  int64_t rows_per_block) {
   extern __shared__ double sred[];
   const Lanes L = make_lanes(C, VEC);
   const int tid = threadIdx.x;
   const int cv = tid % L.cvec, rl = tid / L.cvec;
   const int g = blockIdx.y;
   const bool active = rl < L.lanes;
-  const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK;
-  const int64_t r1 = imin64(r0 + ROWS_PER_BLOCK, rows_per_group);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = imin64(r0 + rows_per_block, rows_per_group);
   float a1[VEC], a2[VEC], mu[VEC], is[VEC], ga[VEC], be[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
@@ -263,6 +264,16 @@ __global__ void rsqrt_eps_kernel(const float* var, int n, float eps, float* out)
   if (i < n) out[i] = (float)(1.0 / sqrt((double)var[i] + (double)eps));
 }
 
+// rows handled by one block of a per-channel reduction: about four waves of blocks over the 148 SMs, never fewer than 8 rows
+// per row lane
+int64_t pick_rows_per_block(int64_t rows_per_group, int groups, int C, int VEC) {
+  const int lanes = make_lanes(C, VEC).lanes;
+  int64_t per_group = cdiv((int64_t)4 * kNumSMs, groups);
+  int64_t rpb = cdiv(rows_per_group, per_group);
+  if (rpb < (int64_t)lanes * 8) rpb = (int64_t)lanes * 8;
+  return rpb;
+}
+
 int pick_vec(int C, const void* p0, const void* p1 = nullptr) {
   bool aligned = (reinterpret_cast<uintptr_t>(p0) % 16 == 0) && (p1 == nullptr || reinterpret_cast<uintptr_t>(p1) % 16 == 0);
   return (C % 4 == 0 && aligned) ? 4 : 1;
@@ -278,14 +289,15 @@ extern "C" int viai_channel_stats(const float* y, int64_t rows_per_group, int gr
   if (sumsq) VIAI_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * groups * C, st));
   const int VEC = pick_vec(C, y);
   VIAI_REQUIRE(C / VEC <= THREADS, "viai_channel_stats: C=%d too large", C);
-  dim3 grid((unsigned)cdiv(rows_per_group, ROWS_PER_BLOCK), (unsigned)groups);
+  const int64_t rpb = pick_rows_per_block(rows_per_group, groups, C, VEC);
+  dim3 grid((unsigned)cdiv(rows_per_group, rpb), (unsigned)groups);
   size_t smem = sizeof(double) * THREADS * 2 * VEC;
   if (VEC == 4) {
-    if (sumsq) stats_kernel<4, true><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq);
-    else stats_kernel<4, false><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq);
+    if (sumsq) stats_kernel<4, true><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq, rpb);
+    else stats_kernel<4, false><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq, rpb);
   } else {
-    if (sumsq) stats_kernel<1, true><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq);
-    else stats_kernel<1, false><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq);
+    if (sumsq) stats_kernel<1, true><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq, rpb);
+    else stats_kernel<1, false><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq, rpb);
   }
   VIAI_LAUNCHED();
   return VIAI_OK;
@@ -325,10 +337,11 @@ extern "C" int viai_norm_act_bwd_reduce(const float* dz, const float* y, int64_t
   VIAI_CUDA(cudaMemsetAsync(s2, 0, sizeof(double) * groups * C, st));
   const int VEC = pick_vec(C, dz, y);
   VIAI_REQUIRE(C / VEC <= THREADS, "viai_norm_act_bwd_reduce: C=%d too large", C);
-  dim3 grid((unsigned)cdiv(rows_per_group, ROWS_PER_BLOCK), (unsigned)groups);
+  const int64_t rpb = pick_rows_per_block(rows_per_group, groups, C, VEC);
+  dim3 grid((unsigned)cdiv(rows_per_group, rpb), (unsigned)groups);
   size_t smem = sizeof(double) * THREADS * 2 * VEC;
-  if (VEC == 4) bwd_reduce_kernel<4><<<grid, THREADS, smem, st>>>(dz, y, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2);
-  else bwd_reduce_kernel<1><<<grid, THREADS, smem, st>>>(dz, y, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2);
+  if (VEC == 4) bwd_reduce_kernel<4><<<grid, THREADS, smem, st>>>(dz, y, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2, rpb);
+  else bwd_reduce_kernel<1><<<grid, THREADS, smem, st>>>(dz, y, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2, rpb);
   VIAI_LAUNCHED();
   return VIAI_OK;
 }

@@ -94,6 +94,10 @@ def _run_conv(g, x, weight, O_dim, I_dim, bias, y, stats=None, groups=1, forward
     """One gather convolution (forward or data gradient) on the tensor cores when possible, else on the CUDA cores.
     Returns True when ``stats`` (2 x groups*C doubles) was filled by the convolution's epilogue."""
     L = _lib.lib()
+    if L.viai_conv2d_thin_supported(ctypes.byref(g)) and x.data_ptr() % 16 == 0:
+        wp = _pack(weight, O_dim, I_dim)
+        _lib.check(L.viai_conv2d_thin(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _stream()), "conv2d_thin")
+        return False
     if _PRECISION != "fp32" and L.viai_conv2d_tc_supported(ctypes.byref(g)):
         x3 = int(forward and _PRECISION == "tf32x3")
         wp = _pack_tc(weight, O_dim, I_dim, x3)
@@ -170,7 +174,10 @@ class _ConvFn(torch.autograd.Function):
             else:                    # U = x (A = Cin_t), G = dOut (B = Cout_t)
                 g = _geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0)
                 U, G = x, dy
-            if _PRECISION != "fp32" and L.viai_conv2d_wgrad_tc_supported(ctypes.byref(g)):
+            if L.viai_conv2d_wgrad_thin_supported(ctypes.byref(g)) and U.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0:
+                _lib.check(L.viai_conv2d_wgrad_thin(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1), dw.stride(2),
+                                                    dw.stride(3), int(wt is not None), _stream()), "conv2d wgrad_thin")
+            elif _PRECISION != "fp32" and L.viai_conv2d_wgrad_tc_supported(ctypes.byref(g)):
                 ws = _workspace(dy.device, L.viai_wgrad_tc_workspace(ctypes.byref(g)))
                 _lib.check(L.viai_conv2d_wgrad_tc(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1), dw.stride(2),
                                                   dw.stride(3), int(wt is not None), _p(ws), _stream()), "conv2d wgrad_tc")
