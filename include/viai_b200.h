@@ -168,6 +168,22 @@ int viai_stft_mel(const float* y, int64_t T, int fft_size, int hop, int pad_left
                   const float* mel_basis, const int* mel_span, int n_mels, float min_level_db, float ref_level_db,
                   float* out, float* mag_out, viai_stream_t stream);
 
+/* WaveNet vocoder synthesis: wavenet_vocoder/wavenet.py:237-364 incremental_forward (+ modules.py:162-210, conv.py:17-62,
+ * mixture.py:117-153) as one persistent cooperative kernel that runs all T autoregressive steps on the device.
+ * L layers (dilation 2^(l % layers_per_stack)), R residual / G gate / S skip / C conditioning channels, K taps, O = 3*nr_mix
+ * outputs, B <= 4 utterances.  nC = viai_wavenet_num_ctas(...) CTAs cooperate (0: unsupported configuration).
+ * packed_layers / first / head1 / head2: parameter blocks in the layout documented in csrc/wavenet_synth.cu (produced by
+ * WaveNet.pack_for_synthesis); cond: (B, T, C) upsampled conditioning; uniforms: (T, B, nr_mix + 1) draws in (0, 1);
+ * test_inputs (optional): (B, Ttest) teacher-forced inputs for the first Ttest steps.  ring (sum_l ((K-1)*d_l + 1) * B * R
+ * floats at offsets ring_off[l]), gbuf (B*G/2), sbuf (B*S), hbuf (B*S), bar (2 x u32): zero-initialised scratch.
+ * out: (B, T) samples in [-1, 1]; logits (optional): (B, T, O) pre-sampling outputs. */
+int viai_wavenet_num_ctas(int R, int G, int S, int C, int K, int O, int B);
+int viai_wavenet_synth(int L, int layers_per_stack, int R, int G, int S, int C, int K, int O, int B, int T, int nC,
+                       const float* packed_layers, const float* first, const float* head1, const float* head2,
+                       const float* cond, const float* uniforms, const float* test_inputs, int Ttest, float log_scale_min,
+                       float* ring, const int64_t* ring_off, float* gbuf, float* sbuf, float* hbuf, unsigned* bar, float* out,
+                       float* logits, viai_stream_t stream);
+
 /* Losses (loss_functions.py:79-104 GANLoss = MSELoss / BCELoss against an expanded scalar; nn.L1Loss).
  * kind 0: mean (p-t)^2   1: BCE(p, t)   2: mean |p - q|  (q = other tensor).  acc: double[1] workspace.
  * loss_out: float[1] on device. */

@@ -1,0 +1,88 @@
+"""Parameter containers of the WaveNet layers.  Drop-in for /root/reference/wavenet_vocoder/modules.py ``Conv1d`` :22-32,
+``ConvTranspose2d`` :41-51, ``Conv1d1x1`` :54-63 and ``ResidualConv1dGLU`` :84-216: same constructors, weight-norm
+parametrisation (``weight_g`` / ``weight_v``) and ``state_dict()`` layout.  The synthesis arithmetic itself lives in
+csrc/wavenet_synth.cu and is driven by ``WaveNet.incremental_forward``; the modules keep no incremental buffers (the kernel
+owns the ring buffers for the duration of one call), so ``clear_buffer`` is a no-op kept for API compatibility."""
+import math
+
+import torch
+from torch import nn
+
+
+def Conv1d(in_channels, out_channels, kernel_size=1, padding=0, dilation=1, bias=True, weight_normalization=True,
+           dropout=0, std_mul=1.0, **kwargs):
+    m = nn.Conv1d(in_channels, out_channels, kernel_size=kernel_size, padding=padding, dilation=dilation, bias=bias, **kwargs)
+    if weight_normalization:
+        assert bias
+        std = math.sqrt((std_mul * (1.0 - dropout)) / (m.kernel_size[0] * in_channels))
+        m.weight.data.normal_(mean=0, std=std)
+        m.bias.data.zero_()
+        return nn.utils.weight_norm(m)
+    return m
+
+
+def ConvTranspose2d(in_channels, out_channels, kernel_size, weight_normalization=True, **kwargs):
+    freq_axis_kernel_size = kernel_size[0]
+    m = nn.ConvTranspose2d(in_channels, out_channels, kernel_size, **kwargs)
+    m.weight.data.fill_(1.0 / freq_axis_kernel_size)
+    m.bias.data.zero_()
+    if weight_normalization:
+        return nn.utils.weight_norm(m)
+    return m
+
+
+def Conv1d1x1(in_channels, out_channels, bias=True, weight_normalization=True):
+    """1-by-1 convolution layer"""
+    if weight_normalization:
+        assert bias
+        return Conv1d(in_channels, out_channels, kernel_size=1, padding=0, dilation=1, bias=bias, std_mul=1.0)
+    return nn.Conv1d(in_channels, out_channels, kernel_size=1, padding=0, dilation=1, bias=bias)
+
+
+def effective_weight(m):
+    """The weight a (possibly weight-normalised) module applies: g * v / ||v|| per slice of dim 0 -- what
+    ``make_generation_fast_`` (wavenet.py:387-393) folds once."""
+    if hasattr(m, "weight_g"):
+        v, g = m.weight_v, m.weight_g
+        nrm = v.reshape(v.size(0), -1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+        return v * (g / nrm)
+    return m.weight
+
+
+class ResidualConv1dGLU(nn.Module):
+    """Residual dilated conv1d + gated linear unit (reference :84-216)."""
+
+    def __init__(self, residual_channels, gate_channels, kernel_size, skip_out_channels=None, cin_channels=-1, gin_channels=-1,
+                 dropout=1 - 0.95, padding=None, dilation=1, causal=True, bias=True, weight_normalization=True, *args, **kwargs):
+        super(ResidualConv1dGLU, self).__init__()
+        self.dropout = dropout
+        if skip_out_channels is None:
+            skip_out_channels = residual_channels
+        if padding is None:
+            padding = (kernel_size - 1) * dilation if causal else (kernel_size - 1) // 2 * dilation
+        self.causal = causal
+        self.dilation = dilation
+        if weight_normalization:
+            assert bias
+            self.conv = Conv1d(residual_channels, gate_channels, kernel_size, dropout=dropout, padding=padding,
+                               dilation=dilation, bias=bias, std_mul=1.0, *args, **kwargs)
+        else:
+            self.conv = nn.Conv1d(residual_channels, gate_channels, kernel_size, padding=padding, dilation=dilation, bias=bias,
+                                  *args, **kwargs)
+        self.conv1x1c = Conv1d1x1(cin_channels, gate_channels, bias=bias,
+                                  weight_normalization=weight_normalization) if cin_channels > 0 else None
+        if gin_channels > 0:
+            raise NotImplementedError("global conditioning (gin_channels > 0) is outside the VIAI hot path")
+        self.conv1x1g = None
+        gate_out_channels = gate_channels // 2
+        self.conv1x1_out = Conv1d1x1(gate_out_channels, residual_channels, bias=bias, weight_normalization=weight_normalization)
+        self.conv1x1_skip = Conv1d1x1(gate_out_channels, skip_out_channels, bias=bias, weight_normalization=weight_normalization)
+
+    def forward(self, x, c=None, g=None):
+        raise RuntimeError("ResidualConv1dGLU runs inside the fused synthesis kernel (WaveNet.incremental_forward); "
+                           "there is no per-layer PyTorch path")
+
+    incremental_forward = forward
+
+    def clear_buffer(self):
+        pass
