@@ -19,6 +19,70 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class GradBucket(object):
+    """One flat fp32 parameter buffer + one flat gradient buffer for a list of parameters (any device).
+
+    ``p.data`` and ``p.grad`` become views of the flat buffers, in list order; ``p._viai_grad`` is the view the
+    weight-gradient kernels accumulate into.  Parameters that never receive a gradient (the reference's dead
+    ``convblock1``, /root/reference/networks/New_Inpainting_Networks.py:57,82) simply keep a zero slice, so every rank
+    all-reduces the same layout whatever its autograd graph touched.  Device-agnostic: the world_size-2 gloo tests
+    exercise exactly this class on CPU."""
+
+    def __init__(self, params, world_size=1, process_group=None):
+        self.params = list(params)
+        if not self.params:
+            raise ValueError("GradBucket needs at least one parameter")
+        self.world_size = int(world_size)
+        self.process_group = process_group
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.numel = n
+        self.flat_param = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            if p.device != dev or p.dtype != torch.float32:
+                raise ValueError("GradBucket: all parameters must be float32 on one device")
+            k = p.numel()
+            view = self.flat_param[off:off + k].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            gview = self.flat_grad[off:off + k].view(p.shape)
+            p._viai_grad = gview          # weight-gradient kernels accumulate here (ops.grad_target)
+            p.grad = gview
+            self.offsets.append(off)
+            off += k
+
+    def rebind(self):
+        """Keeps ``.grad`` pointing at the bucket (autograd may have replaced or dropped it)."""
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != p._viai_grad.data_ptr():
+                p.grad = p._viai_grad
+
+    def all_reduce(self):
+        """One all-reduce (sum) over the whole bucket; the caller folds 1/world_size into its update."""
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.process_group)
+
+    def broadcast_params(self, src=0):
+        """Identical initial weights on every rank (what nn.DataParallel's replicate does each step in the reference)."""
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.broadcast(self.flat_param, src, group=self.process_group)
+
+
+def shard_batch(n_items, rank, world_size):
+    """[begin, end) of the samples rank ``rank`` owns when a global batch of ``n_items`` is split as evenly as possible
+    in rank order (the scatter of nn.DataParallel, /root/reference/utils/model_util.py:137: chunks along dim 0)."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank %d outside world of %d" % (rank, world_size))
+    chunk = -(-n_items // world_size)          # torch.chunk semantics: ceil-sized leading chunks
+    b = min(rank * chunk, n_items)
+    return b, min(b + chunk, n_items)
+
+
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam semantics (no weight decay, no amsgrad).  ``state_dict()`` has the usual per-parameter layout
     (``step``, ``exp_avg``, ``exp_avg_sq``) so reference-style checkpoints (/root/reference/utils/util.py:149-150)
@@ -35,41 +99,28 @@ class FusedAdam(torch.optim.Optimizer):
         dev = plist[0].device
         if dev.type != "cuda":
             raise RuntimeError("FusedAdam needs CUDA parameters; there is no CPU path")
-        n = sum(p.numel() for p in plist)
-        self.numel = n
-        self.flat_param = torch.empty(n, device=dev, dtype=torch.float32)
-        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.bucket = GradBucket(plist, world_size, process_group)
+        n = self.numel = self.bucket.numel
+        self.flat_param, self.flat_grad = self.bucket.flat_param, self.bucket.flat_grad
         self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.float32)
         self.lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
         self._lr_host = float(lr)
-        off = 0
-        for p in plist:
+        for p, off in zip(plist, self.bucket.offsets):
             k = p.numel()
-            view = self.flat_param[off:off + k].view(p.shape)
-            view.copy_(p.data)
-            p.data = view
-            gview = self.flat_grad[off:off + k].view(p.shape)
-            p._viai_grad = gview          # weight-gradient kernels accumulate here (ops.grad_target)
-            p.grad = gview
             self.state[p] = dict(step=self.step_dev[0], exp_avg=self.flat_m[off:off + k].view(p.shape),
                                  exp_avg_sq=self.flat_v[off:off + k].view(p.shape))
-            off += k
         self._plist = plist
 
     def zero_grad(self, set_to_none=False):
         L = _lib.lib()
         _lib.check(L.viai_fill(_p(self.flat_grad), self.numel, 0.0, _stream()), "zero_grad")
-        for p in self._plist:             # keep .grad pointing at the bucket
-            if p.grad is None or p.grad.data_ptr() != p._viai_grad.data_ptr():
-                p.grad = p._viai_grad
+        self.bucket.rebind()
 
     def all_reduce_grads(self):
         """One NCCL all-reduce (sum) over the whole bucket; the 1/world_size is folded into the Adam kernel."""
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.process_group)
+        self.bucket.all_reduce()
 
     @torch.no_grad()
     def step(self, closure=None):
