@@ -70,8 +70,13 @@ int viai_conv2d_simt(const viai_conv_geom* g, const float* in, const float* wp, 
  * flags: VIAI_TC_X3 (4) = error-compensated 3-term product  x*w ~ hi(x)*hi(w) + hi(x)*lo(w) + lo(x)*hi(w)  with
  * hi = tf32(.), lo = tf32(. - hi): three tensor-core MMAs per tile instead of one, product error ~2^-19 instead of
  * ~2^-10 (the precision needed for the north star's 1e-3 end-to-end bound; see DESIGN.md "Precision").  It needs
- * weights packed with split = 1.  Other bits select alternative shared-memory layouts used as cross-checks. */
+ * weights packed with split = 1.
+ * VIAI_TC_BF16X3 (8) = the same 3-term scheme on bf16 pairs (hi = bf16(.), lo = bf16(. - hi); kind::f16 MMAs, K = 16, at
+ * twice the tf32 rate; product error ~2^-17).  The kernel splits each fp32 activation slab in shared memory in place into
+ * [32 x hi | 32 x lo] per 128-byte pixel row; weights are packed with split = 2 (same size as split = 0).
+ * Other bits select alternative shared-memory layouts used as cross-checks. */
 #define VIAI_TC_X3 4
+#define VIAI_TC_BF16X3 8
 int viai_tc_bn(int Cout);
 int64_t viai_tc_packed_size(int O, int I, int R, int S, int split);
 int viai_pack_weight_tc(const float* src, float* dst, int O, int I, int R, int S, int64_t so, int64_t si, int64_t sr,

@@ -13,7 +13,8 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
     config.addinivalue_line("markers", "tf32: single-product tf32 tensor-core convolutions (default in tests: exact fp32)")
-    config.addinivalue_line("markers", "tf32x3: the library default: 3-term tf32 forward, single tf32 backward")
+    config.addinivalue_line("markers", "tf32x3: 3-term tf32 forward, single tf32 backward")
+    config.addinivalue_line("markers", "bf16x3: the library default: 3-term bf16-pair forward, single tf32 backward")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -36,6 +37,7 @@ def _conv_precision(request):
         yield
         return
     from viai_b200 import ops
-    prev = ops.set_precision("tf32x3" if "tf32x3" in request.keywords else "tf32" if "tf32" in request.keywords else "fp32")
+    prev = ops.set_precision("bf16x3" if "bf16x3" in request.keywords else "tf32x3" if "tf32x3" in request.keywords
+                             else "tf32" if "tf32" in request.keywords else "fp32")
     yield
     ops.set_precision(prev)

@@ -44,6 +44,12 @@ CONV_CASES = [
     ("dec.block5", True, 32, 32, 3, 3, (1, 1), (1, 1), 2, 9, 13, True),
     ("dec.conv6_2", True, 32, 1, 3, 3, (1, 1), (1, 1), 2, 12, 10, True),
     ("wavenet.upsample", True, 1, 1, 3, 4, (1, 4), (1, 0), 1, 8, 5, True),
+    # one-channel layers over several (ragged) tiles of the TMA-tiled / multi-pixel kernels, several channel slabs
+    ("dis.conv4.tiles", False, 64, 1, 3, 3, (1, 1), (1, 1), 2, 19, 70, True),
+    ("dis.conv4.slabs", False, 512, 1, 3, 3, (1, 1), (1, 1), 1, 9, 40, False),
+    ("dec.conv6_2.tiles", True, 32, 1, 3, 3, (1, 1), (1, 1), 2, 21, 45, True),
+    ("dis.conv1.tiles", False, 1, 64, 1, 4, (1, 2), (0, 1), 2, 19, 150, False),
+    ("enc.conv1.tiles", False, 1, 32, 3, 3, (2, 2), (1, 1), 2, 37, 70, True),
 ]
 
 

@@ -4,9 +4,10 @@ fused normalisation statistics, and the whole GAN step against the oracle.
 Tolerances.  tf32 keeps 10 mantissa bits, so a single-product convolution differs from exact fp32 by up to ~1e-3 of the
 tensor's largest value (measured 3-9e-4): 2e-3 per kernel (TC_TOL).  Chained through the 22 normalised layers of G that
 becomes ~1e-2 on the spectrogram (measured here and reproduced on the CPU by truncating operands to tf32), which misses the
-north star's 1e-3 bound -- so the library default "tf32x3" runs every FORWARD convolution as the error-compensated 3-term
-product (hi*hi + hi*lo + lo*hi, ~2^-19 per product; X3_TOL = 5e-5 per kernel) and asserts the 1e-3 spectrogram bound
-directly; gradients keep the single product and the gradient criteria of tests/test_gan_gpu.py."""
+north star's 1e-3 bound -- so the library runs every FORWARD convolution as an error-compensated 3-term product
+(hi*hi + hi*lo + lo*hi): "tf32x3" on tf32 pairs (~2^-19 per product) or, the default, "bf16x3" on bf16 pairs (~2^-17 per
+product, twice the MMA rate); X3_TOL = 5e-5 per kernel for both, and the 1e-3 spectrogram bound is asserted directly;
+gradients keep the single tf32 product and the gradient criteria of tests/test_gan_gpu.py."""
 import ctypes
 import math
 
@@ -60,11 +61,11 @@ def test_tc_layer_geometry(layer, N):
 
 
 @pytest.mark.parametrize("layer", [l for l in LAYERS if _supported(l)], ids=[l[0] for l in LAYERS if _supported(l)])
-@pytest.mark.tf32x3
-def test_x3_forward_is_fp32_accurate(layer):
-    """The 3-term product: forward output and fused statistics at fp32-level accuracy."""
+@pytest.mark.parametrize("mode", [pytest.param("tf32x3", marks=pytest.mark.tf32x3), pytest.param("bf16x3", marks=pytest.mark.bf16x3)])
+def test_x3_forward_is_fp32_accurate(layer, mode):
+    """The 3-term products: forward output and fused statistics at fp32-level accuracy."""
     from viai_b200 import ops
-    assert ops.get_precision() == "tf32x3"
+    assert ops.get_precision() == mode
     name, tr, Cin, Cout, kh, kw, stride, pad, Hh, W = layer
     g = torch.Generator().manual_seed(abs(hash(name)) % 100000)
     x = torch.randn(2, Cin, Hh, W, generator=g, dtype=torch.float64).float().double()
@@ -112,11 +113,11 @@ def test_tc_matches_cuda_core_path_bitwise_shapes_and_unsupported_geometries_fal
 
 
 @pytest.mark.parametrize("cfg", [("bn", 1, 80, 64), ("in", 2, 96, 48), ("bn", 2, 128, 128)], ids=["c1", "in96", "s128"])
-@pytest.mark.tf32x3
-def test_tc_train_step_matches_oracle(cfg):
-    """GanTrainer.train_step on the default tensor-core path vs oracle.gan_step (fp32 CPU restatement of the reference)."""
+@pytest.mark.parametrize("mode", [pytest.param("tf32x3", marks=pytest.mark.tf32x3), pytest.param("bf16x3", marks=pytest.mark.bf16x3)])
+def test_tc_train_step_matches_oracle(cfg, mode):
+    """GanTrainer.train_step on the tensor-core paths vs oracle.gan_step (fp32 CPU restatement of the reference)."""
     from viai_b200 import Options_inpainting as OI, ops
-    assert ops.get_precision() == "tf32x3"
+    assert ops.get_precision() == mode
     from viai_b200.step import GanTrainer
     from oracle import viai_oracle as O
     import torch.nn as nn

@@ -100,6 +100,8 @@ struct TcParams {
   uint32_t idesc;
   int32_t a4d;           // 1: sub-patch loaded by 8 rank-4 TMA copies instead of one rank-5 copy
   int32_t x3;            // 1: error-compensated 3-term tf32 product (A*Bhi + A*Blo + Alo*Bhi), ~fp32 accuracy
+  int32_t bx3;           // 1: the same 3-term product on bf16 pairs (x = hi + lo, both bf16): kind::f16 MMAs at twice the tf32
+                         //    rate; the fp32 slab is split IN PLACE into [hi: 32 x bf16 | lo: 32 x bf16] per 128-byte pixel row
   int32_t a_sw128;       // 1: activation patch stored as dense 128-byte pixel rows under the 128-byte swizzle (rank-4 TMA)
 };
 
@@ -214,13 +216,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         uint32_t accumulate = 0;
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(&fullA[sa], pha);
-          if (p.x3) mbar_wait(&loA[sa], pha);
+          if (p.x3 | p.bx3) mbar_wait(&loA[sa], pha);
           const uint32_t a_base = smem_u32(slabA + (size_t)sa * a_stage);
           for (int t = 0; t < p.ntap; ++t) {
             mbar_wait(&fullB[sb], phb);
             tc_fence_after();
             const TcTap& tp = p.tap[t];
             const uint32_t b_base = smem_u32(tileB + (size_t)sb * p.btile_bytes);
+            if (p.bx3) {
+              // bf16 pairs: K = 16 per MMA, two K steps per 32-channel slab; lo halves sit 64 bytes into the pixel row
+              // (A) and 4 chunk planes into the weight tile (B).  Small terms first, then the leading one.
+#pragma unroll
+              for (int kk = 0; kk < KC / 16; ++kk) {
+                const uint32_t a_addr = a_base + tp.a_off + (uint32_t)kk * 32u;
+                const uint32_t b_addr = b_base + (uint32_t)kk * 2u * b_lbo;
+                const uint64_t ad_hi = make_desc_sw128(a_addr, tp.sbo, 0u), ad_lo = make_desc_sw128(a_addr + 64u, tp.sbo, 0u);
+                const uint64_t bd_hi = make_desc(b_addr, b_lbo, b_sbo), bd_lo = make_desc(b_addr + (uint32_t)p.BN * 64u, b_lbo, b_sbo);
+                mma_bf16(d_tmem, ad_lo, bd_hi, p.idesc, accumulate);
+                mma_bf16(d_tmem, ad_hi, bd_lo, p.idesc, 1);
+                mma_bf16(d_tmem, ad_hi, bd_hi, p.idesc, 1);
+                accumulate = 1;
+              }
+            } else {
 #pragma unroll
             for (int kk = 0; kk < KC / 8; ++kk) {
               const uint32_t b_addr = b_base + (uint32_t)kk * 2u * b_lbo;
@@ -241,6 +258,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
               mma_tf32(d_tmem, ad, bd, p.idesc, accumulate);
               accumulate = 1;
             }
+            }
             mma_commit(&emptyB[sb]);
             if (++sb == p.SB) { sb = 0; phb ^= 1u; }
           }
@@ -252,7 +270,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     }
   } else if (warp >= XF_WARP0) {
     // ===== tf32x3: split every landed slab into hi = trunc_tf32(x) (in place) and lo = x - hi (second slab) =====
-    if (p.x3) {
+    if (p.bx3) {
+      // bf16 pair split, one thread per 128-byte pixel row (private to the thread, so the rewrite is in place): logical
+      // 16-byte chunk j of row r sits at physical chunk j ^ (r & 7) under the 128-byte swizzle, before and after.
+      const int tid = threadIdx.x - XF_WARP0 * 32;
+      int sa = 0;
+      uint32_t pha = 0;
+      const uint32_t nrows = p.slab_bytes / 128;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int c = 0; c < p.nchunks; ++c) {
+          mbar_wait(&fullA[sa], pha);
+          uint8_t* base = slabA + (size_t)sa * a_stage;
+          for (uint32_t r = tid; r < nrows; r += 128) {
+            uint8_t* row = base + (size_t)r * 128;
+            const uint32_t sw = r & 7u;
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(row + ((j ^ sw) << 4));
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const float f[8] = {v[2 * m].x, v[2 * m].y, v[2 * m].z, v[2 * m].w, v[2 * m + 1].x, v[2 * m + 1].y, v[2 * m + 1].z, v[2 * m + 1].w};
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * e]), h1 = __float2bfloat16_rn(f[2 * e + 1]);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * e] - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * e + 1] - __bfloat162float(h1));
+                hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              *reinterpret_cast<uint4*>(row + ((m ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(row + (((4 + m) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&loA[sa]);
+          if (++sa == p.SA) { sa = 0; pha ^= 1u; }
+        }
+      }
+    } else if (p.x3) {
       const int tid = threadIdx.x - XF_WARP0 * 32;
       int sa = 0;
       uint32_t pha = 0;
@@ -363,6 +419,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
 
 // dst[tap][slab][cout tile][part][16-byte chunk j][row][4]; part 0 = tf32(w[o][tap][i]), part 1 (split packing only) =
 // tf32(w - part 0);  i = slab*32 + j*4 + e, o = tile*BN + row
+// bf16-pair packing: dst (as 16-bit words) [tap][slab][cout tile][part: hi, lo][8-channel chunk j (4)][row][8]
+__global__ void pack_weight_bf16x2_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int O, int I, int R, int S,
+                                          int64_t so, int64_t si, int64_t sr, int64_t ss, int flip, int BN, int nchunks, int ntilesN) {
+  const int64_t total = (int64_t)R * S * nchunks * ntilesN * 2 * (KC / 8) * BN * 8;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = idx;
+    const int e = t & 7; t >>= 3;
+    const int row = t % BN; t /= BN;
+    const int j = t % (KC / 8); t /= (KC / 8);
+    const int part = t & 1; t >>= 1;
+    const int nt = t % ntilesN; t /= ntilesN;
+    const int c = t % nchunks; t /= nchunks;
+    const int tap = (int)t;
+    const int r = tap / S, s = tap % S;
+    const int o = nt * BN + row, i = c * KC + j * 8 + e;
+    uint16_t v = 0;
+    if (o < O && i < I) {
+      const int rr = flip ? R - 1 - r : r, sw = flip ? S - 1 - s : s;
+      const float w = src[o * so + i * si + rr * sr + sw * ss];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+      v = __bfloat16_as_ushort(part == 0 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi)));
+    }
+    dst[idx] = v;
+  }
+}
+
 __global__ void pack_weight_tc_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int R, int S,
                                       int64_t so, int64_t si, int64_t sr, int64_t ss, int flip, int BN, int nchunks, int ntilesN,
                                       int parts) {
@@ -409,8 +491,10 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   // default: dense 128-byte pixel rows under the 128-byte swizzle.  flags & 1: 16-byte channel chunks, no swizzle (rank-5
   // TMA); flags & 3 == 3: the same through eight rank-4 copies.  Both alternatives are kept as cross-checks of the layout.
   p.x3 = (flags & 4) ? 1 : 0;
+  p.bx3 = (flags & 8) ? 1 : 0;
   p.a_sw128 = (flags & 1) ? 0 : 1;
-  VIAI_REQUIRE(!p.x3 || p.a_sw128, "conv2d_tc: the 3-term product needs the swizzled activation layout");
+  VIAI_REQUIRE(!(p.x3 && p.bx3), "conv2d_tc: VIAI_TC_X3 and VIAI_TC_BF16X3 are exclusive");
+  VIAI_REQUIRE(!(p.x3 | p.bx3) || p.a_sw128, "conv2d_tc: the 3-term products need the swizzled activation layout");
   p.a4d = (!p.a_sw128 && (flags & 2)) ? 1 : 0;
   // sub-patches: one per (suby, subx) parity that occurs
   int sub_id[2][2] = {{-1, -1}, {-1, -1}};
@@ -490,8 +574,8 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   p.nchunks = (inC + KC - 1) / KC;
   p.Cout = Cout;
   p.o_sn = o_sn; p.o_sy = o_sy; p.o_sx = o_sx; p.o_base = o_base;
-  p.btile_bytes = (uint32_t)p.BN * KC * 4 * (p.x3 ? 2u : 1u);
-  p.idesc = make_idesc_tf32(128, p.BN, 0, 0);
+  p.btile_bytes = (uint32_t)p.BN * KC * 4 * (p.x3 ? 2u : 1u);      // bf16 pairs: 2 x 2 bytes per element = the fp32 size
+  p.idesc = p.bx3 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
   // pipeline depths under the 227 KB shared-memory limit
   const size_t fixed = 1024 /*alignment slack*/ + 64 * 8 + 16;
   const size_t budget = 227 * 1024;
@@ -525,7 +609,7 @@ extern "C" int viai_tc_bn(int Cout) { return tc_bn(Cout); }
 
 extern "C" int64_t viai_tc_packed_size(int O, int I, int R, int S, int split) {
   const int BN = tc_bn(O);
-  return (int64_t)R * S * ((I + KC - 1) / KC) * ((O + BN - 1) / BN) * BN * KC * (split ? 2 : 1);
+  return (int64_t)R * S * ((I + KC - 1) / KC) * ((O + BN - 1) / BN) * BN * KC * (split == 1 ? 2 : 1);
 }
 
 extern "C" int viai_pack_weight_tc(const float* src, float* dst, int O, int I, int R, int S, int64_t so, int64_t si, int64_t sr,
@@ -533,6 +617,13 @@ extern "C" int viai_pack_weight_tc(const float* src, float* dst, int O, int I, i
   VIAI_REQUIRE(src && dst && O > 0 && I > 0 && R > 0 && S > 0, "pack_weight_tc: bad arguments");
   const int BN = tc_bn(O), nchunks = (I + KC - 1) / KC, ntilesN = (O + BN - 1) / BN;
   const int64_t total = viai_tc_packed_size(O, I, R, S, split);
+  if (split == 2) {
+    const int blocks = (int)imin64(cdiv(total * 2, 256), 4096);
+    pack_weight_bf16x2_kernel<<<blocks, 256, 0, STR(stream)>>>(src, reinterpret_cast<uint16_t*>(dst), O, I, R, S, so, si, sr, ss, flip,
+                                                              BN, nchunks, ntilesN);
+    VIAI_LAUNCHED();
+    return VIAI_OK;
+  }
   const int blocks = (int)imin64(cdiv(total, 256), 4096);
   pack_weight_tc_kernel<<<blocks, 256, 0, STR(stream)>>>(src, dst, O, I, R, S, so, si, sr, ss, flip, BN, nchunks, ntilesN, split ? 2 : 1);
   VIAI_LAUNCHED();

@@ -2,11 +2,20 @@
 // MelDecoder.conv6_2 32->1, MelDiscriminator.conv4 512->1 and their gradients).  They carry <1 % of the step's FLOPs and are
 // HBM-bound (their cost is reading / writing the wide tensor once), so they are plain CUDA-core kernels shaped for coalesced
 // 128-bit accesses rather than GEMM tiles:
-//   cout1:  one warp per output pixel, lanes stride over (tap, 4-channel vector), shuffle reduction;
-//   cin1:   one thread per (output pixel, 4 output channels), the <= 12 scalar taps come from L1, weights from shared memory;
-//   wgrad:  lanes over 4-channel vectors of the wide tensor, per-thread accumulators for every tap, block reduction, atomics.
+//   cout1:  input-stationary.  A CTA owns a tile of output pixels; the input patch all of its taps read is brought in ONCE by
+//           TMA (32-channel slabs, 128-byte swizzle, zero fill outside the image = the padding), one thread per patch pixel
+//           turns its 128-byte row into one partial dot product per filter tap, the partials are exchanged through shared
+//           memory and every output pixel sums the taps that reach it.  The wide tensor is read exactly once from HBM.
+//           (Geometries the tiler does not cover fall back to a warp-per-output-pixel kernel.)
+//   cin1:   one thread per (4 adjacent output pixels, 4 output channels): weights come from shared memory once per tap and
+//           are reused for the 4 pixels, the scalar taps from L1, the stores are full 128-bit rows of the wide tensor;
+//   wgrad:  wide-tensor-stationary: lanes over 4-channel vectors of the wide tensor, every wide pixel is read once and
+//           multiplied with the <= 12 scalars of the thin tensor its taps touch; per-thread accumulators for every tap,
+//           block reduction, atomics.
 #include "common.cuh"
+#include "tc_common.cuh"
 using namespace viai;
+using namespace viai::tc;
 
 namespace {
 
@@ -54,10 +63,266 @@ __global__ void __launch_bounds__(256) conv_cout1_kernel(viai_conv_geom g, const
   }
 }
 
+
+// ---- Cout == 1, TMA-tiled input-stationary kernel -------------------------------------------------------------------------
+constexpr int C1_THREADS = 256;
+constexpr int C1_MAXPP = 2;          // patch pixels per thread
+constexpr int C1_MAXST = 4;          // slab stages
+
+struct Cout1Params {
+  CUtensorMap map;                   // (C, Win, Hin, N) fp32, box (32, PW, PH, 1), 128-byte swizzle
+  viai_conv_geom g;
+  const float* wp;                   // [R][S][C]
+  const float* bias;
+  float* out;
+  int32_t TY, TX, PH, PW, tilesX, tilesY, nslab, nstage;
+  uint32_t stage_bytes;
+};
+
+__host__ __device__ inline int c1_floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+// first input row / column of the patch that the output tile starting at o0 reads
+__host__ __device__ inline int c1_patch_origin(int mode, int o0, int K, int stride, int pad) {
+  return mode == 0 ? o0 * stride - pad : c1_floordiv(o0 + pad - (K - 1), stride);
+}
+
+template <int TAPS>
+__global__ void __launch_bounds__(C1_THREADS) conv_cout1_tma_kernel(const __grid_constant__ Cout1Params p) {
+  extern __shared__ __align__(1024) uint8_t c1_smem_raw[];
+  uint8_t* smem = c1_smem_raw + ((1024u - (smem_u32(c1_smem_raw) & 1023u)) & 1023u);
+  const viai_conv_geom& g = p.g;
+  const int C = g.Cin;
+  const int npix = p.PH * p.PW;
+  uint8_t* stages = smem;
+  float* wsm = reinterpret_cast<float*>(stages + (size_t)p.nstage * p.stage_bytes);    // [TAPS][C]
+  float* part = wsm + TAPS * C;                                                          // [TAPS][npix]
+  uint64_t* full = reinterpret_cast<uint64_t*>(part + TAPS * npix + ((TAPS * npix) & 1));
+
+  int tile = blockIdx.x;
+  const int tx = tile % p.tilesX; tile /= p.tilesX;
+  const int ty = tile % p.tilesY;
+  const int n = tile / p.tilesY;
+  const int y0 = ty * p.TY, x0 = tx * p.TX;
+  const int Y0 = c1_patch_origin(g.mode, y0, g.R, g.stride_h, g.pad_h);
+  const int X0 = c1_patch_origin(g.mode, x0, g.S, g.stride_w, g.pad_w);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nstage; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
+    prefetch_tmap(&p.map);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstage && s < p.nslab; ++s) {
+      mbar_expect_tx(&full[s], (uint32_t)npix * 128u);
+      tma_load_4d(stages + (size_t)s * p.stage_bytes, &p.map, &full[s], s * 32, X0, Y0, n);
+    }
+  }
+  for (int i = threadIdx.x; i < TAPS * C; i += C1_THREADS) wsm[i] = __ldg(p.wp + i);
+  __syncthreads();
+
+  float acc[C1_MAXPP][TAPS];
+#pragma unroll
+  for (int k = 0; k < C1_MAXPP; ++k)
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) acc[k][t] = 0.f;
+
+  for (int s = 0; s < p.nslab; ++s) {
+    const int st = s % p.nstage;
+    mbar_wait(&full[st], (uint32_t)(s / p.nstage) & 1u);
+    const uint8_t* base = stages + (size_t)st * p.stage_bytes;
+    const float* wslab = wsm + s * 32;
+#pragma unroll
+    for (int k = 0; k < C1_MAXPP; ++k) {
+      const int pix = threadIdx.x + k * C1_THREADS;
+      if (pix < npix) {
+        const uint8_t* row = base + (size_t)pix * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (pix & 7)) << 4));
+#pragma unroll
+          for (int t = 0; t < TAPS; ++t) {
+            const float4 w = *reinterpret_cast<const float4*>(wslab + t * C + j * 4);
+            acc[k][t] = fmaf(v.x, w.x, acc[k][t]); acc[k][t] = fmaf(v.y, w.y, acc[k][t]);
+            acc[k][t] = fmaf(v.z, w.z, acc[k][t]); acc[k][t] = fmaf(v.w, w.w, acc[k][t]);
+          }
+        }
+      }
+    }
+    if (s + p.nstage < p.nslab) {
+      __syncthreads();                               // every thread is done reading this stage
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&full[st], (uint32_t)npix * 128u);
+        tma_load_4d(stages + (size_t)st * p.stage_bytes, &p.map, &full[st], (s + p.nstage) * 32, X0, Y0, n);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < C1_MAXPP; ++k) {
+    const int pix = threadIdx.x + k * C1_THREADS;
+    if (pix < npix) {
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) part[t * npix + pix] = acc[k][t];
+    }
+  }
+  __syncthreads();
+  const float b = p.bias ? __ldg(p.bias) : 0.f;
+  for (int o = threadIdx.x; o < p.TY * p.TX; o += C1_THREADS) {
+    const int ly = o / p.TX, lx = o - ly * p.TX;
+    const int y = y0 + ly, x = x0 + lx;
+    if (y >= g.Hout || x >= g.Wout) continue;
+    float sum = b;
+    for (int r = 0; r < g.R; ++r) {
+      int Y;
+      if (g.mode == 0) {
+        Y = y * g.stride_h - g.pad_h + r;
+      } else {
+        const int t = y + g.pad_h - r;
+        if (t < 0) continue;
+        Y = t / g.stride_h;
+        if (Y * g.stride_h != t) continue;
+      }
+      const int py = Y - Y0;
+      if (py < 0 || py >= p.PH) continue;            // cannot happen for covered geometries; keeps the read in bounds
+      for (int s = 0; s < g.S; ++s) {
+        int X;
+        if (g.mode == 0) {
+          X = x * g.stride_w - g.pad_w + s;
+        } else {
+          const int t = x + g.pad_w - s;
+          if (t < 0) continue;
+          X = t / g.stride_w;
+          if (X * g.stride_w != t) continue;
+        }
+        const int px = X - X0;
+        if (px < 0 || px >= p.PW) continue;
+        sum += part[(r * g.S + s) * npix + py * p.PW + px];
+      }
+    }
+    p.out[((int64_t)n * g.Hout + y) * g.Wout + x] = sum;
+  }
+}
+
+// extent of the input patch along one axis (max over all tiles)
+inline int c1_patch_extent(int mode, int out_len, int T, int K, int stride, int pad) {
+  int ext = 1;
+  for (int o0 = 0; o0 < out_len; o0 += T) {
+    const int last_o = o0 + T - 1;
+    const int first = c1_patch_origin(mode, o0, K, stride, pad);
+    const int last = mode == 0 ? last_o * stride - pad + K - 1 : c1_floordiv(last_o + pad, stride);
+    if (last - first + 1 > ext) ext = last - first + 1;
+  }
+  return ext;
+}
+
+// Returns VIAI_OK when launched, VIAI_ERR_UNSUPPORTED when the geometry is left to the generic kernel.
+int launch_cout1_tma(const viai_conv_geom& g, const float* in, const float* wp, const float* bias, float* out, cudaStream_t st) {
+  const int taps = g.R * g.S;
+  if (g.Cin % 32 != 0 || (taps != 9 && taps != 4)) return VIAI_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) return VIAI_ERR_UNSUPPORTED;
+  Cout1Params p;
+  memset(&p, 0, sizeof(p));
+  p.g = g; p.wp = wp; p.bias = bias; p.out = out;
+  p.TY = 8 * (g.mode == 1 ? g.stride_h : 1);
+  p.TX = 32 * (g.mode == 1 ? g.stride_w : 1);
+  p.PH = c1_patch_extent(g.mode, g.Hout, p.TY, g.R, g.stride_h, g.pad_h);
+  p.PW = c1_patch_extent(g.mode, g.Wout, p.TX, g.S, g.stride_w, g.pad_w);
+  const int npix = p.PH * p.PW;
+  if (npix > C1_MAXPP * C1_THREADS || p.PH > 256 || p.PW > 256) return VIAI_ERR_UNSUPPORTED;
+  p.tilesX = (g.Wout + p.TX - 1) / p.TX;
+  p.tilesY = (g.Hout + p.TY - 1) / p.TY;
+  p.nslab = g.Cin / 32;
+  p.nstage = p.nslab < C1_MAXST ? p.nslab : C1_MAXST;
+  p.stage_bytes = ((uint32_t)npix * 128u + 1023u) & ~1023u;
+  size_t smem = 1024 + (size_t)p.nstage * p.stage_bytes + sizeof(float) * ((size_t)taps * g.Cin + (size_t)taps * npix + 2) + 8 * C1_MAXST;
+  while (smem > 200 * 1024 && p.nstage > 1) { --p.nstage; smem -= p.stage_bytes; }
+  if (smem > 200 * 1024) return VIAI_ERR_UNSUPPORTED;
+  uint64_t dims[4] = {(uint64_t)g.Cin, (uint64_t)g.Win, (uint64_t)g.Hin, (uint64_t)g.N};
+  uint64_t strides[3] = {(uint64_t)g.Cin * 4, (uint64_t)g.Win * g.Cin * 4, (uint64_t)g.Hin * g.Win * g.Cin * 4};
+  uint32_t box[4] = {32, (uint32_t)p.PW, (uint32_t)p.PH, 1};
+  if (encode_f32_map(&p.map, 4, in, dims, strides, box, 1)) return VIAI_ERR_CUDA;
+  static bool attr = false;
+  if (!attr) {
+    VIAI_CUDA(cudaFuncSetAttribute(conv_cout1_tma_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VIAI_CUDA(cudaFuncSetAttribute(conv_cout1_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  const int grid = g.N * p.tilesX * p.tilesY;
+  if (taps == 9) conv_cout1_tma_kernel<9><<<grid, C1_THREADS, smem, st>>>(p);
+  else conv_cout1_tma_kernel<4><<<grid, C1_THREADS, smem, st>>>(p);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
 // ---- Cin == 1 ----------------------------------------------------------------------------------------------------
-// wp: [Cout][R][S]
+// wp: [Cout][R][S].  Eight lanes share CIN1_PX adjacent output pixels: the (tap, pixel) input scalars and their index
+// arithmetic are evaluated once, then the lanes sweep the output channels 32 at a time (128-byte stores per pixel).
+constexpr int CIN1_PX = 4;
+template <int R_, int S_>
 __global__ void __launch_bounds__(256) conv_cin1_kernel(viai_conv_geom g, const float* __restrict__ in, const float* __restrict__ wp,
                                                         const float* __restrict__ bias, float* __restrict__ out) {
+  extern __shared__ float wsm[];   // [tap][Cout] + bias[Cout]
+  constexpr int taps = R_ * S_;
+  for (int i = threadIdx.x; i < taps * g.Cout; i += blockDim.x) {
+    const int co = i / taps, tap = i - co * taps;
+    wsm[tap * g.Cout + co] = wp[i];
+  }
+  for (int i = threadIdx.x; i < g.Cout; i += blockDim.x) wsm[taps * g.Cout + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int c4n = g.Cout >> 2;
+  const int xg_n = (g.Wout + CIN1_PX - 1) / CIN1_PX;
+  const int groups = g.N * g.Hout * xg_n;               // < 2^31 for every tensor that fits the 32-bit geometry struct
+  const int l8 = threadIdx.x & 7;
+  for (int gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; gi < groups; gi += (gridDim.x * blockDim.x) >> 3) {
+    int m = gi;
+    const int xg = m % xg_n; m /= xg_n;
+    const int y = m % g.Hout;
+    const int n = m / g.Hout;
+    const int x0 = xg * CIN1_PX;
+    float a[taps][CIN1_PX];
+    int Xs[S_][CIN1_PX];                                 // column of (tap s, pixel k), or -1
+#pragma unroll
+    for (int s = 0; s < S_; ++s)
+#pragma unroll
+      for (int k = 0; k < CIN1_PX; ++k) {
+        int X;
+        Xs[s][k] = gather_coord(g.mode, x0 + k, s, g.stride_w, g.pad_w, g.Win, X) ? X : -1;
+      }
+#pragma unroll
+    for (int r = 0; r < R_; ++r) {
+      int Y;
+      const bool rv = gather_coord(g.mode, y, r, g.stride_h, g.pad_h, g.Hin, Y);
+      const float* irow = in + ((int64_t)n * g.Hin + (rv ? Y : 0)) * g.Win;
+#pragma unroll
+      for (int s = 0; s < S_; ++s)
+#pragma unroll
+        for (int k = 0; k < CIN1_PX; ++k) a[r * S_ + s][k] = (rv && Xs[s][k] >= 0) ? __ldg(irow + Xs[s][k]) : 0.f;
+    }
+    float* obase = out + (((int64_t)n * g.Hout + y) * g.Wout + x0) * g.Cout;
+    for (int cv = l8; cv < c4n; cv += 8) {
+      const float4 b4 = *reinterpret_cast<const float4*>(wsm + taps * g.Cout + cv * 4);
+      float4 acc[CIN1_PX];
+#pragma unroll
+      for (int k = 0; k < CIN1_PX; ++k) acc[k] = b4;
+#pragma unroll
+      for (int t = 0; t < taps; ++t) {
+        const float4 w = *reinterpret_cast<const float4*>(wsm + t * g.Cout + cv * 4);
+#pragma unroll
+        for (int k = 0; k < CIN1_PX; ++k) {
+          acc[k].x = fmaf(a[t][k], w.x, acc[k].x); acc[k].y = fmaf(a[t][k], w.y, acc[k].y);
+          acc[k].z = fmaf(a[t][k], w.z, acc[k].z); acc[k].w = fmaf(a[t][k], w.w, acc[k].w);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CIN1_PX; ++k)
+        if (x0 + k < g.Wout) *reinterpret_cast<float4*>(obase + (int64_t)k * g.Cout + cv * 4) = acc[k];
+    }
+  }
+}
+
+// generic tap counts: one thread per (output pixel, 4 output channels)
+__global__ void __launch_bounds__(256) conv_cin1_generic_kernel(viai_conv_geom g, const float* __restrict__ in,
+                                                                const float* __restrict__ wp, const float* __restrict__ bias,
+                                                                float* __restrict__ out) {
   extern __shared__ float wsm[];   // [tap][Cout] + bias[Cout]
   const int taps = g.R * g.S;
   for (int i = threadIdx.x; i < taps * g.Cout; i += blockDim.x) {
@@ -107,50 +372,78 @@ __global__ void zero_dw_kernel(float* dw, int A, int B, int R, int S, int64_t sa
 }
 
 // U: (N,Hout,Wout,A), G: (N,Hin,Win,B); WIDE_U: B == 1 (the wide tensor is U), else A == 1 (the wide tensor is G).
+// The loop runs over the pixels of the WIDE tensor (each read once, 128-bit); the thin tensor supplies one scalar per tap.
 template <bool WIDE_U>
 __global__ void __launch_bounds__(256) wgrad_thin_kernel(viai_conv_geom g, const float* __restrict__ U, const float* __restrict__ G,
                                                          float* __restrict__ dw, int64_t sa, int64_t sb, int64_t sr, int64_t ss,
-                                                         int64_t pix_per_block) {
+                                                         int pix_per_block) {
   extern __shared__ float red[];   // [planes][taps][C]
   const int C = WIDE_U ? g.Cout : g.Cin;
   const int c4n = C >> 2;
   const int planes = blockDim.x / c4n;
   const int cv = threadIdx.x % c4n, pl = threadIdx.x / c4n;
   const int taps = g.R * g.S;
+  const int Hw = WIDE_U ? g.Hout : g.Hin, Ww = WIDE_U ? g.Wout : g.Win;       // wide tensor extent
   float4 acc[WG_MAXTAP];
 #pragma unroll
   for (int t = 0; t < WG_MAXTAP; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int64_t M = (int64_t)g.N * g.Hout * g.Wout;
-  const int64_t p0 = blockIdx.x * pix_per_block, p1 = imin64(p0 + pix_per_block, M);
+  const int M = g.N * Hw * Ww;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, M);
+  const float4* wide = reinterpret_cast<const float4*>(WIDE_U ? U : G);
+  const float* thin = WIDE_U ? G : U;
   if (pl < planes) {
-    for (int64_t m = p0 + pl; m < p1; m += planes) {
-      const int x = (int)(m % g.Wout);
-      const int64_t tt = m / g.Wout;
-      const int y = (int)(tt % g.Hout);
-      const int n = (int)(tt / g.Hout);
-      float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      float us = 0.f;
-      if (WIDE_U) u4 = __ldg(reinterpret_cast<const float4*>(U + m * C) + cv);
-      else us = __ldg(U + m);
+    // per-tap offsets, decoded once:  WIDE_U: thin(Y, X) = (y*sh + oy, x*sw + ox);  else: thin = ((y + oy)/sh, (x + ox)/sw)
+    int oy[WG_MAXTAP], ox[WG_MAXTAP];
 #pragma unroll
-      for (int t = 0; t < WG_MAXTAP; ++t) {
-        if (t < taps) {
-          const int r = t / g.S, s = t - r * g.S;
-          const int Y = y * g.stride_h - g.pad_h + r, X = x * g.stride_w - g.pad_w + s;
-          if (Y >= 0 && Y < g.Hin && X >= 0 && X < g.Win) {
-            const int64_t gp = ((int64_t)n * g.Hin + Y) * g.Win + X;
-            if (WIDE_U) {
-              const float gs = __ldg(G + gp);
-              acc[t].x = fmaf(u4.x, gs, acc[t].x); acc[t].y = fmaf(u4.y, gs, acc[t].y);
-              acc[t].z = fmaf(u4.z, gs, acc[t].z); acc[t].w = fmaf(u4.w, gs, acc[t].w);
-            } else {
-              const float4 g4 = __ldg(reinterpret_cast<const float4*>(G + gp * C) + cv);
-              acc[t].x = fmaf(g4.x, us, acc[t].x); acc[t].y = fmaf(g4.y, us, acc[t].y);
-              acc[t].z = fmaf(g4.z, us, acc[t].z); acc[t].w = fmaf(g4.w, us, acc[t].w);
+    for (int t = 0; t < WG_MAXTAP; ++t) {
+      const int r = t / g.S, s = t - r * g.S;
+      oy[t] = WIDE_U ? r - g.pad_h : g.pad_h - r;
+      ox[t] = WIDE_U ? s - g.pad_w : g.pad_w - s;
+    }
+    const bool unit = g.stride_h == 1 && g.stride_w == 1;
+    const int Ht = WIDE_U ? g.Hin : g.Hout, Wt = WIDE_U ? g.Win : g.Wout;       // thin tensor extent
+    int m = p0 + pl;
+    int x = m % Ww, tq = m / Ww;
+    int y = tq % Hw, n = tq / Hw;
+    constexpr int UN = 4;                                 // wide pixels in flight per thread
+    while (m < p1) {
+      float4 w4[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int mu = m + u * planes;
+        w4[u] = mu < p1 ? __ldg(wide + (int64_t)mu * c4n + cv) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        if (m + u * planes < p1) {
+          const float* tbase = thin + (int64_t)n * Ht * Wt;
+#pragma unroll
+          for (int t = 0; t < WG_MAXTAP; ++t) {
+            if (t < taps) {
+              int Y, X;
+              bool ok;
+              if (WIDE_U) {
+                Y = y * g.stride_h + oy[t]; X = x * g.stride_w + ox[t];
+                ok = true;
+              } else if (unit) {
+                Y = y + oy[t]; X = x + ox[t];
+                ok = true;
+              } else {
+                const int ty = y + oy[t], tx = x + ox[t];
+                Y = ty / g.stride_h; X = tx / g.stride_w;
+                ok = ty >= 0 && tx >= 0 && Y * g.stride_h == ty && X * g.stride_w == tx;
+              }
+              ok = ok && (unsigned)Y < (unsigned)Ht && (unsigned)X < (unsigned)Wt;
+              const float v = ok ? __ldg(tbase + Y * Wt + X) : 0.f;
+              acc[t].x = fmaf(w4[u].x, v, acc[t].x); acc[t].y = fmaf(w4[u].y, v, acc[t].y);
+              acc[t].z = fmaf(w4[u].z, v, acc[t].z); acc[t].w = fmaf(w4[u].w, v, acc[t].w);
             }
           }
+          x += planes;
+          while (x >= Ww) { x -= Ww; if (++y == Hw) { y = 0; ++n; } }
         }
       }
+      m += UN * planes;
     }
 #pragma unroll
     for (int t = 0; t < WG_MAXTAP; ++t)
@@ -189,13 +482,21 @@ extern "C" int viai_conv2d_thin(const viai_conv_geom* gp, const float* in, const
   const int64_t M = (int64_t)g.N * g.Hout * g.Wout;
   if (M == 0) return VIAI_OK;
   if (kind == 1) {
+    const int rc = launch_cout1_tma(g, in, wp, bias, out, STR(stream));
+    if (rc != VIAI_ERR_UNSUPPORTED) return rc;
     const int blocks = (int)imin64(cdiv(M, 8), 16 * kNumSMs);
     conv_cout1_kernel<<<blocks, 256, 0, STR(stream)>>>(g, in, wp, bias, out);
   } else {
-    const int64_t total = M * (g.Cout / 4);
-    const int blocks = (int)imin64(cdiv(total, 256), 16 * kNumSMs);
     const size_t smem = sizeof(float) * (size_t)(g.R * g.S * g.Cout + g.Cout);
-    conv_cin1_kernel<<<blocks, 256, smem, STR(stream)>>>(g, in, wp, bias, out);
+    const int64_t total = (int64_t)g.N * g.Hout * ((g.Wout + CIN1_PX - 1) / CIN1_PX) * 8;
+    VIAI_REQUIRE(total < (int64_t)1 << 31, "conv2d_thin: tensor too large");
+    const int blocks = (int)imin64(cdiv(total, 256), 16 * kNumSMs);
+    if (g.R == 3 && g.S == 3) conv_cin1_kernel<3, 3><<<blocks, 256, smem, STR(stream)>>>(g, in, wp, bias, out);
+    else if (g.R == 1 && g.S == 4) conv_cin1_kernel<1, 4><<<blocks, 256, smem, STR(stream)>>>(g, in, wp, bias, out);
+    else {
+      const int64_t tot = M * (g.Cout / 4);
+      conv_cin1_generic_kernel<<<(int)imin64(cdiv(tot, 256), 16 * kNumSMs), 256, smem, STR(stream)>>>(g, in, wp, bias, out);
+    }
   }
   VIAI_LAUNCHED();
   return VIAI_OK;
@@ -222,14 +523,15 @@ extern "C" int viai_conv2d_wgrad_thin(const viai_conv_geom* gp, const float* U, 
     zero_dw_kernel<<<(g.Cout * g.Cin * taps + 255) / 256, 256, 0, st>>>(dw, g.Cout, g.Cin, g.R, g.S, sa, sb, sr, ss);
     VIAI_LAUNCHED();
   }
-  const int64_t M = (int64_t)g.N * g.Hout * g.Wout;
-  if (M == 0) return VIAI_OK;
   const bool wide_u = g.Cin == 1;
+  const int64_t M = wide_u ? (int64_t)g.N * g.Hout * g.Wout : (int64_t)g.N * g.Hin * g.Win;   // pixels of the wide tensor
+  if (M == 0 || (int64_t)g.N * g.Hout * g.Wout == 0) return VIAI_OK;
+  VIAI_REQUIRE(M < (int64_t)1 << 31, "conv2d_wgrad_thin: tensor too large");
   const int C = wide_u ? g.Cout : g.Cin;
   const int c4n = C / 4, planes = 256 / c4n;
-  int64_t blocks = imin64(4 * kNumSMs, cdiv(M, (int64_t)planes * 4));
+  int64_t blocks = imin64(8 * kNumSMs, cdiv(M, (int64_t)planes * 4));
   if (blocks < 1) blocks = 1;
-  const int64_t ppb = cdiv(M, blocks);
+  const int ppb = (int)cdiv(M, blocks);
   blocks = cdiv(M, ppb);
   const size_t smem = sizeof(float) * (size_t)planes * taps * C;
   static bool attr = false;

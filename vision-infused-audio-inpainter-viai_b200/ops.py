@@ -13,18 +13,21 @@ import os
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 
 # Arithmetic of the convolutions (wherever the geometry is tensor-core shaped; CUDA cores otherwise):
-#   "tf32x3" (default): tcgen05 tensor cores; forward convolutions use the error-compensated 3-term tf32 product (~fp32
-#            accuracy: keeps spectrograms within the 1e-3 parity bound), data / weight gradients use one tf32 product;
+#   "bf16x3" (default): tcgen05 tensor cores; forward convolutions split both operands into bf16 pairs (x = hi + lo) and
+#            accumulate hi*hi + hi*lo + lo*hi in fp32 (product error ~2^-17: keeps spectrograms within the 1e-3 parity
+#            bound) at the bf16 MMA rate; data / weight gradients use one tf32 product;
+#   "tf32x3": the same 3-term scheme on tf32 pairs (~2^-21 per product, half the MMA rate of bf16x3);
 #   "tf32":  one tf32 product everywhere (what cuDNN does by default on Ampere+; ~1e-2 end to end on this network);
 #   "fp32":  CUDA-core fp32 everywhere (the exact path, also the on-device validator of the other two).
-_PRECISION = os.environ.get("VIAI_PRECISION", "tf32x3")
+_PRECISION = os.environ.get("VIAI_PRECISION", "bf16x3")
+_FWD_MODE = {"bf16x3": (2, 8), "tf32x3": (1, 4), "tf32": (0, 0)}   # precision -> (weight packing, viai_conv2d_tc flags)
 _WS = {}
 
 
 def set_precision(p):
     global _PRECISION
-    if p not in ("tf32x3", "tf32", "fp32"):
-        raise ValueError("precision must be 'tf32x3', 'tf32' or 'fp32'")
+    if p not in ("bf16x3", "tf32x3", "tf32", "fp32"):
+        raise ValueError("precision must be 'bf16x3', 'tf32x3', 'tf32' or 'fp32'")
     prev, _PRECISION = _PRECISION, p
     return prev
 
@@ -99,10 +102,10 @@ def _run_conv(g, x, weight, O_dim, I_dim, bias, y, stats=None, groups=1, forward
         _lib.check(L.viai_conv2d_thin(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _stream()), "conv2d_thin")
         return False
     if _PRECISION != "fp32" and L.viai_conv2d_tc_supported(ctypes.byref(g)):
-        x3 = int(forward and _PRECISION == "tf32x3")
-        wp = _pack_tc(weight, O_dim, I_dim, x3)
+        split, flags = _FWD_MODE[_PRECISION] if forward else (0, 0)
+        wp = _pack_tc(weight, O_dim, I_dim, split)
         _lib.check(L.viai_conv2d_tc(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _p(stats[0]) if stats is not None else None,
-                                    _p(stats[1]) if stats is not None else None, groups, 4 * x3, _stream()), "conv2d_tc")
+                                    _p(stats[1]) if stats is not None else None, groups, flags, _stream()), "conv2d_tc")
         return stats is not None
     wp = _pack(weight, O_dim, I_dim)
     _lib.check(L.viai_conv2d_simt(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _stream()), "conv2d")
