@@ -86,8 +86,8 @@ int viai_conv2d_tc(const viai_conv_geom* g, const float* in, const float* wp_tc,
                    double* stat_sum, double* stat_sumsq, int stat_groups, int flags, viai_stream_t stream);
 
 /* Tensor-core weight gradient: same meaning as viai_conv2d_wgrad_simt (below).  `workspace` is a caller-owned scratch of
- * viai_wgrad_tc_workspace(g) floats (the per-tap partial sums are reduced there across CTAs before being scattered into
- * the gradient layout). */
+ * viai_wgrad_tc_workspace(g) floats (every CTA of the split-K grid stores its per-tap partial sums in its own slice; a
+ * second kernel adds the slices and scatters into the gradient layout -- no atomics). */
 int viai_conv2d_wgrad_tc_supported(const viai_conv_geom* g);
 int64_t viai_wgrad_tc_workspace(const viai_conv_geom* g);
 int viai_conv2d_wgrad_tc(const viai_conv_geom* g, const float* U, const float* G, float* dw, int64_t sa, int64_t sb,
@@ -107,8 +107,9 @@ int viai_conv2d_thin_supported(const viai_conv_geom* g);
 int viai_conv2d_thin(const viai_conv_geom* g, const float* in, const float* wp, const float* bias, float* out,
                      viai_stream_t stream);
 int viai_conv2d_wgrad_thin_supported(const viai_conv_geom* g);
+int64_t viai_wgrad_thin_workspace(const viai_conv_geom* g);   /* floats of caller-owned scratch (per-CTA partial sums) */
 int viai_conv2d_wgrad_thin(const viai_conv_geom* g, const float* U, const float* G, float* dw, int64_t sa, int64_t sb,
-                           int64_t sr, int64_t ss, int accumulate, viai_stream_t stream);
+                           int64_t sr, int64_t ss, int accumulate, float* workspace, viai_stream_t stream);
 
 /* Per-(group,channel) sum and sum of squares over rows of an NHWC tensor: groups = 1 is BatchNorm2d's
  * batch statistics, groups = N is InstanceNorm2d's (rows_per_group = H*W).  sum/sumsq are double[groups*C],

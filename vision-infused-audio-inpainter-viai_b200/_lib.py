@@ -37,7 +37,7 @@ SIGNATURES = {
     "viai_conv2d_thin_supported": [_GP],
     "viai_conv2d_thin": [_GP, c_p, c_p, c_p, c_p, c_p],
     "viai_conv2d_wgrad_thin_supported": [_GP],
-    "viai_conv2d_wgrad_thin": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p],
+    "viai_conv2d_wgrad_thin": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p, c_p],
     "viai_conv2d_wgrad_simt": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p],
     "viai_channel_stats": [c_p, c_l, c_i, c_i, c_p, c_p, c_p],
     "viai_norm_finalize": [c_p, c_p, c_l, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
@@ -71,6 +71,7 @@ SIGNATURES = {
 VALUE_FUNCS = {
     "viai_tc_packed_size": (ctypes.c_int64, [c_i, c_i, c_i, c_i, c_i]),
     "viai_wgrad_tc_workspace": (ctypes.c_int64, [_GP]),
+    "viai_wgrad_thin_workspace": (ctypes.c_int64, [_GP]),
 }
 
 

@@ -375,8 +375,7 @@ __global__ void zero_dw_kernel(float* dw, int A, int B, int R, int S, int64_t sa
 // The loop runs over the pixels of the WIDE tensor (each read once, 128-bit); the thin tensor supplies one scalar per tap.
 template <bool WIDE_U>
 __global__ void __launch_bounds__(256) wgrad_thin_kernel(viai_conv_geom g, const float* __restrict__ U, const float* __restrict__ G,
-                                                         float* __restrict__ dw, int64_t sa, int64_t sb, int64_t sr, int64_t ss,
-                                                         int pix_per_block) {
+                                                         float* __restrict__ ws, int pix_per_block) {
   extern __shared__ float red[];   // [planes][taps][C]
   const int C = WIDE_U ? g.Cout : g.Cin;
   const int c4n = C >> 2;
@@ -450,13 +449,37 @@ __global__ void __launch_bounds__(256) wgrad_thin_kernel(viai_conv_geom g, const
       if (t < taps) *reinterpret_cast<float4*>(red + ((size_t)(pl * taps + t) * C) + cv * 4) = acc[t];
   }
   __syncthreads();
+  // the block's partial sums go to its own workspace row (no atomics: hundreds of CTAs adding onto the same few hundred
+  // addresses serialise in the L2 atomic units); wgrad_thin_finish_kernel adds the rows up
   for (int i = threadIdx.x; i < taps * C; i += blockDim.x) {
     float s = 0.f;
     for (int q = 0; q < planes; ++q) s += red[(size_t)q * taps * C + i];
+    ws[(size_t)blockIdx.x * taps * C + i] = s;
+  }
+}
+
+// dw[tap, c] (+)= sum over block rows.  Block = 32 consecutive (tap, c) elements x 8 row lanes.
+__global__ void __launch_bounds__(256) wgrad_thin_finish_kernel(const float* __restrict__ ws, int nrows, int taps, int C, int S,
+                                                                int wide_u, float* __restrict__ dw, int64_t sa, int64_t sb,
+                                                                int64_t sr, int64_t ss, int accumulate) {
+  __shared__ float part[8][33];
+  const int total = taps * C;
+  const int li = threadIdx.x & 31, lp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + li;
+  float acc = 0.f;
+  if (i < total)
+    for (int q = lp; q < nrows; q += 8) acc += ws[(size_t)q * total + i];
+  part[lp][li] = acc;
+  __syncthreads();
+  if (lp == 0 && i < total) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += part[q][li];
     const int t = i / C, c = i - t * C;
-    const int r = t / g.S, sx = t - r * g.S;
-    const int a = WIDE_U ? c : 0, b = WIDE_U ? 0 : c;
-    atomicAdd(dw + a * sa + b * sb + r * sr + sx * ss, s);
+    const int r = t / S, sx = t - r * S;
+    const int a = wide_u ? c : 0, b = wide_u ? 0 : c;
+    float* d = dw + a * sa + b * sb + r * sr + sx * ss;
+    *d = accumulate ? (*d + v) : v;
   }
 }
 
@@ -509,30 +532,47 @@ extern "C" int viai_conv2d_wgrad_thin_supported(const viai_conv_geom* g) {
   return (C % 4 == 0 && C / 4 <= 256) ? 1 : 0;
 }
 
-// Same meaning as viai_conv2d_wgrad_simt, for A == 1 or B == 1.
+namespace {
+void wgrad_thin_plan(const viai_conv_geom& g, bool& wide_u, int64_t& M, int& C, int& planes, int64_t& blocks, int& ppb) {
+  wide_u = g.Cin == 1;
+  M = wide_u ? (int64_t)g.N * g.Hout * g.Wout : (int64_t)g.N * g.Hin * g.Win;   // pixels of the wide tensor
+  C = wide_u ? g.Cout : g.Cin;
+  planes = 256 / (C / 4);
+  blocks = imin64(8 * kNumSMs, cdiv(M, (int64_t)planes * 4));
+  if (blocks < 1) blocks = 1;
+  ppb = (int)cdiv(M, blocks);
+  if (ppb < 1) ppb = 1;
+  blocks = M > 0 ? cdiv(M, ppb) : 0;
+}
+}  // namespace
+
+extern "C" int64_t viai_wgrad_thin_workspace(const viai_conv_geom* g) {
+  if (!viai_conv2d_wgrad_thin_supported(g)) return 0;
+  bool wide_u; int64_t M, blocks; int C, planes, ppb;
+  wgrad_thin_plan(*g, wide_u, M, C, planes, blocks, ppb);
+  return (blocks > 0 ? blocks : 1) * (int64_t)g->R * g->S * C;
+}
+
+// Same meaning as viai_conv2d_wgrad_simt, for A == 1 or B == 1.  workspace: viai_wgrad_thin_workspace(g) floats.
 extern "C" int viai_conv2d_wgrad_thin(const viai_conv_geom* gp, const float* U, const float* G, float* dw, int64_t sa, int64_t sb,
-                                      int64_t sr, int64_t ss, int accumulate, viai_stream_t stream) {
-  VIAI_REQUIRE(gp && U && G && dw, "conv2d_wgrad_thin: null argument");
+                                      int64_t sr, int64_t ss, int accumulate, float* workspace, viai_stream_t stream) {
+  VIAI_REQUIRE(gp && U && G && dw && workspace, "conv2d_wgrad_thin: null argument");
   const viai_conv_geom& g = *gp;
   VIAI_REQUIRE(viai_conv2d_wgrad_thin_supported(gp), "conv2d_wgrad_thin: unsupported geometry (A %d, B %d)", g.Cout, g.Cin);
   VIAI_REQUIRE((reinterpret_cast<uintptr_t>(U) & 15) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0,
                "conv2d_wgrad_thin: pointers must be 16-byte aligned");
   cudaStream_t st = STR(stream);
   const int taps = g.R * g.S;
-  if (!accumulate) {
-    zero_dw_kernel<<<(g.Cout * g.Cin * taps + 255) / 256, 256, 0, st>>>(dw, g.Cout, g.Cin, g.R, g.S, sa, sb, sr, ss);
-    VIAI_LAUNCHED();
-  }
-  const bool wide_u = g.Cin == 1;
-  const int64_t M = wide_u ? (int64_t)g.N * g.Hout * g.Wout : (int64_t)g.N * g.Hin * g.Win;   // pixels of the wide tensor
-  if (M == 0 || (int64_t)g.N * g.Hout * g.Wout == 0) return VIAI_OK;
+  bool wide_u; int64_t M, blocks; int C, planes, ppb;
+  wgrad_thin_plan(g, wide_u, M, C, planes, blocks, ppb);
   VIAI_REQUIRE(M < (int64_t)1 << 31, "conv2d_wgrad_thin: tensor too large");
-  const int C = wide_u ? g.Cout : g.Cin;
-  const int c4n = C / 4, planes = 256 / c4n;
-  int64_t blocks = imin64(8 * kNumSMs, cdiv(M, (int64_t)planes * 4));
-  if (blocks < 1) blocks = 1;
-  const int ppb = (int)cdiv(M, blocks);
-  blocks = cdiv(M, ppb);
+  if (M == 0 || (int64_t)g.N * g.Hout * g.Wout == 0) {
+    if (!accumulate) {
+      zero_dw_kernel<<<(g.Cout * g.Cin * taps + 255) / 256, 256, 0, st>>>(dw, g.Cout, g.Cin, g.R, g.S, sa, sb, sr, ss);
+      VIAI_LAUNCHED();
+    }
+    return VIAI_OK;
+  }
   const size_t smem = sizeof(float) * (size_t)planes * taps * C;
   static bool attr = false;
   if (!attr) {
@@ -541,8 +581,11 @@ extern "C" int viai_conv2d_wgrad_thin(const viai_conv_geom* gp, const float* U, 
     attr = true;
   }
   VIAI_REQUIRE(smem <= 64 * 1024, "conv2d_wgrad_thin: reduction buffer too large");
-  if (wide_u) wgrad_thin_kernel<true><<<(unsigned)blocks, 256, smem, st>>>(g, U, G, dw, sa, sb, sr, ss, ppb);
-  else wgrad_thin_kernel<false><<<(unsigned)blocks, 256, smem, st>>>(g, U, G, dw, sa, sb, sr, ss, ppb);
+  if (wide_u) wgrad_thin_kernel<true><<<(unsigned)blocks, 256, smem, st>>>(g, U, G, workspace, ppb);
+  else wgrad_thin_kernel<false><<<(unsigned)blocks, 256, smem, st>>>(g, U, G, workspace, ppb);
+  VIAI_LAUNCHED();
+  wgrad_thin_finish_kernel<<<(taps * C + 31) / 32, 256, 0, st>>>(workspace, (int)blocks, taps, C, g.S, wide_u ? 1 : 0, dw, sa, sb, sr, ss,
+                                                               accumulate);
   VIAI_LAUNCHED();
   return VIAI_OK;
 }

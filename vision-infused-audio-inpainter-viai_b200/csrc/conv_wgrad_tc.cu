@@ -10,8 +10,10 @@
 //   * B operand: the (TH + kh - 1) x (8 + kw - 1) patch of G (32 channels) that ALL taps of the tile read, loaded once; a tap
 //     is a different start row of the descriptor (as in conv_tc.cu), strides become parity sub-grids;
 //   * accumulators: one 128 x 32 fp32 block per tap in TMEM (9 taps -> 288 of the 512 columns), kept for the CTA's whole
-//     pixel range (split-K across CTAs), then added to a packed fp32 workspace with vector reductions (red.global.add.v4.f32);
-//   * a second tiny kernel scatters the workspace into the parameter-gradient layout (overwrite or accumulate).
+//     pixel range (split-K across CTAs), then STORED to the CTA's own slice of a packed fp32 workspace [split][tap][A][B]
+//     (no atomics: measured on B200, red.global.add.v4.f32 from ~300 CTAs onto the same tile ran at ~0.5 clk per
+//     instruction for the whole GPU and was 80 % of this kernel's time);
+//   * a second small kernel sums the split slices and scatters into the parameter-gradient layout (overwrite or accumulate).
 // Ragged tiles and zero padding need no masking: TMA fills out-of-bounds elements of either operand with zeros.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -29,17 +31,28 @@ struct WgSub {
   uint32_t smem_off;     // inside the G region of a stage
 };
 struct WgTap {
-  uint32_t g_off;        // byte offset (inside the G region) of the tap's first pixel row
-  uint32_t row_pitch;    // bytes between consecutive 8-pixel row segments (pw * 128)
+  uint32_t col;          // first TMEM column of the tap's 128 x 32 accumulator block
   uint32_t wtap;
+};
+// A run = horizontally adjacent taps of one parity sub-patch: their B operands are the same patch rows shifted by one pixel
+// (128 bytes) each, so ONE MMA with N = 32 * len covers the whole run by using the pixel pitch as the descriptor's stride
+// between 32-channel blocks.  (Measured on B200: an M=128, N=32, K=8 MN-major MMA costs ~100 cycles whatever N is up to
+// ~128 -- the A fetch dominates -- so 3 taps per instruction make the 3x3 weight gradient ~3x faster.)
+struct WgRun {
+  uint32_t g_off;        // byte offset (inside the G region) of the first tap's first pixel row
+  uint32_t row_pitch;    // bytes between consecutive 8-pixel row segments (pw * 128)
+  uint32_t col;          // first TMEM column
+  uint32_t idesc;        // instruction descriptor with N = 32 * len
 };
 struct WgParams {
   CUtensorMap mapU;
   CUtensorMap mapG[MAX_SUB];
   WgSub sub[MAX_SUB];
   WgTap tap[MAX_TAP];
-  int32_t nsub, ntap;
-  float* ws;             // [tap][A][B] fp32 workspace
+  WgRun run[MAX_TAP];
+  int32_t nsub, ntap, nrun;
+  float* ws;             // [split][tap][A][B] fp32 workspace
+  int64_t ws_split;      // floats per split slice
   int32_t A, B;
   int32_t N, tilesX, tilesY, TH;
   int32_t a_tiles, b_tiles, splits, tiles_per_split, npix_tiles;
@@ -49,9 +62,6 @@ struct WgParams {
   uint32_t idesc;
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -124,16 +134,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
         tc_fence_after();
         const uint32_t u_base = smem_u32(smem + (size_t)st * p.stage_bytes);
         const uint32_t g_base = u_base + p.u_bytes;
-        for (int tp = 0; tp < p.ntap; ++tp) {
-          const WgTap& w = p.tap[tp];
-          const uint32_t d_tmem = tmem_base + (uint32_t)(tp * BNW);
-          // A: MN-major, 4 blocks of 32 channels LBO apart; B: MN-major, one block.  SBO (between K groups of 8) is unused
-          // because every MMA covers exactly one group.
+        for (int rn = 0; rn < p.nrun; ++rn) {
+          const WgRun& w = p.run[rn];
+          const uint32_t d_tmem = tmem_base + w.col;
+          // A: MN-major, 4 blocks of 32 channels LBO apart; B: MN-major, `len` blocks of 32 channels one pixel (128 bytes)
+          // apart = the taps of the run.  SBO (between K groups of 8) is unused: every MMA covers exactly one group.
           uint64_t ad = make_desc_sw128x32_mn(u_base, p.u_slice_bytes, 512u);
-          uint64_t bd = make_desc_sw128x32_mn(g_base + w.g_off, 1024u, 512u);
+          uint64_t bd = make_desc_sw128x32_mn(g_base + w.g_off, 128u, 512u);
           const uint64_t a_step = 1024u >> 4, b_step = w.row_pitch >> 4;
           for (int kk = 0; kk < p.TH; ++kk) {
-            mma_tf32(d_tmem, ad, bd, p.idesc, (t > t_begin || kk > 0) ? 1u : 0u);
+            mma_tf32(d_tmem, ad, bd, w.idesc, (t > t_begin || kk > 0) ? 1u : 0u);
             ad += a_step;
             bd += b_step;
           }
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
       mma_commit(done);
     }
   } else {
-    // epilogue: add the CTA's partial D_t blocks into the workspace
+    // epilogue: store the CTA's partial D_t blocks into its slice of the workspace
     const int q = warp & 3;
     const int a = at * BM + q * 32 + lane;
     if (t_end > t_begin) {
@@ -152,12 +162,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
       tc_fence_after();
       for (int tp = 0; tp < p.ntap; ++tp) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tp * BNW), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + p.tap[tp].col, v);
         if (a < p.A) {
-          float* dst = p.ws + ((size_t)p.tap[tp].wtap * p.A + a) * p.B + (size_t)bt * BNW;
+          float* dst = p.ws + (size_t)split * p.ws_split + ((size_t)p.tap[tp].wtap * p.A + a) * p.B + (size_t)bt * BNW;
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
-            if (bt * BNW + i < p.B) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+            if (bt * BNW + i < p.B) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
       }
     }
@@ -170,17 +180,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
   }
 }
 
-__global__ void wgrad_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw, int A, int B, int R, int S, int64_t sa,
-                                    int64_t sb, int64_t sr, int64_t ss, int accumulate) {
+// dw (+)= sum over split slices.  Block = 32 consecutive elements x 8 split lanes (coalesced 128-byte reads per slice).
+__global__ void __launch_bounds__(256) wgrad_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw, int A, int B, int R,
+                                                           int S, int64_t sa, int64_t sb, int64_t sr, int64_t ss, int accumulate,
+                                                           int splits, int64_t ws_split) {
+  __shared__ float part[8][33];
   const int64_t total = (int64_t)R * S * A * B;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int b = idx % B;
-    int64_t t = idx / B;
-    const int a = t % A;
-    const int tap = (int)(t / A);
-    const int r = tap / S, s = tap % S;
-    float* d = dw + a * sa + b * sb + r * sr + s * ss;
-    *d = accumulate ? (*d + ws[idx]) : ws[idx];
+  const int li = threadIdx.x & 31, lp = threadIdx.x >> 5;
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+    const int64_t idx = base + li;
+    float acc = 0.f;
+    if (idx < total)
+      for (int sp = lp; sp < splits; sp += 8) acc += ws[(int64_t)sp * ws_split + idx];
+    part[lp][li] = acc;
+    __syncthreads();
+    if (lp == 0 && idx < total) {
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v += part[q][li];
+      const int b = idx % B;
+      int64_t t = idx / B;
+      const int a = t % A;
+      const int tap = (int)(t / A);
+      const int r = tap / S, s2 = tap % S;
+      float* d = dw + a * sa + b * sb + r * sr + s2 * ss;
+      *d = accumulate ? (*d + v) : v;
+    }
+    __syncthreads();
   }
 }
 
@@ -197,8 +223,27 @@ extern "C" int viai_conv2d_wgrad_tc_supported(const viai_conv_geom* g) {
   return 1;
 }
 
+namespace {
+// split-K plan shared by the workspace query and the launch: the pixel range is split so that the grid is ~2 waves of the SMs
+void wg_split_plan(const viai_conv_geom& g, int& TH, int& npix_tiles, int& splits, int& tiles_per_split) {
+  const bool strided = g.stride_h > 1 || g.stride_w > 1;
+  TH = strided ? 8 : 16;
+  const int tilesX = (g.Wout + TW - 1) / TW, tilesY = (g.Hout + TH - 1) / TH;
+  npix_tiles = g.N * tilesX * tilesY;
+  const int ab = ((g.Cout + BM - 1) / BM) * ((g.Cin + BNW - 1) / BNW);
+  int sp = (2 * kNumSMs + ab - 1) / ab;
+  if (sp > npix_tiles) sp = npix_tiles;
+  if (sp < 1) sp = 1;
+  tiles_per_split = (npix_tiles + sp - 1) / sp;
+  splits = tiles_per_split > 0 ? (npix_tiles + tiles_per_split - 1) / tiles_per_split : 1;
+}
+}  // namespace
+
 extern "C" int64_t viai_wgrad_tc_workspace(const viai_conv_geom* g) {
-  return g ? (int64_t)g->R * g->S * g->Cout * g->Cin : 0;
+  if (!g) return 0;
+  int TH, npix, splits, tps;
+  wg_split_plan(*g, TH, npix, splits, tps);
+  return (int64_t)(splits > 0 ? splits : 1) * g->R * g->S * g->Cout * g->Cin;
 }
 
 // U: (N,Hout,Wout,Cout=A), G: (N,Hin,Win,Cin=B) as in viai_conv2d_wgrad_simt.  workspace: viai_wgrad_tc_workspace(g) floats.
@@ -215,8 +260,11 @@ extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, co
   memset(&p, 0, sizeof(p));
   const int A = g.Cout, B = g.Cin;
   p.A = A; p.B = B; p.ws = workspace; p.N = g.N;
-  const bool strided = g.stride_h > 1 || g.stride_w > 1;
-  p.TH = strided ? 8 : 16;
+  {
+    int TH, npix, splits, tps;
+    wg_split_plan(g, TH, npix, splits, tps);
+    p.TH = TH; p.npix_tiles = npix; p.splits = splits; p.tiles_per_split = tps;
+  }
   // taps and parity sub-patches of G
   int sub_id[2][2] = {{-1, -1}, {-1, -1}};
   int mn_y[MAX_SUB], mx_y[MAX_SUB], mn_x[MAX_SUB], mx_x[MAX_SUB], sy_of[MAX_SUB], sx_of[MAX_SUB], t_sub[MAX_TAP], t_oy[MAX_TAP], t_ox[MAX_TAP];
@@ -258,10 +306,32 @@ extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, co
     if (encode_f32_map(&p.mapG[s], 4, base, dims, strides, box, 2)) return VIAI_ERR_CUDA;
   }
   p.g_bytes = off;
-  for (int t = 0; t < ntap; ++t) {
-    const WgSub& sb2 = p.sub[t_sub[t]];
-    p.tap[t].g_off = sb2.smem_off + (uint32_t)((t_oy[t] - sb2.oy) * sb2.pw + (t_ox[t] - sb2.ox)) * 128u;
-    p.tap[t].row_pitch = (uint32_t)sb2.pw * 128u;
+  {
+    bool placed[MAX_TAP] = {false};
+    int nrun = 0;
+    uint32_t col = 0;
+    for (int t0 = 0; t0 < ntap; ++t0) {
+      if (placed[t0]) continue;
+      // left-most unplaced tap of its (sub-patch, row): taps are enumerated with increasing s, hence increasing ox
+      const WgSub& sb2 = p.sub[t_sub[t0]];
+      WgRun& rn = p.run[nrun++];
+      rn.g_off = sb2.smem_off + (uint32_t)((t_oy[t0] - sb2.oy) * sb2.pw + (t_ox[t0] - sb2.ox)) * 128u;
+      rn.row_pitch = (uint32_t)sb2.pw * 128u;
+      rn.col = col;
+      int len = 0, cur = t0;
+      while (cur >= 0 && len < 8) {
+        placed[cur] = true;
+        p.tap[cur].col = col;
+        col += BNW;
+        ++len;
+        int nxt = -1;
+        for (int t = 0; t < ntap; ++t)
+          if (!placed[t] && t_sub[t] == t_sub[cur] && t_oy[t] == t_oy[cur] && t_ox[t] == t_ox[cur] + 1) { nxt = t; break; }
+        cur = nxt;
+      }
+      rn.idesc = make_idesc_tf32(BM, BNW * len, 1, 1);
+    }
+    p.nrun = nrun;
   }
   {
     uint64_t dims[4] = {(uint64_t)A, (uint64_t)g.Wout, (uint64_t)g.Hout, (uint64_t)g.N};
@@ -281,14 +351,8 @@ extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, co
   p.stage_bytes = p.u_bytes + p.g_bytes;
   p.tilesX = (g.Wout + TW - 1) / TW;
   p.tilesY = (g.Hout + p.TH - 1) / p.TH;
-  p.npix_tiles = g.N * p.tilesX * p.tilesY;
-  // split the pixel range so that the grid is about two waves of the 148 SMs
   const int ab = p.a_tiles * p.b_tiles;
-  int splits = (2 * kNumSMs + ab - 1) / ab;
-  if (splits > p.npix_tiles) splits = p.npix_tiles;
-  if (splits < 1) splits = 1;
-  p.tiles_per_split = (p.npix_tiles + splits - 1) / splits;
-  p.splits = (p.npix_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.ws_split = (int64_t)ntap * A * B;
   const size_t budget = 227 * 1024, fixed = 1024 + 32 * 8 + 16;
   int stages = 4;
   while (stages > 1 && fixed + (size_t)stages * p.stage_bytes > budget) --stages;
@@ -303,12 +367,17 @@ extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, co
     attr_set = true;
   }
   const int64_t ws_elems = (int64_t)ntap * A * B;
-  VIAI_CUDA(cudaMemsetAsync(workspace, 0, (size_t)ws_elems * sizeof(float), st));
+  if (p.npix_tiles == 0) {
+    VIAI_CUDA(cudaMemsetAsync(workspace, 0, (size_t)ws_elems * sizeof(float), st));
+    p.splits = 1;
+  }
   const int grid = p.splits * ab;
-  wgrad_tc_kernel<<<grid, NTHREADS, smem, st>>>(p);
-  VIAI_LAUNCHED();
-  const int blocks = (int)imin64(cdiv(ws_elems, 256), 2048);
-  wgrad_unpack_kernel<<<blocks, 256, 0, st>>>(workspace, dw, A, B, g.R, g.S, sa, sb, sr, ss, accumulate);
+  if (p.npix_tiles > 0) {
+    wgrad_tc_kernel<<<grid, NTHREADS, smem, st>>>(p);
+    VIAI_LAUNCHED();
+  }
+  const int blocks = (int)imin64(cdiv(ws_elems, 32), 16 * kNumSMs);
+  wgrad_unpack_kernel<<<blocks, 256, 0, st>>>(workspace, dw, A, B, g.R, g.S, sa, sb, sr, ss, accumulate, p.splits, p.ws_split);
   VIAI_LAUNCHED();
   return VIAI_OK;
 }

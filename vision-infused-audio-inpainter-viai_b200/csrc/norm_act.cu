@@ -46,20 +46,27 @@ stats_kernel(const float* __restrict__ y, int64_t rows_per_group, int C, double*
   const bool active = rl < L.lanes;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = imin64(r0 + rows_per_block, rows_per_group);
-  float s[VEC], q[VEC];
+  // Sums and squares are accumulated in double (the square is formed in double too): the variance is later taken as
+  // E[x^2] - E[x]^2, which is only safe for channels whose mean dwarfs their spread (ResNet features after residual adds)
+  // when both moments are exact to ~1e-16.
+  double s[VEC], q[VEC];
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) { s[k] = 0.f; q[k] = 0.f; }
+  for (int k = 0; k < VEC; ++k) { s[k] = 0.0; q[k] = 0.0; }
   if (active) {
     const float* base = y + ((int64_t)g * rows_per_group) * C + cv * VEC;
     for (int64_t r = r0 + rl; r < r1; r += L.lanes) {
+      float v[VEC];
       if (VEC == 4) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(base + r * C));
-        s[0] += v.x; s[1 % VEC] += v.y; s[2 % VEC] += v.z; s[3 % VEC] += v.w;
-        if (SQ) { q[0] += v.x * v.x; q[1 % VEC] += v.y * v.y; q[2 % VEC] += v.z * v.z; q[3 % VEC] += v.w * v.w; }
+        const float4 t = __ldg(reinterpret_cast<const float4*>(base + r * C));
+        v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
       } else {
-        float v = __ldg(base + r * C);
-        s[0] += v;
-        if (SQ) q[0] += v * v;
+        v[0] = __ldg(base + r * C);
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const double d = (double)v[k];
+        s[k] += d;
+        if (SQ) q[k] = fma(d, d, q[k]);
       }
     }
   }
@@ -102,34 +109,57 @@ __global__ void finalize_kernel(const double* sum, const double* sumsq, int64_t 
   }
 }
 
+// Elementwise kernels: a thread owns one channel vector (its per-channel constants live in registers) and walks rows of one
+// statistics group -- no integer division and no parameter loads inside the loop; UNR rows are in flight per thread.
+constexpr int UNR = 4;
+
 template <int VEC>
 __global__ void __launch_bounds__(THREADS)
-apply_kernel(const float* __restrict__ y, int64_t total_vec, int64_t rows_per_group, int C, const float* __restrict__ mean,
+apply_kernel(const float* __restrict__ y, int64_t rows_per_group, int C, const float* __restrict__ mean,
              const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act,
-             float slope, float* __restrict__ out) {
-  const int cvec = C / VEC;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t row = i / cvec;
-    int c0 = (int)(i - row * cvec) * VEC;
-    int64_t sbase = mean ? (row / rows_per_group) * C : 0;
-    float v[VEC];
-    if (VEC == 4) {
-      float4 t = __ldg(reinterpret_cast<const float4*>(y) + i);
-      v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
-    } else {
-      v[0] = __ldg(y + i);
+             float slope, float* __restrict__ out, int64_t rows_per_block) {
+  const Lanes L = make_lanes(C, VEC);
+  const int cv = threadIdx.x % L.cvec, rl = threadIdx.x / L.cvec;
+  if (rl >= L.lanes) return;
+  const int g = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = imin64(r0 + rows_per_block, rows_per_group);
+  // out = act(((y - mu) * is) * ga + be): the subtraction comes first (as in the reference's batch_norm) so that channels
+  // whose mean is large against their spread lose nothing to cancellation
+  float mu[VEC], is[VEC], ga[VEC], be[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const int c = cv * VEC + k;
+    mu[k] = mean ? mean[(int64_t)g * C + c] : 0.f;
+    is[k] = mean ? invstd[(int64_t)g * C + c] : 1.f;
+    ga[k] = gamma ? gamma[c] : 1.f;
+    be[k] = beta ? beta[c] : 0.f;
+  }
+  const int64_t off = ((int64_t)g * rows_per_group) * C + cv * VEC;
+  for (int64_t r = r0 + rl; r < r1; r += (int64_t)L.lanes * UNR) {
+    float v[UNR][VEC];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t rr = r + (int64_t)u * L.lanes;
+      if (rr < r1) {
+        if (VEC == 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(y + off + rr * C));
+          v[u][0] = t.x; v[u][1 % VEC] = t.y; v[u][2 % VEC] = t.z; v[u][3 % VEC] = t.w;
+        } else {
+          v[u][0] = __ldg(y + off + rr * C);
+        }
+      }
     }
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      int c = c0 + k;
-      float x = v[k];
-      if (mean) x = (x - __ldg(mean + sbase + c)) * __ldg(invstd + sbase + c);
-      if (gamma) x = x * __ldg(gamma + c);
-      if (beta) x = x + __ldg(beta + c);
-      v[k] = act_fwd(x, act, slope);
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t rr = r + (int64_t)u * L.lanes;
+      if (rr < r1) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[u][k] = act_fwd(((v[u][k] - mu[k]) * is[k]) * ga[k] + be[k], act, slope);
+        if (VEC == 4) *reinterpret_cast<float4*>(out + off + rr * C) = make_float4(v[u][0], v[u][1 % VEC], v[u][2 % VEC], v[u][3 % VEC]);
+        else out[off + rr * C] = v[u][0];
+      }
     }
-    if (VEC == 4) reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
-    else out[i] = v[0];
   }
 }
 
@@ -210,44 +240,62 @@ bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y, int
 
 template <int VEC>
 __global__ void __launch_bounds__(THREADS)
-bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, int64_t total_vec, int64_t rows_per_group, int C,
+bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, int64_t rows_per_group, int C,
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int act, float slope, const double* __restrict__ s1,
-                 const double* __restrict__ s2, float* __restrict__ dy) {
-  const int cvec = C / VEC;
+                 const double* __restrict__ s2, float* __restrict__ dy, int64_t rows_per_block) {
+  const Lanes L = make_lanes(C, VEC);
+  const int cv = threadIdx.x % L.cvec, rl = threadIdx.x / L.cvec;
+  if (rl >= L.lanes) return;
+  const int g = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = imin64(r0 + rows_per_block, rows_per_group);
   const float inv_cnt = 1.f / (float)rows_per_group;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t row = i / cvec;
-    int c0 = (int)(i - row * cvec) * VEC;
-    int64_t sbase = (row / rows_per_group) * C;
-    float d[VEC], yv[VEC], o[VEC];
-    if (VEC == 4) {
-      float4 t = __ldg(reinterpret_cast<const float4*>(dz) + i);
-      float4 u = __ldg(reinterpret_cast<const float4*>(y) + i);
-      d[0] = t.x; d[1 % VEC] = t.y; d[2 % VEC] = t.z; d[3 % VEC] = t.w;
-      yv[0] = u.x; yv[1 % VEC] = u.y; yv[2 % VEC] = u.z; yv[3 % VEC] = u.w;
-    } else {
-      d[0] = __ldg(dz + i);
-      yv[0] = __ldg(y + i);
-    }
+  const bool has_norm = mean != nullptr;
+  float mu[VEC], is[VEC], ga[VEC], be[VEC], m1[VEC], m2[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      int c = c0 + k;
-      float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
-      if (mean) {
-        float mu = __ldg(mean + sbase + c), is = __ldg(invstd + sbase + c);
-        float gg, xh;
-        bwd_terms(d[k], yv[k], mu, is, ga, be, true, act, slope, gg, xh);
-        float m1 = (float)(s1[sbase + c]) * inv_cnt, m2 = (float)(s2[sbase + c]) * inv_cnt;
-        o[k] = ga * is * (gg - m1 - xh * m2);
-      } else {
-        float gg, xh;
-        bwd_terms(d[k], yv[k], 0.f, 1.f, ga, be, false, act, slope, gg, xh);
-        o[k] = gg * ga;
+  for (int k = 0; k < VEC; ++k) {
+    const int c = cv * VEC + k;
+    mu[k] = has_norm ? mean[(int64_t)g * C + c] : 0.f;
+    is[k] = has_norm ? invstd[(int64_t)g * C + c] : 1.f;
+    ga[k] = gamma ? gamma[c] : 1.f;
+    be[k] = beta ? beta[c] : 0.f;
+    m1[k] = has_norm ? (float)(s1[(int64_t)g * C + c]) * inv_cnt : 0.f;
+    m2[k] = has_norm ? (float)(s2[(int64_t)g * C + c]) * inv_cnt : 0.f;
+  }
+  const int64_t off = ((int64_t)g * rows_per_group) * C + cv * VEC;
+  for (int64_t r = r0 + rl; r < r1; r += (int64_t)L.lanes * UNR) {
+    float d[UNR][VEC], yv[UNR][VEC];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t rr = r + (int64_t)u * L.lanes;
+      if (rr < r1) {
+        if (VEC == 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(dz + off + rr * C));
+          const float4 w = __ldg(reinterpret_cast<const float4*>(y + off + rr * C));
+          d[u][0] = t.x; d[u][1 % VEC] = t.y; d[u][2 % VEC] = t.z; d[u][3 % VEC] = t.w;
+          yv[u][0] = w.x; yv[u][1 % VEC] = w.y; yv[u][2 % VEC] = w.z; yv[u][3 % VEC] = w.w;
+        } else {
+          d[u][0] = __ldg(dz + off + rr * C);
+          yv[u][0] = __ldg(y + off + rr * C);
+        }
       }
     }
-    if (VEC == 4) reinterpret_cast<float4*>(dy)[i] = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
-    else dy[i] = o[0];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t rr = r + (int64_t)u * L.lanes;
+      if (rr < r1) {
+        float o[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          float gg, xh;
+          bwd_terms(d[u][k], yv[u][k], mu[k], is[k], ga[k], be[k], has_norm, act, slope, gg, xh);
+          o[k] = has_norm ? ga[k] * is[k] * (gg - m1[k] - xh * m2[k]) : gg * ga[k];
+        }
+        if (VEC == 4) *reinterpret_cast<float4*>(dy + off + rr * C) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+        else dy[off + rr * C] = o[0];
+      }
+    }
   }
 }
 
@@ -271,6 +319,15 @@ int64_t pick_rows_per_block(int64_t rows_per_group, int groups, int C, int VEC) 
   int64_t per_group = cdiv((int64_t)4 * kNumSMs, groups);
   int64_t rpb = cdiv(rows_per_group, per_group);
   if (rpb < (int64_t)lanes * 8) rpb = (int64_t)lanes * 8;
+  return rpb;
+}
+
+// rows handled by one block of an elementwise pass: ~16 blocks per SM in total, at least UNR rows per row lane
+int64_t pick_rows_per_block_elem(int64_t rows_per_group, int groups, int C, int VEC) {
+  const int lanes = make_lanes(C, VEC).lanes;
+  int64_t per_group = cdiv((int64_t)16 * kNumSMs, groups);
+  int64_t rpb = cdiv(rows_per_group, per_group);
+  if (rpb < (int64_t)lanes * UNR) rpb = (int64_t)lanes * UNR;
   return rpb;
 }
 
@@ -319,11 +376,16 @@ extern "C" int viai_norm_act_fwd(const float* y, int64_t rows_per_group, int gro
                                  float* out, viai_stream_t stream) {
   VIAI_REQUIRE(y && out && rows_per_group > 0 && groups > 0 && C > 0, "viai_norm_act_fwd: bad arguments");
   VIAI_REQUIRE((mean == nullptr) == (invstd == nullptr), "viai_norm_act_fwd: mean/invstd must both be set or NULL");
-  const int VEC = pick_vec(C, y, out);
-  int64_t total = rows_per_group * groups * C / VEC;
-  int blocks = (int)imin64(cdiv(total, THREADS), 16 * kNumSMs);
-  if (VEC == 4) apply_kernel<4><<<blocks, THREADS, 0, STR(stream)>>>(y, total, rows_per_group, C, mean, invstd, gamma, beta, act, slope, out);
-  else apply_kernel<1><<<blocks, THREADS, 0, STR(stream)>>>(y, total, rows_per_group, C, mean, invstd, gamma, beta, act, slope, out);
+  int VEC = pick_vec(C, y, out);
+  if (C / VEC > THREADS) VEC = 0;
+  VIAI_REQUIRE(VEC != 0, "viai_norm_act_fwd: C=%d too large", C);
+  // without statistics every row shares the same constants: treat the tensor as one group
+  const int64_t rpg = mean ? rows_per_group : rows_per_group * groups;
+  const int ngr = mean ? groups : 1;
+  const int64_t rpb = pick_rows_per_block_elem(rpg, ngr, C, VEC);
+  dim3 grid((unsigned)cdiv(rpg, rpb), (unsigned)ngr);
+  if (VEC == 4) apply_kernel<4><<<grid, THREADS, 0, STR(stream)>>>(y, rpg, C, mean, invstd, gamma, beta, act, slope, out, rpb);
+  else apply_kernel<1><<<grid, THREADS, 0, STR(stream)>>>(y, rpg, C, mean, invstd, gamma, beta, act, slope, out, rpb);
   VIAI_LAUNCHED();
   return VIAI_OK;
 }
@@ -354,10 +416,13 @@ extern "C" int viai_norm_act_bwd_apply(const float* dz, const float* y, int64_t 
   VIAI_REQUIRE(mean == nullptr || (s1 && s2 && invstd), "viai_norm_act_bwd_apply: statistics missing");
   cudaStream_t st = STR(stream);
   const int VEC = pick_vec(C, dz, y) == 4 && pick_vec(C, dy) == 4 ? 4 : 1;
-  int64_t total = rows_per_group * groups * C / VEC;
-  int blocks = (int)imin64(cdiv(total, THREADS), 16 * kNumSMs);
-  if (VEC == 4) bwd_apply_kernel<4><<<blocks, THREADS, 0, st>>>(dz, y, total, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy);
-  else bwd_apply_kernel<1><<<blocks, THREADS, 0, st>>>(dz, y, total, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy);
+  VIAI_REQUIRE(C / VEC <= THREADS, "viai_norm_act_bwd_apply: C=%d too large", C);
+  const int64_t rpg = mean ? rows_per_group : rows_per_group * groups;
+  const int ngr = mean ? groups : 1;
+  const int64_t rpb = pick_rows_per_block_elem(rpg, ngr, C, VEC);
+  dim3 grid((unsigned)cdiv(rpg, rpb), (unsigned)ngr);
+  if (VEC == 4) bwd_apply_kernel<4><<<grid, THREADS, 0, st>>>(dz, y, rpg, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy, rpb);
+  else bwd_apply_kernel<1><<<grid, THREADS, 0, st>>>(dz, y, rpg, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy, rpb);
   VIAI_LAUNCHED();
   if (dgamma && s2) {
     fold_kernel<<<(C + 255) / 256, 256, 0, st>>>(s2, groups, C, dgamma, 0);

@@ -178,8 +178,9 @@ class _ConvFn(torch.autograd.Function):
                 g = _geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0)
                 U, G = x, dy
             if L.viai_conv2d_wgrad_thin_supported(ctypes.byref(g)) and U.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0:
+                ws = _workspace(dy.device, L.viai_wgrad_thin_workspace(ctypes.byref(g)))
                 _lib.check(L.viai_conv2d_wgrad_thin(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1), dw.stride(2),
-                                                    dw.stride(3), int(wt is not None), _stream()), "conv2d wgrad_thin")
+                                                    dw.stride(3), int(wt is not None), _p(ws), _stream()), "conv2d wgrad_thin")
             elif _PRECISION != "fp32" and L.viai_conv2d_wgrad_tc_supported(ctypes.byref(g)):
                 ws = _workspace(dy.device, L.viai_wgrad_tc_workspace(ctypes.byref(g)))
                 _lib.check(L.viai_conv2d_wgrad_tc(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1), dw.stride(2),
