@@ -100,6 +100,9 @@ struct TcParams {
   uint32_t idesc;
   int32_t a4d;           // 1: sub-patch loaded by 8 rank-4 TMA copies instead of one rank-5 copy
   int32_t x3;            // 1: error-compensated 3-term tf32 product (A*Bhi + A*Blo + Alo*Bhi), ~fp32 accuracy
+  int32_t b_res;         // 1: the whole packed weight tensor stays resident in shared memory for the CTA's lifetime (layers whose
+                         //    weights are small: the 32/64-channel decoder layers) instead of being streamed per (tile, tap, slab)
+  int32_t nB;            // weight-tile slots in shared memory (= SB when streamed, ntap * nchunks when resident)
   int32_t bx3;           // 1: the same 3-term product on bf16 pairs (x = hi + lo, both bf16): kind::f16 MMAs at twice the tf32
                          //    rate; the fp32 slab is split IN PLACE into [hi: 32 x bf16 | lo: 32 x bf16] per 128-byte pixel row
   int32_t a_sw128;       // 1: activation patch stored as dense 128-byte pixel rows under the 128-byte swizzle (rank-4 TMA)
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   uint8_t* slabA = smem;
   const uint32_t a_stage = p.slab_bytes * (p.x3 ? 2u : 1u);     // [raw / hi slab][lo slab]
   uint8_t* tileB = slabA + (size_t)p.SA * a_stage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tileB + (size_t)p.SB * p.btile_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tileB + (size_t)p.nB * p.btile_bytes);
   uint64_t* fullA = bars;
   uint64_t* emptyA = fullA + p.SA;
   uint64_t* loA = emptyA + p.SA;
@@ -134,6 +137,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   uint64_t* tfull = emptyB + p.SB;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tabA = reinterpret_cast<uint64_t*>(bars + 66);         // [tap][K step][part] A descriptors relative to a stage
+  uint64_t* tabB = tabA + MAX_TAP * 4 * 2;                          // [K step][part] B descriptors relative to a weight tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = (2 * p.BN <= 32) ? 32u : (2 * p.BN <= 64) ? 64u : (2 * p.BN <= 128) ? 128u : (2 * p.BN <= 256) ? 256u : 512u;
@@ -184,7 +189,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===== weight tile producer =====
-    if (lane == 0) {
+    if (lane == 0 && p.b_res) {
+      // resident weights: every (slab, tap) tile is fetched once, all completing on fullB[0]
+      const size_t btile_floats = p.btile_bytes / 4;
+      mbar_expect_tx(&fullB[0], (uint32_t)p.nB * p.btile_bytes);
+      for (int c = 0; c < p.nchunks; ++c)
+        for (int t = 0; t < p.ntap; ++t)
+          bulk_load(tileB + (size_t)(c * p.ntap + t) * p.btile_bytes, p.wp + ((size_t)p.tap[t].wtap * p.nchunks + c) * btile_floats,
+                    p.btile_bytes, &fullB[0]);
+    } else if (lane == 0) {
       int sb = 0;
       uint32_t phb = 0;
       const size_t btile_floats = p.btile_bytes / 4;
@@ -203,70 +216,95 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     }
   } else if (warp == 2) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pha = 0, phb = 0;
-      int it = 0;
-      const uint32_t b_lbo = (uint32_t)p.BN * 16u, b_sbo = 128u;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
+    // The whole warp walks the pipeline (all lanes poll the barriers), one elected lane issues.  Every shared-memory
+    // descriptor is precomputed once, relative to its stage, in two small tables: issuing an MMA is two 64-bit adds.  (With
+    // 32-channel layers an MMA is ~16 tensor cycles; the previous per-MMA descriptor arithmetic under a divergent
+    // `lane == 0` branch cost ~140 cycles per MMA and bounded those layers.)
+    const int bx3 = p.bx3, x3 = p.x3, b_res = p.b_res;
+    const int KK = bx3 ? KC / 16 : KC / 8;
+    const uint32_t b_lbo = (uint32_t)p.BN * 16u, b_sbo = 128u;
+    for (int i = lane; i < p.ntap * KK * 2; i += 32) {
+      const int part = i & 1, kk = (i >> 1) % KK, t = (i >> 1) / KK;
+      const TcTap& tp = p.tap[t];
+      uint64_t d;
+      if (p.a_sw128) d = make_desc_sw128(tp.a_off + (uint32_t)kk * 32u + (part ? (bx3 ? 64u : p.slab_bytes) : 0u), tp.sbo, 0u);
+      else d = make_desc(tp.a_off + (uint32_t)kk * 2u * tp.lbo, tp.lbo, tp.sbo);
+      tabA[i] = d;
+    }
+    if (lane < KK * 2) {
+      const int part = lane & 1, kk = lane >> 1;
+      tabB[lane] = make_desc((uint32_t)kk * 2u * b_lbo + (part ? (uint32_t)p.BN * (bx3 ? 64u : 128u) : 0u), b_lbo, b_sbo);
+    }
+    __syncwarp();
+    uint64_t bdesc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bdesc[i] = (i < KK * 2) ? tabB[i] : 0ull;
+    const bool leader = elect_one();
+    const uint32_t idesc = p.idesc;
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    int it = 0;
+    if (b_res) {
+      mbar_wait(&fullB[0], 0);
+      tc_fence_after();
+    }
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+      uint32_t accumulate = 0;
+      for (int c = 0; c < p.nchunks; ++c) {
+        mbar_wait(&fullA[sa], pha);
+        if (x3 | bx3) mbar_wait(&loA[sa], pha);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-        uint32_t accumulate = 0;
-        for (int c = 0; c < p.nchunks; ++c) {
-          mbar_wait(&fullA[sa], pha);
-          if (p.x3 | p.bx3) mbar_wait(&loA[sa], pha);
-          const uint32_t a_base = smem_u32(slabA + (size_t)sa * a_stage);
-          for (int t = 0; t < p.ntap; ++t) {
+        const uint64_t a16 = (uint64_t)(smem_u32(slabA + (size_t)sa * a_stage) >> 4);
+        for (int t = 0; t < p.ntap; ++t) {
+          if (!b_res) {
             mbar_wait(&fullB[sb], phb);
             tc_fence_after();
-            const TcTap& tp = p.tap[t];
-            const uint32_t b_base = smem_u32(tileB + (size_t)sb * p.btile_bytes);
-            if (p.bx3) {
-              // bf16 pairs: K = 16 per MMA, two K steps per 32-channel slab; lo halves sit 64 bytes into the pixel row
-              // (A) and 4 chunk planes into the weight tile (B).  Small terms first, then the leading one.
+          }
+          const uint64_t b16 = (uint64_t)(smem_u32(tileB + (size_t)(b_res ? c * p.ntap + t : sb) * p.btile_bytes) >> 4);
+          if (leader) {
+            const uint64_t* ta = tabA + t * KK * 2;
+            if (bx3) {          // bf16 pairs, K = 16: small terms first, then the leading one
 #pragma unroll
               for (int kk = 0; kk < KC / 16; ++kk) {
-                const uint32_t a_addr = a_base + tp.a_off + (uint32_t)kk * 32u;
-                const uint32_t b_addr = b_base + (uint32_t)kk * 2u * b_lbo;
-                const uint64_t ad_hi = make_desc_sw128(a_addr, tp.sbo, 0u), ad_lo = make_desc_sw128(a_addr + 64u, tp.sbo, 0u);
-                const uint64_t bd_hi = make_desc(b_addr, b_lbo, b_sbo), bd_lo = make_desc(b_addr + (uint32_t)p.BN * 64u, b_lbo, b_sbo);
-                mma_bf16(d_tmem, ad_lo, bd_hi, p.idesc, accumulate);
-                mma_bf16(d_tmem, ad_hi, bd_lo, p.idesc, 1);
-                mma_bf16(d_tmem, ad_hi, bd_hi, p.idesc, 1);
+                const uint64_t a_hi = ta[kk * 2] + a16, a_lo = ta[kk * 2 + 1] + a16;
+                const uint64_t b_hi = bdesc[kk * 2] + b16, b_lo = bdesc[kk * 2 + 1] + b16;
+                mma_bf16(d_tmem, a_lo, b_hi, idesc, accumulate);
+                mma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
+                mma_bf16(d_tmem, a_hi, b_hi, idesc, 1);
                 accumulate = 1;
               }
-            } else {
+            } else if (x3) {    // tf32 pairs, K = 8
 #pragma unroll
-            for (int kk = 0; kk < KC / 8; ++kk) {
-              const uint32_t b_addr = b_base + (uint32_t)kk * 2u * b_lbo;
-              uint64_t ad, ad_lo = 0;
-              if (p.a_sw128) {
-                const uint32_t a_addr = a_base + tp.a_off + (uint32_t)kk * 32u;
-                ad = make_desc_sw128(a_addr, tp.sbo, 0u);
-                ad_lo = make_desc_sw128(a_addr + p.slab_bytes, tp.sbo, 0u);
-              } else {
-                ad = make_desc(a_base + tp.a_off + (uint32_t)kk * 2u * tp.lbo, tp.lbo, tp.sbo);
-              }
-              const uint64_t bd = make_desc(b_addr, b_lbo, b_sbo);
-              if (p.x3) {   // small terms first, then the leading one
-                mma_tf32(d_tmem, ad_lo, bd, p.idesc, accumulate);
-                mma_tf32(d_tmem, ad, make_desc(b_addr + (uint32_t)p.BN * 128u, b_lbo, b_sbo), p.idesc, 1);
+              for (int kk = 0; kk < KC / 8; ++kk) {
+                const uint64_t a_hi = ta[kk * 2] + a16, a_lo = ta[kk * 2 + 1] + a16;
+                const uint64_t b_hi = bdesc[kk * 2] + b16, b_lo = bdesc[kk * 2 + 1] + b16;
+                mma_tf32(d_tmem, a_lo, b_hi, idesc, accumulate);
+                mma_tf32(d_tmem, a_hi, b_lo, idesc, 1);
+                mma_tf32(d_tmem, a_hi, b_hi, idesc, 1);
                 accumulate = 1;
               }
-              mma_tf32(d_tmem, ad, bd, p.idesc, accumulate);
-              accumulate = 1;
+            } else {            // one tf32 product
+#pragma unroll
+              for (int kk = 0; kk < KC / 8; ++kk) {
+                mma_tf32(d_tmem, ta[kk * 2] + a16, bdesc[kk * 2] + b16, idesc, accumulate);
+                accumulate = 1;
+              }
             }
-            }
-            mma_commit(&emptyB[sb]);
+            if (!b_res) mma_commit(&emptyB[sb]);
+          }
+          accumulate = 1;
+          if (!b_res) {
             if (++sb == p.SB) { sb = 0; phb ^= 1u; }
           }
-          mma_commit(&emptyA[sa]);
-          if (++sa == p.SA) { sa = 0; pha ^= 1u; }
         }
-        mma_commit(&tfull[acc]);
+        if (leader) mma_commit(&emptyA[sa]);
+        if (++sa == p.SA) { sa = 0; pha ^= 1u; }
       }
+      if (leader) mma_commit(&tfull[acc]);
     }
   } else if (warp >= XF_WARP0) {
     // ===== tf32x3: split every landed slab into hi = trunc_tf32(x) (in place) and lo = x - hi (second slab) =====
@@ -292,12 +330,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
               const float f[8] = {v[2 * m].x, v[2 * m].y, v[2 * m].z, v[2 * m].w, v[2 * m + 1].x, v[2 * m + 1].y, v[2 * m + 1].z, v[2 * m + 1].w};
               uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * e]), h1 = __float2bfloat16_rn(f[2 * e + 1]);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * e] - __bfloat162float(h0));
-                const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * e + 1] - __bfloat162float(h1));
-                hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              for (int e = 0; e < 4; ++e) {      // packed conversions: one cvt.rn.bf16x2.f32 per pair
+                hi[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+                const float h0 = __uint_as_float(hi[e] << 16), h1 = __uint_as_float(hi[e] & 0xffff0000u);
+                lo[e] = pack_bf16x2(f[2 * e] - h0, f[2 * e + 1] - h1);
               }
               *reinterpret_cast<uint4*>(row + ((m ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4*>(row + (((4 + m) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -340,11 +376,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     const int ly = row >> 3, lx = row & 7;
     const bool do_stats = p.stat_groups > 0;
     const int nj = p.BN / 32;
+    const bool narrow = nj == 1;                  // 32-channel layers: statistics stay per thread until the group ends
     float rs[8], rq[8];                           // this lane's running sum / sum of squares of channel j*32 + lane
 #pragma unroll
     for (int j = 0; j < 8; ++j) rs[j] = rq[j] = 0.f;
+    float ps[32], pq[32];                         // narrow: this thread's (= pixel row's) running sums per channel
+#pragma unroll
+    for (int i = 0; i < 32; ++i) ps[i] = pq[i] = 0.f;
     int cur_group = -1, cur_nt = -1;
     auto flush = [&]() {
+      if (narrow) {                               // one transposing reduction per group instead of one per tile
+        transpose_reduce32(ps, lane);
+        transpose_reduce32(pq, lane);
+        rs[0] = ps[0]; rq[0] = pq[0];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ps[i] = pq[i] = 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int ch = cur_nt * p.BN + j * 32 + lane;
@@ -379,6 +426,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         if (j >= nj) break;
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + j * 32), v);
+        if (j == nj - 1) {                        // the accumulator is in registers: hand it back to the MMA warp now
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
         const int ch0 = nt * p.BN + j * 32;
         if (p.bias != nullptr) {
 #pragma unroll
@@ -391,21 +443,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
             if (ch0 + i < p.Cout) *reinterpret_cast<float4*>(optr + j * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
         if (do_stats) {
-          float s2[32];
+          if (narrow) {
+            if (valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] = valid ? v[i] : 0.f;
-            s2[i] = v[i] * v[i];
+              for (int i = 0; i < 32; ++i) {
+                ps[i] += v[i];
+                pq[i] = fmaf(v[i], v[i], pq[i]);
+              }
+            }
+          } else {
+            float s2[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              v[i] = valid ? v[i] : 0.f;
+              s2[i] = v[i] * v[i];
+            }
+            transpose_reduce32(v, lane);
+            transpose_reduce32(s2, lane);
+            rs[j] += v[0];
+            rq[j] += s2[0];
           }
-          transpose_reduce32(v, lane);
-          transpose_reduce32(s2, lane);
-          rs[j] += v[0];
-          rq[j] += s2[0];
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
     }
     if (do_stats && cur_group >= 0) flush();
   }
@@ -577,19 +636,28 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   p.btile_bytes = (uint32_t)p.BN * KC * 4 * (p.x3 ? 2u : 1u);      // bf16 pairs: 2 x 2 bytes per element = the fp32 size
   p.idesc = p.bx3 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
   // pipeline depths under the 227 KB shared-memory limit
-  const size_t fixed = 1024 /*alignment slack*/ + 64 * 8 + 16;
+  const size_t fixed = 1024 /*alignment slack*/ + 66 * 8 + (MAX_TAP * 4 * 2 + 8) * 8;   // barriers + tmem slot + descriptor tables
   const size_t budget = 227 * 1024;
   int SA = 3, SB = 4;
   VIAI_REQUIRE(3 * SA + 2 * SB + 4 <= 64, "conv2d_tc: barrier area");
   auto need = [&](int a, int b) { return fixed + (size_t)a * p.slab_bytes * (p.x3 ? 2 : 1) + (size_t)b * p.btile_bytes; };
-  while (need(SA, SB) > budget && SB > 2) --SB;
-  while (need(SA, SB) > budget && SA > 2) --SA;
-  while (need(SA, SB) > budget && SB > 1) --SB;
-  while (need(SA, SB) > budget && SA > 1) --SA;
-  VIAI_REQUIRE(need(SA, SB) <= budget, "conv2d_tc: tile does not fit in shared memory (slab %u B, weight tile %u B)", p.slab_bytes,
-               p.btile_bytes);
-  p.SA = SA; p.SB = SB;
-  size_t smem = need(SA, SB);
+  // resident weights when the whole packed tensor (one cout tile) fits beside >= 2 activation stages
+  const int nB_all = ntap * p.nchunks;
+  if (p.ntilesN == 1 && !(flags & 16) && (size_t)nB_all * p.btile_bytes <= 160 * 1024 && need(2, nB_all) <= budget &&
+      (size_t)nB_all * p.btile_bytes < (1u << 20)) {
+    p.b_res = 1;
+    while (need(SA, nB_all) > budget) --SA;
+    p.SA = SA; p.SB = 1; p.nB = nB_all;
+  } else {
+    while (need(SA, SB) > budget && SB > 2) --SB;
+    while (need(SA, SB) > budget && SA > 2) --SA;
+    while (need(SA, SB) > budget && SB > 1) --SB;
+    while (need(SA, SB) > budget && SA > 1) --SA;
+    VIAI_REQUIRE(need(SA, SB) <= budget, "conv2d_tc: tile does not fit in shared memory (slab %u B, weight tile %u B)", p.slab_bytes,
+                 p.btile_bytes);
+    p.SA = SA; p.SB = SB; p.nB = SB;
+  }
+  size_t smem = need(p.SA, p.nB);
   if (smem < 120 * 1024) smem = 120 * 1024;   // force one CTA per SM (each CTA may allocate up to all 512 TMEM columns)
   static bool attr_set = false;
   if (!attr_set) {
