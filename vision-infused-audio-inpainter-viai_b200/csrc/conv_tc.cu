@@ -17,6 +17,7 @@
 //   * the transposed gather (ConvTranspose2d forward, Conv2d data gradient) runs one launch per output parity class, each
 //     a unit-stride convolution over the tap subset that class touches, writing its outputs with the class stride;
 //   * the weight operand of (tap, slab, cout tile) is one contiguous pre-packed block fetched by a single cp.async.bulk.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 using namespace viai;
@@ -106,6 +107,10 @@ struct TcParams {
   int32_t bx3;           // 1: the same 3-term product on bf16 pairs (x = hi + lo, both bf16): kind::f16 MMAs at twice the tf32
                          //    rate; the fp32 slab is split IN PLACE into [hi: 32 x bf16 | lo: 32 x bf16] per 128-byte pixel row
   int32_t a_sw128;       // 1: activation patch stored as dense 128-byte pixel rows under the 128-byte swizzle (rank-4 TMA)
+  // Shared-memory matrix descriptors relative to a stage / weight tile, built on the host: they live in the constant bank,
+  // so the MMA issuer fetches them with uniform loads and issuing one MMA costs two 64-bit adds.
+  uint64_t tabA[MAX_TAP * 4 * 2];   // [tap][K step][part: 0 = hi / only, 1 = lo]
+  uint64_t tabB[4 * 2];             // [K step][part]
 };
 
 __device__ __forceinline__ void transpose_reduce32(float (&v)[32], int lane) {
@@ -122,11 +127,13 @@ __device__ __forceinline__ void transpose_reduce32(float (&v)[32], int lane) {
   }
 }
 
+// MODE: 0 = one tf32 product, 1 = 3-term tf32, 2 = 3-term bf16 pairs.  BRES: weights resident in shared memory.
+template <int MODE, bool BRES>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzled TMA destinations need 1 KB alignment
   uint8_t* slabA = smem;
-  const uint32_t a_stage = p.slab_bytes * (p.x3 ? 2u : 1u);     // [raw / hi slab][lo slab]
+  const uint32_t a_stage = p.slab_bytes * (MODE == 1 ? 2u : 1u);     // [raw / hi slab][lo slab]
   uint8_t* tileB = slabA + (size_t)p.SA * a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tileB + (size_t)p.nB * p.btile_bytes);
   uint64_t* fullA = bars;
@@ -137,11 +144,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   uint64_t* tfull = emptyB + p.SB;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint64_t* tabA = reinterpret_cast<uint64_t*>(bars + 66);         // [tap][K step][part] A descriptors relative to a stage
-  uint64_t* tabB = tabA + MAX_TAP * 4 * 2;                          // [K step][part] B descriptors relative to a weight tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = (2 * p.BN <= 32) ? 32u : (2 * p.BN <= 64) ? 64u : (2 * p.BN <= 128) ? 128u : (2 * p.BN <= 256) ? 256u : 512u;
+  const int acc_cols = 2 * p.BN;                // two accumulator sets (MMA of tile i+1 overlaps the epilogue of tile i)
+  const uint32_t tmem_cols = (acc_cols <= 32) ? 32u : (acc_cols <= 64) ? 64u : (acc_cols <= 128) ? 128u : (acc_cols <= 256) ? 256u : 512u;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); mbar_init(&loA[i], 128); }
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===== weight tile producer =====
-    if (lane == 0 && p.b_res) {
+    if (lane == 0 && BRES) {
       // resident weights: every (slab, tap) tile is fetched once, all completing on fullB[0]
       const size_t btile_floats = p.btile_bytes / 4;
       mbar_expect_tx(&fullB[0], (uint32_t)p.nB * p.btile_bytes);
@@ -216,35 +222,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     }
   } else if (warp == 2) {
     // ===== MMA issuer =====
-    // The whole warp walks the pipeline (all lanes poll the barriers), one elected lane issues.  Every shared-memory
-    // descriptor is precomputed once, relative to its stage, in two small tables: issuing an MMA is two 64-bit adds.  (With
-    // 32-channel layers an MMA is ~16 tensor cycles; the previous per-MMA descriptor arithmetic under a divergent
-    // `lane == 0` branch cost ~140 cycles per MMA and bounded those layers.)
-    const int bx3 = p.bx3, x3 = p.x3, b_res = p.b_res;
-    const int KK = bx3 ? KC / 16 : KC / 8;
-    const uint32_t b_lbo = (uint32_t)p.BN * 16u, b_sbo = 128u;
-    for (int i = lane; i < p.ntap * KK * 2; i += 32) {
-      const int part = i & 1, kk = (i >> 1) % KK, t = (i >> 1) / KK;
-      const TcTap& tp = p.tap[t];
-      uint64_t d;
-      if (p.a_sw128) d = make_desc_sw128(tp.a_off + (uint32_t)kk * 32u + (part ? (bx3 ? 64u : p.slab_bytes) : 0u), tp.sbo, 0u);
-      else d = make_desc(tp.a_off + (uint32_t)kk * 2u * tp.lbo, tp.lbo, tp.sbo);
-      tabA[i] = d;
-    }
-    if (lane < KK * 2) {
-      const int part = lane & 1, kk = lane >> 1;
-      tabB[lane] = make_desc((uint32_t)kk * 2u * b_lbo + (part ? (uint32_t)p.BN * (bx3 ? 64u : 128u) : 0u), b_lbo, b_sbo);
-    }
-    __syncwarp();
-    uint64_t bdesc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) bdesc[i] = (i < KK * 2) ? tabB[i] : 0ull;
+    // The whole warp walks the pipeline (all lanes poll the barriers), one elected lane issues.  Everything the issue loop
+    // needs is either a template constant or sits in the constant bank (descriptor tables built by the host), so that the
+    // per-tap work is a handful of uniform-datapath instructions: with 32-channel layers an MMA is only ~16 tensor cycles and
+    // the issue loop, not the tensor pipe, bounds the kernel.
+    constexpr int KK = (MODE == 2) ? KC / 16 : KC / 8;
     const bool leader = elect_one();
     const uint32_t idesc = p.idesc;
+    const int ntap = p.ntap, nchunks = p.nchunks;
+    const uint32_t btile16 = p.btile_bytes >> 4;
+    const uint32_t tileB16 = smem_u32(tileB) >> 4;
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
     int it = 0;
-    if (b_res) {
+    if (BRES) {
       mbar_wait(&fullB[0], 0);
       tc_fence_after();
     }
@@ -254,50 +245,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
       uint32_t accumulate = 0;
-      for (int c = 0; c < p.nchunks; ++c) {
+      uint32_t bres16 = tileB16;                      // resident weights: tiles are stored in (slab, tap) order
+      for (int c = 0; c < nchunks; ++c) {
         mbar_wait(&fullA[sa], pha);
-        if (x3 | bx3) mbar_wait(&loA[sa], pha);
+        if (MODE != 0) mbar_wait(&loA[sa], pha);
         tc_fence_after();
         const uint64_t a16 = (uint64_t)(smem_u32(slabA + (size_t)sa * a_stage) >> 4);
-        for (int t = 0; t < p.ntap; ++t) {
-          if (!b_res) {
+        for (int t = 0; t < ntap; ++t) {
+          uint64_t b16;
+          if (BRES) {
+            b16 = bres16;
+            bres16 += btile16;
+          } else {
             mbar_wait(&fullB[sb], phb);
             tc_fence_after();
+            b16 = tileB16 + (uint32_t)sb * btile16;
           }
-          const uint64_t b16 = (uint64_t)(smem_u32(tileB + (size_t)(b_res ? c * p.ntap + t : sb) * p.btile_bytes) >> 4);
           if (leader) {
-            const uint64_t* ta = tabA + t * KK * 2;
-            if (bx3) {          // bf16 pairs, K = 16: small terms first, then the leading one
+            const uint64_t* ta = p.tabA + t * (KK * 2);
 #pragma unroll
-              for (int kk = 0; kk < KC / 16; ++kk) {
+            for (int kk = 0; kk < KK; ++kk) {
+              if (MODE == 0) {
+                mma_tf32(d_tmem, ta[kk * 2] + a16, p.tabB[kk * 2] + b16, idesc, accumulate | (uint32_t)(kk > 0));
+              } else {        // small terms first, then the leading one
                 const uint64_t a_hi = ta[kk * 2] + a16, a_lo = ta[kk * 2 + 1] + a16;
-                const uint64_t b_hi = bdesc[kk * 2] + b16, b_lo = bdesc[kk * 2 + 1] + b16;
-                mma_bf16(d_tmem, a_lo, b_hi, idesc, accumulate);
-                mma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
-                mma_bf16(d_tmem, a_hi, b_hi, idesc, 1);
-                accumulate = 1;
-              }
-            } else if (x3) {    // tf32 pairs, K = 8
-#pragma unroll
-              for (int kk = 0; kk < KC / 8; ++kk) {
-                const uint64_t a_hi = ta[kk * 2] + a16, a_lo = ta[kk * 2 + 1] + a16;
-                const uint64_t b_hi = bdesc[kk * 2] + b16, b_lo = bdesc[kk * 2 + 1] + b16;
-                mma_tf32(d_tmem, a_lo, b_hi, idesc, accumulate);
-                mma_tf32(d_tmem, a_hi, b_lo, idesc, 1);
-                mma_tf32(d_tmem, a_hi, b_hi, idesc, 1);
-                accumulate = 1;
-              }
-            } else {            // one tf32 product
-#pragma unroll
-              for (int kk = 0; kk < KC / 8; ++kk) {
-                mma_tf32(d_tmem, ta[kk * 2] + a16, bdesc[kk * 2] + b16, idesc, accumulate);
-                accumulate = 1;
+                const uint64_t b_hi = p.tabB[kk * 2] + b16, b_lo = p.tabB[kk * 2 + 1] + b16;
+                if (MODE == 2) {
+                  mma_bf16(d_tmem, a_lo, b_hi, idesc, accumulate | (uint32_t)(kk > 0));
+                  mma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
+                  mma_bf16(d_tmem, a_hi, b_hi, idesc, 1);
+                } else {
+                  mma_tf32(d_tmem, a_lo, b_hi, idesc, accumulate | (uint32_t)(kk > 0));
+                  mma_tf32(d_tmem, a_hi, b_lo, idesc, 1);
+                  mma_tf32(d_tmem, a_hi, b_hi, idesc, 1);
+                }
               }
             }
-            if (!b_res) mma_commit(&emptyB[sb]);
+            if (!BRES) mma_commit(&emptyB[sb]);
           }
           accumulate = 1;
-          if (!b_res) {
+          if (!BRES) {
             if (++sb == p.SB) { sb = 0; phb ^= 1u; }
           }
         }
@@ -308,7 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     }
   } else if (warp >= XF_WARP0) {
     // ===== tf32x3: split every landed slab into hi = trunc_tf32(x) (in place) and lo = x - hi (second slab) =====
-    if (p.bx3) {
+    if (MODE == 2) {
       // bf16 pair split, one thread per 128-byte pixel row (private to the thread, so the rewrite is in place): logical
       // 16-byte chunk j of row r sits at physical chunk j ^ (r & 7) under the 128-byte swizzle, before and after.
       const int tid = threadIdx.x - XF_WARP0 * 32;
@@ -344,7 +331,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
           if (++sa == p.SA) { sa = 0; pha ^= 1u; }
         }
       }
-    } else if (p.x3) {
+    } else if (MODE == 1) {
       const int tid = threadIdx.x - XF_WARP0 * 32;
       int sa = 0;
       uint32_t pha = 0;
@@ -409,8 +396,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       const int tx = rest % p.tilesX; rest /= p.tilesX;
       const int ty = rest % p.tilesY;
       const int n = rest / p.tilesY;
-      const int y = ty * TH + ly, x = tx * TW + lx;
-      const bool valid = (y < p.Hv) && (x < p.Wv);
+      const int y = ty * TH + ly;
       const int acc = it & 1;
       if (do_stats) {
         const int grp = (p.stat_groups > 1) ? n : 0;
@@ -420,48 +406,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       }
       mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
-      float* optr = p.out + p.o_base + (int64_t)n * p.o_sn + (int64_t)y * p.o_sy + (int64_t)x * p.o_sx + (int64_t)nt * p.BN;
+      {
+        const int x = tx * TW + lx;
+        const bool valid = (y < p.Hv) && (x < p.Wv);
+        float* optr = p.out + p.o_base + (int64_t)n * p.o_sn + (int64_t)y * p.o_sy + (int64_t)x * p.o_sx + (int64_t)nt * p.BN;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j >= nj) break;
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + j * 32), v);
-        if (j == nj - 1) {                        // the accumulator is in registers: hand it back to the MMA warp now
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
-        }
-        const int ch0 = nt * p.BN + j * 32;
-        if (p.bias != nullptr) {
+        for (int j = 0; j < 8; ++j) {
+          if (j >= nj) break;
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + j * 32), v);
+          if (j == nj - 1) {                        // the accumulator is in registers: hand it back to the MMA warp now
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          const int ch0 = nt * p.BN + j * 32;
+          if (p.bias != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (ch0 + i < p.Cout) v[i] += __ldg(&p.bias[ch0 + i]);
-        }
-        if (valid) {
+            for (int i = 0; i < 32; ++i)
+              if (ch0 + i < p.Cout) v[i] += __ldg(&p.bias[ch0 + i]);
+          }
+          if (valid) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            if (ch0 + i < p.Cout) *reinterpret_cast<float4*>(optr + j * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
-        if (do_stats) {
-          if (narrow) {
-            if (valid) {
+            for (int i = 0; i < 32; i += 4)
+              if (ch0 + i < p.Cout) *reinterpret_cast<float4*>(optr + j * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+          if (do_stats) {
+            if (narrow) {
+              if (valid) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  ps[i] += v[i];
+                  pq[i] = fmaf(v[i], v[i], pq[i]);
+                }
+              }
+            } else {
+              float s2[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                ps[i] += v[i];
-                pq[i] = fmaf(v[i], v[i], pq[i]);
+                v[i] = valid ? v[i] : 0.f;
+                s2[i] = v[i] * v[i];
               }
+              transpose_reduce32(v, lane);
+              transpose_reduce32(s2, lane);
+              rs[j] += v[0];
+              rq[j] += s2[0];
             }
-          } else {
-            float s2[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              v[i] = valid ? v[i] : 0.f;
-              s2[i] = v[i] * v[i];
-            }
-            transpose_reduce32(v, lane);
-            transpose_reduce32(s2, lane);
-            rs[j] += v[0];
-            rq[j] += s2[0];
           }
         }
       }
@@ -530,14 +520,32 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ src, float* __re
   }
 }
 
+// Cout tile.  Capped at 128 so that two M tiles x two accumulator sets fit the 512 TMEM columns: the weight traffic of a layer
+// does not depend on this width (it is K * Cout * pixels / M), only on the number of pixels that share a weight tile.
+inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
 inline int tc_bn(int Cout) {
+  static const int cap = env_int("VIAI_TC_BNCAP", 256);      // tuning knob: N = 128 MMAs run at ~2/3 of the N = 256 rate (measured)
   int bn = ((Cout + 31) / 32) * 32;
-  return bn > 256 ? 256 : bn;
+  return bn > cap ? cap : bn;
 }
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 inline int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
 
 struct TapSpec { int suby, subx, offy, offx, wtap; };
+
+// host copy of make_desc / make_desc_sw128 (layout: 0 = no swizzle, 2 = 128-byte swizzle; see tc_common.cuh)
+inline uint64_t host_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, int layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
 
 // Builds and launches one "virtual unit-stride convolution" (see the file header).
 int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int inC, int sub_sy, int sub_sx,
@@ -636,9 +644,12 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   p.btile_bytes = (uint32_t)p.BN * KC * 4 * (p.x3 ? 2u : 1u);      // bf16 pairs: 2 x 2 bytes per element = the fp32 size
   p.idesc = p.bx3 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
   // pipeline depths under the 227 KB shared-memory limit
-  const size_t fixed = 1024 /*alignment slack*/ + 66 * 8 + (MAX_TAP * 4 * 2 + 8) * 8;   // barriers + tmem slot + descriptor tables
+  const size_t fixed = 1024 /*alignment slack*/ + 66 * 8;   // barriers + tmem slot
   const size_t budget = 227 * 1024;
-  int SA = 3, SB = 4;
+  // Activation stages: the thin layers are HBM-bound streams whose only memory-level parallelism is the TMA loads in flight
+  // (a 24 KB slab per stage and CTA): with 3 stages 148 CTAs keep < 10 MB in flight, half of what ~6.5 TB/s x ~2 us needs.
+  static const int sa_max = env_int("VIAI_TC_SA", 4);
+  int SA = sa_max, SB = 4;
   VIAI_REQUIRE(3 * SA + 2 * SB + 4 <= 64, "conv2d_tc: barrier area");
   auto need = [&](int a, int b) { return fixed + (size_t)a * p.slab_bytes * (p.x3 ? 2 : 1) + (size_t)b * p.btile_bytes; };
   // resident weights when the whole packed tensor (one cout tile) fits beside >= 2 activation stages
@@ -649,6 +660,7 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
     while (need(SA, nB_all) > budget) --SA;
     p.SA = SA; p.SB = 1; p.nB = nB_all;
   } else {
+    while (need(SA, SB) > budget && SA > 3) --SA;
     while (need(SA, SB) > budget && SB > 2) --SB;
     while (need(SA, SB) > budget && SA > 2) --SA;
     while (need(SA, SB) > budget && SB > 1) --SB;
@@ -659,14 +671,38 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   }
   size_t smem = need(p.SA, p.nB);
   if (smem < 120 * 1024) smem = 120 * 1024;   // force one CTA per SM (each CTA may allocate up to all 512 TMEM columns)
-  static bool attr_set = false;
-  if (!attr_set) {
-    VIAI_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  // descriptor tables (addresses relative to the stage / weight tile; the kernel adds the base >> 4 to the low word)
+  {
+    const int KK = p.bx3 ? KC / 16 : KC / 8;
+    const uint32_t b_lbo = (uint32_t)p.BN * 16u, b_sbo = 128u;
+    for (int t = 0; t < ntap; ++t)
+      for (int kk = 0; kk < KK; ++kk)
+        for (int part = 0; part < 2; ++part) {
+          const TcTap& tp = p.tap[t];
+          uint64_t d;
+          if (p.a_sw128) d = host_desc(tp.a_off + (uint32_t)kk * 32u + (part ? (p.bx3 ? 64u : p.slab_bytes) : 0u), 16u, tp.sbo, 2);
+          else d = host_desc(tp.a_off + (uint32_t)kk * 2u * tp.lbo, tp.lbo, tp.sbo, 0);
+          p.tabA[(t * KK + kk) * 2 + part] = d;
+        }
+    for (int kk = 0; kk < KK; ++kk)
+      for (int part = 0; part < 2; ++part)
+        p.tabB[kk * 2 + part] = host_desc((uint32_t)kk * 2u * b_lbo + (part ? (uint32_t)p.BN * (p.bx3 ? 64u : 128u) : 0u), b_lbo, b_sbo, 0);
   }
   if (p.ntiles == 0) return VIAI_OK;
   const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
-  conv_tc_kernel<<<grid, NTHREADS, smem, stream>>>(p);
+  const int mode = p.bx3 ? 2 : p.x3 ? 1 : 0;
+#define VIAI_TC_LAUNCH(M, R)                                                                                            \
+  do {                                                                                                                  \
+    static bool attr_done = false;                                                                                      \
+    if (!attr_done) {                                                                                                   \
+      VIAI_CUDA(cudaFuncSetAttribute(conv_tc_kernel<M, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));    \
+      attr_done = true;                                                                                                 \
+    }                                                                                                                   \
+    conv_tc_kernel<M, R><<<grid, NTHREADS, smem, stream>>>(p);                                                          \
+  } while (0)
+  if (p.b_res) { if (mode == 2) VIAI_TC_LAUNCH(2, true); else if (mode == 1) VIAI_TC_LAUNCH(1, true); else VIAI_TC_LAUNCH(0, true); }
+  else { if (mode == 2) VIAI_TC_LAUNCH(2, false); else if (mode == 1) VIAI_TC_LAUNCH(1, false); else VIAI_TC_LAUNCH(0, false); }
+#undef VIAI_TC_LAUNCH
   VIAI_LAUNCHED();
   return VIAI_OK;
 }

@@ -373,38 +373,35 @@ __global__ void zero_dw_kernel(float* dw, int A, int B, int R, int S, int64_t sa
 
 // U: (N,Hout,Wout,A), G: (N,Hin,Win,B); WIDE_U: B == 1 (the wide tensor is U), else A == 1 (the wide tensor is G).
 // The loop runs over the pixels of the WIDE tensor (each read once, 128-bit); the thin tensor supplies one scalar per tap.
-template <bool WIDE_U>
+// R_ x S_ are compile-time (3x3, 1x4; R_ == 0: generic, up to WG_MAXTAP runtime taps) so that the tap loops unroll into
+// straight-line code with the per-tap offsets folded into immediates.
+template <bool WIDE_U, int R_, int S_>
 __global__ void __launch_bounds__(256) wgrad_thin_kernel(viai_conv_geom g, const float* __restrict__ U, const float* __restrict__ G,
                                                          float* __restrict__ ws, int pix_per_block) {
   extern __shared__ float red[];   // [planes][taps][C]
+  constexpr bool FIXED = R_ > 0;
+  constexpr int NT = FIXED ? R_ * S_ : WG_MAXTAP;
   const int C = WIDE_U ? g.Cout : g.Cin;
   const int c4n = C >> 2;
   const int planes = blockDim.x / c4n;
   const int cv = threadIdx.x % c4n, pl = threadIdx.x / c4n;
-  const int taps = g.R * g.S;
+  const int taps = FIXED ? NT : g.R * g.S;
+  const int Sr = FIXED ? S_ : g.S;
   const int Hw = WIDE_U ? g.Hout : g.Hin, Ww = WIDE_U ? g.Wout : g.Win;       // wide tensor extent
-  float4 acc[WG_MAXTAP];
+  float4 acc[NT];
 #pragma unroll
-  for (int t = 0; t < WG_MAXTAP; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < NT; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int M = g.N * Hw * Ww;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, M);
   const float4* wide = reinterpret_cast<const float4*>(WIDE_U ? U : G);
   const float* thin = WIDE_U ? G : U;
   if (pl < planes) {
-    // per-tap offsets, decoded once:  WIDE_U: thin(Y, X) = (y*sh + oy, x*sw + ox);  else: thin = ((y + oy)/sh, (x + ox)/sw)
-    int oy[WG_MAXTAP], ox[WG_MAXTAP];
-#pragma unroll
-    for (int t = 0; t < WG_MAXTAP; ++t) {
-      const int r = t / g.S, s = t - r * g.S;
-      oy[t] = WIDE_U ? r - g.pad_h : g.pad_h - r;
-      ox[t] = WIDE_U ? s - g.pad_w : g.pad_w - s;
-    }
     const bool unit = g.stride_h == 1 && g.stride_w == 1;
     const int Ht = WIDE_U ? g.Hin : g.Hout, Wt = WIDE_U ? g.Win : g.Wout;       // thin tensor extent
     int m = p0 + pl;
     int x = m % Ww, tq = m / Ww;
     int y = tq % Hw, n = tq / Hw;
-    constexpr int UN = 4;                                 // wide pixels in flight per thread
+    constexpr int UN = 2;                                 // wide pixels in flight per thread
     while (m < p1) {
       float4 w4[UN];
 #pragma unroll
@@ -416,19 +413,17 @@ __global__ void __launch_bounds__(256) wgrad_thin_kernel(viai_conv_geom g, const
       for (int u = 0; u < UN; ++u) {
         if (m + u * planes < p1) {
           const float* tbase = thin + (int64_t)n * Ht * Wt;
+          // WIDE_U: thin(Y, X) = (y*sh - ph + r, x*sw - pw + s);  else: thin = ((y + ph - r)/sh, (x + pw - s)/sw) when divisible
+          const int by = WIDE_U ? y * g.stride_h - g.pad_h : y + g.pad_h;
+          const int bx = WIDE_U ? x * g.stride_w - g.pad_w : x + g.pad_w;
 #pragma unroll
-          for (int t = 0; t < WG_MAXTAP; ++t) {
-            if (t < taps) {
-              int Y, X;
-              bool ok;
-              if (WIDE_U) {
-                Y = y * g.stride_h + oy[t]; X = x * g.stride_w + ox[t];
-                ok = true;
-              } else if (unit) {
-                Y = y + oy[t]; X = x + ox[t];
-                ok = true;
-              } else {
-                const int ty = y + oy[t], tx = x + ox[t];
+          for (int t = 0; t < NT; ++t) {
+            if (FIXED || t < taps) {
+              const int r = FIXED ? t / S_ : t / Sr, s = FIXED ? t % S_ : t - r * Sr;
+              int Y = WIDE_U ? by + r : by - r, X = WIDE_U ? bx + s : bx - s;
+              bool ok = true;
+              if (!WIDE_U && !unit) {
+                const int ty = Y, tx = X;
                 Y = ty / g.stride_h; X = tx / g.stride_w;
                 ok = ty >= 0 && tx >= 0 && Y * g.stride_h == ty && X * g.stride_w == tx;
               }
@@ -445,8 +440,8 @@ __global__ void __launch_bounds__(256) wgrad_thin_kernel(viai_conv_geom g, const
       m += UN * planes;
     }
 #pragma unroll
-    for (int t = 0; t < WG_MAXTAP; ++t)
-      if (t < taps) *reinterpret_cast<float4*>(red + ((size_t)(pl * taps + t) * C) + cv * 4) = acc[t];
+    for (int t = 0; t < NT; ++t)
+      if (FIXED || t < taps) *reinterpret_cast<float4*>(red + ((size_t)(pl * taps + t) * C) + cv * 4) = acc[t];
   }
   __syncthreads();
   // the block's partial sums go to its own workspace row (no atomics: hundreds of CTAs adding onto the same few hundred
@@ -574,15 +569,20 @@ extern "C" int viai_conv2d_wgrad_thin(const viai_conv_geom* gp, const float* U, 
     return VIAI_OK;
   }
   const size_t smem = sizeof(float) * (size_t)planes * taps * C;
-  static bool attr = false;
-  if (!attr) {
-    VIAI_CUDA(cudaFuncSetAttribute(wgrad_thin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    VIAI_CUDA(cudaFuncSetAttribute(wgrad_thin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr = true;
-  }
   VIAI_REQUIRE(smem <= 64 * 1024, "conv2d_wgrad_thin: reduction buffer too large");
-  if (wide_u) wgrad_thin_kernel<true><<<(unsigned)blocks, 256, smem, st>>>(g, U, G, workspace, ppb);
-  else wgrad_thin_kernel<false><<<(unsigned)blocks, 256, smem, st>>>(g, U, G, workspace, ppb);
+#define VIAI_WGT_LAUNCH(WU, RR, SS)                                                                                         \
+  do {                                                                                                                      \
+    static bool attr_done = false;                                                                                          \
+    if (!attr_done) {                                                                                                       \
+      VIAI_CUDA(cudaFuncSetAttribute(wgrad_thin_kernel<WU, RR, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
+      attr_done = true;                                                                                                     \
+    }                                                                                                                       \
+    wgrad_thin_kernel<WU, RR, SS><<<(unsigned)blocks, 256, smem, st>>>(g, U, G, workspace, ppb);                            \
+  } while (0)
+  if (g.R == 3 && g.S == 3) { if (wide_u) VIAI_WGT_LAUNCH(true, 3, 3); else VIAI_WGT_LAUNCH(false, 3, 3); }
+  else if (g.R == 1 && g.S == 4) { if (wide_u) VIAI_WGT_LAUNCH(true, 1, 4); else VIAI_WGT_LAUNCH(false, 1, 4); }
+  else { if (wide_u) VIAI_WGT_LAUNCH(true, 0, 0); else VIAI_WGT_LAUNCH(false, 0, 0); }
+#undef VIAI_WGT_LAUNCH
   VIAI_LAUNCHED();
   wgrad_thin_finish_kernel<<<(taps * C + 31) / 32, 256, 0, st>>>(workspace, (int)blocks, taps, C, g.S, wide_u ? 1 : 0, dw, sa, sb, sr, ss,
                                                                accumulate);

@@ -126,33 +126,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int st = 0;
-      uint32_t ph = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        mbar_wait(&full[st], ph);
-        tc_fence_after();
-        const uint32_t u_base = smem_u32(smem + (size_t)st * p.stage_bytes);
-        const uint32_t g_base = u_base + p.u_bytes;
+    // MMA issuer: the whole warp walks the pipeline, one elected lane issues (no per-MMA lane election loops)
+    const bool leader = elect_one();
+    int st = 0;
+    uint32_t ph = 0;
+    const uint64_t a_step = 1024u >> 4;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(&full[st], ph);
+      tc_fence_after();
+      const uint32_t u_base = smem_u32(smem + (size_t)st * p.stage_bytes);
+      const uint32_t g_base = u_base + p.u_bytes;
+      if (leader) {
+        // A: MN-major, 4 blocks of 32 channels LBO apart; B: MN-major, `len` blocks of 32 channels one pixel (128 bytes)
+        // apart = the taps of the run.  SBO (between K groups of 8) is unused: every MMA covers exactly one group.
+        const uint64_t ad0 = make_desc_sw128x32_mn(u_base, p.u_slice_bytes, 512u);
         for (int rn = 0; rn < p.nrun; ++rn) {
           const WgRun& w = p.run[rn];
           const uint32_t d_tmem = tmem_base + w.col;
-          // A: MN-major, 4 blocks of 32 channels LBO apart; B: MN-major, `len` blocks of 32 channels one pixel (128 bytes)
-          // apart = the taps of the run.  SBO (between K groups of 8) is unused: every MMA covers exactly one group.
-          uint64_t ad = make_desc_sw128x32_mn(u_base, p.u_slice_bytes, 512u);
+          uint64_t ad = ad0;
           uint64_t bd = make_desc_sw128x32_mn(g_base + w.g_off, 128u, 512u);
-          const uint64_t a_step = 1024u >> 4, b_step = w.row_pitch >> 4;
-          for (int kk = 0; kk < p.TH; ++kk) {
-            mma_tf32(d_tmem, ad, bd, w.idesc, (t > t_begin || kk > 0) ? 1u : 0u);
+          const uint64_t b_step = w.row_pitch >> 4;
+          const uint32_t idesc = w.idesc;
+          mma_tf32(d_tmem, ad, bd, idesc, (t > t_begin) ? 1u : 0u);
+          for (int kk = 1; kk < p.TH; ++kk) {
             ad += a_step;
             bd += b_step;
+            mma_tf32(d_tmem, ad, bd, idesc, 1u);
           }
         }
         mma_commit(&empty[st]);
-        if (++st == p.stages) { st = 0; ph ^= 1u; }
       }
-      mma_commit(done);
+      if (++st == p.stages) { st = 0; ph ^= 1u; }
     }
+    if (leader) mma_commit(done);
   } else {
     // epilogue: store the CTA's partial D_t blocks into its slice of the workspace
     const int q = warp & 3;

@@ -198,23 +198,37 @@ bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y, int
   }
   if (active) {
     const int64_t off = ((int64_t)g * rows_per_group) * C + cv * VEC;
-    for (int64_t r = r0 + rl; r < r1; r += L.lanes) {
-      float d[VEC], yv[VEC];
-      if (VEC == 4) {
-        float4 t = __ldg(reinterpret_cast<const float4*>(dz + off + r * C));
-        float4 u = __ldg(reinterpret_cast<const float4*>(y + off + r * C));
-        d[0] = t.x; d[1 % VEC] = t.y; d[2 % VEC] = t.z; d[3 % VEC] = t.w;
-        yv[0] = u.x; yv[1 % VEC] = u.y; yv[2 % VEC] = u.z; yv[3 % VEC] = u.w;
-      } else {
-        d[0] = __ldg(dz + off + r * C);
-        yv[0] = __ldg(y + off + r * C);
+    constexpr int UNR_R = 4;                       // rows in flight per thread
+    for (int64_t r = r0 + rl; r < r1; r += (int64_t)L.lanes * UNR_R) {
+      float d[UNR_R][VEC], yv[UNR_R][VEC];
+#pragma unroll
+      for (int u = 0; u < UNR_R; ++u) {
+        const int64_t rr = r + (int64_t)u * L.lanes;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { d[u][k] = 0.f; yv[u][k] = 0.f; }
+        if (rr < r1) {
+          if (VEC == 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(dz + off + rr * C));
+            const float4 w = __ldg(reinterpret_cast<const float4*>(y + off + rr * C));
+            d[u][0] = t.x; d[u][1 % VEC] = t.y; d[u][2 % VEC] = t.z; d[u][3 % VEC] = t.w;
+            yv[u][0] = w.x; yv[u][1 % VEC] = w.y; yv[u][2 % VEC] = w.z; yv[u][3 % VEC] = w.w;
+          } else {
+            d[u][0] = __ldg(dz + off + rr * C);
+            yv[u][0] = __ldg(y + off + rr * C);
+          }
+        }
       }
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        float gg, xh;
-        bwd_terms(d[k], yv[k], mu[k], is[k], ga[k], be[k], mean != nullptr, act, slope, gg, xh);
-        a1[k] += gg;
-        a2[k] += gg * xh;
+      for (int u = 0; u < UNR_R; ++u) {
+        if (r + (int64_t)u * L.lanes < r1) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            float gg, xh;
+            bwd_terms(d[u][k], yv[u][k], mu[k], is[k], ga[k], be[k], mean != nullptr, act, slope, gg, xh);
+            a1[k] += gg;
+            a2[k] += gg * xh;
+          }
+        }
       }
     }
   }
@@ -316,7 +330,7 @@ __global__ void rsqrt_eps_kernel(const float* var, int n, float eps, float* out)
 // per row lane
 int64_t pick_rows_per_block(int64_t rows_per_group, int groups, int C, int VEC) {
   const int lanes = make_lanes(C, VEC).lanes;
-  int64_t per_group = cdiv((int64_t)4 * kNumSMs, groups);
+  int64_t per_group = cdiv((int64_t)8 * kNumSMs, groups);
   int64_t rpb = cdiv(rows_per_group, per_group);
   if (rpb < (int64_t)lanes * 8) rpb = (int64_t)lanes * 8;
   return rpb;
