@@ -10,8 +10,13 @@ Workload at every N: BASELINE config C2 per GPU (B=32, 256x256 mel, 50% centre t
   value : whole-job frames/s with the inputs resident in HBM (CUDA-graph replay of the step), CUDA events, max over ranks
   e2e   : the same step driven through the public API with HOST (pinned) inputs: H2D copy of mel+mask and D2H read
           of the loss inside the timed region
-  roofline     : the dominant kernel (the discriminator's 256->512 3x3 convolution, 154.6 GFLOP per launch at C2)
-                 timed alone with CUDA events against the measured bf16 tensor peak
+  roofline     : the dominant kernel (the discriminator's 256->512 3x3 convolution, 154.6 GFLOP ALGORITHMIC per launch at
+                 C2; the bf16x3 forward executes 3 MMAs per MAC) timed alone with CUDA events, L2 flushed between
+                 launches, against the measured bf16 tensor peak; traffic = DRAM bytes of that launch from the committed
+                 ncu capture (profiles/)
+  wavenet      : (N=1 only) the second metric BASELINE.json names: WaveNet-vocoder synthesis samples/s (24 layers, 4 stacks,
+                 512/512/256, 16 kHz; a bounded T of the C4 workload, the loop is strictly sequential so the rate is
+                 T-independent)
   cpu_baseline : the oracle (CPU restatement of the reference, oracle/viai_oracle.py) timed on the host cores on a
                  bounded sample of the same workload
 `--impl reference` times that CPU implementation alone (all host threads) and prints the same JSON line.
@@ -65,7 +70,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -142,14 +147,39 @@ def time_dominant_kernel(torch, iters=10):
     return flops, ms
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one D.conv3 forward launch (ncu --set full, profiles/r01_conv_tc_d_conv3_fwd_ncu.csv)
+DOMINANT_KERNEL_DRAM_BYTES = 72.07e6 + 80.0e6
+
+
+def time_wavenet(torch, T=8000):
+    """WaveNet synthesis (BASELINE config C4 shapes, bounded T): samples/s of the persistent synthesis kernel."""
+    from viai_b200.wavenet_vocoder import WaveNet
+    torch.manual_seed(0)
+    m = WaveNet().cuda().eval()
+    m.make_generation_fast_()
+    c = torch.rand(1, 80, T // 160).cuda()
+    with torch.no_grad():
+        m.incremental_forward(c=c[:, :, :5], T=800)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = m.incremental_forward(c=c, T=T)
+        e1.record()
+        e1.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"metric": "WaveNet samples/sec", "value": T / ms * 1e3, "unit": "samples/s", "T": T, "ms": ms,
+            "config": "24 layers / 4 stacks, 512/512/256 channels, 80-bin local conditioning, B=1, scalar (DMoL) output",
+            "finite": bool(torch.isfinite(out).all())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="viai_b200", choices=["viai_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-wavenet", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -232,12 +262,19 @@ def main():
         flops, kms = time_dominant_kernel(torch)
         ach = flops / (kms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tc_burst"], "unit": "TFLOP/s", "frac": ach / pk["tc_burst"],
-                "traffic": None, "kernel": "conv2d fwd 256->512 3x3 (D.conv3) B=32 64x32", "peak_source": pk["src"] + " bf16 burst",
-                "ms_per_launch": kms}
+                "traffic": DOMINANT_KERNEL_DRAM_BYTES, "algorithmic_flops": flops, "executed_flops": 3 * flops,
+                "kernel": "conv2d fwd 256->512 3x3 (D.conv3) B=32 64x32, bf16x3 (3 MMAs per MAC)",
+                "peak_source": pk["src"] + " bf16 burst", "ms_per_launch": kms}
         if not args.no_cpu_baseline and world == 1:
             v, cores, cms, n = cpu_reference_run(6, 1, 4, budget_s=20.0)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "B=4 slice of the C2 batch, %d timed G+D steps of the oracle (torch CPU fp32), %.0f ms/step" % (n, cms)}
+    wn = None
+    if rank == 0 and world == 1 and not args.no_wavenet:
+        try:
+            wn = time_wavenet(torch)
+        except Exception as e:                      # the GAN line must survive a WaveNet failure
+            wn = {"error": repr(e)}
     if rank == 0:
         frames = B * WFR * world
         line = {"metric": METRIC, "value": frames / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -246,11 +283,14 @@ def main():
                 "config": {"workload": "C2: audio-only GAN train step (1 D + 1 G update), B=32 per GPU, 256x256 mel, 50% centre "
                                        "time-band mask, BatchNorm, LSGAN+100*L1, Adam",
                            "global_batch": B * world, "mel_bins": HMEL, "frames": WFR, "parallelism": "dp%d" % world,
-                           "cuda_graph": use_graph, "l2": "no flush: the step streams >5 GB of activations per replay (>> 126 MB L2)"},
+                           "cuda_graph": use_graph,
+                           "precision": "fp32 tensors; forward convolutions as 3-term bf16-pair tensor-core products (fp32 accumulate, "
+                                        "~2^-17 per product), data/weight gradients one tf32 product",
+                           "l2": "no flush: the step streams >5 GB of activations per replay (>> 126 MB L2)"},
                 "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": 2 * mel_h.numel() * 4, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches) * args.steps, "launches_per_step": int(launches),
-                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "wavenet": wn}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

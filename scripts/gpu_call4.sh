@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 ( time timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 ) > gpurun_out/pytest_gpu.log 2>&1
 ( time timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline ) > gpurun_out/bench1.log 2>&1
 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
-   python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+   python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-wavenet > gpurun_out/ncu_launch.log 2>&1
 timeout 600 ncu --set full --clock-control none -k "regex:conv_tc_kernel" --launch-skip ${SKIP:-19} --launch-count 1 -o gpurun_out/prof_one -f \
-   python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_one.log 2>&1
+   python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-wavenet > gpurun_out/ncu_one.log 2>&1
 tail -5 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/bench1.log
