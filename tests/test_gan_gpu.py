@@ -289,3 +289,82 @@ def test_full_size_properties_and_parity(size):
         a = G(E(melB), melB.shape)
         b = G(E(melB[perm]), melB.shape)
     assert H.relerr(b, a[perm]) < 1e-4
+
+
+@pytest.mark.parametrize("size,B", [(128, 4), (256, 2), (512, 1)], ids=["128", "256", "512"])
+@pytest.mark.bf16x3
+def test_freeform_masks_mixed_sizes_default_precision(size, B):
+    """BASELINE config 5: free-form (seeded random-walk stroke) masks at 128 / 256 / 512 square mels, on the library's
+    default tensor-core path.  The mask definition is ours (the reference has none; oracle.freeform_mask is pure integer
+    arithmetic), its application is bit exact, the step matches the oracle within the north star's 1e-3."""
+    IN, NN, DN, nl, OI = _mods("bn")
+    from viai_b200 import ops
+    from viai_b200.step import GanTrainer
+    assert ops.get_precision() == "bf16x3"
+    hp = OI.Inpainting_Config(cin_channels=size)
+    torch.manual_seed(7 + size)
+    tr = GanTrainer(hp, "cuda")
+    cpu = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    esd, gsd, dsd = cpu(tr.Mel_Encoder), cpu(tr.Mel_Decoder), cpu(tr.netD)
+    mel = torch.rand(B, 1, size, size)
+    mask = O.freeform_mask(mel.shape, seed=size)
+    frac = float((mask == 0).float().mean())
+    assert 0.005 < frac < 0.9 and set(mask.unique().tolist()) <= {0.0, 1.0}
+    assert torch.equal(ops.mul(mel.cuda().reshape(B, size, size, 1), mask.cuda().reshape(B, size, size, 1)).cpu().reshape(mel.shape),
+                       mel * mask)                                           # bit exact
+    want = O.gan_step(esd, gsd, dsd, mel, mask, size)
+    got = tr.train_step(mel.cuda(), mask.cuda())
+    assert H.relerr(got["fake"], want["fake"]) < 1e-3
+    for k in ("loss_D", "loss_G_GAN", "loss_L1"):
+        assert math.isclose(float(got[k]), want[k], rel_tol=2e-3), k
+
+
+@pytest.mark.parametrize("precision", ["fp32", pytest.param("bf16x3", marks=pytest.mark.bf16x3)])
+def test_vision_infused_step_matches_oracle(precision):
+    """BASELINE config 3 at the native 80-bin geometry: ResNet-18 ImageEmbedding (RGB + flow) fused at the generator
+    bottleneck through MelDecoderImage, one D + one G update; the video encoder trains with the generator."""
+    IN, NN, DN, nl, OI = _mods("bn")
+    from viai_b200 import ops
+    from viai_b200.networks.Image_Embedding import ImageEmbedding
+    from viai_b200.step import GanTrainer
+    assert ops.get_precision() == precision
+    hp = OI.Inpainting_Config(cin_channels=80)
+    torch.manual_seed(4321)
+    B, W = 1, 64
+    T = W // 4                                                    # 4 mel frames per video frame (H5 = 1)
+    ve = ImageEmbedding(hp).cuda()
+    tr = GanTrainer(hp, "cuda", decoder="MelDecoderImage", video_encoder=ve)
+    cpu = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    esd, gsd, dsd, vsd = cpu(tr.Mel_Encoder), cpu(tr.Mel_Decoder), cpu(tr.netD), cpu(ve)
+    mel = torch.rand(B, 1, 80, W)
+    mask = O.time_band_mask(mel.shape, W // 4, W // 2)
+    video = FX.normal("c3_video", (B, T, 3, 224, 224)).clamp(-1, 1)
+    flow = FX.normal("c3_flow", (B, T, 2, 224, 224)).clamp(-1, 1)
+
+    def oracle(dt):
+        to = lambda sd: {k: (v.to(dt) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+        v_leaf = {k: (t.clone().requires_grad_(True) if t.is_floating_point() and "running" not in k else t.clone())
+                  for k, t in to(vsd).items()}
+        vnet = O.image_embedding_forward(v_leaf, video.to(dt), flow.to(dt))
+        r = O.gan_step(to(esd), to(gsd), to(dsd), mel.to(dt), mask.to(dt), 80, variant="MelDecoderImage", video_net=vnet)
+        r["grads_V"] = {k: t.grad for k, t in v_leaf.items() if t.requires_grad and t.grad is not None}
+        return r
+
+    want, want64 = oracle(torch.float32), oracle(torch.float64)
+    got = tr.train_step(mel.cuda(), mask.cuda(), video.cuda(), flow.cuda())
+    assert H.relerr(got["fake"], want["fake"]) < 1e-3
+    for k in ("loss_D", "loss_G_GAN", "loss_L1"):
+        assert math.isclose(float(got[k]), want[k], rel_tol=2e-3), k
+    ps = dict(ve.named_parameters())
+    gotV = {k: ps[k]._viai_grad for k in want64["grads_V"]}
+    # the video encoder's gradient passes 20 train-mode BatchNorm layers over 16 frames: bound it by the reference's own
+    # fp32-vs-fp64 envelope (see viai_test_helpers)
+    l2_ref, cos_ref, _ = H.whole_net_metrics({k: v for k, v in want["grads_V"].items()}, want64["grads_V"])
+    l2, cos, _ = H.whole_net_metrics(gotV, want64["grads_V"])
+    print("video-encoder grads: cuda vs fp64 L2 %.3e cos %.6f | fp32 oracle vs fp64 L2 %.3e cos %.6f" % (l2, cos, l2_ref, cos_ref))
+    assert l2 <= max(5e-2, 4 * l2_ref) and cos >= 0.998
+    for mod, gk in ((tr.Mel_Encoder, "grads_E"), (tr.Mel_Decoder, "grads_Dec"), (tr.netD, "grads_D")):
+        p2 = dict(mod.named_parameters())
+        H.assert_e2e_grads({k: p2[k]._viai_grad for k in want64[gk]}, want64[gk], gk)
+    # bn_1 of the video encoder never reaches the output (reference :123): its gradient slot stays zero
+    assert float(ps["bn_1.weight"]._viai_grad.abs().max()) == 0.0

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   uint64_t* tfull = emptyB + p.SB;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* bias_s = reinterpret_cast<float*>(bars + 66);               // bias padded to ntilesN * BN floats (zeros when absent)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int acc_cols = 2 * p.BN;                // two accumulator sets (MMA of tile i+1 overlaps the epilogue of tile i)
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     fence_barrier_init();
     for (int i = 0; i < p.nsub; ++i) prefetch_tmap(&p.mapA[i]);
   }
+  for (int i = threadIdx.x; i < p.ntilesN * p.BN; i += NTHREADS) bias_s[i] = (p.bias != nullptr && i < p.Cout) ? __ldg(&p.bias[i]) : 0.f;
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -315,12 +317,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
               const float f[8] = {v[2 * m].x, v[2 * m].y, v[2 * m].z, v[2 * m].w, v[2 * m + 1].x, v[2 * m + 1].y, v[2 * m + 1].z, v[2 * m + 1].w};
+              // hi = x truncated to bf16 (one mask; whatever truncation drops lands in lo, which is x - hi EXACTLY), lo rounded
+              // to nearest: one cvt.rn.bf16x2 per pair instead of two, and the error of hi + lo stays ~2^-17 |x|, unbiased.
               uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {      // packed conversions: one cvt.rn.bf16x2.f32 per pair
-                hi[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
-                const float h0 = __uint_as_float(hi[e] << 16), h1 = __uint_as_float(hi[e] & 0xffff0000u);
-                lo[e] = pack_bf16x2(f[2 * e] - h0, f[2 * e + 1] - h1);
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t b0 = __float_as_uint(f[2 * e]), b1 = __float_as_uint(f[2 * e + 1]);
+                const uint32_t t0 = b0 & 0xffff0000u, t1 = b1 & 0xffff0000u;
+                hi[e] = __byte_perm(t0, t1, 0x7632);          // {t0[31:16] -> low half, t1[31:16] -> high half}
+                lo[e] = pack_bf16x2(f[2 * e] - __uint_as_float(t0), f[2 * e + 1] - __uint_as_float(t1));
               }
               *reinterpret_cast<uint4*>(row + ((m ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4*>(row + (((4 + m) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -422,14 +427,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
           }
           const int ch0 = nt * p.BN + j * 32;
           if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + ch0);      // broadcast reads
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (ch0 + i < p.Cout) v[i] += __ldg(&p.bias[ch0 + i]);
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = b4[i];
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
           }
           if (valid) {
+            const int nvec = min(8, (p.Cout - ch0) >> 2);       // Cout is a multiple of 4
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              if (ch0 + i < p.Cout) *reinterpret_cast<float4*>(optr + j * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < 8; ++i)
+              if (i < nvec) *reinterpret_cast<float4*>(optr + j * 32 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
           if (do_stats) {
             if (narrow) {
@@ -644,7 +653,7 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   p.btile_bytes = (uint32_t)p.BN * KC * 4 * (p.x3 ? 2u : 1u);      // bf16 pairs: 2 x 2 bytes per element = the fp32 size
   p.idesc = p.bx3 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
   // pipeline depths under the 227 KB shared-memory limit
-  const size_t fixed = 1024 /*alignment slack*/ + 66 * 8;   // barriers + tmem slot
+  const size_t fixed = 1024 /*alignment slack*/ + 66 * 8 + (size_t)(((Cout + 31) / 32) * 32 + 256) * 4;   // barriers + tmem slot + bias
   const size_t budget = 227 * 1024;
   // Activation stages: the thin layers are HBM-bound streams whose only memory-level parallelism is the TMA loads in flight
   // (a 24 KB slab per stage and CTA): with 3 stages 148 CTAs keep < 10 MB in flight, half of what ~6.5 TB/s x ~2 us needs.
