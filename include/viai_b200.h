@@ -85,6 +85,26 @@ int viai_conv2d_tc_supported(const viai_conv_geom* g);
 int viai_conv2d_tc(const viai_conv_geom* g, const float* in, const float* wp_tc, const float* bias, float* out,
                    double* stat_sum, double* stat_sumsq, int stat_groups, int flags, viai_stream_t stream);
 
+/* Data gradient fused with the first pass of the producing layer's norm backward.  Same convolution as viai_conv2d_tc without
+ * bias; `out` is dz, the gradient w.r.t. the post-activation tensor z = act(norm(y)) that was this convolution's forward
+ * input.  The epilogue also accumulates, per channel (BatchNorm batch statistics, i.e. one group),
+ *     s1 = sum g,  s2 = sum g * xhat,   g = dz * act'(xhat*gamma + beta),  xhat = (y - mean) * invstd
+ * which is exactly viai_norm_act_bwd_reduce(dz, y, ...) -- the separate two-stream pass over dz and y disappears
+ * (autograd of native_batch_norm_backward + leaky_relu/relu backward, networks/Inpainting_Networks.py:72-76 etc.).
+ * y has the shape of `out`; mean/invstd/gamma/beta: float[Cout] or NULL (as in viai_norm_act_fwd).  s1/s2: double[Cout],
+ * zeroed by the call. */
+typedef struct {
+  const float* y;
+  const float* mean;
+  const float* invstd;
+  const float* gamma;
+  const float* beta;
+  int32_t act;     /* viai_act */
+  float slope;
+} viai_norm_bwd_ctx;
+int viai_conv2d_tc_bwd_reduce(const viai_conv_geom* g, const float* in, const float* wp_tc, float* out,
+                              const viai_norm_bwd_ctx* nb, double* s1, double* s2, int flags, viai_stream_t stream);
+
 /* Tensor-core weight gradient: same meaning as viai_conv2d_wgrad_simt (below).  `workspace` is a caller-owned scratch of
  * viai_wgrad_tc_workspace(g) floats (every CTA of the split-K grid stores its per-tap partial sums in its own slice; a
  * second kernel adds the slices and scatters into the gradient layout -- no atomics). */

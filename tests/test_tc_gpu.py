@@ -161,3 +161,79 @@ def test_single_tf32_step_is_outside_the_parity_bound():
     e = H.relerr(got["fake"], want["fake"])
     print("single tf32 spectrogram relerr %.3e" % e)
     assert 1e-3 < e < 5e-2
+
+
+@pytest.mark.parametrize("case", [("block5 32->32", True, 32, 32, (1, 1), 20, 24, "relu"), ("dis 64->128 s2", False, 64, 128, (2, 2), 18, 20, "lrelu"),
+                                  ("dis 256->512", False, 256, 512, (1, 1), 9, 8, "lrelu"), ("enc 32->64 s(2,1)", False, 32, 64, (2, 1), 17, 9, "lrelu")],
+                         ids=lambda c: c[0])
+@pytest.mark.tf32
+def test_fused_norm_backward_reduction_equals_standalone_pass(case):
+    """viai_conv2d_tc_bwd_reduce: the data gradient's epilogue must deliver the same (sum g, sum g*xhat) as
+    viai_norm_act_bwd_reduce run on the dz it wrote (same arithmetic, different summation order: 1e-4), for stride-1,
+    strided (parity-class launches) and wide (transposing-reduction) geometries."""
+    from viai_b200 import _lib, ops
+    from viai_b200._lib import ConvGeom, NormBwdCtx
+    L = _lib.lib()
+    name, tr, Cin, Cout, stride, Hh, W, actname = case
+    act = {"relu": ops.ACT_RELU, "lrelu": ops.ACT_LRELU}[actname]
+    g = torch.Generator().manual_seed(len(name) * 131 + Cin)
+    N = 3
+    x = torch.randn(N, Hh, W, Cin, generator=g).cuda()                      # z = the convolution's forward input (NHWC)
+    y = (torch.randn(N, Hh, W, Cin, generator=g) * 1.5 + 0.3).cuda()         # pre-normalisation tensor of the producing layer
+    mean, var = y.mean((0, 1, 2)), y.var((0, 1, 2), unbiased=False)
+    inv = (var + 1e-5).rsqrt()
+    gamma = (torch.rand(Cin, generator=g) + 0.5).cuda()
+    beta = (torch.randn(Cin, generator=g) * 0.2).cuda()
+    wshape = (Cin, Cout, 3, 3) if tr else (Cout, Cin, 3, 3)
+    w = (torch.randn(wshape, generator=g) / math.sqrt(Cin * 9)).cuda()
+    Ho = ops._conv_out_size(Hh, 3, stride[0], 1, tr)
+    Wo = ops._conv_out_size(W, 3, stride[1], 1, tr)
+    dy = torch.randn(N, Ho, Wo, Cout, generator=g).cuda()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if not tr:
+        geom, od, idim = ConvGeom(N, Ho, Wo, Cout, Hh, W, Cin, 3, 3, stride[0], stride[1], 1, 1, 1), 1, 0
+    else:
+        geom, od, idim = ConvGeom(N, Ho, Wo, Cout, Hh, W, Cin, 3, 3, stride[0], stride[1], 1, 1, 0), 0, 1
+    wp = ops._pack_tc(w, od, idim, 0)
+    dz = torch.empty_like(x)
+    s = torch.empty(2, Cin, dtype=torch.float64, device="cuda")
+    nb = NormBwdCtx(y.data_ptr(), mean.data_ptr(), inv.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act, 0.2)
+    _lib.check(L.viai_conv2d_tc_bwd_reduce(ctypes.byref(geom), p(dy), p(wp), p(dz), ctypes.byref(nb), p(s[0]), p(s[1]), 0, st), "fused")
+    # the plain data gradient writes the same dz
+    dz2 = torch.empty_like(x)
+    _lib.check(L.viai_conv2d_tc(ctypes.byref(geom), p(dy), p(wp), None, p(dz2), None, None, 0, 0, st), "plain")
+    assert torch.equal(dz, dz2)
+    s_ref = torch.empty(2, Cin, dtype=torch.float64, device="cuda")
+    _lib.check(L.viai_norm_act_bwd_reduce(p(dz), p(y), N * Hh * W, 1, Cin, p(mean), p(inv), p(gamma), p(beta), act, 0.2,
+                                          p(s_ref[0]), p(s_ref[1]), st), "standalone")
+    assert H.relerr(s[0], s_ref[0]) < 1e-4 and H.relerr(s[1], s_ref[1]) < 1e-4
+
+
+@pytest.mark.bf16x3
+def test_fused_reduction_is_taken_in_a_layer_chain_and_changes_nothing():
+    """conv -> BN -> LeakyReLU -> conv -> BN -> LeakyReLU: with the fusion on, the first layer's backward reduction comes from
+    the second convolution's data gradient (one launch fewer) and every gradient agrees with the unfused run."""
+    import torch.nn as nn
+    from viai_b200 import _lib, ops
+    from viai_b200.networks._blocks import conv_norm_act
+
+    def run(fuse):
+        prev, ops._FUSE_BWD_REDUCE = ops._FUSE_BWD_REDUCE, fuse
+        try:
+            torch.manual_seed(5)
+            c1, b1 = nn.Conv2d(32, 64, 3, 1, 1, bias=False).cuda(), nn.BatchNorm2d(64).cuda()
+            c2, b2 = nn.Conv2d(64, 32, 3, 2, 1, bias=False).cuda(), nn.BatchNorm2d(32).cuda()
+            x = torch.randn(2, 24, 20, 32, device="cuda", requires_grad=True)
+            z = conv_norm_act(conv_norm_act(x, c1, b1, ops.ACT_LRELU, 0.2), c2, b2, ops.ACT_LRELU, 0.2)
+            n0 = _lib.launch_count()
+            z.backward(torch.ones_like(z) * 0.01 + z.detach() * 0.1)
+            return _lib.launch_count() - n0, [x.grad] + [p.grad for m in (c1, b1, c2, b2) for p in m.parameters()]
+        finally:
+            ops._FUSE_BWD_REDUCE = prev
+
+    n_fused, g_fused = run(True)
+    n_plain, g_plain = run(False)
+    assert n_fused == n_plain - 1
+    for a, b in zip(g_fused, g_plain):
+        assert H.relerr(a, b) < 1e-4

@@ -22,6 +22,12 @@ class ConvGeom(ctypes.Structure):
         "N", "Hin", "Win", "Cin", "Hout", "Wout", "Cout", "R", "S", "stride_h", "stride_w", "pad_h", "pad_w", "mode")]
 
 
+class NormBwdCtx(ctypes.Structure):
+    """Mirror of ``viai_norm_bwd_ctx``."""
+    _fields_ = [("y", ctypes.c_void_p), ("mean", ctypes.c_void_p), ("invstd", ctypes.c_void_p), ("gamma", ctypes.c_void_p),
+                ("beta", ctypes.c_void_p), ("act", ctypes.c_int32), ("slope", ctypes.c_float)]
+
+
 _GP = ctypes.POINTER(ConvGeom)
 
 # name -> argtypes (return type is always int)
@@ -31,6 +37,7 @@ SIGNATURES = {
     "viai_pack_weight_tc": [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_l, c_l, c_i, c_i, c_p],
     "viai_conv2d_tc_supported": [_GP],
     "viai_conv2d_tc": [_GP, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p],
+    "viai_conv2d_tc_bwd_reduce": [_GP, c_p, c_p, c_p, ctypes.POINTER(NormBwdCtx), c_p, c_p, c_i, c_p],
     "viai_tc_bn": [c_i],
     "viai_conv2d_wgrad_tc_supported": [_GP],
     "viai_conv2d_wgrad_tc": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p, c_p],

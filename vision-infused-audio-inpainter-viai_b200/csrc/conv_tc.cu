@@ -92,6 +92,14 @@ struct TcParams {
   double* ssum;
   double* ssq;
   int32_t stat_groups;   // 0: no statistics, 1: per channel, N: per (image, channel)
+  // red_mode 0: the fused reduction is (sum x, sum x^2) of the OUTPUT (statistics of the following norm layer).
+  // red_mode 1: the output is dz, the gradient w.r.t. the post-activation tensor of the layer that produced this convolution's
+  //             input; the reduction is the first pass of THAT layer's norm backward: g = dz * act'(pre), (sum g, sum g*xhat),
+  //             with xhat = (ry - rmean) * rinv and pre = xhat * rgamma + rbeta read per channel (groups == 1 only).
+  int32_t red_mode;
+  const float* ry;       // pre-normalisation tensor of the producing layer, same shape / strides as `out`
+  const float* rmean; const float* rinv; const float* rgamma; const float* rbeta;
+  int32_t ract; float rslope;
   int32_t N, Hv, Wv;     // virtual output grid (per image)
   int32_t tilesX, tilesY, ntilesN, ntiles;
   int32_t nchunks, BN, Cout;
@@ -145,6 +153,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* bias_s = reinterpret_cast<float*>(bars + 66);               // bias padded to ntilesN * BN floats (zeros when absent)
+  const int npad = p.ntilesN * p.BN;
+  float* rmu_s = bias_s + npad;                                      // red_mode 1: per-channel mean, invstd, gamma, beta
+  float* ris_s = rmu_s + npad;
+  float* rga_s = ris_s + npad;
+  float* rbe_s = rga_s + npad;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int acc_cols = 2 * p.BN;                // two accumulator sets (MMA of tile i+1 overlaps the epilogue of tile i)
@@ -157,7 +170,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     fence_barrier_init();
     for (int i = 0; i < p.nsub; ++i) prefetch_tmap(&p.mapA[i]);
   }
-  for (int i = threadIdx.x; i < p.ntilesN * p.BN; i += NTHREADS) bias_s[i] = (p.bias != nullptr && i < p.Cout) ? __ldg(&p.bias[i]) : 0.f;
+  for (int i = threadIdx.x; i < npad; i += NTHREADS) {
+    const bool in = i < p.Cout;
+    bias_s[i] = (p.bias != nullptr && in) ? __ldg(&p.bias[i]) : 0.f;
+    if (p.red_mode == 1) {
+      rmu_s[i] = (p.rmean != nullptr && in) ? __ldg(&p.rmean[i]) : 0.f;
+      ris_s[i] = (p.rinv != nullptr && in) ? __ldg(&p.rinv[i]) : 1.f;
+      rga_s[i] = (p.rgamma != nullptr && in) ? __ldg(&p.rgamma[i]) : 1.f;
+      rbe_s[i] = (p.rbeta != nullptr && in) ? __ldg(&p.rbeta[i]) : 0.f;
+    }
+  }
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -372,17 +394,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     float rs[8], rq[8];                           // this lane's running sum / sum of squares of channel j*32 + lane
 #pragma unroll
     for (int j = 0; j < 8; ++j) rs[j] = rq[j] = 0.f;
-    float ps[32], pq[32];                         // narrow: this thread's (= pixel row's) running sums per channel
+    // narrow: this thread's (= pixel row's) running sums per channel, reduced across lanes once per group;
+    // wide: acc1 is the scratch for the second reduction operand of the current chunk (acc2 unused)
+    float acc1[32], acc2[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) ps[i] = pq[i] = 0.f;
+    for (int i = 0; i < 32; ++i) acc1[i] = acc2[i] = 0.f;
+    const float neg_slope = (p.ract == VIAI_ACT_RELU) ? 0.f : (p.ract == VIAI_ACT_LRELU) ? p.rslope : 1.f;   // act'(pre <= 0)
     int cur_group = -1, cur_nt = -1;
     auto flush = [&]() {
       if (narrow) {                               // one transposing reduction per group instead of one per tile
-        transpose_reduce32(ps, lane);
-        transpose_reduce32(pq, lane);
-        rs[0] = ps[0]; rq[0] = pq[0];
+        transpose_reduce32(acc1, lane);
+        transpose_reduce32(acc2, lane);
+        rs[0] = acc1[0]; rq[0] = acc2[0];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) ps[i] = pq[i] = 0.f;
+        for (int i = 0; i < 32; ++i) acc1[i] = acc2[i] = 0.f;
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -441,25 +466,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
               if (i < nvec) *reinterpret_cast<float4*>(optr + j * 32 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
           if (do_stats) {
-            if (narrow) {
+            if (p.red_mode == 1) {
+              // v = dz.  g = dz * act'(pre), xhat = (y - mu) * is, pre = xhat * ga + be  (same expressions as norm_act.cu
+              // bwd_terms, so that this pass and viai_norm_act_bwd_apply agree on every sign decision)
+              const float4* y4 = reinterpret_cast<const float4*>(p.ry + (optr - p.out) + j * 32);
+              const float4* mu4 = reinterpret_cast<const float4*>(rmu_s + ch0);
+              const float4* is4 = reinterpret_cast<const float4*>(ris_s + ch0);
+              const float4* ga4 = reinterpret_cast<const float4*>(rga_s + ch0);
+              const float4* be4 = reinterpret_cast<const float4*>(rbe_s + ch0);
+              const int nvec = min(8, (p.Cout - ch0) >> 2);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const bool on = valid && i < nvec;
+                float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (on) yv = __ldg(y4 + i);
+                const float4 mu = mu4[i], is = is4[i], ga = ga4[i], be = be4[i];
+                float xh, pre, gg;
+#define VIAI_RED1(E, YV, MU, IS, GA, BE)                                   \
+                xh = (YV - MU) * IS;                                       \
+                pre = xh * GA + BE;                                        \
+                gg = on ? v[4 * i + E] * (pre > 0.f ? 1.f : neg_slope) : 0.f; \
+                if (narrow) { acc1[4 * i + E] += gg; acc2[4 * i + E] += gg * xh; } \
+                else { v[4 * i + E] = gg; acc1[4 * i + E] = gg * xh; }
+                VIAI_RED1(0, yv.x, mu.x, is.x, ga.x, be.x)
+                VIAI_RED1(1, yv.y, mu.y, is.y, ga.y, be.y)
+                VIAI_RED1(2, yv.z, mu.z, is.z, ga.z, be.z)
+                VIAI_RED1(3, yv.w, mu.w, is.w, ga.w, be.w)
+#undef VIAI_RED1
+              }
+            } else if (narrow) {
               if (valid) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                  ps[i] += v[i];
-                  pq[i] = fmaf(v[i], v[i], pq[i]);
+                  acc1[i] += v[i];
+                  acc2[i] = fmaf(v[i], v[i], acc2[i]);
                 }
               }
             } else {
-              float s2[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 v[i] = valid ? v[i] : 0.f;
-                s2[i] = v[i] * v[i];
+                acc1[i] = v[i] * v[i];
               }
+            }
+            if (!narrow) {
               transpose_reduce32(v, lane);
-              transpose_reduce32(s2, lane);
+              transpose_reduce32(acc1, lane);
               rs[j] += v[0];
-              rq[j] += s2[0];
+              rq[j] += acc1[0];
             }
           }
         }
@@ -560,9 +614,14 @@ inline uint64_t host_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
 int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int inC, int sub_sy, int sub_sx,
                 const TapSpec* taps, int ntap, const float* wp, const float* bias, float* out, int Hv, int Wv, int64_t o_sn,
                 int64_t o_sy, int64_t o_sx, int64_t o_base, int Cout, double* ssum, double* ssq, int stat_groups, int flags,
-                cudaStream_t stream) {
+                const viai_norm_bwd_ctx* nb, cudaStream_t stream) {
   TcParams p;
   memset(&p, 0, sizeof(p));
+  if (nb != nullptr) {
+    p.red_mode = 1;
+    p.ry = nb->y; p.rmean = nb->mean; p.rinv = nb->invstd; p.rgamma = nb->gamma; p.rbeta = nb->beta;
+    p.ract = nb->act; p.rslope = nb->slope;
+  }
   VIAI_REQUIRE(ntap >= 1 && ntap <= MAX_TAP, "conv2d_tc: %d taps (max %d)", ntap, MAX_TAP);
   // default: dense 128-byte pixel rows under the 128-byte swizzle.  flags & 1: 16-byte channel chunks, no swizzle (rank-5
   // TMA); flags & 3 == 3: the same through eight rank-4 copies.  Both alternatives are kept as cross-checks of the layout.
@@ -653,7 +712,7 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   p.btile_bytes = (uint32_t)p.BN * KC * 4 * (p.x3 ? 2u : 1u);      // bf16 pairs: 2 x 2 bytes per element = the fp32 size
   p.idesc = p.bx3 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
   // pipeline depths under the 227 KB shared-memory limit
-  const size_t fixed = 1024 /*alignment slack*/ + 66 * 8 + (size_t)(((Cout + 31) / 32) * 32 + 256) * 4;   // barriers + tmem slot + bias
+  const size_t fixed = 1024 /*alignment slack*/ + 66 * 8 + 5 * (size_t)(((Cout + 31) / 32) * 32 + 256) * 4;   // barriers + tmem slot + bias + 4 norm constants
   const size_t budget = 227 * 1024;
   // Activation stages: the thin layers are HBM-bound streams whose only memory-level parallelism is the TMA loads in flight
   // (a 24 KB slab per stage and CTA): with 3 stages 148 CTAs keep < 10 MB in flight, half of what ~6.5 TB/s x ~2 us needs.
@@ -751,8 +810,9 @@ extern "C" int viai_conv2d_tc_supported(const viai_conv_geom* g) {
   return 1;
 }
 
-extern "C" int viai_conv2d_tc(const viai_conv_geom* gp, const float* in, const float* wp_tc, const float* bias, float* out,
-                              double* stat_sum, double* stat_sumsq, int stat_groups, int flags, viai_stream_t stream) {
+static int conv2d_tc_impl(const viai_conv_geom* gp, const float* in, const float* wp_tc, const float* bias, float* out,
+                          double* stat_sum, double* stat_sumsq, int stat_groups, int flags, const viai_norm_bwd_ctx* nb,
+                          viai_stream_t stream) {
   VIAI_REQUIRE(gp && in && wp_tc && out, "conv2d_tc: null argument");
   const viai_conv_geom& g = *gp;
   VIAI_REQUIRE(viai_conv2d_tc_supported(gp), "conv2d_tc: unsupported geometry (Cin %d Cout %d %dx%d stride %d,%d mode %d)", g.Cin,
@@ -763,9 +823,13 @@ extern "C" int viai_conv2d_tc(const viai_conv_geom* gp, const float* in, const f
   VIAI_REQUIRE((stat_sum == nullptr) == (stat_sumsq == nullptr), "conv2d_tc: stat_sum and stat_sumsq go together");
   cudaStream_t st = STR(stream);
   if (stat_sum) {
-    const size_t nb = (size_t)(stat_groups > 1 ? stat_groups : 1) * g.Cout * sizeof(double);
-    VIAI_CUDA(cudaMemsetAsync(stat_sum, 0, nb, st));
-    VIAI_CUDA(cudaMemsetAsync(stat_sumsq, 0, nb, st));
+    const size_t nbytes = (size_t)(stat_groups > 1 ? stat_groups : 1) * g.Cout * sizeof(double);
+    if (reinterpret_cast<char*>(stat_sumsq) == reinterpret_cast<char*>(stat_sum) + nbytes) {   // one (2, n) buffer: one memset node
+      VIAI_CUDA(cudaMemsetAsync(stat_sum, 0, 2 * nbytes, st));
+    } else {
+      VIAI_CUDA(cudaMemsetAsync(stat_sum, 0, nbytes, st));
+      VIAI_CUDA(cudaMemsetAsync(stat_sumsq, 0, nbytes, st));
+    }
   }
   TapSpec taps[MAX_TAP];
   const int64_t o_row = (int64_t)g.Wout * g.Cout, o_img = (int64_t)g.Hout * o_row;
@@ -778,7 +842,7 @@ extern "C" int viai_conv2d_tc(const viai_conv_geom* gp, const float* in, const f
                              r * g.S + s};
       }
     return launch_plan(g, in, g.Hin, g.Win, g.Cin, g.stride_h, g.stride_w, taps, nt, wp_tc, bias, out, g.Hout, g.Wout, o_img, o_row,
-                       g.Cout, 0, g.Cout, stat_sum, stat_sumsq, stat_groups, flags, st);
+                       g.Cout, 0, g.Cout, stat_sum, stat_sumsq, stat_groups, flags, nb, st);
   }
   // transposed gather: one launch per output parity class
   auto class_taps = [&](int py, int px, TapSpec* out_taps) {
@@ -808,8 +872,21 @@ extern "C" int viai_conv2d_tc(const viai_conv_geom* gp, const float* in, const f
       if (nt == 0) continue;
       int rc = launch_plan(g, in, g.Hin, g.Win, g.Cin, 1, 1, taps, nt, wp_tc, bias, out, Hv, Wv, o_img, o_row * g.stride_h,
                            (int64_t)g.Cout * g.stride_w, (int64_t)py * o_row + (int64_t)px * g.Cout, g.Cout, stat_sum, stat_sumsq,
-                           stat_groups, flags, st);
+                           stat_groups, flags, nb, st);
       if (rc != VIAI_OK) return rc;
     }
   return VIAI_OK;
+}
+
+extern "C" int viai_conv2d_tc(const viai_conv_geom* gp, const float* in, const float* wp_tc, const float* bias, float* out,
+                              double* stat_sum, double* stat_sumsq, int stat_groups, int flags, viai_stream_t stream) {
+  return conv2d_tc_impl(gp, in, wp_tc, bias, out, stat_sum, stat_sumsq, stat_groups, flags, nullptr, stream);
+}
+
+extern "C" int viai_conv2d_tc_bwd_reduce(const viai_conv_geom* gp, const float* in, const float* wp_tc, float* out,
+                                         const viai_norm_bwd_ctx* nb, double* s1, double* s2, int flags, viai_stream_t stream) {
+  VIAI_REQUIRE(nb && nb->y && s1 && s2, "conv2d_tc_bwd_reduce: null argument");
+  VIAI_REQUIRE((nb->mean == nullptr) == (nb->invstd == nullptr), "conv2d_tc_bwd_reduce: mean/invstd must both be set or NULL");
+  VIAI_REQUIRE((reinterpret_cast<uintptr_t>(nb->y) & 15) == 0, "conv2d_tc_bwd_reduce: y must be 16-byte aligned");
+  return conv2d_tc_impl(gp, in, wp_tc, nullptr, out, s1, s2, 1, flags, nb, stream);
 }

@@ -22,6 +22,11 @@ ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 _PRECISION = os.environ.get("VIAI_PRECISION", "bf16x3")
 _FWD_MODE = {"bf16x3": (2, 8), "tf32x3": (1, 4), "tf32": (0, 0)}   # precision -> (weight packing, viai_conv2d_tc flags)
 _WS = {}
+# Fuse the first pass of a layer's norm backward (sum g, sum g*xhat) into the epilogue of the data-gradient convolution that
+# produces dz (tensor-core path, BatchNorm batch statistics): viai_conv2d_tc_bwd_reduce.  Parity-tested, but OFF by default:
+# measured on B200 at C2 the four epilogue warps cannot hide the extra y read + arithmetic (step 15.5 ms fused vs 14.8 ms
+# with the standalone viai_norm_act_bwd_reduce pass, which already runs at 4.7 TB/s).  VIAI_FUSE_BWD_REDUCE=1 enables it.
+_FUSE_BWD_REDUCE = os.environ.get("VIAI_FUSE_BWD_REDUCE", "0") == "1"
 
 
 def set_precision(p):
@@ -51,6 +56,10 @@ def _stream():
 
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
 
 
 def _require_cuda(*ts):
@@ -93,10 +102,22 @@ def _pack_tc(weight, O_dim, I_dim, split):
     return out
 
 
-def _run_conv(g, x, weight, O_dim, I_dim, bias, y, stats=None, groups=1, forward=False):
+def _run_conv(g, x, weight, O_dim, I_dim, bias, y, stats=None, groups=1, forward=False, norm_ctx=None):
     """One gather convolution (forward or data gradient) on the tensor cores when possible, else on the CUDA cores.
-    Returns True when ``stats`` (2 x groups*C doubles) was filled by the convolution's epilogue."""
+    Returns True when ``stats`` (2 x groups*C doubles) was filled by the convolution's epilogue.  With ``norm_ctx`` (data
+    gradients only) the epilogue reduction is the producing layer's norm-backward first pass instead of the statistics."""
     L = _lib.lib()
+    if norm_ctx is not None:
+        if _PRECISION == "fp32" or bias is not None or not L.viai_conv2d_tc_supported(ctypes.byref(g)) or \
+                (L.viai_conv2d_thin_supported(ctypes.byref(g)) and x.data_ptr() % 16 == 0):
+            norm_ctx, stats = None, None        # not fusable here: plain data gradient, the caller keeps the standalone pass
+    if norm_ctx is not None:
+        wp = _pack_tc(weight, O_dim, I_dim, 0)
+        nb = _lib.NormBwdCtx(norm_ctx["y"].data_ptr(), _ptr(norm_ctx["mean"]), _ptr(norm_ctx["invstd"]), _ptr(norm_ctx["gamma"]),
+                             _ptr(norm_ctx["beta"]), norm_ctx["act"], norm_ctx["slope"])
+        _lib.check(L.viai_conv2d_tc_bwd_reduce(ctypes.byref(g), _p(x), _p(wp), _p(y), ctypes.byref(nb), _p(stats[0]), _p(stats[1]),
+                                               0, _stream()), "conv2d_tc_bwd_reduce")
+        return True
     if L.viai_conv2d_thin_supported(ctypes.byref(g)) and x.data_ptr() % 16 == 0:
         wp = _pack(weight, O_dim, I_dim)
         _lib.check(L.viai_conv2d_thin(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _stream()), "conv2d_thin")
@@ -147,6 +168,7 @@ class _ConvFn(torch.autograd.Function):
         ctx.save_for_backward(x, weight)
         ctx.cfg = (stride, padding, transposed, bias is not None)
         ctx.targets = (grad_target(weight), grad_target(bias))
+        ctx.in_norm = getattr(x, "_viai_norm_ctx", None) if _FUSE_BWD_REDUCE else None
         if stats is None:
             stats = torch.empty(0, device=x.device, dtype=torch.float64)
         ctx.mark_non_differentiable(stats)
@@ -164,10 +186,18 @@ class _ConvFn(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
+            nc = ctx.in_norm
+            if nc is not None and (nc["y"].shape != x.shape or not nc["y"].is_contiguous()):
+                nc = None
+            bst = torch.empty((2, C), device=x.device, dtype=torch.float64) if nc is not None else None
             if not transposed:       # dgrad of Conv2d: transposed gather with wp[o=ci][r][s][i=co]
-                _run_conv(_geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 1), dy, weight, 1, 0, None, dx)
+                fused = _run_conv(_geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 1), dy, weight, 1, 0, None, dx, bst,
+                                  norm_ctx=nc)
             else:                    # dgrad of ConvTranspose2d: forward gather with wp[o=ci][r][s][i=co]
-                _run_conv(_geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0), dy, weight, 0, 1, None, dx)
+                fused = _run_conv(_geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0), dy, weight, 0, 1, None, dx, bst,
+                                  norm_ctx=nc)
+            if nc is not None and fused:
+                dx._viai_bwd_stats = (bst, nc["token"])      # consumed by the producing layer's _NormActFn.backward
         wt, bt = ctx.targets
         if ctx.needs_input_grad[1]:
             dw = wt if wt is not None else torch.empty_like(weight, memory_format=torch.contiguous_format)
@@ -216,7 +246,8 @@ class _NormActFn(torch.autograd.Function):
     networks/Discriminator_Networks.py:38-49)."""
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, running_mean, running_var, nbt, norm, training, act, slope, eps, momentum, pre_stats=None):
+    def forward(ctx, y, gamma, beta, running_mean, running_var, nbt, norm, training, act, slope, eps, momentum, pre_stats=None,
+                side=None):
         _require_cuda(y, gamma, beta)
         L = _lib.lib()
         y = y.contiguous()
@@ -250,6 +281,10 @@ class _NormActFn(torch.autograd.Function):
         ctx.save_for_backward(y, mean, invstd, gamma, beta)
         ctx.cfg = (norm, groups, rpg, act, slope, training or norm != "bn")
         ctx.targets = (grad_target(gamma), grad_target(beta))
+        ctx.token = None
+        if side is not None and groups == 1 and mean is not None and (training or norm != "bn") and act != ACT_SIGMOID:
+            ctx.token = object()
+            side.update(y=y, mean=mean, invstd=invstd, gamma=gamma, beta=beta, act=act, slope=float(slope), token=ctx.token)
         return out
 
     @staticmethod
@@ -264,7 +299,10 @@ class _NormActFn(torch.autograd.Function):
         dy = torch.empty_like(y)
         gt, bt = ctx.targets
         s = None
-        if mean is not None:
+        pre = getattr(dz, "_viai_bwd_stats", None)
+        if pre is not None and ctx.token is not None and pre[1] is ctx.token:
+            s = pre[0]               # (sum g, sum g*xhat) came out of the epilogue of the convolution that produced dz
+        elif mean is not None:
             s = torch.empty((2, groups * C), device=y.device, dtype=torch.float64)
             _lib.check(L.viai_norm_act_bwd_reduce(_p(dz), _p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta),
                                                   act, slope, _p(s[0]), _p(s[1]), _stream()), "norm_act_bwd_reduce")
@@ -280,7 +318,7 @@ class _NormActFn(torch.autograd.Function):
             dbeta = bt if bt is not None else torch.empty_like(beta)
             _lib.check(L.viai_fold_groups(_p(s[0]), groups, C, _p(dbeta), int(bt is not None), _stream()), "dbeta")
             dbeta = None if bt is not None else dbeta
-        return dy, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None
+        return dy, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None, None
 
 
 def stat_groups_for(norm_module, norm, batch):
@@ -295,14 +333,18 @@ def stat_groups_for(norm_module, norm, batch):
 def norm_act(y, norm_module, norm, act, slope=0.0, pre_stats=None):
     """``norm_module`` is the nn.BatchNorm2d / nn.InstanceNorm2d parameter container (or None)."""
     if norm == "none" or norm_module is None:
-        return _NormActFn.apply(y, None, None, None, None, None, "none", False, act, slope, 0.0, 0.0, None)
+        return _NormActFn.apply(y, None, None, None, None, None, "none", False, act, slope, 0.0, 0.0, None, None)
     gamma = getattr(norm_module, "weight", None)
     beta = getattr(norm_module, "bias", None)
     rm = getattr(norm_module, "running_mean", None)
     rv = getattr(norm_module, "running_var", None)
     nbt = getattr(norm_module, "num_batches_tracked", None)
     mom = norm_module.momentum if norm_module.momentum is not None else 0.1
-    return _NormActFn.apply(y, gamma, beta, rm, rv, nbt, norm, norm_module.training, act, slope, norm_module.eps, mom, pre_stats)
+    side = {}
+    z = _NormActFn.apply(y, gamma, beta, rm, rv, nbt, norm, norm_module.training, act, slope, norm_module.eps, mom, pre_stats, side)
+    if side and torch.is_grad_enabled() and z.requires_grad:
+        z._viai_norm_ctx = side          # lets the consuming convolution's data gradient fuse this layer's backward reduction
+    return z
 
 
 class _BilinearCatFn(torch.autograd.Function):
