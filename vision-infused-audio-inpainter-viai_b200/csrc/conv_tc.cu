@@ -68,8 +68,12 @@ namespace {
 constexpr int TH = 16, TW = 8;          // output pixels per M tile (TW = 8 = rows of one UMMA core matrix)
 constexpr int KC = 32;                  // input channels per slab (8 chunks of 16 bytes)
 constexpr int MAX_SUB = 4, MAX_TAP = 16;
-constexpr int NTHREADS = 352;          // warps 0-2: producers + MMA, 3-6: epilogue, 7-10: hi/lo split (tf32x3 only)
-constexpr int XF_WARP0 = 7;
+// Four warpgroups: WG0 = warps 0-2 TMA patch producer / weight producer / MMA issuer (warp 3 idle), WG1 and WG2 = two
+// epilogue sets (one per TMEM accumulator set: even / odd tiles, so two tiles' epilogues are in flight), WG3 = operand split.
+// Registers are rebalanced with setmaxnreg after the prologue: the producers and the split warps give theirs to the epilogue.
+constexpr int NTHREADS = 512;
+constexpr int XF_WARP0 = 12;
+constexpr int EPI_WARP0 = 4;
 
 struct TcSub {
   int32_t ox, oy;        // sub-grid coordinate of the patch origin relative to the tile origin
@@ -186,7 +190,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp < EPI_WARP0) {
+   reg_dealloc<56>();
+   if (warp == 0) {
     // ===== activation patch producer =====
     if (lane == 0) {
       int sa = 0;
@@ -317,7 +323,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       }
       if (leader) mma_commit(&tfull[acc]);
     }
+   }
   } else if (warp >= XF_WARP0) {
+    reg_dealloc<80>();
     // ===== tf32x3: split every landed slab into hi = trunc_tf32(x) (in place) and lo = x - hi (second slab) =====
     if (MODE == 2) {
       // bf16 pair split, one thread per 128-byte pixel row (private to the thread, so the rewrite is in place): logical
@@ -384,6 +392,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else {
+    reg_alloc<184>();
     // ===== epilogue: TMEM -> registers -> (+bias, statistics) -> global =====
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;                // accumulator row = pixel of the tile
@@ -419,15 +428,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         rs[j] = rq[j] = 0.f;
       }
     };
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int eset = (warp - EPI_WARP0) >> 2;       // epilogue set = accumulator set = parity of the CTA's tile counter
+    for (int it = eset, tile = blockIdx.x + eset * gridDim.x; tile < p.ntiles; tile += 2 * gridDim.x, it += 2) {
       const int nt = tile % p.ntilesN;
       int rest = tile / p.ntilesN;
       const int tx = rest % p.tilesX; rest /= p.tilesX;
       const int ty = rest % p.tilesY;
       const int n = rest / p.tilesY;
       const int y = ty * TH + ly;
-      const int acc = it & 1;
+      const int acc = eset;
       if (do_stats) {
         const int grp = (p.stat_groups > 1) ? n : 0;
         if ((grp != cur_group || nt != cur_nt) && cur_group >= 0) flush();   // finished (group, cout tile)

@@ -150,6 +150,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Register rebalancing between warpgroups (4 consecutive warps must execute the same instruction): the count is per thread,
+// a multiple of 8 in [24, 256]; the sum over the CTA must not exceed what the launch allocated (threads x maxnreg).
+template <uint32_t R>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <uint32_t R>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
 // true in exactly one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
