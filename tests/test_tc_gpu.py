@@ -223,7 +223,7 @@ def test_fused_reduction_is_taken_in_a_layer_chain_and_changes_nothing():
         try:
             torch.manual_seed(5)
             c1, b1 = nn.Conv2d(32, 64, 3, 1, 1, bias=False).cuda(), nn.BatchNorm2d(64).cuda()
-            c2, b2 = nn.Conv2d(64, 32, 3, 2, 1, bias=False).cuda(), nn.BatchNorm2d(32).cuda()
+            c2, b2 = nn.Conv2d(64, 32, 3, 1, 1, bias=False).cuda(), nn.BatchNorm2d(32).cuda()
             x = torch.randn(2, 24, 20, 32, device="cuda", requires_grad=True)
             z = conv_norm_act(conv_norm_act(x, c1, b1, ops.ACT_LRELU, 0.2), c2, b2, ops.ACT_LRELU, 0.2)
             n0 = _lib.launch_count()

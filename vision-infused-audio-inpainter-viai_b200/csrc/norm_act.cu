@@ -356,8 +356,12 @@ extern "C" int viai_channel_stats(const float* y, int64_t rows_per_group, int gr
                                   viai_stream_t stream) {
   VIAI_REQUIRE(y && sum && rows_per_group > 0 && groups > 0 && C > 0, "viai_channel_stats: bad arguments");
   cudaStream_t st = STR(stream);
-  VIAI_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * groups * C, st));
-  if (sumsq) VIAI_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * groups * C, st));
+  if (sumsq == sum + (size_t)groups * C) {        // one (2, groups*C) buffer: a single memset node
+    VIAI_CUDA(cudaMemsetAsync(sum, 0, 2 * sizeof(double) * groups * C, st));
+  } else {
+    VIAI_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * groups * C, st));
+    if (sumsq) VIAI_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * groups * C, st));
+  }
   const int VEC = pick_vec(C, y);
   VIAI_REQUIRE(C / VEC <= THREADS, "viai_channel_stats: C=%d too large", C);
   const int64_t rpb = pick_rows_per_block(rows_per_group, groups, C, VEC);
@@ -409,8 +413,12 @@ extern "C" int viai_norm_act_bwd_reduce(const float* dz, const float* y, int64_t
                                         int act, float slope, double* s1, double* s2, viai_stream_t stream) {
   VIAI_REQUIRE(dz && y && s1 && s2 && rows_per_group > 0 && groups > 0 && C > 0, "viai_norm_act_bwd_reduce: bad arguments");
   cudaStream_t st = STR(stream);
-  VIAI_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * groups * C, st));
-  VIAI_CUDA(cudaMemsetAsync(s2, 0, sizeof(double) * groups * C, st));
+  if (s2 == s1 + (size_t)groups * C) {
+    VIAI_CUDA(cudaMemsetAsync(s1, 0, 2 * sizeof(double) * groups * C, st));
+  } else {
+    VIAI_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * groups * C, st));
+    VIAI_CUDA(cudaMemsetAsync(s2, 0, sizeof(double) * groups * C, st));
+  }
   const int VEC = pick_vec(C, dz, y);
   VIAI_REQUIRE(C / VEC <= THREADS, "viai_norm_act_bwd_reduce: C=%d too large", C);
   const int64_t rpb = pick_rows_per_block(rows_per_group, groups, C, VEC);

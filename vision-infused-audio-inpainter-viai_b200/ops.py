@@ -92,7 +92,40 @@ def _conv_out_size(H, k, s, p, transposed):
     return (H - 1) * s - 2 * p + k if transposed else (H + 2 * p - k) // s + 1
 
 
+# Packed operands can be cached for the duration of ONE training step (GanTrainer brackets its step with pack_cache_begin /
+# pack_cache_end): the discriminator runs its forward twice and its data gradient twice between two updates of its weights.
+# FusedAdam rewrites the flat parameter buffer from a kernel (no autograd version bump), so it advances the epoch explicitly
+# (weights_updated()).  Outside a bracketed step nothing is cached: a stale operand can never be picked up.
+_PACK_CACHE = {}
+_PACK_STATE = {"on": False, "epoch": 0}
+
+
+def pack_cache_begin():
+    _PACK_CACHE.clear()
+    _PACK_STATE["on"] = True
+
+
+def pack_cache_end():
+    _PACK_CACHE.clear()
+    _PACK_STATE["on"] = False
+
+
+def weights_updated():
+    _PACK_STATE["epoch"] += 1
+    _PACK_CACHE.clear()
+
+
 def _pack_tc(weight, O_dim, I_dim, split):
+    if not _PACK_STATE["on"]:
+        return _pack_tc_uncached(weight, O_dim, I_dim, split)
+    key = (weight.data_ptr(), weight._version, _PACK_STATE["epoch"], O_dim, I_dim, split, tuple(weight.shape), tuple(weight.stride()))
+    hit = _PACK_CACHE.get(key)
+    if hit is None:
+        hit = _PACK_CACHE[key] = _pack_tc_uncached(weight, O_dim, I_dim, split)
+    return hit
+
+
+def _pack_tc_uncached(weight, O_dim, I_dim, split):
     L = _lib.lib()
     O, I = weight.size(O_dim), weight.size(I_dim)
     R, S = weight.size(2), weight.size(3)
@@ -172,10 +205,13 @@ class _ConvFn(torch.autograd.Function):
         if stats is None:
             stats = torch.empty(0, device=x.device, dtype=torch.float64)
         ctx.mark_non_differentiable(stats)
+        ctx.set_materialize_grads(False)      # no zero-filled float64 "gradient" of the statistics output
         return y, stats
 
     @staticmethod
     def backward(ctx, dy, _dstats):
+        if dy is None:
+            return None, None, None, None, None, None, None
         x, weight = ctx.saved_tensors
         stride, padding, transposed, has_bias = ctx.cfg
         L = _lib.lib()
@@ -187,7 +223,9 @@ class _ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             nc = ctx.in_norm
-            if nc is not None and (nc["y"].shape != x.shape or not nc["y"].is_contiguous()):
+            # fused only for unit-stride layers: a strided convolution's data gradient is four low-K parity-class launches
+            # whose short main loops cannot hide the epilogue's extra work
+            if nc is not None and (nc["y"].shape != x.shape or not nc["y"].is_contiguous() or tuple(stride) != (1, 1)):
                 nc = None
             bst = torch.empty((2, C), device=x.device, dtype=torch.float64) if nc is not None else None
             if not transposed:       # dgrad of Conv2d: transposed gather with wp[o=ci][r][s][i=co]

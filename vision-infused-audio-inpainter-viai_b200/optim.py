@@ -134,6 +134,8 @@ class FusedAdam(torch.optim.Optimizer):
         _lib.check(L.viai_adam_step(_p(self.flat_param), _p(self.flat_grad), _p(self.flat_m), _p(self.flat_v),
                                     self.numel, _p(self.lr_dev), float(b1), float(b2), float(g["eps"]),
                                     _p(self.step_dev), 1, 1.0 / self.world_size, _stream()), "adam_step")
+        from . import ops
+        ops.weights_updated()             # the kernel rewrote the parameters in place: cached packed operands are stale
 
     def load_state_dict(self, state_dict):
         sd = state_dict["state"]

@@ -95,11 +95,15 @@ class GanTrainer(object):
     def train_step(self, mel, mask, video=None, flow=None):
         """mel (B,1,H,W) or (B,H,W) fp32 in [0,1]; mask same shape, {0,1}.  Returns dict of device tensors."""
         n0 = _lib.launch_count()
-        self._seg_forward_and_d_backward(mel, mask, video, flow)
-        self.optimizer_D.all_reduce_grads()
-        self._seg_d_update_and_g_backward()
-        self.optimizer_G.all_reduce_grads()
-        self._seg_g_update()
+        ops.pack_cache_begin()
+        try:
+            self._seg_forward_and_d_backward(mel, mask, video, flow)
+            self.optimizer_D.all_reduce_grads()
+            self._seg_d_update_and_g_backward()
+            self.optimizer_G.all_reduce_grads()
+            self._seg_g_update()
+        finally:
+            ops.pack_cache_end()
         self.launches_per_step = _lib.launch_count() - n0
         return self._outputs()
 
@@ -121,6 +125,7 @@ class GanTrainer(object):
         # warm-up stream, and a backward inside the capture would then wait on that (uncaptured) stream.
         self._drop_step_state()
         n0 = _lib.launch_count()
+        ops.pack_cache_begin()
         if self.world_size == 1:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -142,6 +147,7 @@ class GanTrainer(object):
                 self._seg_g_update()
                 self._static_out = self._outputs()
             self._graphs = [g1, g2, g3]
+        ops.pack_cache_end()
         self.launches_per_step = _lib.launch_count() - n0
         return self
 
