@@ -18,40 +18,44 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in, int& i0,
   l0 = 1.f - l1;
 }
 
+// One block per output row (n, y): the row interpolation is evaluated once per block, the column interpolation once per
+// thread-item; no integer division in the item loop (the previous one-item-per-thread version spent most of its time in
+// 64-bit div/mod).
 template <int VEC>
 __global__ void __launch_bounds__(THREADS)
 bilinear_fwd_kernel(const float* __restrict__ in, int N, int Hin, int Win, int C, float* __restrict__ out, int Hout,
                     int Wout, int Ctot, int coff) {
   const int cvec = C / VEC;
-  const int64_t total = (int64_t)N * Hout * Wout * cvec;
   const float sh = ac_scale(Hin, Hout), sw = ac_scale(Win, Wout);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % cvec);
-    int64_t t = i / cvec;
-    int x = (int)(t % Wout); t /= Wout;
-    int y = (int)(t % Hout);
-    int n = (int)(t / Hout);
-    int y0, y1, x0, x1;
-    float ly0, ly1, lx0, lx1;
+  for (int row = blockIdx.x; row < N * Hout; row += gridDim.x) {
+    const int n = row / Hout, y = row - n * Hout;
+    int y0, y1;
+    float ly0, ly1;
     src_index(sh, y, Hin, y0, y1, ly0, ly1);
-    src_index(sw, x, Win, x0, x1, lx0, lx1);
-    const float* b = in + (int64_t)n * Hin * Win * C + cv * VEC;
-    float* o = out + (((int64_t)n * Hout + y) * Wout + x) * Ctot + coff + cv * VEC;
-    if (VEC == 4) {
-      float4 a = __ldg(reinterpret_cast<const float4*>(b + ((int64_t)y0 * Win + x0) * C));
-      float4 bb = __ldg(reinterpret_cast<const float4*>(b + ((int64_t)y0 * Win + x1) * C));
-      float4 c = __ldg(reinterpret_cast<const float4*>(b + ((int64_t)y1 * Win + x0) * C));
-      float4 d = __ldg(reinterpret_cast<const float4*>(b + ((int64_t)y1 * Win + x1) * C));
-      float4 r;
-      r.x = ly0 * (lx0 * a.x + lx1 * bb.x) + ly1 * (lx0 * c.x + lx1 * d.x);
-      r.y = ly0 * (lx0 * a.y + lx1 * bb.y) + ly1 * (lx0 * c.y + lx1 * d.y);
-      r.z = ly0 * (lx0 * a.z + lx1 * bb.z) + ly1 * (lx0 * c.z + lx1 * d.z);
-      r.w = ly0 * (lx0 * a.w + lx1 * bb.w) + ly1 * (lx0 * c.w + lx1 * d.w);
-      *reinterpret_cast<float4*>(o) = r;
-    } else {
-      float a = __ldg(b + ((int64_t)y0 * Win + x0) * C), bb = __ldg(b + ((int64_t)y0 * Win + x1) * C);
-      float c = __ldg(b + ((int64_t)y1 * Win + x0) * C), d = __ldg(b + ((int64_t)y1 * Win + x1) * C);
-      *o = ly0 * (lx0 * a + lx1 * bb) + ly1 * (lx0 * c + lx1 * d);
+    const float* r0 = in + ((int64_t)n * Hin + y0) * Win * C;
+    const float* r1 = in + ((int64_t)n * Hin + y1) * Win * C;
+    float* orow = out + (int64_t)row * Wout * Ctot + coff;
+    const int items = Wout * cvec;
+    for (int i = threadIdx.x; i < items; i += THREADS) {
+      const int x = i / cvec, cv = i - x * cvec;           // 32-bit, cvec is small
+      int x0, x1;
+      float lx0, lx1;
+      src_index(sw, x, Win, x0, x1, lx0, lx1);
+      const int o0 = x0 * C + cv * VEC, o1 = x1 * C + cv * VEC;
+      float* o = orow + (int64_t)x * Ctot + cv * VEC;
+      if (VEC == 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(r0 + o0)), bb = __ldg(reinterpret_cast<const float4*>(r0 + o1));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(r1 + o0)), d = __ldg(reinterpret_cast<const float4*>(r1 + o1));
+        float4 r;
+        r.x = ly0 * (lx0 * a.x + lx1 * bb.x) + ly1 * (lx0 * c.x + lx1 * d.x);
+        r.y = ly0 * (lx0 * a.y + lx1 * bb.y) + ly1 * (lx0 * c.y + lx1 * d.y);
+        r.z = ly0 * (lx0 * a.z + lx1 * bb.z) + ly1 * (lx0 * c.z + lx1 * d.z);
+        r.w = ly0 * (lx0 * a.w + lx1 * bb.w) + ly1 * (lx0 * c.w + lx1 * d.w);
+        *reinterpret_cast<float4*>(o) = r;
+      } else {
+        const float a = __ldg(r0 + o0), bb = __ldg(r0 + o1), c = __ldg(r1 + o0), d = __ldg(r1 + o1);
+        *o = ly0 * (lx0 * a + lx1 * bb) + ly1 * (lx0 * c + lx1 * d);
+      }
     }
   }
 }
@@ -68,48 +72,89 @@ __device__ __forceinline__ void cand_range(float scale, int i, int in, int out, 
   if (hi > out - 1) hi = out - 1;
 }
 
+// One block per input row (n, iy).  The candidate output rows and their weights are the same for the whole block and are
+// evaluated once (shared memory); each thread-item evaluates its candidate columns once and then only loads and accumulates.
+constexpr int BIL_MAXC = 16;       // candidate rows / columns kept; wider footprints fall back to on-the-fly evaluation
 template <int VEC>
 __global__ void __launch_bounds__(THREADS)
 bilinear_bwd_kernel(const float* __restrict__ dout, int N, int Hin, int Win, int C, float* __restrict__ din, int Hout,
                     int Wout, int Ctot, int coff) {
+  __shared__ int ys_s[BIL_MAXC];
+  __shared__ float wy_s[BIL_MAXC];
+  __shared__ int ny_s;
   const int cvec = C / VEC;
-  const int64_t total = (int64_t)N * Hin * Win * cvec;
   const float sh = ac_scale(Hin, Hout), sw = ac_scale(Win, Wout);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % cvec);
-    int64_t t = i / cvec;
-    int ix = (int)(t % Win); t /= Win;
-    int iy = (int)(t % Hin);
-    int n = (int)(t / Hin);
-    int ylo, yhi, xlo, xhi;
-    cand_range(sh, iy, Hin, Hout, ylo, yhi);
-    cand_range(sw, ix, Win, Wout, xlo, xhi);
-    float acc[VEC];
+  for (int row = blockIdx.x; row < N * Hin; row += gridDim.x) {
+    const int n = row / Hin, iy = row - n * Hin;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int ylo, yhi, cnt = 0;
+      cand_range(sh, iy, Hin, Hout, ylo, yhi);
+      for (int y = ylo; y <= yhi; ++y) {
+        int y0, y1; float ly0, ly1;
+        src_index(sh, y, Hin, y0, y1, ly0, ly1);
+        const float wy = (y0 == iy ? ly0 : 0.f) + (y1 == iy ? ly1 : 0.f);
+        if (wy != 0.f && cnt < BIL_MAXC) { ys_s[cnt] = y; wy_s[cnt] = wy; ++cnt; }
+        else if (wy != 0.f) cnt = BIL_MAXC + 1;          // too many: signal the generic path
+      }
+      ny_s = cnt;
+    }
+    __syncthreads();
+    const int ny = ny_s;
+    const int items = Win * cvec;
+    for (int i = threadIdx.x; i < items; i += THREADS) {
+      const int ix = i / cvec, cv = i - ix * cvec;
+      float acc[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
-    for (int y = ylo; y <= yhi; ++y) {
-      int y0, y1; float ly0, ly1;
-      src_index(sh, y, Hin, y0, y1, ly0, ly1);
-      float wy = (y0 == iy ? ly0 : 0.f) + (y1 == iy ? ly1 : 0.f);
-      if (wy == 0.f) continue;
-      for (int x = xlo; x <= xhi; ++x) {
-        int x0, x1; float lx0, lx1;
-        src_index(sw, x, Win, x0, x1, lx0, lx1);
-        float wx = (x0 == ix ? lx0 : 0.f) + (x1 == ix ? lx1 : 0.f);
-        if (wx == 0.f) continue;
-        const float* d = dout + (((int64_t)n * Hout + y) * Wout + x) * Ctot + coff + cv * VEC;
-        float w = wy * wx;
-        if (VEC == 4) {
-          float4 v = __ldg(reinterpret_cast<const float4*>(d));
-          acc[0] += w * v.x; acc[1 % VEC] += w * v.y; acc[2 % VEC] += w * v.z; acc[3 % VEC] += w * v.w;
-        } else {
-          acc[0] += w * __ldg(d);
+      for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+      int xlo, xhi;
+      cand_range(sw, ix, Win, Wout, xlo, xhi);
+      if (ny <= BIL_MAXC) {
+        for (int x = xlo; x <= xhi; ++x) {
+          int x0, x1; float lx0, lx1;
+          src_index(sw, x, Win, x0, x1, lx0, lx1);
+          const float wx = (x0 == ix ? lx0 : 0.f) + (x1 == ix ? lx1 : 0.f);
+          if (wx == 0.f) continue;
+          const float* dcol = dout + ((int64_t)n * Hout * Wout + x) * Ctot + coff + cv * VEC;
+          for (int j = 0; j < ny; ++j) {
+            const float w = wy_s[j] * wx;
+            const float* d = dcol + (int64_t)ys_s[j] * Wout * Ctot;
+            if (VEC == 4) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(d));
+              acc[0] += w * v.x; acc[1 % VEC] += w * v.y; acc[2 % VEC] += w * v.z; acc[3 % VEC] += w * v.w;
+            } else {
+              acc[0] += w * __ldg(d);
+            }
+          }
+        }
+      } else {                       // generic: evaluate every (row, column) candidate
+        int ylo, yhi;
+        cand_range(sh, iy, Hin, Hout, ylo, yhi);
+        for (int y = ylo; y <= yhi; ++y) {
+          int y0, y1; float ly0, ly1;
+          src_index(sh, y, Hin, y0, y1, ly0, ly1);
+          const float wy = (y0 == iy ? ly0 : 0.f) + (y1 == iy ? ly1 : 0.f);
+          if (wy == 0.f) continue;
+          for (int x = xlo; x <= xhi; ++x) {
+            int x0, x1; float lx0, lx1;
+            src_index(sw, x, Win, x0, x1, lx0, lx1);
+            const float wx = (x0 == ix ? lx0 : 0.f) + (x1 == ix ? lx1 : 0.f);
+            if (wx == 0.f) continue;
+            const float* d = dout + (((int64_t)n * Hout + y) * Wout + x) * Ctot + coff + cv * VEC;
+            const float w = wy * wx;
+            if (VEC == 4) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(d));
+              acc[0] += w * v.x; acc[1 % VEC] += w * v.y; acc[2 % VEC] += w * v.z; acc[3 % VEC] += w * v.w;
+            } else {
+              acc[0] += w * __ldg(d);
+            }
+          }
         }
       }
+      float* o = din + ((int64_t)row * Win + ix) * C + cv * VEC;
+      if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+      else *o = acc[0];
     }
-    float* o = din + i * VEC;
-    if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
-    else *o = acc[0];
   }
 }
 
@@ -234,9 +279,9 @@ extern "C" int viai_bilinear_fwd(const float* in, int N, int Hin, int Win, int C
                "viai_bilinear_fwd: bad arguments");
   bool v4 = C % 4 == 0 && Ctot % 4 == 0 && coff % 4 == 0 &&
             (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
-  int64_t total = (int64_t)N * Hout * Wout * (C / (v4 ? 4 : 1));
-  if (v4) bilinear_fwd_kernel<4><<<grid_for(total), THREADS, 0, STR(stream)>>>(in, N, Hin, Win, C, out, Hout, Wout, Ctot, coff);
-  else bilinear_fwd_kernel<1><<<grid_for(total), THREADS, 0, STR(stream)>>>(in, N, Hin, Win, C, out, Hout, Wout, Ctot, coff);
+  const int rows = (int)imin64((int64_t)N * Hout, 32 * kNumSMs);
+  if (v4) bilinear_fwd_kernel<4><<<rows, THREADS, 0, STR(stream)>>>(in, N, Hin, Win, C, out, Hout, Wout, Ctot, coff);
+  else bilinear_fwd_kernel<1><<<rows, THREADS, 0, STR(stream)>>>(in, N, Hin, Win, C, out, Hout, Wout, Ctot, coff);
   VIAI_LAUNCHED();
   return VIAI_OK;
 }
@@ -247,9 +292,9 @@ extern "C" int viai_bilinear_bwd(const float* dout, int N, int Hin, int Win, int
                "viai_bilinear_bwd: bad arguments");
   bool v4 = C % 4 == 0 && Ctot % 4 == 0 && coff % 4 == 0 &&
             (reinterpret_cast<uintptr_t>(din) | reinterpret_cast<uintptr_t>(dout)) % 16 == 0;
-  int64_t total = (int64_t)N * Hin * Win * (C / (v4 ? 4 : 1));
-  if (v4) bilinear_bwd_kernel<4><<<grid_for(total), THREADS, 0, STR(stream)>>>(dout, N, Hin, Win, C, din, Hout, Wout, Ctot, coff);
-  else bilinear_bwd_kernel<1><<<grid_for(total), THREADS, 0, STR(stream)>>>(dout, N, Hin, Win, C, din, Hout, Wout, Ctot, coff);
+  const int rows = (int)imin64((int64_t)N * Hin, 32 * kNumSMs);
+  if (v4) bilinear_bwd_kernel<4><<<rows, THREADS, 0, STR(stream)>>>(dout, N, Hin, Win, C, din, Hout, Wout, Ctot, coff);
+  else bilinear_bwd_kernel<1><<<rows, THREADS, 0, STR(stream)>>>(dout, N, Hin, Win, C, din, Hout, Wout, Ctot, coff);
   VIAI_LAUNCHED();
   return VIAI_OK;
 }
