@@ -221,18 +221,27 @@ def main():
     if use_graph:
         tr.capture(mel_d, mask_d, warmup=2)
         step_dev = lambda: tr.replay()
-        step_e2e = lambda: tr.replay(mel_h, mask_h)
+
+        def step_e2e(last=False):
+            """One step through the public API from pinned HOST inputs: this step's inputs were put in flight by prefetch()
+            (side-stream H2D, overlapping the previous step); the next step's H2D is started right after this step is launched."""
+            out = tr.replay()
+            if not last:
+                tr.prefetch(mel_h, mask_h)
+            return out
     else:
         step_dev = lambda: tr.train_step(mel_d, mask_d)
-        step_e2e = lambda: tr.train_step(mel_h.cuda(non_blocking=True), mask_h.cuda(non_blocking=True))
+        step_e2e = lambda last=False: tr.train_step(mel_h.cuda(non_blocking=True), mask_h.cuda(non_blocking=True))
 
     def timed(fn, steps, read_loss):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         sink = 0.0
-        for _ in range(steps):
-            out = fn()
+        if read_loss and use_graph:
+            tr.prefetch(mel_h, mask_h)                  # H2D of the first timed step's inputs (inside the timed region)
+        for i in range(steps):
+            out = fn(i == steps - 1) if read_loss else fn()
             if read_loss:
                 sink += float(out["loss_L1"])           # D2H read of the step's result
         e1.record()
@@ -252,8 +261,11 @@ def main():
         sampler.start()
     ms_dev = timed(step_dev, args.steps, False)
     clocks = sampler.stop() if rank == 0 else None
+    if use_graph:
+        tr.prefetch(mel_h, mask_h)
     for _ in range(2):
         step_e2e()
+    step_e2e(True)                                      # drains the warm-up prefetch: every timed step copies its own inputs
     ms_e2e = timed(step_e2e, args.steps, True)
 
     roof = cpu = None

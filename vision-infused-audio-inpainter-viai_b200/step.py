@@ -151,8 +151,35 @@ class GanTrainer(object):
         self.launches_per_step = _lib.launch_count() - n0
         return self
 
+    def prefetch(self, mel, mask, video=None, flow=None):
+        """Starts the host->device copy of the NEXT step's inputs on a side stream while the current step runs (the input
+        half of a double-buffered loader: the reference's DataLoader uses pinned memory for the same purpose,
+        Data_loaders/audio_loader.py:573).  The following ``replay()`` without arguments consumes them."""
+        if self._static is None:
+            raise RuntimeError("prefetch() needs a captured step (call capture() first)")
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._staging = {k: (None if v is None else torch.empty_like(v)) for k, v in self._static.items()}
+            self._staging_ready = torch.cuda.Event()
+            self._staging_consumed = torch.cuda.Event()
+            self._staging_consumed.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._staging_consumed)       # the previous device-side hand-over has finished
+            for k, src in (("mel", mel), ("mask", mask), ("video", video), ("flow", flow)):
+                if src is not None:
+                    self._staging[k].copy_(src.reshape(self._staging[k].shape), non_blocking=True)
+            self._staging_ready.record(self._copy_stream)
+        self._prefetched = [k for k, src in (("mel", mel), ("mask", mask), ("video", video), ("flow", flow)) if src is not None]
+
     def replay(self, mel=None, mask=None, video=None, flow=None):
         st = self._static
+        if mel is None and mask is None and getattr(self, "_prefetched", None):
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._staging_ready)
+            for k in self._prefetched:
+                st[k].copy_(self._staging[k], non_blocking=True)      # device-to-device hand-over (microseconds)
+            self._staging_consumed.record(cur)
+            self._prefetched = None
         if mel is not None:
             st["mel"].copy_(mel, non_blocking=True)
         if mask is not None:
