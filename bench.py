@@ -199,7 +199,6 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from viai_b200 import Options_inpainting, _lib
     from viai_b200.step import GanTrainer
-    from oracle import viai_oracle as O   # mask definition only (test infrastructure used as the checker's input generator)
 
     torch.manual_seed(rank)
     hp = Options_inpainting.Inpainting_Config(cin_channels=HMEL)
@@ -209,7 +208,9 @@ def main():
             dist.broadcast(opt.flat_param, 0)
     g = torch.Generator().manual_seed(1000 + rank)
     mel_h = torch.rand(B, 1, HMEL, WFR, generator=g).pin_memory()
-    mask_h = O.time_band_mask(mel_h.shape, WFR // 4, WFR // 2).pin_memory()
+    mask_h = torch.ones_like(mel_h)
+    mask_h[..., WFR // 4:WFR // 4 + WFR // 2] = 0.0            # 50 % centre time band (columns 64:192), all mel bins
+    mask_h = mask_h.pin_memory()
     mel_d, mask_d = mel_h.cuda(), mask_h.cuda()
 
     def barrier():
