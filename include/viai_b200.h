@@ -201,13 +201,15 @@ int viai_stft_mel(const float* y, int64_t T, int fft_size, int hop, int pad_left
  * packed_layers / first / head1 / head2: parameter blocks in the layout documented in csrc/wavenet_synth.cu (produced by
  * WaveNet.pack_for_synthesis); cond: (B, T, C) upsampled conditioning; uniforms: (T, B, nr_mix + 1) draws in (0, 1);
  * test_inputs (optional): (B, Ttest) teacher-forced inputs for the first Ttest steps.  ring (sum_l ((K-1)*d_l + 1) * B * R
- * floats at offsets ring_off[l]), gbuf (B*G/2), sbuf (B*S), hbuf (B*S), bar (2 x u32): zero-initialised scratch.
+ * floats at offsets ring_off[l]): zero-initialised state.  gbuf (B*G/2), sbuf (B*S), hbuf (B*S), xchg (B*R): zero-initialised,
+ * 8-byte aligned exchange buffers of 64-bit {value, stage tag} words, i.e. TWO 32-bit words per element (the CTAs synchronise
+ * through these tagged words; there is no grid barrier).
  * out: (B, T) samples in [-1, 1]; logits (optional): (B, T, O) pre-sampling outputs. */
 int viai_wavenet_num_ctas(int R, int G, int S, int C, int K, int O, int B);
 int viai_wavenet_synth(int L, int layers_per_stack, int R, int G, int S, int C, int K, int O, int B, int T, int nC,
                        const float* packed_layers, const float* first, const float* head1, const float* head2,
                        const float* cond, const float* uniforms, const float* test_inputs, int Ttest, float log_scale_min,
-                       float* ring, const int64_t* ring_off, float* gbuf, float* sbuf, float* hbuf, unsigned* bar, float* out,
+                       float* ring, const int64_t* ring_off, float* gbuf, float* sbuf, float* hbuf, unsigned* xchg, float* out,
                        float* logits, viai_stream_t stream);
 
 /* Losses (loss_functions.py:79-104 GANLoss = MSELoss / BCELoss against an expanded scalar; nn.L1Loss).

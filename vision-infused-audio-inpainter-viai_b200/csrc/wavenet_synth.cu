@@ -13,7 +13,11 @@
 //     512-float current activation crosses CTAs on the critical path;
 //   * per-layer ring buffers of 2d+1 time slots live in global memory (L2-resident) and are indexed modulo -- nothing is
 //     shifted (the reference clones the whole buffer every step, conv.py:39);
-//   * stages are separated by a sense-reversing grid barrier (one atomic per CTA) with a watchdog;
+//   * there is NO grid barrier: every cross-CTA vector (gate outputs, residual outputs, skip sums, head activations) travels
+//     as 64-bit {value, stage tag} words written with st.release and polled with ld.acquire, so that one L2 round trip
+//     delivers both the data and the synchronisation (a counter barrier costs an atomic round trip + a flag round trip per
+//     stage, and there are 2*L+2 = 50 stages per sample).  The alternation of the exchanges makes single buffers safe: a CTA
+//     can only overwrite a buffer after reading a later vector whose producers had all consumed the earlier one;
 //   * skip accumulators stay in the owning CTA's shared memory for the whole sample; the 30-row output layer and the sampler
 //     are evaluated redundantly by every CTA so that the next input needs no extra exchange.
 #include "common.cuh"
@@ -47,10 +51,10 @@ struct WnParams {
   // state (global, zero-initialised by the caller)
   float* ring;                         // per layer: [ring_len_l][B][R], offsets in ring_off
   const int64_t* ring_off;
-  float* gbuf;                         // [B][G/2]
-  float* sbuf;                         // [B][S]   relu(skips)
-  float* hbuf;                         // [B][S]   relu(head1)
-  unsigned* bar;                       // [0] arrival counter, [1] generation
+  unsigned long long* gbuf;            // [B][G/2]  tagged words {value, stage tag}: gate outputs
+  unsigned long long* sbuf;            // [B][S]    relu(skips)
+  unsigned long long* hbuf;            // [B][S]    relu(head1)
+  unsigned long long* xnew;            // [B][R]    residual output of the previous layer = newest tap of the next one
   float* out;                          // (B, T)
   float* logits;                       // (B, T, O) or null
 };
@@ -59,31 +63,22 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+// Tagged exchange words: low 32 bits = float value, high 32 bits = stage tag (0 = never written; buffers start zeroed).
+__device__ __forceinline__ void put_tagged(unsigned long long* p, float v, unsigned tag) {
+  const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, unsigned& gen) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    ++gen;
-    __threadfence();
-    const unsigned prev = atomicAdd(&bar[0], 1u);
-    if (prev == nblocks - 1) {
-      bar[0] = 0;
-      __threadfence();
-      atomicExch(&bar[1], gen);
-    } else {
-      const long long t0 = clock64();
-      while (ld_acquire(&bar[1]) != gen) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-      }
-    }
-    __threadfence();
+__device__ __forceinline__ float get_tagged(const unsigned long long* p, unsigned tag) {
+  unsigned long long w;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  if ((unsigned)(w >> 32) != tag) {
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+      if (clock64() - t0 > 4000000000LL) __trap();          // a protocol bug fails the launch instead of hanging the device
+    } while ((unsigned)(w >> 32) != tag);
   }
-  __syncthreads();
+  return __uint_as_float((unsigned)w);
 }
 
 // rows x K mat-vec for B batch columns: warp w -> row (w % rows), K slice (w / rows); result[row][b] in `res` (shared).
@@ -149,7 +144,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_synth_kernel(const WnParams p) 
   float* h2w = h1w + p.hrows * p.S + pad4(p.hrows);                        // [O][S] + [O]
   float* vec = h2w + p.O * p.S + pad4(p.O);                                    // [B][S] staging of relu(skips)/relu(head1)
   float* cur = vec + p.B * p.S;                                            // [MAXB] current input sample
-  unsigned gen = 0;
+  const unsigned per_sample = 2u * (unsigned)p.L + 2u;             // exchanges per sample; tag = 1 + t * per_sample + index
   const float r2 = 0.70710678118654752440f;
 
   for (int i = tid; i < 2 * p.R; i += NT) first[i] = p.first[i];
@@ -187,7 +182,9 @@ __global__ void __launch_bounds__(NT, 1) wavenet_synth_kernel(const WnParams p) 
       if (tid < p.B) cur[tid] = p.test_inputs[(size_t)tid * p.Ttest + t];
       __syncthreads();
     }
+    const unsigned tag0 = 1u + (unsigned)t * per_sample;
     for (int l = 0; l < p.L; ++l) {
+      const unsigned tag_g = tag0 + 2u * (unsigned)l, tag_x = tag_g + 1u;   // gate exchange of layer l, residual exchange l -> l+1
       const int d = 1 << (l % p.layers_per_stack);
       const int rl = (p.K - 1) * d + 1;
       float* ring = p.ring + p.ring_off[l];
@@ -203,7 +200,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_synth_kernel(const WnParams p) 
       } else {
         for (int i = tid; i < p.B * p.R; i += NT) {
           const int b = i / p.R, r = i - b * p.R;
-          x[b * xlen + (p.K - 1) * p.R + r] = __ldcg(ring + ((size_t)(t % rl) * p.B + b) * p.R + r);
+          x[b * xlen + (p.K - 1) * p.R + r] = get_tagged(p.xnew + i, tag_x - 2u);     // written by layer l-1's stage 2
         }
       }
       cp_async_wait_all();
@@ -222,11 +219,10 @@ __global__ void __launch_bounds__(NT, 1) wavenet_synth_kernel(const WnParams p) 
       for (int i = tid; i < p.pairs * p.B; i += NT) {
         const int pr = i / p.B, b = i - pr * p.B;
         const float a = res[(2 * pr) * MAXB + b] + b1[2 * pr], g = res[(2 * pr + 1) * MAXB + b] + b1[2 * pr + 1];
-        p.gbuf[(size_t)b * p.K2 + cta * p.pairs + pr] = tanhf(a) * (1.f / (1.f + expf(-g)));
+        put_tagged(p.gbuf + (size_t)b * p.K2 + cta * p.pairs + pr, tanhf(a) * (1.f / (1.f + expf(-g))), tag_g);
       }
-      grid_barrier(p.bar, p.nC, gen);
       // ---- stage 2: skip and residual 1x1 convolutions ----
-      for (int i = tid; i < p.B * p.K2; i += NT) gsm[i] = __ldcg(p.gbuf + i);
+      for (int i = tid; i < p.B * p.K2; i += NT) gsm[i] = get_tagged(p.gbuf + i, tag_g);
       __syncthreads();
       matvec(W2, gsm, p.K2, rows2, p.K2, p.B, part, res);
       for (int i = tid; i < rows2 * p.B; i += NT) {
@@ -239,28 +235,31 @@ __global__ void __launch_bounds__(NT, 1) wavenet_synth_kernel(const WnParams p) 
           const float hin = x[b * xlen + (p.K - 1) * p.R + r];
           const int dn = 1 << ((l + 1) % p.layers_per_stack);
           const int rln = (p.K - 1) * dn + 1;
-          p.ring[p.ring_off[l + 1] + ((size_t)(t % rln) * p.B + b) * p.R + r] = (v + hin) * r2;
+          const float xo = (v + hin) * r2;
+          p.ring[p.ring_off[l + 1] + ((size_t)(t % rln) * p.B + b) * p.R + r] = xo;      // for the taps of later samples
+          put_tagged(p.xnew + (size_t)b * p.R + r, xo, tag_x);                            // newest tap of layer l+1, now
         }
       }
       if (l + 1 == p.L) {
         for (int i = tid; i < p.srows * p.B; i += NT) {
           const int row = i / p.B, b = i - row * p.B;
-          p.sbuf[(size_t)b * p.S + cta * p.srows + row] = fmaxf(skips[row * MAXB + b], 0.f);
+          put_tagged(p.sbuf + (size_t)b * p.S + cta * p.srows + row, fmaxf(skips[row * MAXB + b], 0.f), tag0 + per_sample - 2u);
         }
       }
-      grid_barrier(p.bar, p.nC, gen);
+      __syncthreads();                 // x / gsm / res are rewritten by the next stage
       buf ^= 1;
     }
     // ---- output head: ReLU, 1x1 (S -> S), ReLU, 1x1 (S -> O) ----
-    for (int i = tid; i < p.B * p.S; i += NT) vec[i] = __ldcg(p.sbuf + i);
+    for (int i = tid; i < p.B * p.S; i += NT) vec[i] = get_tagged(p.sbuf + i, tag0 + per_sample - 2u);
     __syncthreads();
     matvec(h1w, vec, p.S, p.hrows, p.S, p.B, part, res);
     for (int i = tid; i < p.hrows * p.B; i += NT) {
       const int row = i / p.B, b = i - row * p.B;
-      p.hbuf[(size_t)b * p.S + cta * p.hrows + row] = fmaxf(res[row * MAXB + b] + h1w[p.hrows * p.S + row], 0.f);
+      put_tagged(p.hbuf + (size_t)b * p.S + cta * p.hrows + row, fmaxf(res[row * MAXB + b] + h1w[p.hrows * p.S + row], 0.f),
+                 tag0 + per_sample - 1u);
     }
-    grid_barrier(p.bar, p.nC, gen);
-    for (int i = tid; i < p.B * p.S; i += NT) vec[i] = __ldcg(p.hbuf + i);
+    __syncthreads();                   // vec is refilled below
+    for (int i = tid; i < p.B * p.S; i += NT) vec[i] = get_tagged(p.hbuf + i, tag0 + per_sample - 1u);
     __syncthreads();
     matvec(h2w, vec, p.S, p.O, p.S, p.B, part, res);
     // ---- sample from the discretised mixture of logistics (every CTA computes the same value) ----
@@ -319,15 +318,18 @@ extern "C" int viai_wavenet_num_ctas(int R, int G, int S, int C, int K, int O, i
   return 0;
 }
 
-// All pointers are device pointers; ring / gbuf / sbuf / hbuf / bar must be zero-initialised by the caller.
+// All pointers are device pointers; ring / gbuf / sbuf / hbuf / xchg must be zero-initialised by the caller.
 // packed layer weights: see viai_b200/wavenet_vocoder/wavenet.py (pack_for_synthesis).
 extern "C" int viai_wavenet_synth(int L, int layers_per_stack, int R, int G, int S, int C, int K, int O, int B, int T, int nC,
                                   const float* packed_layers, const float* first, const float* head1, const float* head2,
                                   const float* cond, const float* uniforms, const float* test_inputs, int Ttest,
                                   float log_scale_min, float* ring, const int64_t* ring_off, float* gbuf, float* sbuf,
-                                  float* hbuf, unsigned* bar, float* out, float* logits, viai_stream_t stream) {
-  VIAI_REQUIRE(packed_layers && first && head1 && head2 && cond && uniforms && ring && ring_off && gbuf && sbuf && hbuf && bar && out,
+                                  float* hbuf, unsigned* xchg, float* out, float* logits, viai_stream_t stream) {
+  VIAI_REQUIRE(packed_layers && first && head1 && head2 && cond && uniforms && ring && ring_off && gbuf && sbuf && hbuf && xchg && out,
                "wavenet_synth: null argument");
+  VIAI_REQUIRE(((reinterpret_cast<uintptr_t>(gbuf) | reinterpret_cast<uintptr_t>(sbuf) | reinterpret_cast<uintptr_t>(hbuf) |
+                 reinterpret_cast<uintptr_t>(xchg)) & 7) == 0, "wavenet_synth: exchange buffers must be 8-byte aligned");
+  VIAI_REQUIRE((int64_t)T * (2 * L + 2) < 4000000000LL, "wavenet_synth: T too large for the 32-bit stage tags");
   VIAI_REQUIRE(nC >= 1 && nC == viai_wavenet_num_ctas(R, G, S, C, K, O, B), "wavenet_synth: nC must come from viai_wavenet_num_ctas");
   VIAI_REQUIRE(L >= 1 && layers_per_stack >= 1 && L % layers_per_stack == 0 && T >= 0, "wavenet_synth: bad layer configuration");
   if (T == 0) return VIAI_OK;
@@ -342,7 +344,9 @@ extern "C" int viai_wavenet_synth(int L, int layers_per_stack, int R, int G, int
   p.layer_stride = p.cta_stride * nC;
   p.wl = packed_layers; p.first = first; p.head1 = head1; p.head2 = head2; p.cond = cond; p.uniforms = uniforms;
   p.test_inputs = test_inputs; p.Ttest = test_inputs ? Ttest : 0; p.log_scale_min = log_scale_min;
-  p.ring = ring; p.ring_off = ring_off; p.gbuf = gbuf; p.sbuf = sbuf; p.hbuf = hbuf; p.bar = bar; p.out = out; p.logits = logits;
+  p.ring = ring; p.ring_off = ring_off; p.out = out; p.logits = logits;
+  p.gbuf = reinterpret_cast<unsigned long long*>(gbuf); p.sbuf = reinterpret_cast<unsigned long long*>(sbuf);
+  p.hbuf = reinterpret_cast<unsigned long long*>(hbuf); p.xnew = reinterpret_cast<unsigned long long*>(xchg);
   const size_t smem = (size_t)wn_smem_bytes(R, G, S, C, K, O, B, nC);
   VIAI_CUDA(cudaFuncSetAttribute(wavenet_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {&p};

@@ -210,8 +210,10 @@ class WaveNet(nn.Module):
             tot += rl * B * R
         ring = torch.zeros(tot, device=dev)
         ring_off = torch.tensor(offs, device=dev, dtype=torch.int64)
-        gbuf, sbuf, hbuf = torch.zeros(B * (G // 2), device=dev), torch.zeros(B * S, device=dev), torch.zeros(B * S, device=dev)
-        bar = torch.zeros(2, device=dev, dtype=torch.int32)
+        # exchange buffers of 64-bit {value, stage tag} words, zero = "never written"
+        gbuf, sbuf, hbuf = (torch.zeros(2 * B * (G // 2), device=dev), torch.zeros(2 * B * S, device=dev),
+                            torch.zeros(2 * B * S, device=dev))
+        bar = torch.zeros(2 * B * R, device=dev, dtype=torch.int32)
         out = torch.empty((B, T), device=dev)
         logits = torch.empty((B, T, O), device=dev) if return_logits else None
         ti = None
