@@ -64,17 +64,20 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // Tagged exchange words: low 32 bits = float value, high 32 bits = stage tag (0 = never written; buffers start zeroed).
+// Value and tag share one 64-bit word, so the exchange itself needs no ordering between locations: relaxed gpu-scope accesses
+// (served by L2) are enough and avoid a release fence per stage.  The plain ring-buffer stores, which other CTAs read one or
+// more samples later, are ordered by ONE fence pair per sample around the last exchange (see the head stage).
 __device__ __forceinline__ void put_tagged(unsigned long long* p, float v, unsigned tag) {
   const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
 __device__ __forceinline__ float get_tagged(const unsigned long long* p, unsigned tag) {
   unsigned long long w;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
   if ((unsigned)(w >> 32) != tag) {
     const long long t0 = clock64();
     do {
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
       if (clock64() - t0 > 4000000000LL) __trap();          // a protocol bug fails the launch instead of hanging the device
     } while ((unsigned)(w >> 32) != tag);
   }
@@ -205,11 +208,6 @@ __global__ void __launch_bounds__(NT, 1) wavenet_synth_kernel(const WnParams p) 
       }
       cp_async_wait_all();
       __syncthreads();
-      // prefetch the next stage-1 operands (next layer of this step, or layer 0 of the next step) into the other buffer
-      {
-        const int nl = (l + 1 == p.L) ? 0 : l + 1, nt = (l + 1 == p.L) ? t + 1 : t;
-        if (nt < p.T) prefetch(nl, nt, buf ^ 1);
-      }
       const float* W1 = wbuf[buf];
       const float* b1 = W1 + rows1 * p.K1;
       const float* W2 = b1 + pad4(rows1);
@@ -220,6 +218,12 @@ __global__ void __launch_bounds__(NT, 1) wavenet_synth_kernel(const WnParams p) 
         const int pr = i / p.B, b = i - pr * p.B;
         const float a = res[(2 * pr) * MAXB + b] + b1[2 * pr], g = res[(2 * pr + 1) * MAXB + b] + b1[2 * pr + 1];
         put_tagged(p.gbuf + (size_t)b * p.K2 + cta * p.pairs + pr, tanhf(a) * (1.f / (1.f + expf(-g))), tag_g);
+      }
+      // prefetch the next stage-1 operands (next layer of this step, or layer 0 of the next step) into the other buffer: issued
+      // here, while the other CTAs' gate outputs are in flight, instead of on the critical path before the mat-vec
+      {
+        const int nl = (l + 1 == p.L) ? 0 : l + 1, nt = (l + 1 == p.L) ? t + 1 : t;
+        if (nt < p.T) prefetch(nl, nt, buf ^ 1);
       }
       // ---- stage 2: skip and residual 1x1 convolutions ----
       for (int i = tid; i < p.B * p.K2; i += NT) gsm[i] = get_tagged(p.gbuf + i, tag_g);
@@ -253,6 +257,8 @@ __global__ void __launch_bounds__(NT, 1) wavenet_synth_kernel(const WnParams p) 
     for (int i = tid; i < p.B * p.S; i += NT) vec[i] = get_tagged(p.sbuf + i, tag0 + per_sample - 2u);
     __syncthreads();
     matvec(h1w, vec, p.S, p.hrows, p.S, p.B, part, res);
+    __threadfence();                   // release: this sample's ring-buffer stores are visible before the tagged words below
+    __syncthreads();
     for (int i = tid; i < p.hrows * p.B; i += NT) {
       const int row = i / p.B, b = i - row * p.B;
       put_tagged(p.hbuf + (size_t)b * p.S + cta * p.hrows + row, fmaxf(res[row * MAXB + b] + h1w[p.hrows * p.S + row], 0.f),
@@ -260,6 +266,7 @@ __global__ void __launch_bounds__(NT, 1) wavenet_synth_kernel(const WnParams p) 
     }
     __syncthreads();                   // vec is refilled below
     for (int i = tid; i < p.B * p.S; i += NT) vec[i] = get_tagged(p.hbuf + i, tag0 + per_sample - 1u);
+    __threadfence();                   // acquire: every CTA's ring-buffer stores of this sample are visible from here on
     __syncthreads();
     matvec(h2w, vec, p.S, p.O, p.S, p.B, part, res);
     // ---- sample from the discretised mixture of logistics (every CTA computes the same value) ----
