@@ -347,15 +347,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
               const float f[8] = {v[2 * m].x, v[2 * m].y, v[2 * m].z, v[2 * m].w, v[2 * m + 1].x, v[2 * m + 1].y, v[2 * m + 1].z, v[2 * m + 1].w};
-              // hi = x truncated to bf16 (one mask; whatever truncation drops lands in lo, which is x - hi EXACTLY), lo rounded
-              // to nearest: one cvt.rn.bf16x2 per pair instead of two, and the error of hi + lo stays ~2^-17 |x|, unbiased.
+              // hi and lo are both rounded to nearest (packed cvt.rn.bf16x2): hi + lo represents x to ~2^-17 |x|.  (Truncating hi
+              // saves one conversion per pair but doubles the representation error; measured speed difference: none.)
               uint32_t hi[4], lo[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const uint32_t b0 = __float_as_uint(f[2 * e]), b1 = __float_as_uint(f[2 * e + 1]);
-                const uint32_t t0 = b0 & 0xffff0000u, t1 = b1 & 0xffff0000u;
-                hi[e] = __byte_perm(t0, t1, 0x7632);          // {t0[31:16] -> low half, t1[31:16] -> high half}
-                lo[e] = pack_bf16x2(f[2 * e] - __uint_as_float(t0), f[2 * e + 1] - __uint_as_float(t1));
+                hi[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+                const float h0 = __uint_as_float(hi[e] << 16), h1 = __uint_as_float(hi[e] & 0xffff0000u);
+                lo[e] = pack_bf16x2(f[2 * e] - h0, f[2 * e + 1] - h1);
               }
               *reinterpret_cast<uint4*>(row + ((m ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4*>(row + (((4 + m) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
