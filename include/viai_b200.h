@@ -212,6 +212,17 @@ int viai_wavenet_synth(int L, int layers_per_stack, int R, int G, int S, int C, 
                        float* ring, const int64_t* ring_off, float* gbuf, float* sbuf, float* hbuf, unsigned* xchg, float* out,
                        float* logits, viai_stream_t stream);
 
+/* The same synthesis on ONE 16-CTA thread-block cluster: cross-CTA vectors travel through distributed shared memory instead of
+ * global memory (an exchange costs a few hundred ns instead of ~1.3 us), the weights are streamed by 16 SMs.  Operands as
+ * viai_wavenet_synth with the parameter blocks packed for nC = 16; B <= 2; only `ring` is caller-owned state.
+ * viai_wavenet_cluster_supported returns 16 when the configuration fits, else 0 (use viai_wavenet_synth). */
+int viai_wavenet_cluster_supported(int R, int G, int S, int C, int K, int O, int B);
+int viai_wavenet_synth_cluster(int L, int layers_per_stack, int R, int G, int S, int C, int K, int O, int B, int T,
+                               const float* packed_layers, const float* first, const float* head1, const float* head2,
+                               const float* cond, const float* uniforms, const float* test_inputs, int Ttest,
+                               float log_scale_min, float* ring, const int64_t* ring_off, float* out, float* logits,
+                               viai_stream_t stream);
+
 /* Losses (loss_functions.py:79-104 GANLoss = MSELoss / BCELoss against an expanded scalar; nn.L1Loss).
  * kind 0: mean (p-t)^2   1: BCE(p, t)   2: mean |p - q|  (q = other tensor).  acc: double[1] workspace.
  * loss_out: float[1] on device. */
