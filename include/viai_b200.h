@@ -243,6 +243,49 @@ int viai_fill(float* p, int64_t n, float value, viai_stream_t stream);
 /* out[i] = 1/sqrt(var[i] + eps)  (eval-mode BatchNorm uses running_var) */
 int viai_rsqrt_eps(const float* var, int n, float eps, float* out, viai_stream_t stream);
 
+/* ---- WaveNet teacher-forced training path: wavenet_vocoder/wavenet.py:177-235 forward,
+ * wavenet_vocoder/modules.py:162-210 ResidualConv1dGLU._forward (is_incremental = False), wavenet_vocoder/mixture.py:25-105,
+ * loss_functions.py:11-76.  Activations are (B, T, C) rows ("NHWC" with H*W = B*T pixels). */
+/* Operand of a dilated causal nn.Conv1d (modules.py:175-178: conv + "remove future time steps") joined with the
+ * local-conditioning features (modules.py:183-187), so that conv + conv1x1c is ONE 1x1 GEMM with the linearised weight of
+ * conv.py:51-62:  out[b,t,k*R + r] = x[b, t - (K-1-k)*dilation, r] (0 before t = 0), out[b,t,K*R + j] = c[b,t,j], zero up to
+ * Kpad.  R, Cc, Kpad multiples of 4; c may be NULL when Cc == 0. */
+int viai_shiftcat_fwd(const float* x, const float* c, int B, int T, int R, int Cc, int K, int dilation, int Kpad, float* out,
+                      viai_stream_t stream);
+/* dx (B,T,R) and dc (B,T,Cc; may be NULL) from dout (B,T,Kpad) */
+int viai_shiftcat_bwd(const float* dout, int B, int T, int R, int Cc, int K, int dilation, int Kpad, float* dx, float* dc,
+                      viai_stream_t stream);
+/* out[row,i] = tanh(y[row,i]) * sigmoid(y[row,G/2+i])  (modules.py:180,196) and its backward; G % 8 == 0 */
+int viai_glu_fwd(const float* y, int64_t rows, int G, float* out, viai_stream_t stream);
+int viai_glu_bwd(const float* y, const float* dout, int64_t rows, int G, float* dy, viai_stream_t stream);
+/* out = alpha*a + beta*b (b may be NULL; out may alias a): (x + residual)*sqrt(0.5) modules.py:204, skip accumulation
+ * wavenet.py:222-223, ExponentialMovingAverage.update loss_functions.py:70-73 */
+int viai_axpby(const float* a, float alpha, const float* b, float beta, float* out, int64_t n, viai_stream_t stream);
+/* discretized_mix_logistic_loss(reduce=False) (mixture.py:25-105): y_hat rows of 3*nr_mix floats (logits | means | log
+ * scales), target rows in [-1,1].  nll[row] = -log_sum_exp(log_probs) (may be NULL); with dnll/dy_hat also the analytic
+ * gradient dy_hat[row,:] = dnll[row] * d nll / d y_hat.  nr_mix <= 32. */
+int viai_dmol_nll(const float* y_hat, const float* target, int64_t rows, int nr_mix, int num_classes, float log_scale_min, float* nll,
+                  const float* dnll, float* dy_hat, viai_stream_t stream);
+/* mean != 0: (v*mask).sum() / mask.sum() (loss_functions.py:59); mean == 0: (v*mask).sum().  mask may be NULL (ones).
+ * acc: double[2] workspace kept for the backward (sum v*m, sum m); out / gout: float[1] on device. */
+int viai_masked_sum_fwd(const float* v, const float* mask, int64_t n, int mean, double* acc, float* out, viai_stream_t stream);
+int viai_masked_sum_bwd(const float* mask, int64_t n, int mean, const double* acc, const float* gout, float* dv, viai_stream_t stream);
+/* sequence_mask (loss_functions.py:11-21): out[b,t] = t < lengths[b] */
+int viai_sequence_mask(const int64_t* lengths, int B, int T, float* out, viai_stream_t stream);
+
+/* ---- Audio-visual synchronisation heads */
+/* utils/util.py:94-96 l2_norm = F.normalize(x, p=2, dim=1): y = x / max(||x||, eps); norms: float[rows] kept for the backward */
+int viai_l2norm_fwd(const float* x, int rows, int cols, float eps, float* y, float* norms, viai_stream_t stream);
+int viai_l2norm_bwd(const float* y, const float* norms, const float* dy, int rows, int cols, float eps, float* dx, viai_stream_t stream);
+/* loss_functions.py:106-108 l2_sim: scores[a][b] = ||f1[a] - f2[b]||_2 (also the distance matrix of utils/util.py:99-121 L2retrieval) */
+int viai_pairdist_fwd(const float* f1, const float* f2, int n1, int n2, int F, float* scores, viai_stream_t stream);
+int viai_pairdist_bwd(const float* f1, const float* f2, const float* scores, const float* dscores, int n1, int n2, int F, float* df1,
+                      float* df2, viai_stream_t stream);
+/* loss_functions.py:111-148 L2ContrastiveLoss on a (B,B) score matrix: loss (float[1], may be NULL) and, with gout/dscores,
+ * dscores = gout * d loss / d scores */
+int viai_l2_contrastive(const float* scores, int B, float margin, int max_violation, float* loss, const float* gout, float* dscores,
+                        viai_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,6 +138,113 @@ def image_embedding_fixture(ref):
     print("image embedding", tuple(out.shape))
 
 
+def next_rows_inputs():
+    """Inputs of the next-row fixtures: a pure function of names, rebuilt by the tests."""
+    yh = FX.normal("dmol_yhat", (2, 30, 40)) * 2.0
+    yh[:, 20:, :8] -= 12.0                  # log scales under both clamps -> the bin-centre pdf branch
+    yh[:, 20:, 8:16] -= 5.0
+    y = FX.uniform("dmol_y", (2, 40, 1), -1.0, 1.0)
+    y[0, :4] = -1.0                         # edge bins
+    y[1, :4] = 1.0
+    y[1, 4:6] = 0.9995
+    return dict(dmol_yhat=yh, dmol_y=y, dmol_len=torch.tensor([40, 27]),
+                f1=FX.normal("ctr_f1", (6, 32)), f2=FX.normal("ctr_f2", (6, 32)) * 0.5 + FX.normal("ctr_f1", (6, 32)) * 0.7,
+                f3=FX.normal("ctr_f3", (6, 32)) + FX.normal("ctr_f1", (6, 32)) * 0.25,
+                dis_mel=FX.uniform("dis_mel", (2, 1, 80, 64)), dis_fea=FX.normal("dis_fea", (2, 512, 16)),
+                dom_x=FX.normal("dom_x", (3, 256, 13)),
+                video=FX.normal("video", (1, 4, 3, 224, 224)).clamp(-1, 1), flow=FX.normal("flow", (1, 4, 2, 224, 224)).clamp(-1, 1),
+                feat=FX.normal("ft_feat", (2, 8, 256)))
+
+
+WAVENET_TRAIN_KW = dict(layers=8, stacks=2, residual_channels=32, gate_channels=32, skip_out_channels=16, cin_channels=8,
+                        upsample_scales=[2, 4])
+
+
+def next_rows_fixture(ref):
+    import math
+    I = next_rows_inputs()
+    fx = {}
+    LF, MX = ref.loss_functions, ref.mixture
+    # --- DMoL loss: values + autograd gradients of the reference
+    for tag, nc, lsm in (("256", 256, -7.0), ("65536", 65536, float(math.log(1e-14)))):
+        yh = I["dmol_yhat"].clone().requires_grad_(True)
+        nll = MX.discretized_mix_logistic_loss(yh, I["dmol_y"], num_classes=nc, log_scale_min=lsm, reduce=False)
+        tot = MX.discretized_mix_logistic_loss(yh, I["dmol_y"], num_classes=nc, log_scale_min=lsm, reduce=True)
+        g, = torch.autograd.grad(nll.sum(), yh)
+        fx["dmol_" + tag] = dict(nll=nll.detach(), total=float(tot), grad=g)
+    yh = I["dmol_yhat"].clone().requires_grad_(True)
+    ml = LF.DiscretizedMixturelogisticLoss()(yh, I["dmol_y"], lengths=I["dmol_len"])
+    g, = torch.autograd.grad(ml, yh)
+    fx["dmol_masked"] = dict(loss=float(ml), grad=g, mask=LF.sequence_mask(I["dmol_len"]))
+    # --- EMA
+    ema = LF.ExponentialMovingAverage(0.9)
+    ema.register("w", I["f1"])
+    ema.update("w", I["f2"])
+    fx["ema"] = ema.shadow["w"].clone()
+    # --- L2 contrastive loss / l2_norm / retrieval
+    for tag, margin, mv in (("m0", 0, False), ("m8", 8.0, False), ("m8max", 8.0, True)):
+        a, b = I["f1"].clone().requires_grad_(True), I["f2"].clone().requires_grad_(True)
+        loss = LF.L2ContrastiveLoss(margin=margin, max_violation=mv)(a, b)
+        ga, gb = torch.autograd.grad(loss, (a, b))
+        fx["ctr_" + tag] = dict(loss=float(loss), g1=ga, g2=gb)
+    fx["l2_sim"] = LF.l2_sim(I["f1"], I["f2"])
+    try:
+        import importlib
+        U = importlib.import_module("utils.util")
+        fx["l2_norm"] = U.l2_norm(I["f1"])
+        fx["retrieval"] = tuple(float(v) for v in U.L2retrieval(I["f1"].numpy(), I["f2"].numpy()))
+        fx["retrieval_noisy"] = tuple(float(v) for v in U.L2retrieval(I["f1"].numpy(), I["f3"].numpy()))
+    except Exception as e:        # sklearn / cv2 ... missing: restated by torch
+        print("utils.util not importable (%s); l2_norm / L2retrieval golden from their one-line definitions" % e)
+        fx["l2_norm"] = torch.nn.functional.normalize(I["f1"], p=2, dim=1)
+    # --- discriminator heads
+    DN = ref.Discriminator_Networks
+    D = _fill(DN.Inpainting_Dis())
+    out = D(I["dis_mel"], I["dis_fea"])
+    out.pow(2).sum().backward()
+    fx["inpainting_dis"] = dict(out=out.detach(), shapes={k: tuple(v.shape) for k, v in D.state_dict().items()},
+                                grads={k: p.grad.clone() for k, p in D.named_parameters() if p.numel() <= 8192},
+                                gnorm={k: float(p.grad.norm()) for k, p in D.named_parameters()},
+                                rm={k: v.clone() for k, v in D.state_dict().items() if "running_mean" in k})
+    D = _fill(DN.DomainDis())
+    out = D(I["dom_x"])
+    out.sum().backward()
+    fx["domain_dis"] = dict(out=out.detach(), shapes={k: tuple(v.shape) for k, v in D.state_dict().items()},
+                            gnorm={k: float(p.grad.norm()) for k, p in D.named_parameters()})
+    # --- visual branches
+    if ref.Image_Embedding is not None:
+        IE = ref.Image_Embedding
+        M = _fill(IE.ImageEmbedding2())
+        out, fea = M(I["video"], I["flow"])
+        fx["ie2"] = dict(out=out.detach(), fea=fea.detach(), shapes={k: tuple(v.shape) for k, v in M.state_dict().items()})
+        M = _fill(IE.ImageEmbedding_single(image=1))
+        fx["ie_single"] = dict(out=M(I["video"]).detach(), bn_1_running_mean=M.state_dict()["bn_1.running_mean"].clone(),
+                               shapes={k: tuple(v.shape) for k, v in M.state_dict().items()})
+        M = _fill(IE.ImageEmbedding_finetune())
+        fx["ie_finetune"] = dict(out=M(I["feat"]).detach(), shapes={k: tuple(v.shape) for k, v in M.state_dict().items()})
+    # --- WaveNet teacher-forced training step (eval mode: dropout off), loss on the shifted targets, gradients
+    kw = WAVENET_TRAIN_KW
+    W = _fill(ref.wavenet.WaveNet(**kw)).eval()
+    T = 48
+    x = FX.uniform("wav_xsmall", (1, 1, T), -1.0, 1.0)
+    c = FX.uniform("wav_csmall", (1, kw["cin_channels"], T // 8))
+    x2 = torch.cat((x, FX.uniform("wav_x2", (1, 1, T), -1.0, 1.0)), 0)
+    c2 = torch.cat((c, FX.uniform("wav_c2", (1, kw["cin_channels"], T // 8))), 0)
+    lengths = torch.tensor([T - 1, T - 11])
+    y_hat = W(x2, c2)
+    loss = LF.DiscretizedMixturelogisticLoss()(y_hat[:, :, :-1], x2.transpose(1, 2)[:, 1:, :], lengths=lengths)
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in W.named_parameters() if p.grad is not None}
+    keep = ["first_conv.bias", "first_conv.weight_g", "conv_layers.0.conv.weight_v", "conv_layers.3.conv1x1c.weight_g",
+            "conv_layers.6.conv1x1_out.weight_v", "conv_layers.5.conv1x1_skip.bias", "last_conv_layers.3.bias",
+            "last_conv_layers.1.weight_v", "upsample_conv.0.weight_v", "upsample_conv.2.bias"]
+    fx["wavenet_train"] = dict(T=T, loss=float(loss), y_hat=y_hat.detach(), lengths=lengths, grads={k: grads[k] for k in keep},
+                               gnorm={k: float(v.norm()) for k, v in grads.items()},
+                               dead=[k for k, p in W.named_parameters() if p.grad is None])
+    torch.save(fx, os.path.join(OUT, "next_rows.pt"))
+    print("next rows:", sorted(fx.keys()), "wavenet train loss %.6f" % fx["wavenet_train"]["loss"])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load(normlayer=nn.BatchNorm2d, cin_channels=80)
@@ -152,6 +259,7 @@ def main():
     wavenet_fixture(ref, "full", 320, layers=24, stacks=4, residual_channels=512, gate_channels=512,
                     skip_out_channels=256, cin_channels=80, upsample_scales=[4, 4, 10])
     image_embedding_fixture(ref)
+    next_rows_fixture(ref)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,147 @@
+"""TEST INFRASTRUCTURE ONLY: plain-torch stand-ins for ``viai_b200.ops`` so that the HOST logic of the product modules
+(tensor layouts, weight re-packing, shape glue, state_dict contracts) can be exercised by the ``-m "not gpu"`` tests in a
+container without a GPU.  Nothing in the product package imports this file; the product ops have no CPU path and raise on
+CPU tensors.  ``with installed():`` swaps the functions in for the duration of one test and restores the CUDA-only originals."""
+import contextlib
+
+import torch
+import torch.nn.functional as F
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2)
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def conv2d(x, weight, bias=None, stride=(1, 1), padding=(0, 0), transposed=False):
+    f = F.conv_transpose2d if transposed else F.conv2d
+    return _nhwc(f(_nchw(x), weight, bias, tuple(stride), tuple(padding)))
+
+
+def conv2d_stats(x, weight, bias, stride, padding, transposed, stat_groups):
+    return conv2d(x, weight, bias, stride, padding, transposed), torch.empty(0, dtype=torch.float64)
+
+
+def _act(x, act, slope):
+    if act == 1:
+        return F.relu(x)
+    if act == 2:
+        return F.leaky_relu(x, slope)
+    if act == 3:
+        return torch.sigmoid(x)
+    return x
+
+
+def norm_act(y, norm_module, norm, act, slope=0.0, pre_stats=None):
+    if norm == "none" or norm_module is None:
+        return _act(y, act, slope)
+    x = _nchw(y)
+    m = norm_module
+    if norm == "bn":
+        if m.training and m.num_batches_tracked is not None:
+            m.num_batches_tracked += 1
+        out = F.batch_norm(x, m.running_mean, m.running_var, m.weight, m.bias, m.training or m.running_mean is None,
+                           m.momentum if m.momentum is not None else 0.1, m.eps)
+    else:
+        out = F.instance_norm(x, None, None, m.weight, m.bias, True, 0.1, m.eps)
+    return _act(_nhwc(out), act, slope)
+
+
+def cat_channels(a, b):
+    return torch.cat((a, b), 3)
+
+
+def mul(a, b):
+    return a * b
+
+
+def avgpool_h(x, kh):
+    return _nhwc(F.avg_pool2d(_nchw(x), (kh, 1)))
+
+
+def maxpool3s2(x):
+    return _nhwc(F.max_pool2d(_nchw(x), 3, 2, 1))
+
+
+def add_act(a, b, act=1):
+    return _act(a + b, act, 0.0)
+
+
+def shiftcat(x, c, K, dilation, Kpad):
+    B, T, R = x.shape
+    cols = []
+    for k in range(K):
+        sh = (K - 1 - k) * dilation
+        cols.append(F.pad(x, (0, 0, sh, 0))[:, :T])
+    if c is not None:
+        cols.append(c)
+    out = torch.cat(cols, 2)
+    return F.pad(out, (0, Kpad - out.size(2)))
+
+
+def glu_tanh_sigmoid(y):
+    a, b = y.split(y.size(-1) // 2, dim=-1)
+    return torch.tanh(a) * torch.sigmoid(b)
+
+
+def axpby(a, alpha, b=None, beta=0.0):
+    return alpha * a if b is None else alpha * a + beta * b
+
+
+def axpby_(a, alpha, b, beta):
+    a.mul_(alpha).add_(b, alpha=beta)
+    return a
+
+
+def dmol_nll(rows, target, num_classes=256, log_scale_min=-7.0):
+    from oracle import viai_oracle as O
+    shp = rows.shape[:-1]
+    r = rows.reshape(1, -1, rows.size(-1))
+    return O.dmol_nll(r.transpose(1, 2), target.reshape(1, -1, 1), num_classes, log_scale_min).reshape(shp)
+
+
+def masked_sum(v, mask=None, mean=True):
+    if mask is None:
+        return v.mean() if mean else v.sum()
+    s = (v * mask).sum()
+    return s / mask.sum() if mean else s
+
+
+def sequence_mask(lengths, max_len):
+    return (torch.arange(0, int(max_len)).unsqueeze(0) < lengths.unsqueeze(1)).float()
+
+
+def l2_normalize(x, eps=1e-12):
+    return F.normalize(x, p=2, dim=1, eps=eps)
+
+
+def pairdist(f1, f2):
+    return torch.norm(f1.unsqueeze(1) - f2.unsqueeze(0), p=2, dim=2)
+
+
+def l2_contrastive(scores, margin=0.0, max_violation=False):
+    cost = (margin - scores).clamp(min=0).masked_fill(torch.eye(scores.size(0)) > 0.5, 0)
+    if max_violation:
+        cost = cost.max(1)[0]
+    return (torch.sum(cost ** 2) + torch.sum(scores.diag() ** 2)) / (2 * scores.size(0))
+
+
+_NAMES = ["conv2d", "conv2d_stats", "norm_act", "cat_channels", "mul", "avgpool_h", "maxpool3s2", "add_act", "shiftcat",
+          "glu_tanh_sigmoid", "axpby", "axpby_", "dmol_nll", "masked_sum", "sequence_mask", "l2_normalize", "pairdist",
+          "l2_contrastive"]
+
+
+@contextlib.contextmanager
+def installed():
+    from viai_b200 import ops
+    saved = {n: getattr(ops, n) for n in _NAMES}
+    try:
+        for n in _NAMES:
+            setattr(ops, n, globals()[n])
+        yield ops
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)

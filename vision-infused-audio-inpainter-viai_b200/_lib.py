@@ -73,6 +73,20 @@ SIGNATURES = {
     "viai_adam_step": [c_p, c_p, c_p, c_p, c_l, c_p, c_d, c_d, c_d, c_p, c_i, c_f, c_p],
     "viai_lincomb2": [c_p, c_f, c_p, c_f, c_p, c_p],
     "viai_fill": [c_p, c_l, c_f, c_p],
+    "viai_shiftcat_fwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
+    "viai_shiftcat_bwd": [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
+    "viai_glu_fwd": [c_p, c_l, c_i, c_p, c_p],
+    "viai_glu_bwd": [c_p, c_p, c_l, c_i, c_p, c_p],
+    "viai_axpby": [c_p, c_f, c_p, c_f, c_p, c_l, c_p],
+    "viai_dmol_nll": [c_p, c_p, c_l, c_i, c_i, c_f, c_p, c_p, c_p, c_p],
+    "viai_masked_sum_fwd": [c_p, c_p, c_l, c_i, c_p, c_p, c_p],
+    "viai_masked_sum_bwd": [c_p, c_l, c_i, c_p, c_p, c_p, c_p],
+    "viai_sequence_mask": [c_p, c_i, c_i, c_p, c_p],
+    "viai_l2norm_fwd": [c_p, c_i, c_i, c_f, c_p, c_p, c_p],
+    "viai_l2norm_bwd": [c_p, c_p, c_p, c_i, c_i, c_f, c_p, c_p],
+    "viai_pairdist_fwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_p],
+    "viai_pairdist_bwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
+    "viai_l2_contrastive": [c_p, c_i, c_f, c_i, c_p, c_p, c_p, c_p],
 }
 
 

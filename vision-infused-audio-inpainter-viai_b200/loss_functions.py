@@ -1,10 +1,53 @@
-"""Losses of the GAN step.  Drop-in for GANLoss in /root/reference/loss_functions.py:79-104 (+ nn.L1Loss)."""
+"""Losses.  Drop-in for /root/reference/loss_functions.py: ``sequence_mask`` :11-21, ``DiscretizedMixturelogisticLoss`` :43-59,
+``ExponentialMovingAverage`` :62-76, ``GANLoss`` :79-104, ``l2_sim`` :106-108, ``L2ContrastiveLoss`` :111-148 (+ nn.L1Loss).
+``MaskedCrossEntropyLoss`` :24-40 belongs to the mu-law (one-hot input) WaveNet, which VIAI does not use (input_type "raw")."""
 import random
 
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import Config, ops
+from .wavenet_vocoder.mixture import discretized_mix_logistic_loss
+
+hparams = Config.Config()
+
+
+def sequence_mask(sequence_length, max_len=None):
+    """(B,) lengths -> (B, max_len) float mask, 1 where t < length."""
+    if max_len is None:
+        max_len = int(sequence_length.max())
+    return ops.sequence_mask(sequence_length, max_len)
+
+
+class DiscretizedMixturelogisticLoss(nn.Module):
+    def __init__(self):
+        super(DiscretizedMixturelogisticLoss, self).__init__()
+
+    def forward(self, input, target, lengths=None, mask=None, max_len=None):
+        """input (B, C, T) network outputs, target (B, T, 1); returns (losses * mask).sum() / mask.sum()."""
+        if lengths is None and mask is None:
+            raise RuntimeError("Should provide either lengths or mask")
+        if mask is None:
+            mask = sequence_mask(lengths, max_len).unsqueeze(-1)
+        mask_ = mask.expand_as(target)
+        losses = discretized_mix_logistic_loss(input, target, num_classes=hparams.quantize_channels,
+                                               log_scale_min=hparams.log_scale_min, reduce=False)
+        assert losses.size() == target.size()
+        return ops.masked_sum(losses, mask_.float(), mean=True)
+
+
+class ExponentialMovingAverage(object):
+    def __init__(self, decay):
+        self.decay = decay
+        self.shadow = {}
+
+    def register(self, name, val):
+        self.shadow[name] = val.detach().clone()
+
+    def update(self, name, x):
+        """shadow -= (1 - decay) * (shadow - x), one kernel, in place."""
+        assert name in self.shadow
+        ops.axpby_(self.shadow[name], self.decay, x.detach().contiguous(), 1.0 - self.decay)
 
 
 class GANLoss(nn.Module):
@@ -34,3 +77,22 @@ class L1Loss(nn.Module):
         if input.dim() == 4:
             input, target = input.permute(0, 2, 3, 1), target.permute(0, 2, 3, 1)
         return ops.l1_loss(input, target)
+
+
+def l2_sim(feature1, feature2):
+    """scores[a][b] = ||feature1[a] - feature2[b]||_2."""
+    return ops.pairdist(feature1, feature2)
+
+
+class L2ContrastiveLoss(nn.Module):
+    """Compute L2 contrastive loss: (sum_{a != b} max(margin - s_ab, 0)^2 + sum_a s_aa^2) / (2 B); with max_violation only the
+    hardest negative of each row counts."""
+
+    def __init__(self, margin=0, measure=False, max_violation=False):
+        super(L2ContrastiveLoss, self).__init__()
+        self.margin = margin
+        self.sim = l2_sim
+        self.max_violation = max_violation
+
+    def forward(self, feature1, feature2):
+        return ops.l2_contrastive(self.sim(feature1, feature2), self.margin, self.max_violation)

@@ -1,6 +1,7 @@
 """Visual encoder.  Drop-in for /root/reference/networks/Image_Embedding.py: ``ResNet`` :13-71, ``ImageResnet18`` :74-84,
 ``FlowResnet18`` :87-97, ``ImageEmbedding`` :100-126 -- same constructors, ``state_dict()`` keys/shapes and forward contract.
-``ImageEmbedding_single`` / ``_finetune`` / ``ImageEmbedding2`` belong to the AV-sync heads."""
+``ImageEmbedding_single`` :128-148, ``ImageEmbedding_finetune`` :150-171 and ``ImageEmbedding2`` :174-200 are the visual
+branches of the AV-sync heads."""
 import math
 
 import torch
@@ -131,3 +132,79 @@ class ImageEmbedding(nn.Module):
                 ops.norm_act(out.detach(), self.bn_1, "bn", ops.ACT_RELU)
         out = self._conv1d(out, self.conv_2)                       # (B,1,T/4,F)
         return out.permute(0, 3, 1, 2)                             # (B, F, 1, T/4)
+
+
+def _temporal_convs(mod, fea, discard_bn):
+    """conv_1 -> [relu(bn_1(.)) evaluated and discarded, as the reference does] -> conv_2 on (B, 1, T, C) rows."""
+    out = ImageEmbedding._conv1d(fea, mod.conv_1)
+    if discard_bn and mod.bn_1.training:
+        with torch.no_grad():
+            ops.norm_act(out.detach(), mod.bn_1, "bn", ops.ACT_RELU)        # only bn_1's running statistics change
+    return ImageEmbedding._conv1d(out, mod.conv_2)
+
+
+class ImageEmbedding_single(nn.Module):
+    """One visual stream (frames or flow) + the two temporal convolutions; returns (B, length_feature, T/4)."""
+
+    def __init__(self, hparams=hparams, image=1):
+        super(ImageEmbedding_single, self).__init__()
+        self.image = image
+        self.hparams = hparams
+        self.image_single_model = ImageResnet18(hparams) if image else FlowResnet18(hparams)
+        self.conv_1 = torch.nn.Conv1d(hparams.length_feature, hparams.length_feature, 3, 2, 1, bias=False)
+        self.bn_1 = nn.BatchNorm1d(hparams.length_feature)
+        self.conv_2 = torch.nn.Conv1d(hparams.length_feature, hparams.length_feature, 3, 2, 1, bias=False)
+        self.bn_2 = nn.BatchNorm1d(hparams.length_feature)
+        self.relu = nn.ReLU(True)
+
+    def forward(self, video_block):
+        S = self.hparams.image_size
+        B = video_block.size(0)
+        image_out = self.image_single_model(video_block.reshape(-1, 3 if self.image else 2, S, S))
+        fea = image_out.reshape(B, 1, -1, self.hparams.length_feature)
+        out = _temporal_convs(self, fea, True)                              # (B, 1, T/4, F)
+        return out.squeeze(1).permute(0, 2, 1)
+
+
+class ImageEmbedding_finetune(nn.Module):
+    """The temporal convolutions alone on precomputed per-frame features (B, T, length_feature) -> (B, F, 1, T/4)."""
+
+    def __init__(self, hparams=hparams, image=1):
+        super(ImageEmbedding_finetune, self).__init__()
+        self.image = image
+        self.hparams = hparams
+        self.conv_1 = torch.nn.Conv1d(hparams.length_feature, hparams.length_feature, 3, 2, 1, bias=False)
+        self.bn_1 = nn.BatchNorm1d(hparams.length_feature)
+        self.conv_2 = torch.nn.Conv1d(hparams.length_feature, hparams.length_feature, 3, 2, 1, bias=False)
+        self.bn_2 = nn.BatchNorm1d(hparams.length_feature)
+        self.relu = nn.ReLU(True)
+
+    def forward(self, image_out):
+        out = _temporal_convs(self, image_out.unsqueeze(1), True)           # (B, 1, T/4, F)
+        return out.permute(0, 3, 1, 2)
+
+
+class ImageEmbedding2(nn.Module):
+    """ImageEmbedding that also returns the concatenated per-frame features: (out (B, F, 1, T/4), fea_cat (B, 2F, T)).
+    (Unlike ImageEmbedding.forward, the reference does not evaluate bn_1 here: the call is commented out at :195.)"""
+
+    def __init__(self, hparams=hparams):
+        super(ImageEmbedding2, self).__init__()
+        self.hparams = hparams
+        self.image_single_model = ImageResnet18(hparams)
+        self.flow_single_model = FlowResnet18(hparams)
+        self.conv_1 = torch.nn.Conv1d(2 * hparams.length_feature, 2 * hparams.length_feature, 3, 2, 1, bias=False)
+        self.bn_1 = nn.BatchNorm1d(2 * hparams.length_feature)
+        self.conv_2 = torch.nn.Conv1d(2 * hparams.length_feature, hparams.length_feature, 3, 2, 1, bias=False)
+        self.bn_2 = nn.BatchNorm1d(hparams.length_feature)
+        self.relu = nn.ReLU(True)
+
+    def forward(self, video_block, flow_block):
+        S = self.hparams.image_size
+        B = video_block.size(0)
+        F_ = self.hparams.length_feature
+        image_out = self.image_single_model(video_block.reshape(-1, 3, S, S)).reshape(B, 1, -1, F_)
+        flow_out = self.flow_single_model(flow_block.reshape(-1, 2, S, S)).reshape(B, 1, -1, F_)
+        fea_cat = ops.cat_channels(image_out, flow_out)                     # (B, 1, T, 2F)
+        out = _temporal_convs(self, fea_cat, False)
+        return out.permute(0, 3, 1, 2), fea_cat.squeeze(1).permute(0, 2, 1)

@@ -662,3 +662,284 @@ def to_nhwc(t):
 def to_nchw(t):
     """(N,H,W,C) -> (N,C,H,W) view (channels-last strides; no copy)."""
     return t.permute(0, 3, 1, 2)
+
+
+# ---- WaveNet teacher-forced training path (SURVEY 8f-2) ------------------------------------------------------------------
+class _ShiftCatFn(torch.autograd.Function):
+    """Operand of a dilated causal Conv1d joined with the conditioning features (viai_shiftcat_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, c, K, dilation, Kpad):
+        _require_cuda(x, c)
+        L = _lib.lib()
+        x = x.contiguous()
+        B, T, R = x.shape
+        Cc = 0
+        if c is not None:
+            c = c.contiguous()
+            Cc = c.size(2)
+            assert tuple(c.shape[:2]) == (B, T), "conditioning features must cover the same (B, T) as the input"
+        out = torch.empty((B, T, Kpad), device=x.device, dtype=torch.float32)
+        _lib.check(L.viai_shiftcat_fwd(_p(x), _p(c), B, T, R, Cc, K, dilation, Kpad, _p(out), _stream()), "shiftcat_fwd")
+        ctx.cfg = (B, T, R, Cc, K, dilation, Kpad)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, T, R, Cc, K, dilation, Kpad = ctx.cfg
+        L = _lib.lib()
+        dout = dout.contiguous()
+        dx = torch.empty((B, T, R), device=dout.device, dtype=torch.float32)
+        dc = torch.empty((B, T, Cc), device=dout.device, dtype=torch.float32) if (Cc > 0 and ctx.needs_input_grad[1]) else None
+        _lib.check(L.viai_shiftcat_bwd(_p(dout), B, T, R, Cc, K, dilation, Kpad, _p(dx), _p(dc), _stream()), "shiftcat_bwd")
+        return dx, dc, None, None, None
+
+
+def shiftcat(x, c, K, dilation, Kpad):
+    """x (B,T,R), c (B,T,Cc) or None -> (B,T,Kpad) with [x(t-(K-1)d) | ... | x(t) | c(t) | 0]."""
+    return _ShiftCatFn.apply(x, c, int(K), int(dilation), int(Kpad))
+
+
+class _GluFn(torch.autograd.Function):
+    """tanh(a) * sigmoid(b) on the two channel halves (wavenet_vocoder/modules.py:180,196)."""
+
+    @staticmethod
+    def forward(ctx, y):
+        _require_cuda(y)
+        L = _lib.lib()
+        y = y.contiguous()
+        G = y.size(-1)
+        rows = y.numel() // G
+        out = torch.empty(y.shape[:-1] + (G // 2,), device=y.device, dtype=torch.float32)
+        _lib.check(L.viai_glu_fwd(_p(y), rows, G, _p(out), _stream()), "glu_fwd")
+        ctx.save_for_backward(y)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (y,) = ctx.saved_tensors
+        L = _lib.lib()
+        dout = dout.contiguous()
+        G = y.size(-1)
+        dy = torch.empty_like(y)
+        _lib.check(L.viai_glu_bwd(_p(y), _p(dout), y.numel() // G, G, _p(dy), _stream()), "glu_bwd")
+        return dy
+
+
+def glu_tanh_sigmoid(y):
+    return _GluFn.apply(y)
+
+
+class _AxpbyFn(torch.autograd.Function):
+    """alpha * a + beta * b (same shapes)."""
+
+    @staticmethod
+    def forward(ctx, a, b, alpha, beta):
+        _require_cuda(a, b)
+        L = _lib.lib()
+        a = a.contiguous()
+        b = b.contiguous() if b is not None else None
+        assert b is None or b.shape == a.shape
+        out = torch.empty_like(a)
+        _lib.check(L.viai_axpby(_p(a), alpha, _p(b), beta, _p(out), a.numel(), _stream()), "axpby")
+        ctx.cfg = (alpha, beta, b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        alpha, beta, has_b = ctx.cfg
+        L = _lib.lib()
+        g = g.contiguous()
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty_like(g)
+            _lib.check(L.viai_axpby(_p(g), alpha, None, 0.0, _p(da), g.numel(), _stream()), "axpby bwd")
+        if has_b and ctx.needs_input_grad[1]:
+            db = torch.empty_like(g)
+            _lib.check(L.viai_axpby(_p(g), beta, None, 0.0, _p(db), g.numel(), _stream()), "axpby bwd")
+        return da, db, None, None
+
+
+def axpby(a, alpha, b=None, beta=0.0):
+    return _AxpbyFn.apply(a, b, float(alpha), float(beta))
+
+
+def axpby_(a, alpha, b, beta):
+    """In place on ``a`` (no autograd): the EMA update of loss_functions.py:70-73."""
+    _require_cuda(a, b)
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    _lib.check(_lib.lib().viai_axpby(_p(a), float(alpha), _p(b), float(beta), _p(a), a.numel(), _stream()), "axpby_")
+    return a
+
+
+class _DmolNllFn(torch.autograd.Function):
+    """discretized_mix_logistic_loss(reduce=False) on rows of 3*nr_mix parameters (wavenet_vocoder/mixture.py:25-105)."""
+
+    @staticmethod
+    def forward(ctx, y_hat, target, num_classes, log_scale_min):
+        _require_cuda(y_hat, target)
+        L = _lib.lib()
+        y_hat = y_hat.contiguous()
+        target = target.contiguous()
+        C = y_hat.size(-1)
+        assert C % 3 == 0
+        rows = y_hat.numel() // C
+        assert target.numel() == rows, "one target per row of y_hat"
+        nll = torch.empty(y_hat.shape[:-1], device=y_hat.device, dtype=torch.float32)
+        _lib.check(L.viai_dmol_nll(_p(y_hat), _p(target), rows, C // 3, num_classes, log_scale_min, _p(nll), None, None, _stream()),
+                   "dmol_nll")
+        ctx.save_for_backward(y_hat, target)
+        ctx.cfg = (rows, C // 3, num_classes, log_scale_min)
+        return nll
+
+    @staticmethod
+    def backward(ctx, dnll):
+        y_hat, target = ctx.saved_tensors
+        rows, nm, num_classes, lsm = ctx.cfg
+        L = _lib.lib()
+        dnll = dnll.contiguous()
+        dy = torch.empty_like(y_hat)
+        _lib.check(L.viai_dmol_nll(_p(y_hat), _p(target), rows, nm, num_classes, lsm, None, _p(dnll), _p(dy), _stream()), "dmol_nll bwd")
+        return dy, None, None, None
+
+
+def dmol_nll(y_hat_rows, target, num_classes=256, log_scale_min=-7.0):
+    """y_hat_rows (..., 3*nr_mix), target (...) -> per-sample negative log-likelihood (...)."""
+    return _DmolNllFn.apply(y_hat_rows, target, int(num_classes), float(log_scale_min))
+
+
+class _MaskedSumFn(torch.autograd.Function):
+    """(v * mask).sum() / mask.sum() (mean=True) or (v * mask).sum(); mask None = ones."""
+
+    @staticmethod
+    def forward(ctx, v, mask, mean):
+        _require_cuda(v, mask)
+        L = _lib.lib()
+        v = v.contiguous()
+        mask = mask.contiguous() if mask is not None else None
+        assert mask is None or mask.numel() == v.numel()
+        acc = torch.empty(2, device=v.device, dtype=torch.float64)
+        out = torch.empty((), device=v.device, dtype=torch.float32)
+        _lib.check(L.viai_masked_sum_fwd(_p(v), _p(mask), v.numel(), int(mean), _p(acc), _p(out), _stream()), "masked_sum_fwd")
+        ctx.save_for_backward(mask, acc)
+        ctx.cfg = (tuple(v.shape), int(mean))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        mask, acc = ctx.saved_tensors
+        shape, mean = ctx.cfg
+        L = _lib.lib()
+        gout = gout.contiguous().float()
+        dv = torch.empty(shape, device=gout.device, dtype=torch.float32)
+        _lib.check(L.viai_masked_sum_bwd(_p(mask), dv.numel(), mean, _p(acc), _p(gout), _p(dv), _stream()), "masked_sum_bwd")
+        return dv, None, None
+
+
+def masked_sum(v, mask=None, mean=True):
+    return _MaskedSumFn.apply(v, mask, bool(mean))
+
+
+def sequence_mask(lengths, max_len):
+    """loss_functions.py:11-21 on the device: (B, max_len) float mask, 1 where t < lengths[b]."""
+    if not lengths.is_cuda:
+        raise RuntimeError("VIAI ops need CUDA tensors; there is no CPU path")
+    lengths = lengths.to(torch.int64).contiguous()
+    B = lengths.numel()
+    out = torch.empty((B, int(max_len)), device=lengths.device, dtype=torch.float32)
+    _lib.check(_lib.lib().viai_sequence_mask(_p(lengths), B, int(max_len), _p(out), _stream()), "sequence_mask")
+    return out
+
+
+# ---- audio-visual synchronisation heads (SURVEY 8f-3) ----------------------------------------------------------------------
+class _L2NormFn(torch.autograd.Function):
+    """F.normalize(x, p=2, dim=1) for (rows, cols) (utils/util.py:94-96)."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        _require_cuda(x)
+        L = _lib.lib()
+        x = x.contiguous()
+        rows, cols = x.shape
+        y = torch.empty_like(x)
+        nrm = torch.empty(rows, device=x.device, dtype=torch.float32)
+        _lib.check(L.viai_l2norm_fwd(_p(x), rows, cols, eps, _p(y), _p(nrm), _stream()), "l2norm_fwd")
+        ctx.save_for_backward(y, nrm)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, nrm = ctx.saved_tensors
+        L = _lib.lib()
+        dy = dy.contiguous()
+        dx = torch.empty_like(y)
+        _lib.check(L.viai_l2norm_bwd(_p(y), _p(nrm), _p(dy), y.size(0), y.size(1), ctx.eps, _p(dx), _stream()), "l2norm_bwd")
+        return dx, None
+
+
+def l2_normalize(x, eps=1e-12):
+    return _L2NormFn.apply(x, float(eps))
+
+
+class _PairDistFn(torch.autograd.Function):
+    """scores[a][b] = ||f1[a] - f2[b]||_2 (loss_functions.py:106-108)."""
+
+    @staticmethod
+    def forward(ctx, f1, f2):
+        _require_cuda(f1, f2)
+        L = _lib.lib()
+        f1, f2 = f1.contiguous(), f2.contiguous()
+        assert f1.dim() == 2 and f2.dim() == 2 and f1.size(1) == f2.size(1)
+        s = torch.empty((f1.size(0), f2.size(0)), device=f1.device, dtype=torch.float32)
+        _lib.check(L.viai_pairdist_fwd(_p(f1), _p(f2), f1.size(0), f2.size(0), f1.size(1), _p(s), _stream()), "pairdist_fwd")
+        ctx.save_for_backward(f1, f2, s)
+        return s
+
+    @staticmethod
+    def backward(ctx, ds):
+        f1, f2, s = ctx.saved_tensors
+        L = _lib.lib()
+        ds = ds.contiguous()
+        df1 = torch.empty_like(f1) if ctx.needs_input_grad[0] else None
+        df2 = torch.empty_like(f2) if ctx.needs_input_grad[1] else None
+        if df1 is None and df2 is None:
+            return None, None
+        _lib.check(L.viai_pairdist_bwd(_p(f1), _p(f2), _p(s), _p(ds), f1.size(0), f2.size(0), f1.size(1), _p(df1), _p(df2), _stream()),
+                   "pairdist_bwd")
+        return df1, df2
+
+
+def pairdist(f1, f2):
+    return _PairDistFn.apply(f1, f2)
+
+
+class _L2ContrastiveFn(torch.autograd.Function):
+    """The hinge / diagonal reduction of L2ContrastiveLoss on a (B, B) score matrix (loss_functions.py:127-148)."""
+
+    @staticmethod
+    def forward(ctx, scores, margin, max_violation):
+        _require_cuda(scores)
+        L = _lib.lib()
+        scores = scores.contiguous()
+        B = scores.size(0)
+        assert scores.dim() == 2 and scores.size(1) == B
+        out = torch.empty((), device=scores.device, dtype=torch.float32)
+        _lib.check(L.viai_l2_contrastive(_p(scores), B, margin, int(max_violation), _p(out), None, None, _stream()), "l2_contrastive")
+        ctx.save_for_backward(scores)
+        ctx.cfg = (margin, int(max_violation))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (scores,) = ctx.saved_tensors
+        margin, mv = ctx.cfg
+        L = _lib.lib()
+        gout = gout.contiguous().float()
+        ds = torch.empty_like(scores)
+        _lib.check(L.viai_l2_contrastive(_p(scores), scores.size(0), margin, mv, None, _p(gout), _p(ds), _stream()), "l2_contrastive bwd")
+        return ds, None, None
+
+
+def l2_contrastive(scores, margin=0.0, max_violation=False):
+    return _L2ContrastiveFn.apply(scores, float(margin), bool(max_violation))

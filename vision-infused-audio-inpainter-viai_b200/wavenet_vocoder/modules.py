@@ -2,11 +2,14 @@
 ``ConvTranspose2d`` :41-51, ``Conv1d1x1`` :54-63 and ``ResidualConv1dGLU`` :84-216: same constructors, weight-norm
 parametrisation (``weight_g`` / ``weight_v``) and ``state_dict()`` layout.  The synthesis arithmetic itself lives in
 csrc/wavenet_synth.cu and is driven by ``WaveNet.incremental_forward``; the modules keep no incremental buffers (the kernel
-owns the ring buffers for the duration of one call), so ``clear_buffer`` is a no-op kept for API compatibility."""
+owns the ring buffers for the duration of one call), so ``clear_buffer`` is a no-op kept for API compatibility.  The
+teacher-forced training path (``forward``) runs per layer: csrc/wavenet_train.cu + the implicit-GEMM convolution kernels."""
 import math
 
 import torch
 from torch import nn
+
+from .. import ops
 
 
 def Conv1d(in_channels, out_channels, kernel_size=1, padding=0, dilation=1, bias=True, weight_normalization=True,
@@ -78,11 +81,62 @@ class ResidualConv1dGLU(nn.Module):
         self.conv1x1_out = Conv1d1x1(gate_out_channels, residual_channels, bias=bias, weight_normalization=weight_normalization)
         self.conv1x1_skip = Conv1d1x1(gate_out_channels, skip_out_channels, bias=bias, weight_normalization=weight_normalization)
 
-    def forward(self, x, c=None, g=None):
-        raise RuntimeError("ResidualConv1dGLU runs inside the fused synthesis kernel (WaveNet.incremental_forward); "
-                           "there is no per-layer PyTorch path")
+    # ---- teacher-forced (T-parallel) path: reference ``_forward(x, c, g, is_incremental=False)`` :162-210 ------------------
+    def forward_rows(self, x, c=None):
+        """x (B, T, R), c (B, T, Cc) or None, channels innermost -> (x_out (B, T, R), skip (B, T, S)).
+        The dilated causal convolution and the conditioning 1x1 are ONE GEMM over the B*T rows: the operand is
+        [x(t-2d) | x(t-d) | x(t) | c(t)] (ops.shiftcat) and the weight the tap-major linearised one of conv.py:51-62."""
+        if not self.causal:
+            raise NotImplementedError("non-causal ResidualConv1dGLU is outside the VIAI hot path")
+        if (c is None) != (self.conv1x1c is None):
+            raise RuntimeError("local conditioning features and conv1x1c go together (modules.py:184)")
+        residual = x
+        if self.training and self.dropout > 0:                      # F.dropout(x, p, training) :173
+            keep = 1.0 - self.dropout
+            x = ops.mul(x, torch.bernoulli(torch.full_like(x, keep)) / keep)
+        K = self.conv.kernel_size[0]
+        G, R = self.conv.out_channels, self.conv.in_channels
+        Cc = c.size(2) if c is not None else 0
+        Kpad = (K * R + Cc + 31) // 32 * 32
+        X = ops.shiftcat(x, c, K, self.dilation, Kpad)
+        lin = effective_weight(self.conv).permute(0, 2, 1).reshape(G, K * R)
+        b = self.conv.bias
+        if c is not None:
+            lin = torch.cat((lin, effective_weight(self.conv1x1c).reshape(G, Cc)), 1)
+            b = b + self.conv1x1c.bias
+        if Kpad > K * R + Cc:
+            lin = torch.cat((lin, lin.new_zeros(G, Kpad - K * R - Cc)), 1)
+        z = ops.glu_tanh_sigmoid(rows_linear(X, lin, b))            # tanh(a) * sigmoid(b) :196
+        s = rows_linear(z, effective_weight(self.conv1x1_skip).reshape(self.conv1x1_skip.out_channels, -1), self.conv1x1_skip.bias)
+        o = rows_linear(z, effective_weight(self.conv1x1_out).reshape(R, -1), self.conv1x1_out.bias)
+        return ops.axpby(o, math.sqrt(0.5), residual, math.sqrt(0.5)), s
 
-    incremental_forward = forward
+    def forward(self, x, c=None, g=None):
+        """Reference layout: x (B, R, T), c (B, Cc, T) -> (x (B, R, T), s (B, S, T))."""
+        if g is not None:
+            raise NotImplementedError("global conditioning is outside the VIAI hot path")
+        xo, s = self.forward_rows(x.transpose(1, 2).contiguous(), None if c is None else c.transpose(1, 2).contiguous())
+        return xo.transpose(1, 2), s.transpose(1, 2)
+
+    def incremental_forward(self, x, c=None, g=None):
+        raise RuntimeError("ResidualConv1dGLU's incremental path runs inside the fused synthesis kernel "
+                           "(WaveNet.incremental_forward); there is no per-layer incremental path")
 
     def clear_buffer(self):
         pass
+
+
+def _fold(P):
+    """Width of the 2-D view of P rows handed to the implicit-GEMM kernels (their M tile is 16 x 8 pixels)."""
+    for w in (128, 64, 32, 16, 8, 4, 2):
+        if P % w == 0:
+            return w
+    return 1
+
+
+def rows_linear(x, weight, bias=None):
+    """x (B, T, Cin) @ weight (Cout, Cin)^T + bias as a 1x1 convolution over the B*T rows (F.conv1d with kernel 1)."""
+    B, T, C = x.shape
+    W = _fold(B * T)
+    y = ops.conv2d(x.reshape(1, (B * T) // W, W, C), weight.reshape(weight.size(0), C, 1, 1), bias)
+    return y.reshape(B, T, weight.size(0))

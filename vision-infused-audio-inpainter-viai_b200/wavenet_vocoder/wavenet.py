@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from .. import Config, _lib, ops
-from .modules import Conv1d1x1, ConvTranspose2d, ResidualConv1dGLU, effective_weight
+from .modules import Conv1d1x1, ConvTranspose2d, ResidualConv1dGLU, effective_weight, rows_linear
 
 hparams = Config.Config()
 
@@ -244,9 +244,33 @@ class WaveNet(nn.Module):
         return (out, logits) if return_logits else out
 
     def forward(self, x, c=None, g=None, softmax=False):
-        """Teacher-forced outputs (B, out_channels, T) for x (B, 1, T) (reference :177-235), evaluated with the synthesis kernel
-        (incremental == batch).  The T-parallel training formulation is a next row."""
+        """Teacher-forced, T-parallel outputs (B, out_channels, T) for x (B, 1, T) (reference :177-235), differentiable:
+        every layer is one tensor-core GEMM over the B*T rows for the dilated convolution + conditioning, a gate kernel and
+        two 1x1 GEMMs (``ResidualConv1dGLU.forward_rows``).  This is the training path."""
         if softmax:
             raise TypeError("softmax() got an unexpected keyword argument 'dim'")   # reference :233 fails the same way
-        _, logits = self.incremental_forward(c=c, g=g, T=x.size(-1), test_inputs=x, return_logits=True)
+        if g is not None:
+            raise NotImplementedError("global conditioning is outside the VIAI hot path")
+        B, _, T = x.size()                     # CPU tensors are refused by the first op (there is no CPU path)
+        cond = None
+        if c is not None:
+            cond = self._upsample(c.float())
+            assert cond.size(1) == T, "upsampled conditioning covers %d steps, x has %d" % (cond.size(1), T)
+        h = rows_linear(x.float().reshape(B, T, 1), effective_weight(self.first_conv).reshape(-1, 1), self.first_conv.bias)
+        skips = None
+        for f in self.conv_layers:
+            h, s = f.forward_rows(h, cond)
+            skips = s if skips is None else ops.axpby(skips, math.sqrt(0.5), s, math.sqrt(0.5))      # :219-223
+        y = skips
+        for f in self.last_conv_layers:
+            if isinstance(f, nn.ReLU):
+                y = ops.norm_act(y.unsqueeze(0), None, "none", ops.ACT_RELU).squeeze(0)
+            else:
+                y = rows_linear(y, effective_weight(f).reshape(f.out_channels, -1), f.bias)
+        return y.transpose(1, 2)
+
+    def forward_incremental_kernel(self, x, c=None):
+        """The same teacher-forced outputs evaluated by the synthesis kernel (incremental == batch); no
+        autograd.  Kept as a cross-check of the two paths."""
+        _, logits = self.incremental_forward(c=c, T=x.size(-1), test_inputs=x, return_logits=True)
         return logits.transpose(1, 2).contiguous()
