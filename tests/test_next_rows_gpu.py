@@ -1,0 +1,331 @@
+"""SURVEY 8f "next" rows on the B200, all through the C ABI: the new kernels (shift-cat operand, GLU, axpby, DMoL loss,
+masked mean, sequence mask, l2 norm, pairwise distance, L2 contrastive) against the oracle, and the product modules built on
+them (WaveNet teacher-forced forward + one training step, DiscretizedMixturelogisticLoss, EMA, L2ContrastiveLoss,
+Inpainting_Dis, DomainDis, ImageEmbedding_single/_finetune/2) against golden vectors produced by the reference itself
+(tests/golden/next_rows.pt).  Tolerances: 1e-3 rel for network outputs / losses / gradients (north star), 1e-5..1e-4 per
+kernel; index work (sequence mask, retrieval ranks) exact."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import viai_test_helpers as H
+from oracle import fixtures as FX
+from oracle import make_golden as MG
+from oracle import viai_oracle as O
+
+pytestmark = pytest.mark.gpu
+PREC = [pytest.param("fp32", id="fp32"), pytest.param("bf16x3", marks=pytest.mark.bf16x3, id="bf16x3")]
+
+
+@pytest.fixture(scope="module")
+def fx():
+    return H.load_golden("next_rows.pt")
+
+
+@pytest.fixture(scope="module")
+def inp():
+    return MG.next_rows_inputs()
+
+
+def _filled(module, salt=0):
+    sd = module.state_dict()
+    FX.deterministic_fill(sd, salt)
+    module.load_state_dict(sd)
+    return module.cuda()
+
+
+# ---- kernels ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [(2, 37, 8, 4, 3, 1), (1, 64, 32, 80, 3, 8), (3, 20, 16, 0, 3, 16), (2, 9, 4, 8, 2, 32), (1, 130, 512, 80, 3, 2)],
+                         ids=lambda c: "B%d_T%d_R%d_C%d_K%d_d%d" % c)
+def test_shiftcat_forward_backward(cfg):
+    from viai_b200 import ops
+    B, T, R, Cc, K, d = cfg
+    g = torch.Generator().manual_seed(sum(cfg))
+    x = torch.randn(B, T, R, generator=g)
+    c = torch.randn(B, T, Cc, generator=g) if Cc else None
+    Kpad = (K * R + Cc + 31) // 32 * 32
+    cols = [F.pad(x, (0, 0, (K - 1 - k) * d, 0))[:, :T] for k in range(K)] + ([c] if Cc else [])
+    want = torch.cat(cols, 2)
+    want = F.pad(want, (0, Kpad - want.size(2)))
+    xg = x.cuda().requires_grad_(True)
+    cg = c.cuda().requires_grad_(True) if Cc else None
+    got = ops.shiftcat(xg, cg, K, d, Kpad)
+    assert torch.equal(got.cpu(), want)                       # pure data movement: bit exact
+    dout = torch.randn(B, T, Kpad, generator=g)
+    got.backward(dout.cuda())
+    xr = x.clone().requires_grad_(True)
+    cr = c.clone().requires_grad_(True) if Cc else None
+    cols = [F.pad(xr, (0, 0, (K - 1 - k) * d, 0))[:, :T] for k in range(K)] + ([cr] if Cc else [])
+    F.pad(torch.cat(cols, 2), (0, Kpad - K * R - Cc)).backward(dout)
+    assert H.relerr(xg.grad, xr.grad) < 1e-6
+    if Cc:
+        assert torch.equal(cg.grad.cpu(), cr.grad)
+
+
+def test_glu_axpby_masked_sum_sequence_mask():
+    from viai_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    y = torch.randn(3, 17, 64, generator=g) * 2
+    yg = y.cuda().requires_grad_(True)
+    out = ops.glu_tanh_sigmoid(yg)
+    yr = y.clone().requires_grad_(True)
+    a, b = yr.split(32, dim=-1)
+    want = torch.tanh(a) * torch.sigmoid(b)
+    assert H.relerr(out, want) < 1e-6
+    dout = torch.randn(3, 17, 32, generator=g)
+    out.backward(dout.cuda())
+    want.backward(dout)
+    assert H.relerr(yg.grad, yr.grad) < 1e-5
+    p, q = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
+    pg, qg = p.cuda().requires_grad_(True), q.cuda().requires_grad_(True)
+    r = ops.axpby(pg, 0.25, qg, -1.5)
+    assert H.relerr(r, 0.25 * p - 1.5 * q) < 1e-6
+    r.sum().backward()
+    assert torch.allclose(pg.grad.cpu(), torch.full((1000,), 0.25)) and torch.allclose(qg.grad.cpu(), torch.full((1000,), -1.5))
+    sh = p.cuda().clone()
+    ops.axpby_(sh, 0.9, q.cuda(), 0.1)
+    assert H.relerr(sh, O.ema_update(p, q, 0.9)) < 1e-6
+    lengths = torch.tensor([5, 0, 9, 3])
+    m = ops.sequence_mask(lengths.cuda(), 9)
+    assert torch.equal(m.cpu(), O.sequence_mask(lengths, 9))
+    v = torch.randn(4, 9, generator=g)
+    vg = v.cuda().requires_grad_(True)
+    s = ops.masked_sum(vg, m, mean=True)
+    vr = v.clone().requires_grad_(True)
+    want = (vr * m.cpu()).sum() / m.cpu().sum()
+    assert abs(float(s) - float(want)) < 1e-6
+    (s * 3.0).backward()
+    (want * 3.0).backward()
+    assert H.relerr(vg.grad, vr.grad) < 1e-6
+    assert abs(float(ops.masked_sum(vg, None, mean=False)) - float(v.sum())) < 1e-4
+
+
+@pytest.mark.parametrize("tag,nc,lsm", [("256", 256, -7.0), ("65536", 65536, math.log(1e-14))])
+def test_dmol_loss_kernel_matches_reference_golden(fx, inp, tag, nc, lsm):
+    from viai_b200.wavenet_vocoder.mixture import discretized_mix_logistic_loss
+    g = fx["dmol_" + tag]
+    yh = inp["dmol_yhat"].cuda().requires_grad_(True)
+    y = inp["dmol_y"].cuda()
+    nll = discretized_mix_logistic_loss(yh, y, nc, lsm, reduce=False)
+    assert tuple(nll.shape) == tuple(g["nll"].shape)
+    assert H.relerr(nll, g["nll"]) < 1e-5
+    nll.sum().backward()
+    assert H.relerr(yh.grad, g["grad"]) < 1e-4
+    tot = discretized_mix_logistic_loss(yh.detach(), y, nc, lsm, reduce=True)
+    assert abs(float(tot) - g["total"]) / abs(g["total"]) < 1e-5
+
+
+def test_dmol_loss_random_rows_match_oracle_at_scale():
+    from viai_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    rows = 20000
+    yh = torch.randn(rows, 30, generator=g) * 1.5
+    yh[:, 20:] -= 3.0
+    y = (torch.rand(rows, generator=g) * 2.2 - 1.1).clamp(-1, 1)           # a share of exact +-1 edge samples
+    yg = yh.cuda().requires_grad_(True)
+    nll = ops.dmol_nll(yg, y.cuda(), 65536, math.log(1e-14))
+    want = O.dmol_nll(yh.t().unsqueeze(0).double(), y.view(1, rows, 1).double(), 65536, math.log(1e-14)).view(rows)
+    assert H.relerr(nll, want) < 1e-5
+    nll.sum().backward()
+    wg = O.dmol_nll_grad(yh.t().unsqueeze(0).double(), y.view(1, rows, 1).double(), 65536, math.log(1e-14))[0].t()
+    assert H.relerr(yg.grad, wg) < 1e-4
+
+
+def test_masked_dmol_loss_ema_contrastive_modules(fx, inp):
+    from viai_b200 import loss_functions as LF
+    g = fx["dmol_masked"]
+    yh = inp["dmol_yhat"].cuda().requires_grad_(True)
+    loss = LF.DiscretizedMixturelogisticLoss()(yh, inp["dmol_y"].cuda(), lengths=inp["dmol_len"].cuda())
+    assert abs(float(loss) - g["loss"]) / g["loss"] < 1e-5
+    loss.backward()
+    assert H.relerr(yh.grad, g["grad"]) < 1e-4
+    assert torch.equal(LF.sequence_mask(inp["dmol_len"].cuda()).cpu(), g["mask"])
+    ema = LF.ExponentialMovingAverage(0.9)
+    ema.register("w", inp["f1"].cuda())
+    ema.update("w", inp["f2"].cuda())
+    assert H.relerr(ema.shadow["w"], fx["ema"]) < 1e-6
+    for tag, margin, mv in (("m0", 0, False), ("m8", 8.0, False), ("m8max", 8.0, True)):
+        a, b = inp["f1"].cuda().requires_grad_(True), inp["f2"].cuda().requires_grad_(True)
+        l = LF.L2ContrastiveLoss(margin=margin, max_violation=mv)(a, b)
+        assert abs(float(l) - fx["ctr_" + tag]["loss"]) / fx["ctr_" + tag]["loss"] < 1e-5, tag
+        l.backward()
+        assert H.relerr(a.grad, fx["ctr_" + tag]["g1"]) < 1e-4 and H.relerr(b.grad, fx["ctr_" + tag]["g2"]) < 1e-4, tag
+    assert H.relerr(LF.l2_sim(inp["f1"].cuda(), inp["f2"].cuda()), fx["l2_sim"]) < 1e-6
+
+
+def test_l2_norm_and_retrieval(fx, inp):
+    from viai_b200.utils import util
+    x = inp["f1"].cuda().requires_grad_(True)
+    y = util.l2_norm(x)
+    assert H.relerr(y, fx["l2_norm"]) < 1e-6
+    w = torch.randn(6, 32, generator=torch.Generator().manual_seed(2))
+    (y * w.cuda()).sum().backward()
+    xr = inp["f1"].clone().requires_grad_(True)
+    (F.normalize(xr, p=2, dim=1) * w).sum().backward()
+    assert H.relerr(x.grad, xr.grad) < 1e-5
+    z = torch.zeros(2, 8, device="cuda", requires_grad=True)              # below the eps clamp: y = x / eps, finite gradient
+    util.l2_norm(z).sum().backward()
+    assert torch.isfinite(z.grad).all()
+    assert util.L2retrieval(inp["f1"].cuda(), inp["f2"].cuda()) == pytest.approx(fx["retrieval"])
+    assert util.L2retrieval(inp["f1"].numpy(), inp["f3"].numpy()) == pytest.approx(fx["retrieval_noisy"])
+    big1, big2 = torch.randn(300, 256, generator=torch.Generator().manual_seed(3)), torch.randn(200, 256, generator=torch.Generator().manual_seed(4))
+    from viai_b200 import ops
+    assert H.relerr(ops.pairdist(big1.cuda(), big2.cuda()), O.pairdist(big1.double(), big2.double())) < 1e-5
+
+
+# ---- AV-sync heads ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", PREC)
+def test_inpainting_dis_and_domain_dis_match_reference_golden(fx, inp, prec):
+    from viai_b200 import ops
+    from viai_b200.networks.Discriminator_Networks import DomainDis, Inpainting_Dis
+    assert ops.get_precision() == prec
+    g = fx["inpainting_dis"]
+    D = _filled(Inpainting_Dis())
+    out = D(inp["dis_mel"].cuda(), inp["dis_fea"].cuda())
+    assert tuple(out.shape) == tuple(g["out"].shape)
+    assert H.relerr(out, g["out"]) < 1e-3
+    out.pow(2).sum().backward()
+    params = dict(D.named_parameters())
+    tol = 1e-3 if prec == "fp32" else 2e-2                                 # single-tf32 gradients on the tensor-core path
+    for k, want in g["gnorm"].items():
+        assert abs(float(params[k].grad.norm()) - want) <= tol * max(want, 1e-6), k
+    for k, want in g["grads"].items():
+        assert H.relerr(params[k].grad, want) < tol, k
+    for k, want in g["rm"].items():
+        assert H.relerr(D.state_dict()[k], want) < 1e-3, k
+    g = fx["domain_dis"]
+    D = _filled(DomainDis())
+    out = D(inp["dom_x"].cuda())
+    assert tuple(out.shape) == (3, 1) and H.relerr(out, g["out"]) < 1e-3
+    out.sum().backward()
+    for k, want in g["gnorm"].items():
+        assert abs(float(dict(D.named_parameters())[k].grad.norm()) - want) <= tol * max(want, 1e-6), k
+
+
+def test_visual_branches_match_reference_golden(fx, inp):
+    from viai_b200.networks import Image_Embedding as IE
+    g = fx["ie2"]
+    M = _filled(IE.ImageEmbedding2())
+    out, fea = M(inp["video"].cuda(), inp["flow"].cuda())
+    assert tuple(out.shape) == tuple(g["out"].shape) and tuple(fea.shape) == tuple(g["fea"].shape)
+    assert H.relerr(out, g["out"]) < 1e-3 and H.relerr(fea, g["fea"]) < 1e-3
+    g = fx["ie_single"]
+    M = _filled(IE.ImageEmbedding_single(image=1))
+    out = M(inp["video"].cuda())
+    assert tuple(out.shape) == tuple(g["out"].shape) and H.relerr(out, g["out"]) < 1e-3
+    assert H.relerr(M.state_dict()["bn_1.running_mean"], g["bn_1_running_mean"]) < 1e-3
+    g = fx["ie_finetune"]
+    M = _filled(IE.ImageEmbedding_finetune())
+    out = M(inp["feat"].cuda())
+    assert tuple(out.shape) == tuple(g["out"].shape) and H.relerr(out, g["out"]) < 1e-4
+
+
+# ---- WaveNet teacher-forced training path ----------------------------------------------------------------------------------
+def _train_inputs(fx):
+    kw = MG.WAVENET_TRAIN_KW
+    T = fx["wavenet_train"]["T"]
+    x = torch.cat((FX.uniform("wav_xsmall", (1, 1, T), -1.0, 1.0), FX.uniform("wav_x2", (1, 1, T), -1.0, 1.0)), 0)
+    c = torch.cat((FX.uniform("wav_csmall", (1, kw["cin_channels"], T // 8)), FX.uniform("wav_c2", (1, kw["cin_channels"], T // 8))), 0)
+    return kw, T, x, c
+
+
+@pytest.mark.parametrize("prec", PREC)
+def test_wavenet_training_step_matches_reference_golden(fx, prec):
+    """One teacher-forced step of the reference (forward -> DiscretizedMixturelogisticLoss on the shifted targets -> backward):
+    outputs, loss and parameter gradients."""
+    from viai_b200 import loss_functions as LF, ops
+    from viai_b200.wavenet_vocoder import WaveNet
+    assert ops.get_precision() == prec
+    g = fx["wavenet_train"]
+    kw, T, x, c = _train_inputs(fx)
+    m = _filled(WaveNet(**kw)).eval()
+    y_hat = m(x.cuda(), c.cuda())
+    assert tuple(y_hat.shape) == tuple(g["y_hat"].shape)
+    assert H.relerr(y_hat, g["y_hat"]) < 1e-3
+    loss = LF.DiscretizedMixturelogisticLoss()(y_hat[:, :, :-1], x.cuda().transpose(1, 2)[:, 1:, :], lengths=g["lengths"].cuda())
+    assert abs(float(loss) - g["loss"]) / g["loss"] < 1e-3
+    loss.backward()
+    params = dict(m.named_parameters())
+    tol = 1e-3 if prec == "fp32" else 2e-2
+    for k, want in g["grads"].items():
+        assert H.relerr(params[k].grad, want) < tol, k
+    for k, want in g["gnorm"].items():
+        assert abs(float(params[k].grad.norm()) - want) <= tol * max(want, 1e-3), k
+    for k in g["dead"]:
+        assert params[k].grad is None or float(params[k].grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("prec", PREC)
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_wavenet_parallel_forward_matches_reference_logits_and_synthesis_kernel(tag, prec):
+    """The T-parallel forward against the reference's own batch-forward golden (24 x 512-channel layers for 'full') and
+    against the teacher-forced synthesis kernel (incremental == batch)."""
+    from viai_b200 import ops
+    from viai_b200.wavenet_vocoder import WaveNet
+    assert ops.get_precision() == prec
+    gold = H.load_golden("wavenet_%s.pt" % tag)
+    kw, T = gold["kw"], gold["T"]
+    m = WaveNet(**kw)
+    m.load_state_dict({k: v.clone() for k, v in H.filled(H.wavenet_sd(**kw)).items()})
+    m = m.cuda().eval()
+    hop = 1
+    for s in kw["upsample_scales"]:
+        hop *= s
+    x = FX.uniform("wav_x" + tag, (1, 1, T), -1.0, 1.0).cuda()
+    c = FX.uniform("wav_c" + tag, (1, kw["cin_channels"], T // hop)).cuda()
+    with torch.no_grad():
+        yb = m(x, c)
+        yk = m.forward_incremental_kernel(x, c)
+    assert tuple(yb.shape) == tuple(gold["logits"].shape)
+    assert H.relerr(yb, gold["logits"]) < 1e-3
+    assert H.relerr(yk, gold["logits"]) < 1e-3
+    assert H.relerr(yb, yk) < 1e-3
+
+
+def test_wavenet_dropout_only_in_training_mode(fx):
+    from viai_b200.wavenet_vocoder import WaveNet
+    kw, T, x, c = _train_inputs(fx)
+    m = _filled(WaveNet(**kw))
+    m.eval()
+    with torch.no_grad():
+        a, b = m(x.cuda(), c.cuda()), m(x.cuda(), c.cuda())
+    assert torch.equal(a, b)
+    m.train()
+    torch.manual_seed(0)
+    with torch.no_grad():
+        d = m(x.cuda(), c.cuda())
+    assert d.shape == a.shape and not torch.allclose(d, a) and torch.isfinite(d).all()
+
+
+@pytest.mark.bf16x3
+def test_wavenet_training_step_full_width_gradients_match_oracle():
+    """Full-width layers (512/512/256, 80-bin conditioning) on the tensor-core path: K = 1616 -> 1632 operand, 1x1 GEMMs over
+    B*T rows.  Reference = the oracle in fp64 (itself pinned against the reference classes); gradients carry one tf32 product."""
+    from viai_b200 import loss_functions as LF
+    from viai_b200.wavenet_vocoder import WaveNet
+    kw = dict(layers=4, stacks=2, residual_channels=512, gate_channels=512, skip_out_channels=256, cin_channels=80, out_channels=30,
+              upsample_scales=[4, 4], kernel_size=3)
+    B, T = 2, 256
+    m = WaveNet(**kw)
+    sd0 = H.filled(H.wavenet_sd(**kw))
+    m.load_state_dict({k: v.clone() for k, v in sd0.items()})
+    m = m.cuda().eval()
+    x = FX.uniform("wt_x", (B, 1, T), -1.0, 1.0)
+    c = FX.uniform("wt_c", (B, 80, T // 16))
+    lengths = torch.tensor([T - 1, T - 40])
+    y_hat = m(x.cuda(), c.cuda())
+    loss = LF.DiscretizedMixturelogisticLoss()(y_hat[:, :, :-1], x.cuda().transpose(1, 2)[:, 1:, :], lengths=lengths.cuda())
+    loss.backward()
+    sd = {k: v.double().requires_grad_(True) for k, v in sd0.items()}
+    yo = O.wavenet_forward(sd, x.double(), c.double(), 2, [4, 4])
+    lo = O.masked_dmol_loss(yo[:, :, :-1], x.double().transpose(1, 2)[:, 1:, :], lengths=lengths)
+    lo.backward()
+    assert H.relerr(y_hat, yo) < 1e-3
+    assert abs(float(loss) - float(lo)) / float(lo) < 1e-3
+    params = dict(m.named_parameters())
+    for k in ("first_conv.bias", "conv_layers.0.conv.weight_v", "conv_layers.1.conv.weight_g", "conv_layers.2.conv1x1c.weight_v",
+              "conv_layers.2.conv1x1_out.weight_v", "conv_layers.3.conv1x1_skip.weight_v", "last_conv_layers.1.weight_v",
+              "last_conv_layers.3.bias", "upsample_conv.0.weight_v"):
+        assert H.relerr_l2(params[k].grad, sd[k].grad) < 2e-2, k
