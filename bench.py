@@ -171,42 +171,43 @@ def time_wavenet(torch, T=8000):
             "finite": bool(torch.isfinite(out).all())}
 
 
-def time_wavenet_train(torch, B=2, T=8000, steps=5, warmup=3):
-    """WaveNet teacher-forced training step (full C4 network): forward over B*T samples in parallel, masked DMoL
-    loss on the shifted targets, backward, fused Adam.  samples/s = B*T / step time; algorithmic FLOPs 3 x 49.3 MFLOP/sample."""
-    from viai_b200 import loss_functions as LF
-    from viai_b200.optim import FusedAdam
+def time_wavenet_train(torch, B=4, T=8000, steps=5, warmup=3, graph=True):
+    """WaveNet teacher-forced training step (full C4 network) through ``WaveNetTrainer``: forward over B*T samples
+    in parallel, masked DMoL loss on the shifted targets, backward, fused Adam + EMA, captured as one CUDA graph.  The timed
+    region includes the host->device copy of each step's audio / conditioning from pinned memory and the read-back of the
+    loss.  samples/s = B*T / step time; algorithmic FLOPs 3 x 49.3 MFLOP/sample."""
+    from viai_b200.wavenet_step import WaveNetTrainer
     from viai_b200.wavenet_vocoder import WaveNet
     torch.manual_seed(0)
     m = WaveNet().cuda().train()
-    opt = FusedAdam(m.parameters(), lr=1e-3, betas=(0.9, 0.999))
-    crit = LF.DiscretizedMixturelogisticLoss()
+    tr = WaveNetTrainer(m)
     x_h = (torch.rand(B, 1, T) * 2 - 1).pin_memory()
     c_h = torch.rand(B, 80, T // 160).pin_memory()
-    mask = LF.sequence_mask(torch.full((B,), T - 1, dtype=torch.long).cuda(), T - 1).unsqueeze(-1)
-
-    def step():
-        x, c = x_h.cuda(non_blocking=True), c_h.cuda(non_blocking=True)
-        opt.zero_grad()
-        y_hat = m(x, c)
-        loss = crit(y_hat[:, :, :-1], x.transpose(1, 2)[:, 1:, :], mask=mask)
-        loss.backward()
-        opt.step()
-        return loss
+    mask = torch.ones(B, T, 1).cuda()
+    x, c = x_h.cuda(), c_h.cuda()
+    y = x.transpose(1, 2).contiguous()
+    if graph:
+        tr.capture(x, y, c, mask, warmup=2)
+        step = lambda: tr.replay(x_h, x_h, c_h)          # y is the same signal as x for raw audio: (B,1,T) and (B,T,1) share memory
+    else:
+        def step():
+            xd = x_h.cuda(non_blocking=True)
+            return tr.train_step(xd, xd.transpose(1, 2), c_h.cuda(non_blocking=True), mask)
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        loss = step()
+        loss = float(step())
     e1.record()
     e1.synchronize()
     ms = e0.elapsed_time(e1) / steps
     return {"metric": "WaveNet teacher-forced training samples/sec", "value": B * T / ms * 1e3, "unit": "samples/s", "B": B, "T": T,
-            "ms_per_step": ms, "algorithmic_tflops": 3 * 49.30e6 * B * T / (ms * 1e-3) / 1e12, "loss": float(loss),
-            "config": "24 layers / 4 stacks, 512/512/256 channels, 80-bin local conditioning, dropout 0.05, masked DMoL loss, Adam; "
-                      "eager launches, inputs from pinned host memory each step"}
+            "ms_per_step": ms, "algorithmic_tflops": 3 * 49.30e6 * B * T / (ms * 1e-3) / 1e12, "loss": loss,
+            "launches_per_step": int(tr.launches_per_step), "cuda_graph": bool(graph),
+            "config": "24 layers / 4 stacks, 512/512/256 channels, 80-bin local conditioning, dropout 0.05, masked DMoL loss, "
+                      "Adam + EMA; inputs from pinned host memory and loss read back every step"}
 
 
 def main():

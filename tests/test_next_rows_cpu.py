@@ -259,3 +259,15 @@ def test_product_visual_branches(fx, inp, cpu_ops):
     assert {k: tuple(v.shape) for k, v in M.state_dict().items()} == g["shapes"]
     out = M(inp["feat"])
     assert tuple(out.shape) == tuple(g["out"].shape) and H.relerr(out, g["out"]) < 1e-5
+
+
+def test_trainer_shifted_targets_equal_the_sliced_loss(fx, inp):
+    """WaveNetTrainer aligns targets / weights with y_hat instead of slicing y_hat[:, :, :-1]: same loss (pure torch glue)."""
+    from viai_b200.wavenet_step import WaveNetTrainer
+    yh, y = inp["dmol_yhat"], inp["dmol_y"]
+    mask = O.sequence_mask(inp["dmol_len"], 40).unsqueeze(-1)
+    want = O.masked_dmol_loss(yh[:, :, :-1], y[:, 1:, :], mask=mask[:, 1:, :], num_classes=256, log_scale_min=-7.0)
+    target, weight = WaveNetTrainer.shifted_targets(y, mask)
+    nll = O.dmol_nll(yh, target.unsqueeze(-1), 256, -7.0).squeeze(-1)
+    got = (nll * weight).sum() / weight.sum()
+    assert abs(float(got) - float(want)) / float(want) < 1e-6
