@@ -249,12 +249,18 @@ int viai_rsqrt_eps(const float* var, int n, float eps, float* out, viai_stream_t
 /* Operand of a dilated causal nn.Conv1d (modules.py:175-178: conv + "remove future time steps") joined with the
  * local-conditioning features (modules.py:183-187), so that conv + conv1x1c is ONE 1x1 GEMM with the linearised weight of
  * conv.py:51-62:  out[b,t,k*R + r] = x[b, t - (K-1-k)*dilation, r] (0 before t = 0), out[b,t,K*R + j] = c[b,t,j], zero up to
- * Kpad.  R, Cc, Kpad multiples of 4; c may be NULL when Cc == 0. */
-int viai_shiftcat_fwd(const float* x, const float* c, int B, int T, int R, int Cc, int K, int dilation, int Kpad, float* out,
-                      viai_stream_t stream);
+ * Kpad.  R, Cc, Kpad multiples of 4; c may be NULL when Cc == 0.  mask (B,T,R; may be NULL) and scale fuse the dropout of
+ * modules.py:173: x is read as x * mask * scale. */
+int viai_shiftcat_fwd(const float* x, const float* c, const float* mask, float scale, int B, int T, int R, int Cc, int K, int dilation,
+                      int Kpad, float* out, viai_stream_t stream);
 /* dx (B,T,R) and dc (B,T,Cc; may be NULL) from dout (B,T,Kpad) */
-int viai_shiftcat_bwd(const float* dout, int B, int T, int R, int Cc, int K, int dilation, int Kpad, float* dx, float* dc,
-                      viai_stream_t stream);
+int viai_shiftcat_bwd(const float* dout, const float* mask, float scale, int B, int T, int R, int Cc, int K, int dilation, int Kpad,
+                      float* dx, float* dc, viai_stream_t stream);
+/* DeepVoice3-style weight normalisation (wavenet_vocoder/modules.py:22-32 via nn.utils.weight_norm, dim 0):
+ * w[row,:] = v[row,:] * g[row] / ||v[row,:]||; norms: float[rows] kept for the backward (dv, dg from dw). */
+int viai_weight_norm_fwd(const float* v, const float* g, int rows, int cols, float* w, float* norms, viai_stream_t stream);
+int viai_weight_norm_bwd(const float* v, const float* g, const float* norms, const float* dw, int rows, int cols, float* dv, float* dg,
+                         viai_stream_t stream);
 /* out[row,i] = tanh(y[row,i]) * sigmoid(y[row,G/2+i])  (modules.py:180,196) and its backward; G % 8 == 0 */
 int viai_glu_fwd(const float* y, int64_t rows, int G, float* out, viai_stream_t stream);
 int viai_glu_bwd(const float* y, const float* dout, int64_t rows, int G, float* dy, viai_stream_t stream);

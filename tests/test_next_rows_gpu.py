@@ -64,6 +64,38 @@ def test_shiftcat_forward_backward(cfg):
         assert torch.equal(cg.grad.cpu(), cr.grad)
 
 
+def test_shiftcat_with_dropout_mask_and_weight_norm():
+    from viai_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    B, T, R, Cc, K, d = 2, 33, 16, 8, 3, 4
+    x, c = torch.randn(B, T, R, generator=g), torch.randn(B, T, Cc, generator=g)
+    mask = (torch.rand(B, T, R, generator=g) < 0.7).float()
+    scale = 1.0 / 0.7
+    xg, cg = x.cuda().requires_grad_(True), c.cuda().requires_grad_(True)
+    got = ops.shiftcat(xg, cg, K, d, 64, mask.cuda(), scale)
+    xr, cr = x.clone().requires_grad_(True), c.clone().requires_grad_(True)
+    xd = xr * mask * scale
+    want = F.pad(torch.cat([F.pad(xd, (0, 0, (K - 1 - k) * d, 0))[:, :T] for k in range(K)] + [cr], 2), (0, 64 - K * R - Cc))
+    assert H.relerr(got, want) < 1e-6
+    dout = torch.randn(B, T, 64, generator=g)
+    got.backward(dout.cuda())
+    want.backward(dout)
+    assert H.relerr(xg.grad, xr.grad) < 1e-6 and torch.equal(cg.grad.cpu(), cr.grad)
+    # weight norm: conv (512, 512, 3), 1x1 (256, 256, 1), the single-row ConvTranspose2d (1, 1, 3, 10)
+    for shape in ((512, 512, 3), (256, 256, 1), (1, 1, 3, 10), (30, 256, 1)):
+        v = torch.randn(shape, generator=g)
+        gg = torch.rand((shape[0],) + (1,) * (len(shape) - 1), generator=g) + 0.5
+        vg, ggg = v.cuda().requires_grad_(True), gg.cuda().requires_grad_(True)
+        w = ops.weight_norm(vg, ggg)
+        vr, gr = v.clone().requires_grad_(True), gg.clone().requires_grad_(True)
+        wr = torch._weight_norm(vr, gr, 0)
+        assert H.relerr(w, wr) < 1e-6, shape
+        dw = torch.randn(shape, generator=g)
+        w.backward(dw.cuda())
+        wr.backward(dw)
+        assert H.relerr(vg.grad, vr.grad) < 1e-5 and H.relerr(ggg.grad, gr.grad) < 1e-5, shape
+
+
 def test_glu_axpby_masked_sum_sequence_mask():
     from viai_b200 import ops
     g = torch.Generator().manual_seed(5)
@@ -84,6 +116,9 @@ def test_glu_axpby_masked_sum_sequence_mask():
     assert H.relerr(r, 0.25 * p - 1.5 * q) < 1e-6
     r.sum().backward()
     assert torch.allclose(pg.grad.cpu(), torch.full((1000,), 0.25)) and torch.allclose(qg.grad.cpu(), torch.full((1000,), -1.5))
+    pg.grad, qg.grad = None, None
+    (ops.axpby(pg, 0.5, qg, 0.5) * pg.detach()).sum().backward()          # equal coefficients: one shared gradient tensor
+    assert H.relerr(pg.grad, 0.5 * p) < 1e-6 and H.relerr(qg.grad, 0.5 * p) < 1e-6
     sh = p.cuda().clone()
     ops.axpby_(sh, 0.9, q.cuda(), 0.1)
     assert H.relerr(sh, O.ema_update(p, q, 0.9)) < 1e-6

@@ -70,8 +70,15 @@ def add_act(a, b, act=1):
     return _act(a + b, act, 0.0)
 
 
-def shiftcat(x, c, K, dilation, Kpad):
+def weight_norm(v, g):
+    nrm = v.reshape(v.size(0), -1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+    return v * (g / nrm)
+
+
+def shiftcat(x, c, K, dilation, Kpad, mask=None, scale=1.0):
     B, T, R = x.shape
+    if mask is not None:
+        x = x * mask * scale
     cols = []
     for k in range(K):
         sh = (K - 1 - k) * dilation
@@ -129,7 +136,7 @@ def l2_contrastive(scores, margin=0.0, max_violation=False):
     return (torch.sum(cost ** 2) + torch.sum(scores.diag() ** 2)) / (2 * scores.size(0))
 
 
-_NAMES = ["conv2d", "conv2d_stats", "norm_act", "cat_channels", "mul", "avgpool_h", "maxpool3s2", "add_act", "shiftcat",
+_NAMES = ["conv2d", "conv2d_stats", "norm_act", "cat_channels", "mul", "avgpool_h", "maxpool3s2", "add_act", "shiftcat", "weight_norm",
           "glu_tanh_sigmoid", "axpby", "axpby_", "dmol_nll", "masked_sum", "sequence_mask", "l2_normalize", "pairdist",
           "l2_contrastive"]
 

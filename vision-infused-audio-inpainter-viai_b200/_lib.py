@@ -73,8 +73,10 @@ SIGNATURES = {
     "viai_adam_step": [c_p, c_p, c_p, c_p, c_l, c_p, c_d, c_d, c_d, c_p, c_i, c_f, c_p],
     "viai_lincomb2": [c_p, c_f, c_p, c_f, c_p, c_p],
     "viai_fill": [c_p, c_l, c_f, c_p],
-    "viai_shiftcat_fwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
-    "viai_shiftcat_bwd": [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
+    "viai_shiftcat_fwd": [c_p, c_p, c_p, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
+    "viai_shiftcat_bwd": [c_p, c_p, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
+    "viai_weight_norm_fwd": [c_p, c_p, c_i, c_i, c_p, c_p, c_p],
+    "viai_weight_norm_bwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
     "viai_glu_fwd": [c_p, c_l, c_i, c_p, c_p],
     "viai_glu_bwd": [c_p, c_p, c_l, c_i, c_p, c_p],
     "viai_axpby": [c_p, c_f, c_p, c_f, c_p, c_l, c_p],

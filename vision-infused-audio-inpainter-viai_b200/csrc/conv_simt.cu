@@ -227,6 +227,45 @@ wgrad_kernel(viai_conv_geom g, const float* __restrict__ U, const float* __restr
   }
 }
 
+// Single-channel weight gradient (A == B == 1, e.g. the WaveNet conditioning upsampler ConvTranspose2d(1,1,(3,s)),
+// wavenet_vocoder/wavenet.py:153-166): dw[r][s] = sum_p U[p] * G[gather(p, r, s)].  Every thread keeps the taps in registers
+// over a grid-stride range of pixels; one shuffle reduction + one atomic per tap and warp.
+constexpr int C1_MAXTAP = 32;
+__global__ void __launch_bounds__(256)
+wgrad_c1_kernel(viai_conv_geom g, const float* __restrict__ U, const float* __restrict__ G, float* __restrict__ dw, int64_t sr,
+                int64_t ss) {
+  const int taps = g.R * g.S;
+  const int64_t M = (int64_t)g.N * g.Hout * g.Wout;
+  const int HWo = g.Hout * g.Wout;
+  float acc[C1_MAXTAP];
+#pragma unroll
+  for (int t = 0; t < C1_MAXTAP; ++t) acc[t] = 0.f;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < M; p += (int64_t)gridDim.x * blockDim.x) {
+    const float u = __ldg(U + p);
+    const int n = (int)(p / HWo);
+    const int rem = (int)(p - (int64_t)n * HWo);
+    const int y = rem / g.Wout, x = rem - y * g.Wout;
+    const float* base = G + (int64_t)n * g.Hin * g.Win;
+#pragma unroll
+    for (int t = 0; t < C1_MAXTAP; ++t) {
+      if (t < taps) {
+        const int r = t / g.S, s = t - r * g.S;
+        const int Y = y * g.stride_h - g.pad_h + r, X = x * g.stride_w - g.pad_w + s;
+        if (Y >= 0 && Y < g.Hin && X >= 0 && X < g.Win) acc[t] = fmaf(u, __ldg(base + (int64_t)Y * g.Win + X), acc[t]);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < C1_MAXTAP; ++t) {
+    if (t < taps) {
+      float v = acc[t];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(dw + (t / g.S) * sr + (t % g.S) * ss, v);
+    }
+  }
+}
+
 __global__ void zero_strided_kernel(float* dw, int A, int B, int R, int S, int64_t sa, int64_t sb, int64_t sr, int64_t ss) {
   int64_t total = (int64_t)A * B * R * S;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -292,6 +331,11 @@ extern "C" int viai_conv2d_wgrad_simt(const viai_conv_geom* g, const float* U, c
     int64_t total = (int64_t)A * B * taps;
     zero_strided_kernel<<<(int)imin64(cdiv(total, 256), 2 * kNumSMs), 256, 0, st>>>(dw, A, B, g->R, g->S, sa, sb, sr, ss);
     VIAI_LAUNCHED();
+  }
+  if (A == 1 && B == 1 && taps <= C1_MAXTAP && M > 0) {
+    wgrad_c1_kernel<<<(int)imin64(cdiv(M, 256 * 16), 4 * kNumSMs), 256, 0, st>>>(*g, U, G, dw, sr, ss);
+    VIAI_LAUNCHED();
+    return VIAI_OK;
   }
   int BA, BB;
   if (A > 32 && B > 32) { BA = 64; BB = 64; }

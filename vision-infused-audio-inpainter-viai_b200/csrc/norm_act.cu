@@ -54,6 +54,7 @@ stats_kernel(const float* __restrict__ y, int64_t rows_per_group, int C, double*
   for (int k = 0; k < VEC; ++k) { s[k] = 0.0; q[k] = 0.0; }
   if (active) {
     const float* base = y + ((int64_t)g * rows_per_group) * C + cv * VEC;
+#pragma unroll 4
     for (int64_t r = r0 + rl; r < r1; r += L.lanes) {
       float v[VEC];
       if (VEC == 4) {
@@ -332,7 +333,9 @@ int64_t pick_rows_per_block(int64_t rows_per_group, int groups, int C, int VEC) 
   const int lanes = make_lanes(C, VEC).lanes;
   int64_t per_group = cdiv((int64_t)8 * kNumSMs, groups);
   int64_t rpb = cdiv(rows_per_group, per_group);
-  if (rpb < (int64_t)lanes * 8) rpb = (int64_t)lanes * 8;
+  // at least 32 rows per row lane: every block ends with C double atomics per moment, which dominate short tensors
+  // (bias gradients of 32 000 x 512 rows: 1 143 blocks x 512 atomics took 60 us, HBM time is 11 us)
+  if (rpb < (int64_t)lanes * 32) rpb = (int64_t)lanes * 32;
   return rpb;
 }
 

@@ -14,10 +14,11 @@ constexpr int THREADS = 256;
 constexpr int MAX_MIX = 32;
 inline int grid_for(int64_t total) { return (int)imin64(cdiv(total, THREADS), 16 * kNumSMs); }
 
-// out[b, t, k*R + r] = x[b, t - (K-1-k)*d, r] (0 before the start);  out[b, t, K*R + j] = c[b, t, j];  zero up to Kpad
+// out[b, t, k*R + r] = x[b, t - (K-1-k)*d, r] (0 before the start);  out[b, t, K*R + j] = c[b, t, j];  zero up to Kpad.
+// With a dropout mask (F.dropout on the convolution input, modules.py:173) x is read as x * mask * scale.
 __global__ void __launch_bounds__(THREADS)
-shiftcat_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ c, int B, int T, int R4, int C4, int K, int dil,
-                    int P4, float4* __restrict__ out) {
+shiftcat_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ c, const float4* __restrict__ mask, float scale, int B,
+                    int T, int R4, int C4, int K, int dil, int P4, float4* __restrict__ out) {
   const int64_t total = (int64_t)B * T * P4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int col = (int)(i % P4);
@@ -27,7 +28,13 @@ shiftcat_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ c, 
     if (col < K * R4) {
       const int k = col / R4, r = col - k * R4;
       const int ts = t - (K - 1 - k) * dil;
-      if (ts >= 0) v = __ldg(x + (bt - t + ts) * R4 + r);
+      if (ts >= 0) {
+        v = __ldg(x + (bt - t + ts) * R4 + r);
+        if (mask) {
+          const float4 m = __ldg(mask + (bt - t + ts) * R4 + r);
+          v.x *= m.x * scale; v.y *= m.y * scale; v.z *= m.z * scale; v.w *= m.w * scale;
+        }
+      }
     } else if (col < K * R4 + C4) {
       v = __ldg(c + bt * C4 + (col - K * R4));
     }
@@ -37,8 +44,8 @@ shiftcat_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ c, 
 
 // dx[b, t, r] = sum_k dout[b, t + (K-1-k)*d, k*R + r] (inside the sequence);  dc[b, t, j] = dout[b, t, K*R + j]
 __global__ void __launch_bounds__(THREADS)
-shiftcat_bwd_kernel(const float4* __restrict__ dout, int B, int T, int R4, int C4, int K, int dil, int P4,
-                    float4* __restrict__ dx, float4* __restrict__ dc) {
+shiftcat_bwd_kernel(const float4* __restrict__ dout, const float4* __restrict__ mask, float scale, int B, int T, int R4, int C4,
+                    int K, int dil, int P4, float4* __restrict__ dx, float4* __restrict__ dc) {
   const int W4 = R4 + (dc ? C4 : 0);
   const int64_t total = (int64_t)B * T * W4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -53,6 +60,10 @@ shiftcat_bwd_kernel(const float4* __restrict__ dout, int B, int T, int R4, int C
           const float4 g = __ldg(dout + (bt - t + td) * P4 + k * R4 + col);
           s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
         }
+      }
+      if (mask) {
+        const float4 m = __ldg(mask + bt * R4 + col);
+        s.x *= m.x * scale; s.y *= m.y * scale; s.z *= m.z * scale; s.w *= m.w * scale;
       }
       dx[bt * R4 + col] = s;
     } else {
@@ -219,6 +230,42 @@ masked_sum_bwd_kernel(const float* __restrict__ mask, int64_t n, const double* _
     dv[i] = mask ? g * mask[i] : g;
 }
 
+// torch weight_norm (dim 0): w[row] = v[row] * g[row] / ||v[row]||.  One block per row.
+__global__ void __launch_bounds__(128)
+weight_norm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, int cols, float* __restrict__ w, float* __restrict__ nrm) {
+  __shared__ float sh[4];
+  const int row = blockIdx.x;
+  const float* pv = v + (int64_t)row * cols;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < cols; k += 128) s += pv[k] * pv[k];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  const float n = sqrtf(sh[0] + sh[1] + sh[2] + sh[3]);
+  const float f = g[row] / n;
+  for (int k = threadIdx.x; k < cols; k += 128) w[(int64_t)row * cols + k] = pv[k] * f;
+  if (threadIdx.x == 0) nrm[row] = n;
+}
+// dg[row] = <dw, v> / n;  dv = (g / n) * dw - (g <dw, v> / n^3) * v
+__global__ void __launch_bounds__(128)
+weight_norm_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ nrm,
+                       const float* __restrict__ dw, int cols, float* __restrict__ dv, float* __restrict__ dg) {
+  __shared__ float sh[4];
+  const int row = blockIdx.x;
+  const float* pv = v + (int64_t)row * cols;
+  const float* pd = dw + (int64_t)row * cols;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < cols; k += 128) s += pv[k] * pd[k];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  const float dot = sh[0] + sh[1] + sh[2] + sh[3];
+  const float n = nrm[row], gg = g[row];
+  const float a = gg / n, b = gg * dot / (n * n * n);
+  for (int k = threadIdx.x; k < cols; k += 128) dv[(int64_t)row * cols + k] = a * pd[k] - b * pv[k];
+  if (threadIdx.x == 0) dg[row] = dot / n;
+}
+
 __global__ void sequence_mask_kernel(const int64_t* __restrict__ lengths, int B, int T, float* __restrict__ out) {
   const int64_t total = (int64_t)B * T;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
@@ -228,29 +275,29 @@ __global__ void sequence_mask_kernel(const int64_t* __restrict__ lengths, int B,
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-extern "C" int viai_shiftcat_fwd(const float* x, const float* c, int B, int T, int R, int Cc, int K, int dilation, int Kpad,
-                                 float* out, viai_stream_t stream) {
+extern "C" int viai_shiftcat_fwd(const float* x, const float* c, const float* mask, float scale, int B, int T, int R, int Cc, int K,
+                                 int dilation, int Kpad, float* out, viai_stream_t stream) {
   VIAI_REQUIRE(x && out && B > 0 && T > 0 && K > 0 && dilation > 0, "shiftcat_fwd: bad arguments");
   VIAI_REQUIRE(R > 0 && R % 4 == 0 && Cc >= 0 && Cc % 4 == 0 && Kpad % 4 == 0 && Kpad >= K * R + Cc && (Cc == 0 || c),
                "shiftcat_fwd: channel counts must be multiples of 4 and Kpad >= K*R + Cc (R %d Cc %d K %d Kpad %d)", R, Cc, K, Kpad);
-  VIAI_REQUIRE(aligned16(x) && aligned16(out) && aligned16(c), "shiftcat_fwd: pointers must be 16-byte aligned");
+  VIAI_REQUIRE(aligned16(x) && aligned16(out) && aligned16(c) && aligned16(mask), "shiftcat_fwd: pointers must be 16-byte aligned");
   shiftcat_fwd_kernel<<<grid_for((int64_t)B * T * (Kpad / 4)), THREADS, 0, STR(stream)>>>(
-      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(c), B, T, R / 4, Cc / 4, K, dilation, Kpad / 4,
-      reinterpret_cast<float4*>(out));
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(c), reinterpret_cast<const float4*>(mask), scale, B, T, R / 4,
+      Cc / 4, K, dilation, Kpad / 4, reinterpret_cast<float4*>(out));
   VIAI_LAUNCHED();
   return VIAI_OK;
 }
 
-extern "C" int viai_shiftcat_bwd(const float* dout, int B, int T, int R, int Cc, int K, int dilation, int Kpad, float* dx, float* dc,
-                                 viai_stream_t stream) {
+extern "C" int viai_shiftcat_bwd(const float* dout, const float* mask, float scale, int B, int T, int R, int Cc, int K, int dilation,
+                                 int Kpad, float* dx, float* dc, viai_stream_t stream) {
   VIAI_REQUIRE(dout && dx && B > 0 && T > 0 && K > 0 && dilation > 0, "shiftcat_bwd: bad arguments");
   VIAI_REQUIRE(R > 0 && R % 4 == 0 && Cc >= 0 && Cc % 4 == 0 && Kpad % 4 == 0 && Kpad >= K * R + Cc && (Cc > 0 || !dc),
                "shiftcat_bwd: channel counts must be multiples of 4 and Kpad >= K*R + Cc");
-  VIAI_REQUIRE(aligned16(dout) && aligned16(dx) && aligned16(dc), "shiftcat_bwd: pointers must be 16-byte aligned");
+  VIAI_REQUIRE(aligned16(dout) && aligned16(dx) && aligned16(dc) && aligned16(mask), "shiftcat_bwd: pointers must be 16-byte aligned");
   const int W4 = R / 4 + (dc ? Cc / 4 : 0);
   shiftcat_bwd_kernel<<<grid_for((int64_t)B * T * W4), THREADS, 0, STR(stream)>>>(
-      reinterpret_cast<const float4*>(dout), B, T, R / 4, Cc / 4, K, dilation, Kpad / 4, reinterpret_cast<float4*>(dx),
-      reinterpret_cast<float4*>(dc));
+      reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(mask), scale, B, T, R / 4, Cc / 4, K, dilation, Kpad / 4,
+      reinterpret_cast<float4*>(dx), reinterpret_cast<float4*>(dc));
   VIAI_LAUNCHED();
   return VIAI_OK;
 }
@@ -316,6 +363,21 @@ extern "C" int viai_masked_sum_bwd(const float* mask, int64_t n, int mean, const
 extern "C" int viai_sequence_mask(const int64_t* lengths, int B, int T, float* out, viai_stream_t stream) {
   VIAI_REQUIRE(lengths && out && B > 0 && T > 0, "sequence_mask: bad arguments");
   sequence_mask_kernel<<<grid_for((int64_t)B * T), THREADS, 0, STR(stream)>>>(lengths, B, T, out);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_weight_norm_fwd(const float* v, const float* g, int rows, int cols, float* w, float* norms, viai_stream_t stream) {
+  VIAI_REQUIRE(v && g && w && norms && rows > 0 && cols > 0, "weight_norm_fwd: bad arguments");
+  weight_norm_fwd_kernel<<<rows, 128, 0, STR(stream)>>>(v, g, cols, w, norms);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_weight_norm_bwd(const float* v, const float* g, const float* norms, const float* dw, int rows, int cols, float* dv,
+                                    float* dg, viai_stream_t stream) {
+  VIAI_REQUIRE(v && g && norms && dw && dv && dg && rows > 0 && cols > 0, "weight_norm_bwd: bad arguments");
+  weight_norm_bwd_kernel<<<rows, 128, 0, STR(stream)>>>(v, g, norms, dw, cols, dv, dg);
   VIAI_LAUNCHED();
   return VIAI_OK;
 }

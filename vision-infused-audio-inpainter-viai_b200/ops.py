@@ -666,11 +666,12 @@ def to_nchw(t):
 
 # ---- WaveNet teacher-forced training path ------------------------------------------------------------------
 class _ShiftCatFn(torch.autograd.Function):
-    """Operand of a dilated causal Conv1d joined with the conditioning features (viai_shiftcat_fwd / _bwd)."""
+    """Operand of a dilated causal Conv1d joined with the conditioning features (viai_shiftcat_fwd / _bwd); an optional
+    {0,1} dropout mask and its 1/keep scale are applied to x on the fly."""
 
     @staticmethod
-    def forward(ctx, x, c, K, dilation, Kpad):
-        _require_cuda(x, c)
+    def forward(ctx, x, c, K, dilation, Kpad, mask, scale):
+        _require_cuda(x, c, mask)
         L = _lib.lib()
         x = x.contiguous()
         B, T, R = x.shape
@@ -679,25 +680,64 @@ class _ShiftCatFn(torch.autograd.Function):
             c = c.contiguous()
             Cc = c.size(2)
             assert tuple(c.shape[:2]) == (B, T), "conditioning features must cover the same (B, T) as the input"
+        if mask is not None:
+            mask = mask.contiguous()
+            assert mask.shape == x.shape
         out = torch.empty((B, T, Kpad), device=x.device, dtype=torch.float32)
-        _lib.check(L.viai_shiftcat_fwd(_p(x), _p(c), B, T, R, Cc, K, dilation, Kpad, _p(out), _stream()), "shiftcat_fwd")
-        ctx.cfg = (B, T, R, Cc, K, dilation, Kpad)
+        _lib.check(L.viai_shiftcat_fwd(_p(x), _p(c), _p(mask), scale, B, T, R, Cc, K, dilation, Kpad, _p(out), _stream()), "shiftcat_fwd")
+        ctx.save_for_backward(mask)
+        ctx.cfg = (B, T, R, Cc, K, dilation, Kpad, scale)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        B, T, R, Cc, K, dilation, Kpad = ctx.cfg
+        (mask,) = ctx.saved_tensors
+        B, T, R, Cc, K, dilation, Kpad, scale = ctx.cfg
         L = _lib.lib()
         dout = dout.contiguous()
         dx = torch.empty((B, T, R), device=dout.device, dtype=torch.float32)
         dc = torch.empty((B, T, Cc), device=dout.device, dtype=torch.float32) if (Cc > 0 and ctx.needs_input_grad[1]) else None
-        _lib.check(L.viai_shiftcat_bwd(_p(dout), B, T, R, Cc, K, dilation, Kpad, _p(dx), _p(dc), _stream()), "shiftcat_bwd")
-        return dx, dc, None, None, None
+        _lib.check(L.viai_shiftcat_bwd(_p(dout), _p(mask), scale, B, T, R, Cc, K, dilation, Kpad, _p(dx), _p(dc), _stream()),
+                   "shiftcat_bwd")
+        return dx, dc, None, None, None, None, None
 
 
-def shiftcat(x, c, K, dilation, Kpad):
-    """x (B,T,R), c (B,T,Cc) or None -> (B,T,Kpad) with [x(t-(K-1)d) | ... | x(t) | c(t) | 0]."""
-    return _ShiftCatFn.apply(x, c, int(K), int(dilation), int(Kpad))
+def shiftcat(x, c, K, dilation, Kpad, mask=None, scale=1.0):
+    """x (B,T,R), c (B,T,Cc) or None -> (B,T,Kpad) with [x(t-(K-1)d) | ... | x(t) | c(t) | 0]; x is read as x * mask * scale
+    when a dropout mask is given."""
+    return _ShiftCatFn.apply(x, c, int(K), int(dilation), int(Kpad), mask, float(scale))
+
+
+class _WeightNormFn(torch.autograd.Function):
+    """w = v * g / ||v|| per slice of dim 0 (nn.utils.weight_norm, dim 0) in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, v, g):
+        _require_cuda(v, g)
+        L = _lib.lib()
+        v, g = v.contiguous(), g.contiguous()
+        rows = v.size(0)
+        cols = v.numel() // rows
+        w = torch.empty_like(v)
+        nrm = torch.empty(rows, device=v.device, dtype=torch.float32)
+        _lib.check(L.viai_weight_norm_fwd(_p(v), _p(g), rows, cols, _p(w), _p(nrm), _stream()), "weight_norm_fwd")
+        ctx.save_for_backward(v, g, nrm)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        v, g, nrm = ctx.saved_tensors
+        L = _lib.lib()
+        dw = dw.contiguous()
+        rows = v.size(0)
+        dv, dg = torch.empty_like(v), torch.empty_like(g)
+        _lib.check(L.viai_weight_norm_bwd(_p(v), _p(g), _p(nrm), _p(dw), rows, v.numel() // rows, _p(dv), _p(dg), _stream()),
+                   "weight_norm_bwd")
+        return dv, dg
+
+
+def weight_norm(v, g):
+    return _WeightNormFn.apply(v, g)
 
 
 class _GluFn(torch.autograd.Function):
@@ -755,8 +795,11 @@ class _AxpbyFn(torch.autograd.Function):
             da = torch.empty_like(g)
             _lib.check(L.viai_axpby(_p(g), alpha, None, 0.0, _p(da), g.numel(), _stream()), "axpby bwd")
         if has_b and ctx.needs_input_grad[1]:
-            db = torch.empty_like(g)
-            _lib.check(L.viai_axpby(_p(g), beta, None, 0.0, _p(db), g.numel(), _stream()), "axpby bwd")
+            if da is not None and alpha == beta:
+                db = da                  # (a + b) * s: both inputs receive the same gradient tensor
+            else:
+                db = torch.empty_like(g)
+                _lib.check(L.viai_axpby(_p(g), beta, None, 0.0, _p(db), g.numel(), _stream()), "axpby bwd")
         return da, db, None, None
 
 

@@ -46,9 +46,7 @@ def effective_weight(m):
     """The weight a (possibly weight-normalised) module applies: g * v / ||v|| per slice of dim 0 -- what
     ``make_generation_fast_`` (wavenet.py:387-393) folds once."""
     if hasattr(m, "weight_g"):
-        v, g = m.weight_v, m.weight_g
-        nrm = v.reshape(v.size(0), -1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
-        return v * (g / nrm)
+        return ops.weight_norm(m.weight_v, m.weight_g)
     return m.weight
 
 
@@ -91,14 +89,15 @@ class ResidualConv1dGLU(nn.Module):
         if (c is None) != (self.conv1x1c is None):
             raise RuntimeError("local conditioning features and conv1x1c go together (modules.py:184)")
         residual = x
-        if self.training and self.dropout > 0:                      # F.dropout(x, p, training) :173
+        mask, scale = None, 1.0
+        if self.training and self.dropout > 0:                      # F.dropout(x, p, training) :173, applied while gathering
             keep = 1.0 - self.dropout
-            x = ops.mul(x, torch.bernoulli(torch.full_like(x, keep)) / keep)
+            mask, scale = torch.empty_like(x).bernoulli_(keep), 1.0 / keep
         K = self.conv.kernel_size[0]
         G, R = self.conv.out_channels, self.conv.in_channels
         Cc = c.size(2) if c is not None else 0
         Kpad = (K * R + Cc + 31) // 32 * 32
-        X = ops.shiftcat(x, c, K, self.dilation, Kpad)
+        X = ops.shiftcat(x, c, K, self.dilation, Kpad, mask, scale)
         lin = effective_weight(self.conv).permute(0, 2, 1).reshape(G, K * R)
         b = self.conv.bias
         if c is not None:
