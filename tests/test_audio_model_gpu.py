@@ -75,3 +75,55 @@ def test_audio_model_runs_the_reference_step_contract(tmp_path):
     with torch.no_grad():
         model2.test()
     assert torch.allclose(model2.fake, model.fake, atol=1e-5)
+
+
+def test_audio_model_update_wavenet_reports_the_reconstruction_loss():
+    """hparams.update_wavenet: one teacher-forced WaveNet step per batch on (x_batch, y_batch, input_lengths), conditioned on the
+    inpainted mel; train_whole_sync.py:105-107 accumulates ``reconstruct_loss_item``."""
+    from viai_b200 import Options_inpainting as OI
+    from viai_b200.Models.Whole_Sync_inpainting_modify import AudioModel
+    hp = OI.Inpainting_Config(cin_channels=80)
+    hp.max_mel_lengths, hp.update_wavenet = 64, True
+    hp.wavenet_kwargs = dict(layers=4, stacks=2, residual_channels=32, gate_channels=32, skip_out_channels=16, dropout=0.0)
+    torch.manual_seed(5)
+    model = AudioModel(hp, device=torch.device("cuda"))
+    assert model.update_wavenet and model.wavenet is not None
+    B, W = 2, 64
+    g = torch.Generator().manual_seed(1)
+    wav = (torch.rand(B, W * 160, generator=g) * 2 - 1) * 0.5
+    batch = (torch.zeros(B, 1), torch.zeros(B, 1), torch.rand(B, 80, W, generator=g), wav.unsqueeze(1), wav.unsqueeze(2), None,
+             torch.tensor([W * 160, W * 160 - 999]), ["a", "b"])
+    losses = []
+    for step in range(4):
+        model.get_blank_space_length(step)
+        model.set_inputs(batch)
+        model.optimize_parameters(step)
+        model.get_loss_items()
+        losses.append(model.reconstruct_loss_item)
+        model.del_no_need()
+    assert all(l == l and l > 0 for l in losses) and losses[-1] < losses[0]
+    assert model.loss_mel_L1_item > 0
+
+
+@pytest.mark.bf16x3
+def test_audio_model_embedding_l2_matches_oracle_contrastive_loss():
+    """Vision-infused model, eval forward: EmbeddingL2_item == L2ContrastiveLoss(l2_norm(audio bottleneck), l2_norm(visual
+    embedding)) (train_whole_sync.py:109), checked with the oracle on the embeddings the model exposes."""
+    from oracle import viai_oracle as O
+    from viai_b200 import Options_inpainting as OI
+    from viai_b200.Models.Whole_Sync_inpainting_modify import AudioModel
+    hp = OI.Inpainting_Config(cin_channels=80)
+    hp.max_mel_lengths, hp.image, hp.embedding_margin = 64, True, 0.5
+    torch.manual_seed(6)
+    model = AudioModel(hp, device=torch.device("cuda"))
+    B, W = 2, 64
+    g = torch.Generator().manual_seed(2)
+    batch = (torch.randn(B, W // 4, 3, 224, 224, generator=g).clamp(-1, 1), torch.randn(B, W // 4, 2, 224, 224, generator=g).clamp(-1, 1),
+             torch.rand(B, 80, W, generator=g), torch.zeros(B, 1, 8), torch.zeros(B, 8, 1), None, torch.tensor([8, 8]), ["a", "b"])
+    model.set_inputs(batch)
+    with torch.no_grad():
+        model.test()
+    model.get_loss_items()
+    assert model.mel_net_norm.shape == model.video_net_norm.shape == (B, 1024)
+    want = float(O.l2_contrastive(model.mel_net_norm.cpu(), model.video_net_norm.cpu(), 0.5))
+    assert want > 0 and abs(model.EmbeddingL2_item - want) / want < 1e-4

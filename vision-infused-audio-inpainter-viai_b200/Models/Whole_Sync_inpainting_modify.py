@@ -10,6 +10,12 @@ schedule, loss weights, optimizer settings) is OURS and read from ``hparams`` wi
                      grown linearly from ``blank_length_start`` over ``blank_warmup_steps`` steps
     input tuple    : the 8-tuple of Data_loaders/audio_loader.py:532
                      (video_batch, flow_batch, c_batch (B, n_mel, W), x_batch, y_batch, g_batch, input_lengths, path_batch)
+    update_wavenet : (``hparams.update_wavenet``, default False) also runs one teacher-forced WaveNet step per batch on the
+                     waveform (x_batch, y_batch, input_lengths) conditioned on the inpainted mel (detached) and reports its masked
+                     DMoL loss as ``reconstruct_loss_item`` (train_whole_sync.py:105-107); ``hparams.wavenet_kwargs`` overrides the
+                     WaveNet constructor defaults
+    EmbeddingL2    : ``test()`` reports the L2 contrastive loss between the l2-normalised audio bottleneck and visual embedding
+                     (``EmbeddingL2_item``, train_whole_sync.py:109) when the two have the same width (native 80-bin mels)
 """
 import os
 from collections import OrderedDict
@@ -18,13 +24,10 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..loss_functions import L2ContrastiveLoss, sequence_mask
 from ..networks.Image_Embedding import ImageEmbedding
 from ..step import GanTrainer
-
-
-def _l2_normalize(x, eps=1e-10):
-    """utils/util.py l2_norm: row-wise x / ||x||."""
-    return x / (x.pow(2).sum(1, keepdim=True).add(eps).sqrt())
+from ..utils.util import l2_norm
 
 
 class AudioModel(object):
@@ -39,7 +42,18 @@ class AudioModel(object):
         self.Mel_Encoder, self.Mel_Decoder, self.netD, self.VideoEncoder = t.Mel_Encoder, t.Mel_Decoder, t.netD, ve
         self.optimizer_G, self.optimizer_D = t.optimizer_G, t.optimizer_D
         self.train = 1
-        self.update_wavenet = False                   # WaveNet training is outside the hot path
+        self.update_wavenet = bool(getattr(hparams, "update_wavenet", False))
+        self.wavenet = self.wavenet_trainer = None
+        if self.update_wavenet:
+            from ..wavenet_step import WaveNetTrainer
+            from ..wavenet_vocoder import WaveNet
+            kw = dict(cin_channels=hparams.cin_channels)
+            kw.update(getattr(hparams, "wavenet_kwargs", {}))
+            self.wavenet = WaveNet(**kw).to(self.device)
+            self.wavenet_trainer = WaveNetTrainer(self.wavenet, lr=float(getattr(hparams, "wavenet_lr", 1e-3)),
+                                                  world_size=int(getattr(hparams, "world_size", 1)))
+        self.criterionEmbedding = L2ContrastiveLoss(margin=float(getattr(hparams, "embedding_margin", 0.0)))
+        self.audio = self.audio_target = self.input_lengths = None
         self.blank_length = 0
         self.reconstruct_loss_item = 0.0
         self.EmbeddingL2_item = 0.0
@@ -75,11 +89,20 @@ class AudioModel(object):
         if self.use_video:
             self.video = video.to(self.device, non_blocking=True).float().reshape(B, -1, 3, video.size(-2), video.size(-1))
             self.flow = flow.to(self.device, non_blocking=True).float().reshape(B, -1, 2, flow.size(-2), flow.size(-1))
+        if self.update_wavenet:
+            self.audio = data[3].to(self.device, non_blocking=True).float()            # x_batch (B, 1, T)
+            self.audio_target = data[4].to(self.device, non_blocking=True).float()     # y_batch (B, T, 1)
+            self.input_lengths = data[6].to(self.device, non_blocking=True)
 
     # ---- one optimisation step / one evaluation forward ----------------------------------------------------------------
     def optimize_parameters(self, global_step):
         self._out = self.trainer.train_step(self.mel, self.mask, self.video, self.flow)
         self.fake = self._out["fake"]
+        if self.update_wavenet:
+            T = self.audio.size(-1)
+            mask = sequence_mask(self.input_lengths, T).unsqueeze(-1)
+            self._out["reconstruct_loss"] = self.wavenet_trainer.train_step(self.audio, self.audio_target,
+                                                                            self.fake.detach()[:, 0], mask)
 
     def test(self):
         t = self.trainer
@@ -91,16 +114,18 @@ class AudioModel(object):
         l1 = t.criterionL1(self.fake, self.mel)
         self._out = dict(fake=self.fake, loss_L1=l1, loss_D=torch.zeros((), device=self.device),
                          loss_G_GAN=torch.zeros((), device=self.device), loss_G=l1 * t.lambda_L1)
-        self.mel_net_norm = _l2_normalize(feats[-1].reshape(B, -1))
-        self.video_net_norm = _l2_normalize(vnet.reshape(B, -1)) if vnet is not None else torch.zeros_like(self.mel_net_norm)
+        self.mel_net_norm = l2_norm(feats[-1].reshape(B, -1))
+        self.video_net_norm = l2_norm(vnet.reshape(B, -1)) if vnet is not None else torch.zeros_like(self.mel_net_norm)
+        if vnet is not None and self.video_net_norm.shape == self.mel_net_norm.shape:
+            self._out["EmbeddingL2"] = self.criterionEmbedding(self.mel_net_norm, self.video_net_norm)
 
     def get_loss_items(self):
         o = self._out
         self.loss_mel_L1_item = float(o["loss_L1"])
         self.loss_D_item = float(o["loss_D"])
         self.loss_G_GAN_item = float(o["loss_G_GAN"])
-        self.EmbeddingL2_item = 0.0
-        self.reconstruct_loss_item = 0.0
+        self.EmbeddingL2_item = float(o["EmbeddingL2"]) if "EmbeddingL2" in o else 0.0
+        self.reconstruct_loss_item = float(o["reconstruct_loss"]) if "reconstruct_loss" in o else 0.0
 
     def get_current_errors(self):
         return OrderedDict([("loss_D", self.loss_D_item), ("loss_G_GAN", self.loss_G_GAN_item), ("loss_mel_L1", self.loss_mel_L1_item)])
