@@ -432,3 +432,31 @@ def test_wavenet_trainer_cuda_graph_replay_equals_eager(fx):
     pa, pb = dict(a.model.named_parameters()), dict(b.model.named_parameters())
     for k in ("conv_layers.0.conv.weight_v", "last_conv_layers.3.bias"):
         assert H.relerr(pb[k], pa[k]) < 1e-4, k
+
+
+@pytest.mark.tf32
+@pytest.mark.parametrize("cfg", [(1632, 512, 250, 128), (256, 256, 37, 24), (256, 512, 16, 8), (48, 40, 9, 5), (160, 96, 3, 130)],
+                         ids=lambda c: "Cin%d_Cout%d_%dx%d" % c)
+def test_tc_pointwise_convolution_all_three_gemms(cfg):
+    """1x1 convolutions over rows (the WaveNet training GEMMs) on the tensor-core path: forward, data gradient and the
+    channel-group weight gradient (N = 4 slabs of 32 G channels per MMA; ragged channel and pixel tiles) against fp64."""
+    from viai_b200 import ops
+    assert ops.get_precision() == "tf32"
+    Cin, Cout, Hh, W = cfg
+    g = torch.Generator().manual_seed(Cin + Cout + Hh)
+    x = torch.randn(1, Cin, Hh, W, generator=g, dtype=torch.float64).float().double().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g, dtype=torch.float64) / math.sqrt(Cin)).float().double().requires_grad_(True)
+    b = (torch.randn(Cout, generator=g, dtype=torch.float64) * 0.1).float().double().requires_grad_(True)
+    y = F.conv2d(x, w, b)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64).float().double()
+    y.backward(dy)
+    nhwc = lambda t: t.float().permute(0, 2, 3, 1).contiguous().cuda()
+    xg = nhwc(x.detach()).requires_grad_(True)
+    wg = w.detach().float().cuda().requires_grad_(True)
+    bg = b.detach().float().cuda().requires_grad_(True)
+    yg = ops.conv2d(xg, wg, bg)
+    yg.backward(nhwc(dy))
+    assert H.relerr(yg.permute(0, 3, 1, 2), y) < 2e-3
+    assert H.relerr(xg.grad.permute(0, 3, 1, 2), x.grad) < 2e-3
+    assert H.relerr(wg.grad, w.grad) < 2e-3
+    assert H.relerr(bg.grad, b.grad) < 1e-4

@@ -16,6 +16,7 @@
 //   * a second small kernel sums the split slices and scatters into the parameter-gradient layout (overwrite or accumulate).
 // Ragged tiles and zero padding need no masking: TMA fills out-of-bounds elements of either operand with zeros.
 #include "common.cuh"
+#include <stdlib.h>
 #include "tc_common.cuh"
 using namespace viai;
 using namespace viai::tc;
@@ -29,10 +30,12 @@ constexpr int NTHREADS = 192;   // warp 0: TMA producer, warp 1: TMEM + MMA issu
 struct WgSub {
   int32_t ox, oy, pw, ph;
   uint32_t smem_off;     // inside the G region of a stage
+  int32_t c_off;         // channel offset of this box inside the work item's G channel range (channel-group mode)
 };
 struct WgTap {
   uint32_t col;          // first TMEM column of the tap's 128 x 32 accumulator block
   uint32_t wtap;
+  uint32_t b_off;        // G channel offset of the block inside the work item's range (channel-group mode, else 0)
 };
 // A run = horizontally adjacent taps of one parity sub-patch: their B operands are the same patch rows shifted by one pixel
 // (128 bytes) each, so ONE MMA with N = 32 * len covers the whole run by using the pixel pitch as the descriptor's stride
@@ -43,6 +46,8 @@ struct WgRun {
   uint32_t row_pitch;    // bytes between consecutive 8-pixel row segments (pw * 128)
   uint32_t col;          // first TMEM column
   uint32_t idesc;        // instruction descriptor with N = 32 * len
+  uint32_t n_pitch;      // bytes between the 32-channel blocks of the B operand: one pixel (128) for adjacent taps, one box for
+                         // adjacent channel slabs (channel-group mode)
 };
 struct WgParams {
   CUtensorMap mapU;
@@ -54,6 +59,7 @@ struct WgParams {
   float* ws;             // [split][tap][A][B] fp32 workspace
   int64_t ws_split;      // floats per split slice
   int32_t A, B;
+  int32_t b_tile_ch;     // G channels per work item: 32, or 32 * NB in channel-group mode
   int32_t N, tilesX, tilesY, TH;
   int32_t a_tiles, b_tiles, splits, tiles_per_split, npix_tiles;
   int32_t u_slices;      // 32-channel boxes of U actually loaded per stage (<= 4)
@@ -121,7 +127,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
         for (int s = 0; s < p.u_slices; ++s)
           tma_load_4d(u + (size_t)s * p.u_slice_bytes, &p.mapU, &full[st], at * BM + s * KC, x0, y0, n);
         for (int s = 0; s < p.nsub; ++s)
-          tma_load_4d(g + p.sub[s].smem_off, &p.mapG[s], &full[st], bt * BNW, x0 + p.sub[s].ox, y0 + p.sub[s].oy, n);
+          tma_load_4d(g + p.sub[s].smem_off, &p.mapG[s], &full[st], bt * p.b_tile_ch + p.sub[s].c_off, x0 + p.sub[s].ox,
+                      y0 + p.sub[s].oy, n);
         if (++st == p.stages) { st = 0; ph ^= 1u; }
       }
     }
@@ -144,7 +151,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
           const WgRun& w = p.run[rn];
           const uint32_t d_tmem = tmem_base + w.col;
           uint64_t ad = ad0;
-          uint64_t bd = make_desc_sw128x32_mn(g_base + w.g_off, 128u, 512u);
+          uint64_t bd = make_desc_sw128x32_mn(g_base + w.g_off, w.n_pitch, 512u);
           const uint64_t b_step = w.row_pitch >> 4;
           const uint32_t idesc = w.idesc;
           mma_tf32(d_tmem, ad, bd, idesc, (t > t_begin) ? 1u : 0u);
@@ -170,10 +177,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + p.tap[tp].col, v);
         if (a < p.A) {
-          float* dst = p.ws + (size_t)split * p.ws_split + ((size_t)p.tap[tp].wtap * p.A + a) * p.B + (size_t)bt * BNW;
+          const int b0 = bt * p.b_tile_ch + (int)p.tap[tp].b_off;
+          float* dst = p.ws + (size_t)split * p.ws_split + ((size_t)p.tap[tp].wtap * p.A + a) * p.B + (size_t)b0;
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
-            if (bt * BNW + i < p.B) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            if (b0 + i < p.B) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
       }
     }
@@ -230,13 +238,29 @@ extern "C" int viai_conv2d_wgrad_tc_supported(const viai_conv_geom* g) {
 }
 
 namespace {
+// Channel-group mode for 1x1 / stride-1 / unpadded convolutions (the WaveNet training GEMMs, ResNet projections): there is a
+// single tap, so instead of the taps of a run the N = 32 * NB columns of one MMA are NB adjacent 32-channel slabs of G (the
+// descriptor's block stride is the box pitch, exactly as for the A operand).  One work item then covers 128 x (32 NB) of dW:
+// NB x fewer passes over U (the kernel is L2->SM bound here: 4.2 GB -> 1.7 GB for the 1632 -> 512 WaveNet layer at 32 000 rows).
+// VIAI_WGRAD_GROUP=1 restores one slab per work item.
+int wg_group(const viai_conv_geom& g) {
+  static int nb_env = -1;
+  if (nb_env < 0) {
+    const char* e = getenv("VIAI_WGRAD_GROUP");
+    nb_env = e ? atoi(e) : 4;
+    if (nb_env < 1 || nb_env > 4) nb_env = 4;
+  }
+  const bool one = g.R == 1 && g.S == 1 && g.stride_h == 1 && g.stride_w == 1 && g.pad_h == 0 && g.pad_w == 0;
+  return (one && g.Cin > BNW) ? nb_env : 1;
+}
 // split-K plan shared by the workspace query and the launch: the pixel range is split so that the grid is ~2 waves of the SMs
 void wg_split_plan(const viai_conv_geom& g, int& TH, int& npix_tiles, int& splits, int& tiles_per_split) {
   const bool strided = g.stride_h > 1 || g.stride_w > 1;
-  TH = strided ? 8 : 16;
+  const int nb = wg_group(g);
+  TH = (strided || nb > 1) ? 8 : 16;
   const int tilesX = (g.Wout + TW - 1) / TW, tilesY = (g.Hout + TH - 1) / TH;
   npix_tiles = g.N * tilesX * tilesY;
-  const int ab = ((g.Cout + BM - 1) / BM) * ((g.Cin + BNW - 1) / BNW);
+  const int ab = ((g.Cout + BM - 1) / BM) * ((g.Cin + BNW * nb - 1) / (BNW * nb));
   int sp = (2 * kNumSMs + ab - 1) / ab;
   if (sp > npix_tiles) sp = npix_tiles;
   if (sp < 1) sp = 1;
@@ -271,6 +295,8 @@ extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, co
     wg_split_plan(g, TH, npix, splits, tps);
     p.TH = TH; p.npix_tiles = npix; p.splits = splits; p.tiles_per_split = tps;
   }
+  const int nb = wg_group(g);
+  p.b_tile_ch = BNW * nb;
   // taps and parity sub-patches of G
   int sub_id[2][2] = {{-1, -1}, {-1, -1}};
   int mn_y[MAX_SUB], mx_y[MAX_SUB], mn_x[MAX_SUB], mx_x[MAX_SUB], sy_of[MAX_SUB], sx_of[MAX_SUB], t_sub[MAX_TAP], t_oy[MAX_TAP], t_ox[MAX_TAP];
@@ -292,6 +318,15 @@ extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, co
       p.tap[ntap].wtap = (uint32_t)(r * g.S + s);
       ++ntap;
     }
+  if (nb > 1) {            // one real tap at offset (0, 0): replicate its box / accumulator block per channel slab
+    nsub = ntap = nb;
+    for (int i = 1; i < nb; ++i) {
+      sy_of[i] = sy_of[0]; sx_of[i] = sx_of[0];
+      mn_y[i] = mx_y[i] = mn_y[0]; mn_x[i] = mx_x[i] = mn_x[0];
+      t_sub[i] = i; t_oy[i] = t_oy[0]; t_ox[i] = t_ox[0];
+      p.tap[i].wtap = 0;
+    }
+  }
   p.nsub = nsub; p.ntap = ntap;
   uint32_t off = 0;
   for (int s = 0; s < nsub; ++s) {
@@ -300,6 +335,7 @@ extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, co
     sb2.pw = TW + (mx_x[s] - mn_x[s]);
     sb2.ph = p.TH + (mx_y[s] - mn_y[s]);
     sb2.smem_off = off;
+    sb2.c_off = nb > 1 ? s * BNW : 0;
     off += (uint32_t)(sb2.pw * sb2.ph) * 128u;
     p.g_tx_bytes += (uint32_t)(sb2.pw * sb2.ph) * 128u;
     off = (off + 1023u) & ~1023u;
@@ -312,7 +348,16 @@ extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, co
     if (encode_f32_map(&p.mapG[s], 4, base, dims, strides, box, 2)) return VIAI_ERR_CUDA;
   }
   p.g_bytes = off;
-  {
+  if (nb > 1) {
+    WgRun& rn = p.run[0];
+    rn.g_off = p.sub[0].smem_off;
+    rn.row_pitch = (uint32_t)p.sub[0].pw * 128u;
+    rn.col = 0;
+    rn.n_pitch = p.sub[1].smem_off - p.sub[0].smem_off;
+    rn.idesc = make_idesc_tf32(BM, BNW * nb, 1, 1);
+    for (int i = 0; i < nb; ++i) { p.tap[i].col = (uint32_t)(BNW * i); p.tap[i].b_off = (uint32_t)(BNW * i); }
+    p.nrun = 1;
+  } else {
     bool placed[MAX_TAP] = {false};
     int nrun = 0;
     uint32_t col = 0;
@@ -323,6 +368,7 @@ extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, co
       WgRun& rn = p.run[nrun++];
       rn.g_off = sb2.smem_off + (uint32_t)((t_oy[t0] - sb2.oy) * sb2.pw + (t_ox[t0] - sb2.ox)) * 128u;
       rn.row_pitch = (uint32_t)sb2.pw * 128u;
+      rn.n_pitch = 128u;
       rn.col = col;
       int len = 0, cur = t0;
       while (cur >= 0 && len < 8) {
@@ -348,7 +394,7 @@ extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, co
   p.u_slice_bytes = (uint32_t)(p.TH * TW) * 128u;
   p.u_bytes = 4 * p.u_slice_bytes;
   p.a_tiles = (A + BM - 1) / BM;
-  p.b_tiles = (B + BNW - 1) / BNW;
+  p.b_tiles = (B + p.b_tile_ch - 1) / p.b_tile_ch;
   {
     const int rem = A - 0;   // slices needed by the widest a-tile; narrower (last) tiles read zero-filled boxes
     const int need = rem >= BM ? 4 : (rem + KC - 1) / KC;
@@ -358,7 +404,7 @@ extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, co
   p.tilesX = (g.Wout + TW - 1) / TW;
   p.tilesY = (g.Hout + p.TH - 1) / p.TH;
   const int ab = p.a_tiles * p.b_tiles;
-  p.ws_split = (int64_t)ntap * A * B;
+  p.ws_split = (int64_t)g.R * g.S * A * B;
   const size_t budget = 227 * 1024, fixed = 1024 + 32 * 8 + 16;
   int stages = 4;
   while (stages > 1 && fixed + (size_t)stages * p.stage_bytes > budget) --stages;
@@ -372,7 +418,7 @@ extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, co
     VIAI_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int64_t ws_elems = (int64_t)ntap * A * B;
+  const int64_t ws_elems = (int64_t)g.R * g.S * A * B;
   if (p.npix_tiles == 0) {
     VIAI_CUDA(cudaMemsetAsync(workspace, 0, (size_t)ws_elems * sizeof(float), st));
     p.splits = 1;
