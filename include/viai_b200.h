@@ -272,6 +272,10 @@ int viai_axpby(const float* a, float alpha, const float* b, float beta, float* o
  * gradient dy_hat[row,:] = dnll[row] * d nll / d y_hat.  nr_mix <= 32. */
 int viai_dmol_nll(const float* y_hat, const float* target, int64_t rows, int nr_mix, int num_classes, float log_scale_min, float* nll,
                   const float* dnll, float* dy_hat, viai_stream_t stream);
+/* sample_from_discretized_mix_logistic (mixture.py:117-153): uniforms rows of nr_mix + 1 draws in (1e-5, 1 - 1e-5)
+ * ([0:nr_mix] Gumbel-max over the logits, [nr_mix] the logistic sample); out[row] in [-1, 1] */
+int viai_dmol_sample(const float* y_hat, const float* uniforms, int64_t rows, int nr_mix, float log_scale_min, float* out,
+                     viai_stream_t stream);
 /* mean != 0: (v*mask).sum() / mask.sum() (loss_functions.py:59); mean == 0: (v*mask).sum().  mask may be NULL (ones).
  * acc: double[2] workspace kept for the backward (sum v*m, sum m); out / gout: float[1] on device. */
 int viai_masked_sum_fwd(const float* v, const float* mask, int64_t n, int mean, double* acc, float* out, viai_stream_t stream);

@@ -147,7 +147,7 @@ def next_rows_inputs():
     y[0, :4] = -1.0                         # edge bins
     y[1, :4] = 1.0
     y[1, 4:6] = 0.9995
-    return dict(dmol_yhat=yh, dmol_y=y, dmol_len=torch.tensor([40, 27]),
+    return dict(dmol_yhat=yh, dmol_y=y, dmol_len=torch.tensor([40, 27]), dmol_u=FX.uniform("dmol_u", (2, 40, 11), 1e-5, 1.0 - 1e-5),
                 f1=FX.normal("ctr_f1", (6, 32)), f2=FX.normal("ctr_f2", (6, 32)) * 0.5 + FX.normal("ctr_f1", (6, 32)) * 0.7,
                 f3=FX.normal("ctr_f3", (6, 32)) + FX.normal("ctr_f1", (6, 32)) * 0.25,
                 dis_mel=FX.uniform("dis_mel", (2, 1, 80, 64)), dis_fea=FX.normal("dis_fea", (2, 512, 16)),
@@ -176,6 +176,20 @@ def next_rows_fixture(ref):
     ml = LF.DiscretizedMixturelogisticLoss()(yh, I["dmol_y"], lengths=I["dmol_len"])
     g, = torch.autograd.grad(ml, yh)
     fx["dmol_masked"] = dict(loss=float(ml), grad=g, mask=LF.sequence_mask(I["dmol_len"]))
+    # --- sampling with pinned uniforms (mixture.py:136 draws (B,T,nr_mix), :148 draws (B,T))
+    calls = {"i": 0}
+    orig = torch.Tensor.uniform_
+
+    def fake_uniform(self, a=0.0, b=1.0, **k):
+        i = calls["i"]
+        calls["i"] += 1
+        self.copy_(I["dmol_u"][..., :10] if i == 0 else I["dmol_u"][..., 10])
+        return self
+    torch.Tensor.uniform_ = fake_uniform
+    try:
+        fx["dmol_sample"] = MX.sample_from_discretized_mix_logistic(I["dmol_yhat"], log_scale_min=-7.0)
+    finally:
+        torch.Tensor.uniform_ = orig
     # --- EMA
     ema = LF.ExponentialMovingAverage(0.9)
     ema.register("w", I["f1"])

@@ -61,6 +61,9 @@ def test_oracle_masked_loss_ema_mask(fx, inp):
     assert H.relerr(grad, g["grad"]) < 1e-5
     assert torch.equal(O.sequence_mask(inp["dmol_len"]), g["mask"])
     assert H.relerr(O.ema_update(inp["f1"], inp["f2"], 0.9), fx["ema"]) < 1e-6
+    u = inp["dmol_u"].reshape(-1, 11)
+    got = O.sample_dmol(inp["dmol_yhat"].transpose(1, 2).reshape(-1, 30), u[:, :10], u[:, 10], -7.0).reshape(2, 40)
+    assert H.relerr(got, fx["dmol_sample"]) < 1e-6
 
 
 @pytest.mark.parametrize("tag,margin,mv", [("m0", 0.0, False), ("m8", 8.0, False), ("m8max", 8.0, True)])
@@ -199,6 +202,9 @@ def test_product_losses_and_metrics(fx, inp, cpu_ops):
     assert abs(float(discretized_mix_logistic_loss(inp["dmol_yhat"], inp["dmol_y"], 256, -7.0)) - g["total"]) / abs(g["total"]) < 1e-6
     assert abs(float(LF.DiscretizedMixturelogisticLoss()(inp["dmol_yhat"], inp["dmol_y"], lengths=inp["dmol_len"])) -
                fx["dmol_masked"]["loss"]) / fx["dmol_masked"]["loss"] < 1e-6
+    from viai_b200.wavenet_vocoder.mixture import sample_from_discretized_mix_logistic
+    smp = sample_from_discretized_mix_logistic(inp["dmol_yhat"], -7.0, uniforms=inp["dmol_u"])
+    assert tuple(smp.shape) == (2, 40) and H.relerr(smp, fx["dmol_sample"]) < 1e-6
     with pytest.raises(RuntimeError, match="either lengths or mask"):
         LF.DiscretizedMixturelogisticLoss()(inp["dmol_yhat"], inp["dmol_y"])
     assert torch.equal(LF.sequence_mask(inp["dmol_len"]), fx["dmol_masked"]["mask"])

@@ -150,6 +150,12 @@ def test_dmol_loss_kernel_matches_reference_golden(fx, inp, tag, nc, lsm):
     assert H.relerr(yh.grad, g["grad"]) < 1e-4
     tot = discretized_mix_logistic_loss(yh.detach(), y, nc, lsm, reduce=True)
     assert abs(float(tot) - g["total"]) / abs(g["total"]) < 1e-5
+    if tag == "256":
+        from viai_b200.wavenet_vocoder.mixture import sample_from_discretized_mix_logistic
+        smp = sample_from_discretized_mix_logistic(yh.detach(), -7.0, uniforms=inp["dmol_u"].cuda())
+        assert tuple(smp.shape) == (2, 40) and H.relerr(smp, fx["dmol_sample"]) < 1e-5
+        free = sample_from_discretized_mix_logistic(yh.detach())
+        assert float(free.min()) >= -1.0 and float(free.max()) <= 1.0
 
 
 def test_dmol_loss_random_rows_match_oracle_at_scale():

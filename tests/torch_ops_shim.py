@@ -110,6 +110,13 @@ def dmol_nll(rows, target, num_classes=256, log_scale_min=-7.0):
     return O.dmol_nll(r.transpose(1, 2), target.reshape(1, -1, 1), num_classes, log_scale_min).reshape(shp)
 
 
+def dmol_sample(rows, uniforms, log_scale_min=-7.0):
+    from oracle import viai_oracle as O
+    nm = rows.size(-1) // 3
+    r, u = rows.reshape(-1, 3 * nm), uniforms.reshape(-1, nm + 1)
+    return O.sample_dmol(r, u[:, :nm], u[:, nm], log_scale_min).reshape(rows.shape[:-1])
+
+
 def masked_sum(v, mask=None, mean=True):
     if mask is None:
         return v.mean() if mean else v.sum()
@@ -137,7 +144,7 @@ def l2_contrastive(scores, margin=0.0, max_violation=False):
 
 
 _NAMES = ["conv2d", "conv2d_stats", "norm_act", "cat_channels", "mul", "avgpool_h", "maxpool3s2", "add_act", "shiftcat", "weight_norm",
-          "glu_tanh_sigmoid", "axpby", "axpby_", "dmol_nll", "masked_sum", "sequence_mask", "l2_normalize", "pairdist",
+          "glu_tanh_sigmoid", "axpby", "axpby_", "dmol_nll", "dmol_sample", "masked_sum", "sequence_mask", "l2_normalize", "pairdist",
           "l2_contrastive"]
 
 

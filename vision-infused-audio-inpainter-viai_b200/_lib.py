@@ -81,6 +81,7 @@ SIGNATURES = {
     "viai_glu_bwd": [c_p, c_p, c_l, c_i, c_p, c_p],
     "viai_axpby": [c_p, c_f, c_p, c_f, c_p, c_l, c_p],
     "viai_dmol_nll": [c_p, c_p, c_l, c_i, c_i, c_f, c_p, c_p, c_p, c_p],
+    "viai_dmol_sample": [c_p, c_p, c_l, c_i, c_f, c_p, c_p],
     "viai_masked_sum_fwd": [c_p, c_p, c_l, c_i, c_p, c_p, c_p],
     "viai_masked_sum_bwd": [c_p, c_l, c_i, c_p, c_p, c_p, c_p],
     "viai_sequence_mask": [c_p, c_i, c_i, c_p, c_p],

@@ -198,6 +198,26 @@ dmol_kernel(const float* __restrict__ y_hat, const float* __restrict__ target, i
   }
 }
 
+// sample_from_discretized_mix_logistic (mixture.py:117-153): Gumbel-max over the mixture logits with the supplied uniforms
+// u[row, 0:nm], logistic sample from u[row, nm], clamped to [-1, 1].  (The synthesis kernel has the same arithmetic inline.)
+__global__ void __launch_bounds__(THREADS)
+dmol_sample_kernel(const float* __restrict__ y_hat, const float* __restrict__ u, int64_t rows, int nm, float lsm, float* __restrict__ out) {
+  for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
+    const float* p = y_hat + row * 3 * nm;
+    const float* ur = u + row * (nm + 1);
+    int best = 0;
+    float bv = -INFINITY;
+    for (int i = 0; i < nm; ++i) {
+      const float v = __ldg(p + i) - logf(-logf(__ldg(ur + i)));
+      if (v > bv) { bv = v; best = i; }
+    }
+    const float mean = __ldg(p + nm + best), ls = fmaxf(__ldg(p + 2 * nm + best), lsm);
+    const float ul = __ldg(ur + nm);
+    const float x = mean + expf(ls) * (logf(ul) - logf(1.f - ul));
+    out[row] = fminf(fmaxf(x, -1.f), 1.f);
+  }
+}
+
 // acc[0] = sum v*m, acc[1] = sum m
 __global__ void __launch_bounds__(THREADS)
 masked_sum_kernel(const float* __restrict__ v, const float* __restrict__ mask, int64_t n, double* acc) {
@@ -336,6 +356,14 @@ extern "C" int viai_dmol_nll(const float* y_hat, const float* target, int64_t ro
   VIAI_REQUIRE((dy_hat == nullptr) == (dnll == nullptr), "dmol_nll: dnll and dy_hat go together");
   dmol_kernel<<<grid_for(rows), THREADS, 0, STR(stream)>>>(y_hat, target, rows, nr_mix, 1.f / (float)(num_classes - 1), log_scale_min,
                                                           (float)log((double)(num_classes - 1) / 2.0), nll, dnll, dy_hat);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_dmol_sample(const float* y_hat, const float* uniforms, int64_t rows, int nr_mix, float log_scale_min, float* out,
+                                viai_stream_t stream) {
+  VIAI_REQUIRE(y_hat && uniforms && out && rows > 0 && nr_mix > 0, "dmol_sample: bad arguments");
+  dmol_sample_kernel<<<grid_for(rows), THREADS, 0, STR(stream)>>>(y_hat, uniforms, rows, nr_mix, log_scale_min, out);
   VIAI_LAUNCHED();
   return VIAI_OK;
 }

@@ -851,6 +851,17 @@ def dmol_nll(y_hat_rows, target, num_classes=256, log_scale_min=-7.0):
     return _DmolNllFn.apply(y_hat_rows, target, int(num_classes), float(log_scale_min))
 
 
+def dmol_sample(y_hat_rows, uniforms, log_scale_min=-7.0):
+    """y_hat_rows (..., 3*nr_mix), uniforms (..., nr_mix + 1) -> samples (...) in [-1, 1] (no gradient, as in the reference)."""
+    _require_cuda(y_hat_rows, uniforms)
+    y, u = y_hat_rows.detach().contiguous(), uniforms.contiguous()
+    nm = y.size(-1) // 3
+    assert y.size(-1) == 3 * nm and u.size(-1) == nm + 1 and u.numel() // (nm + 1) == y.numel() // (3 * nm)
+    out = torch.empty(y.shape[:-1], device=y.device, dtype=torch.float32)
+    _lib.check(_lib.lib().viai_dmol_sample(_p(y), _p(u), out.numel(), nm, float(log_scale_min), _p(out), _stream()), "dmol_sample")
+    return out
+
+
 class _MaskedSumFn(torch.autograd.Function):
     """(v * mask).sum() / mask.sum() (mean=True) or (v * mask).sum(); mask None = ones."""
 

@@ -1,6 +1,9 @@
-"""Discretized mixture of logistics.  Drop-in for ``discretized_mix_logistic_loss`` of
-/root/reference/wavenet_vocoder/mixture.py:25-105 (forward value and gradient come from one CUDA kernel, csrc/wavenet_train.cu
-``viai_dmol_nll``).  Sampling (mixture.py:117-153) runs inside the synthesis kernel (csrc/wavenet_synth.cu)."""
+"""Discretized mixture of logistics.  Drop-in for /root/reference/wavenet_vocoder/mixture.py: ``discretized_mix_logistic_loss``
+:25-105 (value and gradient from one CUDA kernel, csrc/wavenet_train.cu ``viai_dmol_nll``) and
+``sample_from_discretized_mix_logistic`` :117-153 (``viai_dmol_sample``; the synthesis kernel csrc/wavenet_synth.cu has the same
+arithmetic inline for the autoregressive loop)."""
+import torch
+
 from .. import ops
 
 
@@ -14,3 +17,14 @@ def discretized_mix_logistic_loss(y_hat, y, num_classes=256, log_scale_min=-7.0,
     if reduce:
         return ops.masked_sum(nll, None, mean=False)
     return nll.unsqueeze(-1)
+
+
+def sample_from_discretized_mix_logistic(y, log_scale_min=-7.0, uniforms=None):
+    """y (B, C, T) -> samples (B, T) in [-1, 1].  ``uniforms`` (B, T, nr_mix + 1) supplies the draws of :136,148 (default: fresh
+    uniform(1e-5, 1 - 1e-5) draws, as in the reference)."""
+    assert y.size(1) % 3 == 0
+    nr_mix = y.size(1) // 3
+    rows = y.transpose(1, 2)
+    if uniforms is None:
+        uniforms = torch.empty(rows.shape[:2] + (nr_mix + 1,), device=y.device).uniform_(1e-5, 1.0 - 1e-5)
+    return ops.dmol_sample(rows, uniforms, log_scale_min)
