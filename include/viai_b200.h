@@ -296,6 +296,15 @@ int viai_pairdist_bwd(const float* f1, const float* f2, const float* scores, con
 int viai_l2_contrastive(const float* scores, int B, float margin, int max_violation, float* loss, const float* gout, float* dscores,
                         viai_stream_t stream);
 
+/* ---- Loader: video-frame preprocessing, Data_loaders/audio_loader.py:199-246 (sample_data_new) and :262-300.
+ * src: n_frames decoded uint8 frames (src_h, src_w, src_c) as cv2.imread returns them (BGR for src_c = 3, gray for 1).
+ * Per frame: cv2.resize(frame, (resize_w, resize_h)) (INTER_LINEAR 8-bit fixed point, bit exact) -> BGR->RGB when swap_rb ->
+ * np.fliplr when flip -> (v - 127) / 128 -> crop [crop_row, crop_row+out_h) x [crop_col, crop_col+out_w) -> written to channels
+ * [c_off, c_off+src_c) of the float NHWC block out (n_frames, out_h, out_w, out_c) (flow_x / flow_y fill channels 0 / 1). */
+int viai_frames_preprocess(const uint8_t* src, int n_frames, int src_h, int src_w, int src_c, int swap_rb, int resize_h, int resize_w,
+                           int flip, int crop_row, int crop_col, int out_h, int out_w, int out_c, int c_off, float* out,
+                           viai_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

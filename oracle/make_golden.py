@@ -259,6 +259,45 @@ def next_rows_fixture(ref):
     print("next rows:", sorted(fx.keys()), "wavenet train loss %.6f" % fx["wavenet_train"]["loss"])
 
 
+LOADER_HP = dict(sample_rate=16000, max_time_steps=1920, image_hope_size=1, load_num=2, image_rescal_size=16, image_size=12,
+                 image=True, flow=True)
+
+
+def loader_fixture():
+    """tests/golden/loader_frames.pt: a small JPEG tree (two clips: 24x20 frames that are down-scaled, 10x13 frames that are
+    up-scaled) and what the reference's own sample_data_new / load_image return on it for seeded np.random draws."""
+    import tempfile
+    import types
+    import numpy as np
+    from oracle import loader_oracle as LO
+    hp = types.SimpleNamespace(**LOADER_HP)
+    sample_ref, load_ref = LO.reference_functions(hp)
+    trees = {"clipA": LO.synthetic_clip(1, 58, 24, 20), "clipB": LO.synthetic_clip(2, 56, 10, 13)}
+    cases = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, tree in trees.items():
+            LO.write_tree(os.path.join(tmp, name), tree)
+        for name in trees:
+            for train in (True, False):
+                for seed in (0, 1, 2):
+                    np.random.seed(seed)
+                    v, f, start = sample_ref(os.path.join(tmp, name), train, hparams=hp)
+                    cases.append(dict(kind="sample", clip=name, train=train, seed=seed, start=[int(s) for s in start],
+                                      video=torch.from_numpy(np.ascontiguousarray(v)).float(),
+                                      flow=torch.from_numpy(np.ascontiguousarray(f)).float()))
+        hp1 = types.SimpleNamespace(**dict(LOADER_HP, load_num=1))
+        _, load_ref1 = LO.reference_functions(hp1)
+        # (train=False is unusable upstream: the block is allocated with load_num rows, audio_loader.py:266-269 -> IndexError)
+        for train in (True,):
+            np.random.seed(5)
+            v, f = load_ref1(os.path.join(tmp, "clipB"), train, hparams=hp1)
+            cases.append(dict(kind="load", clip="clipB", train=train, seed=5,
+                              video=torch.from_numpy(np.ascontiguousarray(v[:6])).float(),
+                              flow=torch.from_numpy(np.ascontiguousarray(f[:6])).float(), n=int(v.shape[0])))
+    torch.save(dict(hp=LOADER_HP, trees=trees, cases=cases), os.path.join(OUT, "loader_frames.pt"))
+    print("loader frames:", len(cases), "cases,", sum(len(b) for t in trees.values() for b in t.values()), "JPEG bytes")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load(normlayer=nn.BatchNorm2d, cin_channels=80)
@@ -274,6 +313,7 @@ def main():
                     skip_out_channels=256, cin_channels=80, upsample_scales=[4, 4, 10])
     image_embedding_fixture(ref)
     next_rows_fixture(ref)
+    loader_fixture()
 
 
 if __name__ == "__main__":

@@ -143,9 +143,24 @@ def l2_contrastive(scores, margin=0.0, max_violation=False):
     return (torch.sum(cost ** 2) + torch.sum(scores.diag() ** 2)) / (2 * scores.size(0))
 
 
+def frames_preprocess(frames_u8, out, c_off, resize_hw, flip, crop_rc, swap_rb):
+    from oracle import loader_oracle as LO
+    src = frames_u8.numpy()
+    for i in range(src.shape[0]):
+        img = LO.resize_linear_u8(src[i], int(resize_hw[1]), int(resize_hw[0]))
+        img = img.reshape(img.shape[0], img.shape[1], -1)
+        if swap_rb:
+            img = img[:, :, ::-1]
+        if flip:
+            img = img[:, ::-1]
+        img = img[crop_rc[0]:crop_rc[0] + out.size(1), crop_rc[1]:crop_rc[1] + out.size(2)]
+        out[i, :, :, c_off:c_off + img.shape[2]] = torch.from_numpy(((img.astype("float64") - 127.) / 128.).astype("float32"))
+    return out
+
+
 _NAMES = ["conv2d", "conv2d_stats", "norm_act", "cat_channels", "mul", "avgpool_h", "maxpool3s2", "add_act", "shiftcat", "weight_norm",
           "glu_tanh_sigmoid", "axpby", "axpby_", "dmol_nll", "dmol_sample", "masked_sum", "sequence_mask", "l2_normalize", "pairdist",
-          "l2_contrastive"]
+          "l2_contrastive", "frames_preprocess"]
 
 
 @contextlib.contextmanager

@@ -25,6 +25,14 @@ class Inpainting_Config(object):
     use_lsgan = True
     blank_ratio = 0.5             # fraction of time frames blanked by the time-band mask
     checkpoint_dir = "checkpoints"
+    # loader (Data_loaders/audio_loader.py; SURVEY.md Appendix A "Loader" row -- free parameters, upstream-style defaults)
+    new_split_name = "_new_split.txt"
+    load_num = 1
+    image_hope_size = 1           # video frames per step of the window (25 fps: 0.04 s each)
+    image_rescal_size = 256       # training frames are resized to this, then randomly cropped to image_size
+    max_time_steps = 40960        # samples per clip window (= 64 frames * 4 mel frames * hop 160)
+    image = False
+    flow = False
 
     def __init__(self, **overrides):
         for k, v in overrides.items():

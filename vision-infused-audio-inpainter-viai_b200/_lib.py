@@ -85,6 +85,7 @@ SIGNATURES = {
     "viai_masked_sum_fwd": [c_p, c_p, c_l, c_i, c_p, c_p, c_p],
     "viai_masked_sum_bwd": [c_p, c_l, c_i, c_p, c_p, c_p, c_p],
     "viai_sequence_mask": [c_p, c_i, c_i, c_p, c_p],
+    "viai_frames_preprocess": [c_p] + [c_i] * 14 + [c_p, c_p],
     "viai_l2norm_fwd": [c_p, c_i, c_i, c_f, c_p, c_p, c_p],
     "viai_l2norm_bwd": [c_p, c_p, c_p, c_i, c_i, c_f, c_p, c_p],
     "viai_pairdist_fwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_p],

@@ -997,3 +997,19 @@ class _L2ContrastiveFn(torch.autograd.Function):
 
 def l2_contrastive(scores, margin=0.0, max_violation=False):
     return _L2ContrastiveFn.apply(scores, float(margin), bool(max_violation))
+
+
+# ---- loader: frame preprocessing -------------------------------------------------------------------------------
+def frames_preprocess(frames_u8, out, c_off, resize_hw, flip, crop_rc, swap_rb):
+    """frames_u8: (n, h, w[, c]) uint8 CUDA tensor of decoded frames; writes channels [c_off, c_off + c) of the float NHWC block
+    ``out`` (n, out_h, out_w, out_c) with cv2.resize -> BGR->RGB -> fliplr -> (v - 127) / 128 -> crop (bit exact)."""
+    if not (frames_u8.is_cuda and out.is_cuda) or frames_u8.dtype != torch.uint8 or out.dtype != torch.float32:
+        raise RuntimeError("frames_preprocess needs a uint8 CUDA source and a float32 CUDA block; there is no CPU path")
+    src = frames_u8.contiguous()
+    n, h, w = src.shape[:3]
+    c = src.size(3) if src.dim() == 4 else 1
+    assert out.is_contiguous() and out.size(0) == n
+    _lib.check(_lib.lib().viai_frames_preprocess(_p(src), n, h, w, c, int(swap_rb), int(resize_hw[0]), int(resize_hw[1]), int(flip),
+                                                 int(crop_rc[0]), int(crop_rc[1]), out.size(1), out.size(2), out.size(3), int(c_off),
+                                                 _p(out), _stream()), "frames_preprocess")
+    return out
