@@ -27,7 +27,7 @@ if __name__ == "__main__":
     agg = collections.OrderedDict()
     for ev in prof.events():
         if ev.device_type == torch.autograd.DeviceType.CUDA:
-            name = re.sub(r"\(.*", "", ev.name)
+            name = re.sub(r"\(.*", "", ev.name.replace("(anonymous namespace)::", "").replace("void ", ""))
             a = agg.setdefault(name, [0, 0.0])
             a[0] += 1
             a[1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
