@@ -248,6 +248,12 @@ def test_product_discriminator_heads(fx, inp, cpu_ops):
 
 def test_product_visual_branches(fx, inp, cpu_ops):
     from viai_b200.networks import Image_Embedding as IE
+    g0 = H.load_golden("image_embedding.pt")
+    M = _filled(IE.ImageEmbedding())
+    out = M(inp["video"], inp["flow"])
+    assert tuple(out.shape) == tuple(g0["out"].shape) and H.relerr(out, g0["out"]) < 1e-4
+    assert H.relerr(M.state_dict()["bn_1.running_mean"], g0["bn_1_running_mean"]) < 1e-4
+    assert H.relerr(M.state_dict()["image_single_model.bn1.running_mean"], g0["img_bn1_running_mean"]) < 1e-4
     g = fx["ie2"]
     M = _filled(IE.ImageEmbedding2())
     assert {k: tuple(v.shape) for k, v in M.state_dict().items()} == g["shapes"]

@@ -20,33 +20,33 @@ def sequence_mask(sequence_length, max_len=None):
 
 
 class DiscretizedMixturelogisticLoss(nn.Module):
-    def __init__(self):
-        super(DiscretizedMixturelogisticLoss, self).__init__()
+    """Masked mean of the per-sample DMoL negative log-likelihood: ``input`` (B, C, T) network outputs, ``target`` (B, T, 1);
+    the mask comes from ``lengths`` (+ ``max_len``) or is given as (B, T, 1).  Mixture settings (``quantize_channels``,
+    ``log_scale_min``) are read from ``Config``, as upstream."""
 
     def forward(self, input, target, lengths=None, mask=None, max_len=None):
-        """input (B, C, T) network outputs, target (B, T, 1); returns (losses * mask).sum() / mask.sum()."""
         if lengths is None and mask is None:
             raise RuntimeError("Should provide either lengths or mask")
-        if mask is None:
-            mask = sequence_mask(lengths, max_len).unsqueeze(-1)
-        mask_ = mask.expand_as(target)
-        losses = discretized_mix_logistic_loss(input, target, num_classes=hparams.quantize_channels,
-                                               log_scale_min=hparams.log_scale_min, reduce=False)
-        assert losses.size() == target.size()
-        return ops.masked_sum(losses, mask_.float(), mean=True)
+        weights = mask if mask is not None else sequence_mask(lengths, max_len).unsqueeze(-1)
+        nll = discretized_mix_logistic_loss(input, target, num_classes=hparams.quantize_channels, log_scale_min=hparams.log_scale_min,
+                                            reduce=False)
+        assert nll.size() == target.size()
+        return ops.masked_sum(nll, weights.expand_as(target).float(), mean=True)
 
 
 class ExponentialMovingAverage(object):
+    """``shadow[name] <- decay * shadow[name] + (1 - decay) * x`` (written upstream as ``shadow -= (1 - decay) * (shadow - x)``);
+    one in-place kernel per update."""
+
     def __init__(self, decay):
-        self.decay = decay
-        self.shadow = {}
+        self.decay, self.shadow = decay, {}
 
     def register(self, name, val):
         self.shadow[name] = val.detach().clone()
 
     def update(self, name, x):
-        """shadow -= (1 - decay) * (shadow - x), one kernel, in place."""
-        assert name in self.shadow
+        if name not in self.shadow:
+            raise AssertionError("%s was never registered" % name)
         ops.axpby_(self.shadow[name], self.decay, x.detach().contiguous(), 1.0 - self.decay)
 
 
@@ -85,14 +85,12 @@ def l2_sim(feature1, feature2):
 
 
 class L2ContrastiveLoss(nn.Module):
-    """Compute L2 contrastive loss: (sum_{a != b} max(margin - s_ab, 0)^2 + sum_a s_aa^2) / (2 B); with max_violation only the
-    hardest negative of each row counts."""
+    """(sum_{a != b} max(margin - s_ab, 0)^2 + sum_a s_aa^2) / (2 B) on the pairwise distances s = l2_sim(f1, f2); with
+    ``max_violation`` only the hardest negative of each row counts.  (``measure`` is accepted and ignored, as upstream.)"""
 
     def __init__(self, margin=0, measure=False, max_violation=False):
         super(L2ContrastiveLoss, self).__init__()
-        self.margin = margin
-        self.sim = l2_sim
-        self.max_violation = max_violation
+        self.margin, self.max_violation, self.sim = margin, max_violation, l2_sim
 
     def forward(self, feature1, feature2):
         return ops.l2_contrastive(self.sim(feature1, feature2), self.margin, self.max_violation)

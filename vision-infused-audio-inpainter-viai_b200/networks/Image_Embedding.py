@@ -99,39 +99,33 @@ def FlowResnet18(hparams=hparams):
 
 
 class ImageEmbedding(nn.Module):
+    """Frames + optical flow -> two ResNet-18 streams -> per-frame features concatenated over channels -> temporal head
+    (two stride-2 Conv1d) -> (B, length_feature, 1, T/4) (reference :100-126)."""
+
     def __init__(self, hparams=hparams):
         super(ImageEmbedding, self).__init__()
         self.hparams = hparams
-        self.image_single_model = ImageResnet18(hparams)
-        self.flow_single_model = FlowResnet18(hparams)
-        self.conv_1 = torch.nn.Conv1d(2 * hparams.length_feature, 2 * hparams.length_feature, 3, 2, 1, bias=False)
-        self.bn_1 = nn.BatchNorm1d(2 * hparams.length_feature)
-        self.conv_2 = torch.nn.Conv1d(2 * hparams.length_feature, hparams.length_feature, 3, 2, 1, bias=False)
-        self.bn_2 = nn.BatchNorm1d(hparams.length_feature)
-        self.relu = nn.ReLU(True)
+        self.image_single_model, self.flow_single_model = ImageResnet18(hparams), FlowResnet18(hparams)
+        _add_temporal_head(self, 2 * hparams.length_feature, 2 * hparams.length_feature, hparams.length_feature)
 
     @staticmethod
     def _conv1d(x, conv):
         """x: (B, 1, T, C) NHWC; nn.Conv1d (k=3, s=2, p=1) as a 1x3 convolution."""
-        w = conv.weight.unsqueeze(2)                               # (Cout, Cin, 1, k)
-        return ops.conv2d(x, w, conv.bias, (1, conv.stride[0]), (0, conv.padding[0]))
+        return ops.conv2d(x, conv.weight.unsqueeze(2), conv.bias, (1, conv.stride[0]), (0, conv.padding[0]))
 
     def forward(self, video_block, flow_block):
-        S = self.hparams.image_size
-        B = video_block.size(0)
-        input_image = video_block.reshape(-1, 3, S, S)
-        input_flow = flow_block.reshape(-1, 2, S, S)
-        image_out = self.image_single_model(input_image).reshape(B, -1, self.hparams.length_feature)
-        flow_out = self.flow_single_model(input_flow).reshape(B, -1, self.hparams.length_feature)
-        T = image_out.size(1)
-        fea_cat = ops.cat_channels(image_out.reshape(B, 1, T, -1), flow_out.reshape(B, 1, T, -1))    # (B,1,T,2F) == transpose(2,1) in NCT
-        out = self._conv1d(fea_cat, self.conv_1)
+        fea_cat = ops.cat_channels(_per_frame_features(self.image_single_model, video_block, 3, self.hparams),
+                                   _per_frame_features(self.flow_single_model, flow_block, 2, self.hparams))      # (B, 1, T, 2F)
         # the reference evaluates relu(bn_1(out)) and discards it (:123): only bn_1's running statistics change
-        if self.bn_1.training:
-            with torch.no_grad():
-                ops.norm_act(out.detach(), self.bn_1, "bn", ops.ACT_RELU)
-        out = self._conv1d(out, self.conv_2)                       # (B,1,T/4,F)
-        return out.permute(0, 3, 1, 2)                             # (B, F, 1, T/4)
+        return _temporal_convs(self, fea_cat, True).permute(0, 3, 1, 2)                                            # (B, F, 1, T/4)
+
+
+def _add_temporal_head(mod, cin, mid, cout):
+    """Registers the reference's temporal head on ``mod`` under its names: conv_1 (k3 s2 p1) / bn_1 / conv_2 (k3 s2 p1) / bn_2 / relu."""
+    for idx, (a, b) in enumerate(((cin, mid), (mid, cout)), start=1):
+        mod.add_module("conv_%d" % idx, torch.nn.Conv1d(a, b, 3, 2, 1, bias=False))
+        mod.add_module("bn_%d" % idx, nn.BatchNorm1d(b))
+    mod.relu = nn.ReLU(True)
 
 
 def _temporal_convs(mod, fea, discard_bn):
@@ -143,68 +137,51 @@ def _temporal_convs(mod, fea, discard_bn):
     return ImageEmbedding._conv1d(out, mod.conv_2)
 
 
+def _per_frame_features(net, block, channels, hp):
+    """(B, T, channels, S, S) frames -> (B, 1, T, length_feature) rows through one ResNet-18 stream."""
+    B = block.size(0)
+    return net(block.reshape(-1, channels, hp.image_size, hp.image_size)).reshape(B, 1, -1, hp.length_feature)
+
+
 class ImageEmbedding_single(nn.Module):
-    """One visual stream (frames or flow) + the two temporal convolutions; returns (B, length_feature, T/4)."""
+    """One visual stream (frames when ``image``, else flow) + the temporal head; (B, T, c, S, S) -> (B, length_feature, T/4)
+    (reference :128-148)."""
 
     def __init__(self, hparams=hparams, image=1):
         super(ImageEmbedding_single, self).__init__()
-        self.image = image
-        self.hparams = hparams
-        self.image_single_model = ImageResnet18(hparams) if image else FlowResnet18(hparams)
-        self.conv_1 = torch.nn.Conv1d(hparams.length_feature, hparams.length_feature, 3, 2, 1, bias=False)
-        self.bn_1 = nn.BatchNorm1d(hparams.length_feature)
-        self.conv_2 = torch.nn.Conv1d(hparams.length_feature, hparams.length_feature, 3, 2, 1, bias=False)
-        self.bn_2 = nn.BatchNorm1d(hparams.length_feature)
-        self.relu = nn.ReLU(True)
+        self.image, self.hparams = image, hparams
+        self.image_single_model = (ImageResnet18 if image else FlowResnet18)(hparams)
+        _add_temporal_head(self, hparams.length_feature, hparams.length_feature, hparams.length_feature)
 
     def forward(self, video_block):
-        S = self.hparams.image_size
-        B = video_block.size(0)
-        image_out = self.image_single_model(video_block.reshape(-1, 3 if self.image else 2, S, S))
-        fea = image_out.reshape(B, 1, -1, self.hparams.length_feature)
-        out = _temporal_convs(self, fea, True)                              # (B, 1, T/4, F)
-        return out.squeeze(1).permute(0, 2, 1)
+        fea = _per_frame_features(self.image_single_model, video_block, 3 if self.image else 2, self.hparams)
+        return _temporal_convs(self, fea, True).squeeze(1).permute(0, 2, 1)
 
 
 class ImageEmbedding_finetune(nn.Module):
-    """The temporal convolutions alone on precomputed per-frame features (B, T, length_feature) -> (B, F, 1, T/4)."""
+    """The temporal head alone on precomputed per-frame features (B, T, length_feature) -> (B, F, 1, T/4) (reference :150-171)."""
 
     def __init__(self, hparams=hparams, image=1):
         super(ImageEmbedding_finetune, self).__init__()
-        self.image = image
-        self.hparams = hparams
-        self.conv_1 = torch.nn.Conv1d(hparams.length_feature, hparams.length_feature, 3, 2, 1, bias=False)
-        self.bn_1 = nn.BatchNorm1d(hparams.length_feature)
-        self.conv_2 = torch.nn.Conv1d(hparams.length_feature, hparams.length_feature, 3, 2, 1, bias=False)
-        self.bn_2 = nn.BatchNorm1d(hparams.length_feature)
-        self.relu = nn.ReLU(True)
+        self.image, self.hparams = image, hparams
+        _add_temporal_head(self, hparams.length_feature, hparams.length_feature, hparams.length_feature)
 
     def forward(self, image_out):
-        out = _temporal_convs(self, image_out.unsqueeze(1), True)           # (B, 1, T/4, F)
-        return out.permute(0, 3, 1, 2)
+        return _temporal_convs(self, image_out.unsqueeze(1), True).permute(0, 3, 1, 2)
 
 
 class ImageEmbedding2(nn.Module):
-    """ImageEmbedding that also returns the concatenated per-frame features: (out (B, F, 1, T/4), fea_cat (B, 2F, T)).
-    (Unlike ImageEmbedding.forward, the reference does not evaluate bn_1 here: the call is commented out at :195.)"""
+    """ImageEmbedding that also hands back the concatenated per-frame features: (out (B, F, 1, T/4), fea_cat (B, 2F, T))
+    (reference :174-200; unlike ImageEmbedding.forward it does not evaluate bn_1 -- that call is commented out at :195)."""
 
     def __init__(self, hparams=hparams):
         super(ImageEmbedding2, self).__init__()
         self.hparams = hparams
-        self.image_single_model = ImageResnet18(hparams)
-        self.flow_single_model = FlowResnet18(hparams)
-        self.conv_1 = torch.nn.Conv1d(2 * hparams.length_feature, 2 * hparams.length_feature, 3, 2, 1, bias=False)
-        self.bn_1 = nn.BatchNorm1d(2 * hparams.length_feature)
-        self.conv_2 = torch.nn.Conv1d(2 * hparams.length_feature, hparams.length_feature, 3, 2, 1, bias=False)
-        self.bn_2 = nn.BatchNorm1d(hparams.length_feature)
-        self.relu = nn.ReLU(True)
+        self.image_single_model, self.flow_single_model = ImageResnet18(hparams), FlowResnet18(hparams)
+        _add_temporal_head(self, 2 * hparams.length_feature, 2 * hparams.length_feature, hparams.length_feature)
 
     def forward(self, video_block, flow_block):
-        S = self.hparams.image_size
-        B = video_block.size(0)
-        F_ = self.hparams.length_feature
-        image_out = self.image_single_model(video_block.reshape(-1, 3, S, S)).reshape(B, 1, -1, F_)
-        flow_out = self.flow_single_model(flow_block.reshape(-1, 2, S, S)).reshape(B, 1, -1, F_)
-        fea_cat = ops.cat_channels(image_out, flow_out)                     # (B, 1, T, 2F)
+        fea_cat = ops.cat_channels(_per_frame_features(self.image_single_model, video_block, 3, self.hparams),
+                                   _per_frame_features(self.flow_single_model, flow_block, 2, self.hparams))      # (B, 1, T, 2F)
         out = _temporal_convs(self, fea_cat, False)
         return out.permute(0, 3, 1, 2), fea_cat.squeeze(1).permute(0, 2, 1)
