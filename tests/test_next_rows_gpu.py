@@ -437,7 +437,7 @@ def test_wavenet_trainer_cuda_graph_replay_equals_eager(fx):
     assert float(la2) < float(la) + 1.0 and b.launches_per_step > 0
     pa, pb = dict(a.model.named_parameters()), dict(b.model.named_parameters())
     for k in ("conv_layers.0.conv.weight_v", "last_conv_layers.3.bias"):
-        assert H.relerr(pb[k], pa[k]) < 1e-4, k
+        assert H.relerr_l2(pb[k], pa[k]) < 1e-4, k         # L2: an Adam step is +-lr per element, one ~0 gradient may flip
 
 
 @pytest.mark.tf32
