@@ -305,6 +305,16 @@ int viai_frames_preprocess(const uint8_t* src, int n_frames, int src_h, int src_
                            int flip, int crop_row, int crop_col, int out_h, int out_w, int out_c, int c_off, float* out,
                            viai_stream_t stream);
 
+/* ---- Opt-in fast paths of the ResNet stem (networks/Image_Embedding.py:18-21), off by default (VIAI_FAST_STEM=1): they were
+ * written from the C3 per-kernel table (profiles/r01_c3_step_kernels.csv: the CUDA-core 7x7 weight gradient is 56 % of that step,
+ * the max-pool backward 15 %) after the round's GPU budget was spent and are NOT yet validated on a B200. */
+/* im2col of a mode-0 convolution, channel-major columns k = c*R*S + r*S + s, rows = output pixels, zero-padded to Kpad
+ * (multiple of 4): turns the weight gradient of a few-channel convolution into a 1x1 weight gradient (viai_conv2d_wgrad_tc). */
+int viai_im2col(const viai_conv_geom* g, const float* in, int Kpad, float* out, viai_stream_t stream);
+/* nn.MaxPool2d(3, 2, 1) backward that also reads the forward output (rejects non-maximal elements after one load); C % 4 == 0 */
+int viai_maxpool3s2_bwd_out(const float* in, const float* out, const float* dout, int N, int H, int W, int C, float* din, int Ho,
+                            int Wo, viai_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,9 +158,19 @@ def frames_preprocess(frames_u8, out, c_off, resize_hw, flip, crop_rc, swap_rb):
     return out
 
 
+def im2col(g, x, Kpad):
+    cols = F.unfold(_nchw(x), (g.R, g.S), padding=(g.pad_h, g.pad_w), stride=(g.stride_h, g.stride_w))     # (N, C*R*S, L), channel-major
+    cols = cols.transpose(1, 2).reshape(-1, cols.size(1))
+    return F.pad(cols, (0, Kpad - cols.size(1)))
+
+
+def pointwise_wgrad(U, G):
+    return U.t() @ G
+
+
 _NAMES = ["conv2d", "conv2d_stats", "norm_act", "cat_channels", "mul", "avgpool_h", "maxpool3s2", "add_act", "shiftcat", "weight_norm",
           "glu_tanh_sigmoid", "axpby", "axpby_", "dmol_nll", "dmol_sample", "masked_sum", "sequence_mask", "l2_normalize", "pairdist",
-          "l2_contrastive", "frames_preprocess"]
+          "l2_contrastive", "frames_preprocess", "im2col", "pointwise_wgrad"]
 
 
 @contextlib.contextmanager

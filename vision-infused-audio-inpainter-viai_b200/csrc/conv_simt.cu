@@ -266,6 +266,37 @@ wgrad_c1_kernel(viai_conv_geom g, const float* __restrict__ U, const float* __re
   }
 }
 
+// im2col of a forward convolution, channel-major columns: out[p][c*R*S + r*S + s] = in[n, y*sh - ph + r, x*sw - pw + s, c]
+// (0 outside the image and for columns >= Cin*R*S up to Kpad).  With this column order a (Cout, Kpad) GEMM result IS the
+// (Cout, Cin, kh, kw) weight layout: the weight gradient of a few-channel convolution (the ResNet stem, Cin = 3 / 2) becomes a
+// 1x1 weight gradient on the tensor-core kernel instead of a CUDA-core loop over 49 taps with Cin padded to 16.
+__global__ void __launch_bounds__(256)
+im2col_kernel(viai_conv_geom g, const float* __restrict__ in, int Kpad, float* __restrict__ out) {
+  const int K4 = Kpad / 4, RS = g.R * g.S, K = g.Cin * RS;
+  const int64_t M = (int64_t)g.N * g.Hout * g.Wout, total = M * K4;
+  const int HWo = g.Hout * g.Wout;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k0 = (int)(i % K4) * 4;
+    const int64_t p = i / K4;
+    const int n = (int)(p / HWo);
+    const int rem = (int)(p - (int64_t)n * HWo);
+    const int y = rem / g.Wout, x = rem - y * g.Wout;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + j;
+      v[j] = 0.f;
+      if (k < K) {
+        const int c = k / RS, t = k - c * RS;
+        const int r = t / g.S, q = t - r * g.S;
+        const int Y = y * g.stride_h - g.pad_h + r, X = x * g.stride_w - g.pad_w + q;
+        if (Y >= 0 && Y < g.Hin && X >= 0 && X < g.Win) v[j] = __ldg(in + (((int64_t)n * g.Hin + Y) * g.Win + X) * g.Cin + c);
+      }
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 __global__ void zero_strided_kernel(float* dw, int A, int B, int R, int S, int64_t sa, int64_t sb, int64_t sr, int64_t ss) {
   int64_t total = (int64_t)A * B * R * S;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -352,6 +383,16 @@ extern "C" int viai_conv2d_wgrad_simt(const viai_conv_geom* g, const float* U, c
   else if (BA == 64 && BB == 16) wgrad_kernel<64, 16><<<grid, 256, 0, st>>>(*g, U, G, dw, sa, sb, sr, ss, ksplit);
   else if (BA == 16 && BB == 64) wgrad_kernel<16, 64><<<grid, 256, 0, st>>>(*g, U, G, dw, sa, sb, sr, ss, ksplit);
   else wgrad_kernel<32, 32><<<grid, 256, 0, st>>>(*g, U, G, dw, sa, sb, sr, ss, ksplit);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_im2col(const viai_conv_geom* g, const float* in, int Kpad, float* out, viai_stream_t stream) {
+  VIAI_REQUIRE(g && in && out && g->mode == 0 && Kpad % 4 == 0 && Kpad >= g->Cin * g->R * g->S, "viai_im2col: bad arguments");
+  VIAI_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "viai_im2col: out must be 16-byte aligned");
+  const int64_t total = (int64_t)g->N * g->Hout * g->Wout * (Kpad / 4);
+  VIAI_REQUIRE(total > 0, "viai_im2col: empty tensor");
+  im2col_kernel<<<(int)imin64(cdiv(total, 256), 32 * kNumSMs), 256, 0, STR(stream)>>>(*g, in, Kpad, out);
   VIAI_LAUNCHED();
   return VIAI_OK;
 }

@@ -256,6 +256,60 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ in, const float* __
   }
 }
 
+// Max-pool backward that reads the forward OUTPUT: an input element can only receive the gradient of a window whose maximum it
+// equals, so almost every (element, window) pair is rejected after one load; the tie scan (first maximum in row-major order,
+// ATen's rule) runs only for the elements that do equal the maximum.  4 channels per thread (C % 4 == 0).
+__global__ void __launch_bounds__(256)
+maxpool_bwd_out_kernel(const float4* __restrict__ in, const float4* __restrict__ out, const float4* __restrict__ dout, int N, int H,
+                       int W, int C4, float4* __restrict__ din, int Ho, int Wo) {
+  const int64_t total = (int64_t)N * H * W * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    int64_t t = i / C4;
+    const int x = (int)(t % W); t /= W;
+    const int y = (int)(t % H);
+    const int n = (int)(t / H);
+    const float4 v4 = __ldg(in + i);
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int yo = (y + 1) / 2 - 1; yo <= (y + 1) / 2; ++yo) {
+      if (yo < 0 || yo >= Ho || yo * 2 - 1 > y || yo * 2 + 1 < y) continue;
+      for (int xo = (x + 1) / 2 - 1; xo <= (x + 1) / 2; ++xo) {
+        if (xo < 0 || xo >= Wo || xo * 2 - 1 > x || xo * 2 + 1 < x) continue;
+        const int64_t o = (((int64_t)n * Ho + yo) * Wo + xo) * C4 + c;
+        const float4 m4 = __ldg(out + o);
+        const float m[4] = {m4.x, m4.y, m4.z, m4.w};
+        bool hit[4];
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { hit[k] = (v[k] == m[k]); any |= hit[k]; }
+        if (!any) continue;
+        // first maximum only: no element EARLIER in the window's scan order may equal the maximum as well
+        for (int r = 0; r < 3; ++r) {
+          const int yy = yo * 2 - 1 + r;
+          if (yy < 0 || yy >= H || yy > y) continue;
+          for (int q = 0; q < 3; ++q) {
+            const int xx = xo * 2 - 1 + q;
+            if (xx < 0 || xx >= W) continue;
+            if (!(yy < y || xx < x)) continue;
+            const float4 u4 = __ldg(in + (((int64_t)n * H + yy) * W + xx) * C4 + c);
+            const float u[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (u[k] == m[k]) hit[k] = false;
+          }
+        }
+        const float4 g4 = __ldg(dout + o);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (hit[k]) acc[k] += g[k];
+      }
+    }
+    din[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
 __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = a[i] * b[i];
@@ -332,6 +386,20 @@ extern "C" int viai_maxpool3s2_bwd(const float* in, const float* dout, int N, in
   VIAI_REQUIRE(in && dout && din && N > 0 && H > 0 && W > 0 && C > 0 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1,
                "viai_maxpool3s2_bwd: bad arguments");
   maxpool_bwd_kernel<<<grid_for((int64_t)N * H * W * C), THREADS, 0, STR(stream)>>>(in, dout, N, H, W, C, din, Ho, Wo);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+extern "C" int viai_maxpool3s2_bwd_out(const float* in, const float* out, const float* dout, int N, int H, int W, int C, float* din,
+                                       int Ho, int Wo, viai_stream_t stream) {
+  VIAI_REQUIRE(in && out && dout && din && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && Ho == (H - 1) / 2 + 1 &&
+                   Wo == (W - 1) / 2 + 1,
+               "viai_maxpool3s2_bwd_out: bad arguments (C must be a multiple of 4)");
+  VIAI_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout) |
+                 reinterpret_cast<uintptr_t>(din)) & 15) == 0,
+               "viai_maxpool3s2_bwd_out: pointers must be 16-byte aligned");
+  maxpool_bwd_out_kernel<<<grid_for((int64_t)N * H * W * (C / 4)), 256, 0, STR(stream)>>>(
+      reinterpret_cast<const float4*>(in), reinterpret_cast<const float4*>(out), reinterpret_cast<const float4*>(dout), N, H, W, C / 4,
+      reinterpret_cast<float4*>(din), Ho, Wo);
   VIAI_LAUNCHED();
   return VIAI_OK;
 }

@@ -29,6 +29,13 @@ _WS = {}
 _FUSE_BWD_REDUCE = os.environ.get("VIAI_FUSE_BWD_REDUCE", "0") == "1"
 
 
+# Opt-in fast paths of the ResNet stem (VIAI_FAST_STEM=1; see include/viai_b200.h): the 7x7 / Cin <= 4 weight gradient as im2col +
+# the tensor-core 1x1 weight gradient, and the max-pool backward that reads the forward output.  OFF by default: written from the
+# C3 per-kernel table after this round's GPU budget was spent, validated on the CPU only (host logic) -- to be switched on after a
+# B200 run of tests/test_fast_stem_gpu.py.
+_FAST_STEM = os.environ.get("VIAI_FAST_STEM", "0") == "1"
+
+
 def set_precision(p):
     global _PRECISION
     if p not in ("bf16x3", "tf32x3", "tf32", "fp32"):
@@ -245,7 +252,9 @@ class _ConvFn(torch.autograd.Function):
             else:                    # U = x (A = Cin_t), G = dOut (B = Cout_t)
                 g = _geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0)
                 U, G = x, dy
-            if L.viai_conv2d_wgrad_thin_supported(ctypes.byref(g)) and U.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0:
+            if _FAST_STEM and not transposed and C <= 4 and _PRECISION != "fp32" and Cout % 4 == 0 and Cout >= 16 and R * S > 1:
+                _stem_wgrad(g, x, dy, dw, wt is not None)
+            elif L.viai_conv2d_wgrad_thin_supported(ctypes.byref(g)) and U.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0:
                 ws = _workspace(dy.device, L.viai_wgrad_thin_workspace(ctypes.byref(g)))
                 _lib.check(L.viai_conv2d_wgrad_thin(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1), dw.stride(2),
                                                     dw.stride(3), int(wt is not None), _p(ws), _stream()), "conv2d wgrad_thin")
@@ -267,6 +276,41 @@ class _ConvFn(torch.autograd.Function):
             if bt is not None:
                 db = None
         return dx, dw, db, None, None, None, None
+
+
+def im2col(g, x, Kpad):
+    """(N*Hout*Wout, Kpad) channel-major patches of the forward convolution ``g`` reads from x (viai_im2col)."""
+    out = torch.empty((g.N * g.Hout * g.Wout, Kpad), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().viai_im2col(ctypes.byref(g), _p(x), Kpad, _p(out), _stream()), "im2col")
+    return out
+
+
+def pointwise_wgrad(U, G):
+    """dW (A, B) = U^T G for row tensors U (P, A), G (P, B) on the tensor-core weight-gradient kernel (1x1 geometry)."""
+    L = _lib.lib()
+    P, A = U.shape
+    B = G.size(1)
+    W = next(w for w in (128, 64, 32, 16, 8, 4, 2, 1) if P % w == 0)
+    g1 = _geom(1, P // W, W, B, P // W, W, A, 1, 1, (1, 1), (0, 0), 0)
+    if not L.viai_conv2d_wgrad_tc_supported(ctypes.byref(g1)):
+        raise RuntimeError("pointwise_wgrad: unsupported sizes (A %d, B %d)" % (A, B))
+    dw = torch.empty((A, B), device=U.device, dtype=torch.float32)
+    ws = _workspace(U.device, L.viai_wgrad_tc_workspace(ctypes.byref(g1)))
+    _lib.check(L.viai_conv2d_wgrad_tc(ctypes.byref(g1), _p(U), _p(G), _p(dw), B, 1, 0, 0, 0, _p(ws), _stream()), "pointwise wgrad")
+    return dw
+
+
+def _stem_wgrad(g, x, dy, dw, accumulate):
+    """Weight gradient of a few-channel Conv2d (the ResNet stem) as im2col + one 1x1 weight gradient; ``dw`` is the
+    (Cout, Cin, kh, kw) target (a gradient-bucket view when ``accumulate``)."""
+    K = g.Cin * g.R * g.S
+    Kpad = (K + 31) // 32 * 32
+    cols = im2col(g, x, Kpad)
+    part = pointwise_wgrad(dy.reshape(-1, g.Cout), cols)[:, :K].reshape(dw.shape)
+    if accumulate:
+        dw.add_(part)
+    else:
+        dw.copy_(part)
 
 
 def conv2d(x, weight, bias=None, stride=(1, 1), padding=(0, 0), transposed=False):
@@ -504,17 +548,24 @@ class _MaxPoolFn(torch.autograd.Function):
         Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         out = torch.empty((N, Ho, Wo, C), device=x.device, dtype=torch.float32)
         _lib.check(L.viai_maxpool3s2_fwd(_p(x), N, H, W, C, _p(out), Ho, Wo, _stream()), "maxpool fwd")
-        ctx.save_for_backward(x)
+        if _FAST_STEM and C % 4 == 0:
+            ctx.save_for_backward(x, out)
+        else:
+            ctx.save_for_backward(x)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        (x,) = ctx.saved_tensors
+        x = ctx.saved_tensors[0]
         L = _lib.lib()
         dout = dout.contiguous()
         N, H, W, C = x.shape
         dx = torch.empty_like(x)
-        _lib.check(L.viai_maxpool3s2_bwd(_p(x), _p(dout), N, H, W, C, _p(dx), dout.size(1), dout.size(2), _stream()), "maxpool bwd")
+        if len(ctx.saved_tensors) == 2:
+            _lib.check(L.viai_maxpool3s2_bwd_out(_p(x), _p(ctx.saved_tensors[1]), _p(dout), N, H, W, C, _p(dx), dout.size(1),
+                                                 dout.size(2), _stream()), "maxpool bwd (with output)")
+        else:
+            _lib.check(L.viai_maxpool3s2_bwd(_p(x), _p(dout), N, H, W, C, _p(dx), dout.size(1), dout.size(2), _stream()), "maxpool bwd")
         return dx
 
 
