@@ -122,6 +122,20 @@ def reference_functions(hp, reference_root="/root/reference"):
     return ns["sample_data_new"], ns["load_image"]
 
 
+def reference_collate(hp, reference_root="/root/reference"):
+    """The reference's own ``collate_fn`` (:431-532) with its helpers, compiled out of the module (build container only)."""
+    import types
+    import torch
+    path = os.path.join(reference_root, "Data_loaders", "audio_loader.py")
+    tree = ast.parse(open(path).read())
+    names = ("collate_fn", "_pad", "_pad_2d", "ensure_divisible", "assert_ready_for_upsampling")
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    audio = types.SimpleNamespace(get_hop_size=lambda: hp.hop_size)
+    ns = dict(os=os, np=np, torch=torch, hparams=hp, audio=audio, is_mulaw_quantize=lambda s: s == "mulaw-quantize")
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return ns["collate_fn"]
+
+
 def write_tree(root, tree):
     """tree: {relative path: bytes} -> files under root."""
     for rel, blob in tree.items():

@@ -92,3 +92,13 @@ def test_audio_model_exposes_the_train_script_contract():
         fn = getattr(AudioModel, name)
         assert list(inspect.signature(fn).parameters)[1:] == params, name
     assert list(inspect.signature(AudioModel.__init__).parameters)[1:] == ["hparams", "device"]
+
+
+def test_lr_schedule_known_answers():
+    """SURVEY 8c KAT (4) on the product module (no reference needed)."""
+    import math
+    from viai_b200.utils import lrschedule as P
+    assert math.isclose(P.noam_learning_rate_decay(1e-3, 0), 5e-7, rel_tol=1e-3)
+    assert math.isclose(P.noam_learning_rate_decay(1e-3, 1999), 1e-3, rel_tol=1e-9)
+    assert math.isclose(P.step_learning_rate_decay(1e-3, 100000), 9.604e-4, rel_tol=1e-9)
+    assert math.isclose(P.cyclic_cosine_annealing(1e-3, 1, 1000, 5), 1e-3, rel_tol=1e-12)

@@ -126,3 +126,75 @@ def test_split_file_sources_padding_and_collate(tmp_path):
     assert torch.equal(x[0, 0], y[0, :, 0]) and torch.equal(c[1, :, :8], torch.from_numpy(c1).t())
     xs, cs = AL.slice_clip(np.arange(160 * 200), np.arange(200 * 80).reshape(200, 80), start=5, use_image_num=3, hop_size=160)
     assert len(xs) == 12 * 160 and xs[0] == 23 * 160 and cs.shape == (12, 80) and cs[0, 0] == 23 * 80
+
+
+def _clips(hp, seed=0):
+    rng = np.random.default_rng(seed)
+    T = 3                                                      # use_image_num for max_time_steps = 1920
+    batch = []
+    for i, frames in enumerate((40, 1, 64)):                   # the 1-frame clip (1920 samples) is not longer than the window: dropped
+        mel_frames = frames * 4 + 8
+        x = rng.uniform(-1, 1, mel_frames * hp.hop_size).astype(np.float32)
+        c = rng.uniform(0, 1, (mel_frames, hp.cin_channels)).astype(np.float32)
+        start = [int(s) for s in rng.integers(0, max(frames - T - 1, 1), hp.load_num)]
+        video = rng.normal(size=(hp.load_num, T, 3, 12, 12))
+        flow = rng.normal(size=(hp.load_num, T, 2, 12, 12))
+        batch.append((x, c, video, flow, start, None, "clip%d" % i))
+    return batch
+
+
+def _collate_hp():
+    return types.SimpleNamespace(cin_channels=80, file_channel=-1, max_time_sec=None, max_time_steps=1920, sample_rate=16000,
+                                 image_hope_size=1, upsample_conditional_features=True, load_num=2, hop_size=160, input_type="raw")
+
+
+@pytest.mark.reference
+def test_collate_fn_equals_reference_collate(tmp_path):
+    from viai_b200.Data_loaders import audio_loader as AL
+    hp = _collate_hp()
+    want = LO.reference_collate(hp)(_clips(hp))
+    got = AL.collate_fn(_clips(hp), hparams=hp)
+    assert len(want) == len(got) == 8
+    for w, g in zip(want[:5], got[:5]):
+        assert tuple(w.shape) == tuple(g.shape) and torch.equal(w, g)
+    assert want[5] is None and got[5] is None and torch.equal(want[6], got[6]) and want[7] == got[7]
+
+
+def test_collate_fn_shapes_and_alignment():
+    from viai_b200.Data_loaders import audio_loader as AL
+    hp = _collate_hp()
+    batch = _clips(hp)
+    v, f, c, x, y, g, lengths, paths = AL.collate_fn(batch, hparams=hp)
+    assert tuple(v.shape) == (4, 3, 3, 12, 12) and tuple(f.shape) == (4, 3, 2, 12, 12)          # 2 clips x load_num windows
+    assert tuple(x.shape) == (4, 1, 1920) and tuple(y.shape) == (4, 1920, 1) and tuple(c.shape) == (4, 80, 12)
+    assert lengths.tolist() == [1920] * 4 and paths[0] == os.path.join("clip0", str(batch[0][4][0])) and paths[2].startswith("clip2")
+    m0 = 3 + 4 * batch[0][4][0]
+    assert torch.equal(x[0, 0], torch.from_numpy(batch[0][0][m0 * 160:(m0 + 12) * 160]))
+    assert torch.equal(c[0], torch.from_numpy(batch[0][1][m0:m0 + 12]).t())
+
+
+def test_file_source_dataset_and_image_dataset(tmp_path, gold):
+    from viai_b200.Data_loaders import audio_loader as AL
+    root = str(tmp_path)
+    hp = types.SimpleNamespace(**dict(gold["hp"], new_split_name="_new_split.txt", cin_channels=80, batch_size=2, hop_size=160))
+    for name, tree in gold["trees"].items():
+        LO.write_tree(os.path.join(root, name), tree)
+    for phase in ("train", "test"):
+        with open(os.path.join(root, phase + hp.new_split_name), "w") as fh:
+            for name in gold["trees"]:
+                fh.write("%s|%s-mel.npy|%s-audio.npy|1|6\n" % (name, name, name))
+    for name in gold["trees"]:
+        np.save(os.path.join(root, name + "-mel.npy"), np.zeros((6 * 8, 80), np.float32))
+        np.save(os.path.join(root, name + "-audio.npy"), np.zeros(6 * 1280, np.float32))
+    X = AL.FileSourceDataset(AL.RawAudioDataSource(root, train=True, hparams=hp))
+    Mel = AL.FileSourceDataset(AL.MelSpecDataSource(root, train=True, hparams=hp))
+    assert len(X) == len(Mel) == 2 and X[0].shape == (7680,) and Mel[1].shape == (48, 80)
+    assert X.file_data_source.lengths == [7680, 7680] and X.file_data_source.speaker_ids == [1, 1]
+    with shim.installed():                                      # frame kernel replaced by its torch stand-in (CPU)
+        Image = AL.FileSourceDataset(AL.ImageSpecDataSource(root, train=True, hparams=hp))
+        Image.file_data_source.device = "cpu"
+        ds = AL.PyTorchImageDataset(X, Mel, Image)
+        np.random.seed(3)
+        raw, mel, video, flow, start, spk, path = ds[0]
+    assert raw.shape == (7680,) and mel.shape == (48, 80) and tuple(video.shape) == (2, 3, 3, 12, 12) and tuple(flow.shape) == (2, 3, 2, 12, 12)
+    assert spk == 1 and len(start) == 2 and path.endswith("clipA")

@@ -152,3 +152,14 @@ def test_param_counts(ref):
     assert n(ref.Inpainting_Networks.MelEncoder()) == 978656
     assert n(ref.New_Inpainting_Networks.MelDecoder()) == 3202497
     assert n(ref.Discriminator_Networks.MelDiscriminator()) == 1555072
+
+
+def test_product_lr_schedules_equal_reference(ref):
+    from viai_b200.utils import lrschedule as P
+    L = ref.lrschedule
+    for s in (0, 1, 1999, 2000, 5000, 123456):
+        assert math.isclose(P.noam_learning_rate_decay(1e-3, s), float(L.noam_learning_rate_decay(1e-3, s)), rel_tol=1e-12)
+        assert math.isclose(P.step_learning_rate_decay(1e-3, s), float(L.step_learning_rate_decay(1e-3, s)), rel_tol=1e-12)
+    for s in (1, 2, 199, 200, 201, 999):
+        assert math.isclose(P.cyclic_cosine_annealing(1e-3, s, 1000, 5), float(L.cyclic_cosine_annealing(1e-3, s, 1000, 5)),
+                            rel_tol=1e-12, abs_tol=1e-18)

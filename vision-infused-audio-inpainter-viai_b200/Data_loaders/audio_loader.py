@@ -88,7 +88,8 @@ class _NPYDataSource(_SplitFileSource):
 
 
 class ImageDataSource(_SplitFileSource):
-    """frame-folder column (reference :113-153); ``collect_features`` samples a window of frames on the GPU."""
+    """frame-folder column (reference :113-153); ``collect_features`` samples a window of frames on ``self.device`` (the GPU)."""
+    device = "cuda"
 
     def collect_files(self):
         lines = self._lines()
@@ -96,7 +97,7 @@ class ImageDataSource(_SplitFileSource):
         return sorted(join(self.data_root, l[self.col]) for l in lines)
 
     def collect_features(self, path):
-        video_block, flow_block, start = sample_data_new(path, self.train, hparams=self.hparams)
+        video_block, flow_block, start = sample_data_new(path, self.train, hparams=self.hparams, device=self.device)
         return video_block, flow_block, start, path
 
 
@@ -213,6 +214,88 @@ def collate_raw(batch, video_block, flow_block, local_conditioning=True):
     x_batch = torch.FloatTensor(x_batch).transpose(1, 2).contiguous()
     y_batch = torch.FloatTensor(y_batch).unsqueeze(-1).contiguous()
     return video_batch, flow_batch, c_batch, x_batch, y_batch, g_batch, torch.LongTensor(input_lengths), path_batch
+
+
+def assert_ready_for_upsampling(x, c, hop_size):
+    assert len(x) % len(c) == 0 and len(x) // len(c) == hop_size
+
+
+def collate_fn(batch, hparams=hparams):
+    """Reference collate_fn (:431-532) for the raw-audio input type.  ``batch``: list of
+    ``(x (T,), c (frames, n_mel), video, flow, start, g, path)`` as ``PyTorchImageDataset`` yields them; every clip longer than the
+    window contributes ``load_num`` (audio, mel) windows aligned with its frame windows (4 mel frames per video frame, offset 3),
+    shorter clips are dropped (as upstream).  Returns the 8-tuple ``(video, flow, c, x, y, g, input_lengths, paths)``."""
+    local_conditioning = len(batch[0]) >= 2 and hparams.cin_channels > 0
+    if getattr(hparams, "max_time_sec", None) is not None:
+        max_time_steps = int(hparams.max_time_sec * hparams.sample_rate)
+    else:
+        max_time_steps = hparams.max_time_steps
+    use_image_num = int(np.floor((max_time_steps / hparams.sample_rate) / (0.04 * hparams.image_hope_size)))
+    video_block, flow_block = [], []
+    if local_conditioning:
+        new_batch = []
+        max_steps = ensure_divisible(max_time_steps, hparams.hop_size, True)
+        for x, c, video, flow, start, g, path in batch:
+            assert_ready_for_upsampling(x, c, hparams.hop_size)
+            if len(x) > max_steps:
+                for ln in range(hparams.load_num):
+                    x1, c1 = slice_clip(x, c, start[ln], use_image_num, hparams.hop_size)
+                    new_batch.append((x1, c1, g, os.path.join(path, str(start[ln]))))
+                video_block.append(torch.as_tensor(video).float())
+                flow_block.append(torch.as_tensor(flow).float())
+        batch = new_batch
+    return collate_raw(batch, video_block, flow_block, local_conditioning)
+
+
+class FileSourceDataset(object):
+    """The slice of nnmnkwii.datasets.FileSourceDataset the reference uses: files collected once, features loaded per item."""
+
+    def __init__(self, file_data_source):
+        self.file_data_source = file_data_source
+        self.collected_files = file_data_source.collect_files()
+
+    def __getitem__(self, idx):
+        return self.file_data_source.collect_features(self.collected_files[idx])
+
+    def __len__(self):
+        return len(self.collected_files)
+
+
+class PyTorchImageDataset(object):
+    """(raw_audio, mel, video_block, flow_block, start, speaker_id, path) per clip (reference :393-419)."""
+
+    def __init__(self, X, Mel, Image):
+        self.X, self.Mel, self.Image = X, Mel, Image
+        self.multi_speaker = X.file_data_source.multi_speaker
+
+    def __getitem__(self, idx):
+        mel = None if self.Mel is None else self.Mel[idx]
+        raw_audio = self.X[idx]
+        video_block, flow_block, start, path = self.Image[idx]
+        speaker_id = self.X.file_data_source.speaker_ids[idx] if self.multi_speaker else None
+        return raw_audio, mel, video_block, flow_block, start, speaker_id, path
+
+    def __len__(self):
+        return len(self.X)
+
+
+def get_data_loaders(data_root, speaker_id=None, test_shuffle=True, hparams=hparams):
+    """{"train": DataLoader, "test": DataLoader} over the split files (reference :536-587).  The frame path runs on the GPU inside
+    ``__getitem__``, so the loaders use the main process (``num_workers = 0``): CUDA work does not belong in forked workers."""
+    from torch.utils import data as data_utils
+    loaders = {}
+    for phase in ("train", "test"):
+        train = phase == "train"
+        kw = dict(speaker_id=speaker_id, train=train, hparams=hparams)
+        X = FileSourceDataset(RawAudioDataSource(data_root, **kw))
+        Image = FileSourceDataset(ImageSpecDataSource(data_root, **kw))
+        Mel = FileSourceDataset(MelSpecDataSource(data_root, **kw)) if hparams.cin_channels > 0 else None
+        assert Mel is None or len(X) == len(Mel)
+        dataset = PyTorchImageDataset(X, Mel, Image)
+        loaders[phase] = data_utils.DataLoader(dataset, batch_size=hparams.batch_size, num_workers=0,
+                                               shuffle=True if train else test_shuffle,
+                                               collate_fn=lambda b: collate_fn(b, hparams))
+    return loaders
 
 
 def slice_clip(x, c, start, use_image_num, hop_size):
