@@ -12,9 +12,11 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
-    config.addinivalue_line("markers", "tf32: single-product tf32 tensor-core convolutions (default in tests: exact fp32)")
-    config.addinivalue_line("markers", "tf32x3: 3-term tf32 forward, single tf32 backward")
-    config.addinivalue_line("markers", "bf16x3: the library default: 3-term bf16-pair forward, single tf32 backward")
+    config.addinivalue_line("markers", "fp32: the CUDA-core fp32 convolutions (the on-device validator), NOT the benched path")
+    config.addinivalue_line("markers", "tf32: single-product tf32 tensor-core convolutions")
+    config.addinivalue_line("markers", "tf32x3: 3-term tf32 forward / data gradient, single tf32 weight gradient")
+    config.addinivalue_line("markers", "bf16x3: the library default (what unmarked GPU tests run and what bench.py measures): 3-term "
+                                       "bf16-pair forward / data gradient, single tf32 weight gradient")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -30,14 +32,17 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(autouse=True)
 def _conv_precision(request):
-    """Parity tests written against fp32 tolerances run the exact CUDA-core convolutions; tests marked ``tf32`` run the
-    tensor-core path (the library default) and state their own tolerance."""
+    """Unmarked GPU tests run the LIBRARY DEFAULT precision -- the path bench.py measures (tcgen05 convolutions, bf16x3 forward
+    and data gradient, tf32 weight gradient).  ``fp32`` selects the CUDA-core validator, ``tf32`` / ``tf32x3`` the alternative
+    tensor-core arithmetics; each test states its own tolerance."""
     import torch
     if not torch.cuda.is_available() or "gpu" not in request.keywords:
         yield
         return
     from viai_b200 import ops
-    prev = ops.set_precision("bf16x3" if "bf16x3" in request.keywords else "tf32x3" if "tf32x3" in request.keywords
-                             else "tf32" if "tf32" in request.keywords else "fp32")
+    prev = ops.set_precision("fp32" if "fp32" in request.keywords else "tf32x3" if "tf32x3" in request.keywords
+                             else "tf32" if "tf32" in request.keywords else "bf16x3")
+    prev_d = ops.set_dgrad_x3(True)
     yield
     ops.set_precision(prev)
+    ops.set_dgrad_x3(prev_d)

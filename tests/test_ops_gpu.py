@@ -1,6 +1,8 @@
 """Per-operator parity of the CUDA path (through the C ABI) against plain torch fp32 on the CPU.
 Tolerance: fp32 operators must agree to 1e-4 normwise-relative (viai_test_helpers.relerr) -- one order tighter than
-the 1e-3 the north star asks of whole spectrograms, so that error can accumulate over ~25 layers."""
+the 1e-3 the north star asks of whole spectrograms, so that error can accumulate over ~25 layers.  The convolution cases run
+twice: on the library default (tensor cores; weight gradient = one tf32 product on rounded operands: 5e-4 with these
+random-sign inputs, see tests/test_layers_gpu.py) and on the CUDA-core fp32 validator."""
 import math
 
 import pytest
@@ -53,8 +55,10 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize("prec", [pytest.param("bf16x3", id="default"), pytest.param("fp32", marks=pytest.mark.fp32, id="fp32")])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_conv2d_forward_backward(ops, case):
+def test_conv2d_forward_backward(ops, case, prec):
+    assert ops.get_precision() == prec
     name, tr, Cin, Cout, kh, kw, stride, pad, N, Hh, W, has_bias = case
     g = torch.Generator().manual_seed(hash(name) & 0xFFFF)
     x = torch.randn(N, Cin, Hh, W, generator=g, requires_grad=True)
@@ -72,7 +76,7 @@ def test_conv2d_forward_backward(ops, case):
     assert H.relerr(nchw(yg), y) < TOL
     yg.backward(nhwc(dy))
     assert H.relerr(nchw(xg.grad), x.grad) < TOL
-    assert H.relerr(wg.grad, w.grad) < TOL
+    assert H.relerr(wg.grad, w.grad) < (TOL if prec == "fp32" else 5e-4)
     if has_bias:
         assert H.relerr(bg.grad, b.grad) < TOL
 

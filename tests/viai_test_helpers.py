@@ -240,10 +240,48 @@ def whole_net_metrics(got, ref, skip_below=1e-7):
     return float((A - B).norm() / B.norm()), float((A @ B) / (A.norm() * B.norm())), worst
 
 
-# End-to-end gradient tolerances (see DESIGN.md "Parity"): LeakyReLU/ReLU derivative and the L1 sign are discontinuous, so
-# two fp32 evaluations of the reference (or fp32 vs fp64) differ by O(1e-3..1e-2) on gradients once any pre-activation
-# changes sign; measured on the B200: CUDA vs fp64 oracle whole-net L2 error 6.5e-4..1.7e-2, fp32 oracle vs fp64 oracle
-# 1.5e-5..3.7e-3, cosine >= 0.99986.  Wiring mistakes (a missing 0.5, a wrong detach, a swapped label) move these by O(1).
+# ------------------------------------------------------------------------------------------------
+# Per-tensor gradient gate of the BENCHED path (bf16x3 forward + data gradient, tf32 weight gradient with rounded operands).
+#   err(cuda, fp64 oracle) <= max(GRAD_FLOOR, GRAD_K * err(fp32 oracle, fp64 oracle))      for EVERY parameter tensor,
+# err = max|a-b| / max|b| (the metric of every other tolerance in tests/).  GRAD_FLOOR is BASELINE.md section 3's 1e-3; K
+# allows the CUDA path a different (equally valid) fp32 summation order / a different set of ReLU- and L1-sign decisions than
+# the CPU oracle took.  Every comparison made through grad_table() is also appended to $VIAI_PARITY_TABLE (CSV) so that the
+# per-tensor table of a B200 run can be committed under profiles/.
+# ------------------------------------------------------------------------------------------------
+GRAD_FLOOR = 1e-3
+GRAD_K = 4.0
+
+
+def grad_table(got, r32, r64, what, floor=GRAD_FLOOR, K=GRAD_K, check=True):
+    """got / r32 / r64: {name: tensor}.  Asserts the per-tensor gate for every tensor of ``r64`` whose gradient is not
+    numerically zero relative to the net; returns rows (name, cuda_err, fp32_oracle_err, ratio, bound)."""
+    scale = max(float(v.abs().max()) for v in r64.values())
+    rows, bad = [], []
+    for k, ref in r64.items():
+        if float(ref.abs().max()) < 1e-7 * scale:
+            assert float(got[k].detach().abs().max()) <= 1e-4 * scale, "%s %s: expected ~0" % (what, k)
+            continue
+        env = relerr(r32[k], ref)
+        err = relerr(got[k], ref)
+        bound = max(floor, K * env)
+        rows.append((k, err, env, err / max(env, 1e-30), bound))
+        if err > bound:
+            bad.append("%s: err %.3e > max(%.0e, %g x fp32 envelope %.3e)" % (k, err, floor, K, env))
+    path = os.environ.get("VIAI_PARITY_TABLE")
+    if path:
+        new = not os.path.exists(path)
+        with open(path, "a") as f:
+            if new:
+                f.write("case,tensor,cuda_err_vs_fp64,fp32_oracle_err_vs_fp64,ratio,bound,ok\n")
+            for k, err, env, ratio, bound in rows:
+                f.write("%s,%s,%.3e,%.3e,%.2f,%.3e,%d\n" % (what, k, err, env, ratio, bound, int(err <= bound)))
+    if check:
+        assert not bad, "%s: %d of %d tensors outside the gate:\n  %s" % (what, len(bad), len(rows), "\n  ".join(bad))
+    return rows
+
+
+# Whole-net sanity criterion kept for the alternative arithmetics (single tf32 data gradient, tf32x3) and the wiring checks:
+# a missing 0.5, a wrong detach or a swapped label moves these by O(1).
 E2E_GRAD_L2 = 5e-2
 E2E_GRAD_COS = 0.999
 E2E_GRAD_WORST = 0.25

@@ -25,7 +25,8 @@ namespace {
 
 constexpr int TW = 8, KC = 32, BM = 128, BNW = 32;
 constexpr int MAX_SUB = 4, MAX_TAP = 16;
-constexpr int NTHREADS = 192;   // warp 0: TMA producer, warp 1: TMEM + MMA issuer, warps 2..5: epilogue
+constexpr int NTHREADS = 320;   // warp 0: TMA producer, warp 1: TMEM + MMA issuer, warps 2..5: epilogue, warps 6..9: operand rounding
+constexpr int RND_WARP0 = 6;
 
 struct WgSub {
   int32_t ox, oy, pw, ph;
@@ -66,6 +67,10 @@ struct WgParams {
   uint32_t u_bytes, u_slice_bytes, g_bytes, g_tx_bytes, stage_bytes;
   int32_t stages;
   uint32_t idesc;
+  int32_t round_rn;      // 1: warps 6..9 round every landed operand word to the nearest tf32 in place (the tensor core TRUNCATES
+                         //    fp32 operands to tf32: both operands shrink, every product is ~2^-10 too small and the weight
+                         //    gradient carries that as a one-sided bias; rounded operands leave a zero-mean error that averages
+                         //    out over the >= 10^4 pixels of the reduction)
 };
 
 
@@ -76,7 +81,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
   uint64_t* full = bars;
   uint64_t* empty = full + p.stages;
   uint64_t* done = empty + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* ready = done + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + p.stages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = 512;
 
@@ -89,7 +95,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
   const int t_end = min(p.npix_tiles, t_begin + p.tiles_per_split);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], 128); }
     mbar_init(done, 1);
     fence_barrier_init();
     prefetch_tmap(&p.mapU);
@@ -138,8 +144,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
     int st = 0;
     uint32_t ph = 0;
     const uint64_t a_step = 1024u >> 4;
+    uint64_t* const landed = p.round_rn ? ready : full;
     for (int t = t_begin; t < t_end; ++t) {
-      mbar_wait(&full[st], ph);
+      mbar_wait(&landed[st], ph);
       tc_fence_after();
       const uint32_t u_base = smem_u32(smem + (size_t)st * p.stage_bytes);
       const uint32_t g_base = u_base + p.u_bytes;
@@ -166,6 +173,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
       if (++st == p.stages) { st = 0; ph ^= 1u; }
     }
     if (leader) mma_commit(done);
+  } else if (warp >= RND_WARP0) {
+    // operand rounding: x -> nearest tf32 (ties away from zero) by adding half a tf32 ulp to the bit pattern; the tensor core
+    // then drops the 13 low bits.  Elementwise and in place, so the swizzled layout does not matter.
+    if (p.round_rn) {
+      const int tid = threadIdx.x - RND_WARP0 * 32;
+      const uint32_t n16 = (p.u_slices * p.u_slice_bytes) >> 4, g16 = p.g_bytes >> 4;
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&full[st], ph);
+        uint4* u = reinterpret_cast<uint4*>(smem + (size_t)st * p.stage_bytes);
+        uint4* g = reinterpret_cast<uint4*>(smem + (size_t)st * p.stage_bytes + p.u_bytes);
+#pragma unroll 4
+        for (uint32_t i = tid; i < n16; i += 128) {
+          uint4 v = u[i];
+          v.x += 0x1000u; v.y += 0x1000u; v.z += 0x1000u; v.w += 0x1000u;
+          u[i] = v;
+        }
+#pragma unroll 4
+        for (uint32_t i = tid; i < g16; i += 128) {
+          uint4 v = g[i];
+          v.x += 0x1000u; v.y += 0x1000u; v.z += 0x1000u; v.w += 0x1000u;
+          g[i] = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&ready[st]);
+        if (++st == p.stages) { st = 0; ph ^= 1u; }
+      }
+    }
   } else {
     // epilogue: store the CTA's partial D_t blocks into its slice of the workspace
     const int q = warp & 3;
@@ -405,6 +441,8 @@ extern "C" int viai_conv2d_wgrad_tc(const viai_conv_geom* gp, const float* U, co
   p.tilesY = (g.Hout + p.TH - 1) / p.TH;
   const int ab = p.a_tiles * p.b_tiles;
   p.ws_split = (int64_t)g.R * g.S * A * B;
+  static const int round_env = [] { const char* e = getenv("VIAI_WGRAD_ROUND"); return e ? atoi(e) : 1; }();
+  p.round_rn = round_env ? 1 : 0;
   const size_t budget = 227 * 1024, fixed = 1024 + 32 * 8 + 16;
   int stages = 4;
   while (stages > 1 && fixed + (size_t)stages * p.stage_bytes > budget) --stages;

@@ -13,9 +13,13 @@ import os
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 
 # Arithmetic of the convolutions (wherever the geometry is tensor-core shaped; CUDA cores otherwise):
-#   "bf16x3" (default): tcgen05 tensor cores; forward convolutions split both operands into bf16 pairs (x = hi + lo) and
-#            accumulate hi*hi + hi*lo + lo*hi in fp32 (product error ~2^-17: keeps spectrograms within the 1e-3 parity
-#            bound) at the bf16 MMA rate; data / weight gradients use one tf32 product;
+#   "bf16x3" (default): tcgen05 tensor cores; forward convolutions AND data gradients split both operands into bf16 pairs
+#            (x = hi + lo) and accumulate hi*hi + hi*lo + lo*hi in fp32 (product error ~2^-17: keeps spectrograms within
+#            the 1e-3 parity bound, and keeps the gradient that is chained through ~30 layers at the reference's own fp32
+#            envelope) at the bf16 MMA rate; weight gradients (one hop off the chain, nothing propagates) use one tf32
+#            product.  A single-tf32 data gradient truncates both operands, which shrinks every layer's gradient by
+#            ~2^-11 and compounds to 1.4e-2 at the encoder (scratch experiment reproduced on the CPU);
+#            VIAI_DGRAD=tf32 / set_dgrad_x3(False) restores it for comparison;
 #   "tf32x3": the same 3-term scheme on tf32 pairs (~2^-21 per product, half the MMA rate of bf16x3);
 #   "tf32":  one tf32 product everywhere (what cuDNN does by default on Ampere+; ~1e-2 end to end on this network);
 #   "fp32":  CUDA-core fp32 everywhere (the exact path, also the on-device validator of the other two).
@@ -27,6 +31,7 @@ _WS = {}
 # measured on B200 at C2 the four epilogue warps cannot hide the extra y read + arithmetic (step 15.5 ms fused vs 14.8 ms
 # with the standalone viai_norm_act_bwd_reduce pass, which already runs at 4.7 TB/s).  VIAI_FUSE_BWD_REDUCE=1 enables it.
 _FUSE_BWD_REDUCE = os.environ.get("VIAI_FUSE_BWD_REDUCE", "0") == "1"
+_DGRAD_X3 = os.environ.get("VIAI_DGRAD", "x3") != "tf32"
 
 
 # Opt-in fast paths of the ResNet stem (VIAI_FAST_STEM=1; see include/viai_b200.h): the 7x7 / Cin <= 4 weight gradient as im2col +
@@ -46,6 +51,13 @@ def set_precision(p):
 
 def get_precision():
     return _PRECISION
+
+
+def set_dgrad_x3(flag):
+    """True (default): data gradients use the forward's 3-term product; False: one tf32 product (round-1 behaviour)."""
+    global _DGRAD_X3
+    prev, _DGRAD_X3 = _DGRAD_X3, bool(flag)
+    return prev
 
 
 def _workspace(device, n):
@@ -152,18 +164,19 @@ def _run_conv(g, x, weight, O_dim, I_dim, bias, y, stats=None, groups=1, forward
                 (L.viai_conv2d_thin_supported(ctypes.byref(g)) and x.data_ptr() % 16 == 0):
             norm_ctx, stats = None, None        # not fusable here: plain data gradient, the caller keeps the standalone pass
     if norm_ctx is not None:
-        wp = _pack_tc(weight, O_dim, I_dim, 0)
+        split, flags = _FWD_MODE[_PRECISION] if _DGRAD_X3 else (0, 0)
+        wp = _pack_tc(weight, O_dim, I_dim, split)
         nb = _lib.NormBwdCtx(norm_ctx["y"].data_ptr(), _ptr(norm_ctx["mean"]), _ptr(norm_ctx["invstd"]), _ptr(norm_ctx["gamma"]),
                              _ptr(norm_ctx["beta"]), norm_ctx["act"], norm_ctx["slope"])
         _lib.check(L.viai_conv2d_tc_bwd_reduce(ctypes.byref(g), _p(x), _p(wp), _p(y), ctypes.byref(nb), _p(stats[0]), _p(stats[1]),
-                                               0, _stream()), "conv2d_tc_bwd_reduce")
+                                               flags, _stream()), "conv2d_tc_bwd_reduce")
         return True
     if L.viai_conv2d_thin_supported(ctypes.byref(g)) and x.data_ptr() % 16 == 0:
         wp = _pack(weight, O_dim, I_dim)
         _lib.check(L.viai_conv2d_thin(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _stream()), "conv2d_thin")
         return False
     if _PRECISION != "fp32" and L.viai_conv2d_tc_supported(ctypes.byref(g)):
-        split, flags = _FWD_MODE[_PRECISION] if forward else (0, 0)
+        split, flags = _FWD_MODE[_PRECISION] if (forward or _DGRAD_X3) else (0, 0)
         wp = _pack_tc(weight, O_dim, I_dim, split)
         _lib.check(L.viai_conv2d_tc(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _p(stats[0]) if stats is not None else None,
                                     _p(stats[1]) if stats is not None else None, groups, flags, _stream()), "conv2d_tc")
