@@ -74,10 +74,18 @@ int viai_conv2d_simt(const viai_conv_geom* g, const float* in, const float* wp, 
  * VIAI_TC_BF16X3 (8) = the same 3-term scheme on bf16 pairs (hi = bf16(.), lo = bf16(. - hi); kind::f16 MMAs, K = 16, at
  * twice the tf32 rate; product error ~2^-17).  The kernel splits each fp32 activation slab in shared memory in place into
  * [32 x hi | 32 x lo] per 128-byte pixel row; weights are packed with split = 2 (same size as split = 0).
+ * VIAI_TC_F16 (32, together with VIAI_TC_BF16X3) = the pairs are fp16 instead of bf16: x * 8 = hi + lo keeps 22 significand
+ * bits (product error ~2^-21, the accuracy of VIAI_TC_X3 at the bf16 MMA rate); weights are packed with split = 3, which scales
+ * them by a per-tensor power of two (computed on the device from max|w|) and appends 4 floats {max|w| bits, w_scale,
+ * 1 / (8 * w_scale), 0} that the epilogue reads to undo the scales (exact: powers of two).  |x| >= 8188 saturates (the result
+ * stays finite) and is counted: viai_tc_f16_overflow(reset, &count) returns the number of saturating threads since the last
+ * reset (synchronises with the device; the host side checks it where it already reads the loss).
  * Other bits select alternative shared-memory layouts used as cross-checks. */
 #define VIAI_TC_X3 4
 #define VIAI_TC_BF16X3 8
+#define VIAI_TC_F16 32
 int viai_tc_bn(int Cout);
+int viai_tc_f16_overflow(int reset, unsigned int* count);
 int64_t viai_tc_packed_size(int O, int I, int R, int S, int split);
 int viai_pack_weight_tc(const float* src, float* dst, int O, int I, int R, int S, int64_t so, int64_t si, int64_t sr,
                         int64_t ss, int flip, int split, viai_stream_t stream);

@@ -129,22 +129,27 @@ def test_two_rank_bucket_allreduce_matches_mean_of_replica_grads(tmp_path):
 
 
 def test_shard_batch_covers_every_sample_once():
+    """Same chunks as torch.chunk (DataParallel's scatter); a split that would leave a rank empty is refused loudly (an empty
+    shard fails the kernels' n > 0 checks or hangs the other ranks' all-reduce)."""
     from viai_b200.optim import shard_batch
-    for n in (0, 1, 5, 32, 33):
+    for n in (1, 5, 32, 33):
         for w in (1, 2, 3, 8):
+            want = [c.numel() for c in torch.arange(n).chunk(w)]
+            if len(want) < w:
+                with pytest.raises(ValueError, match="without samples"):
+                    [shard_batch(n, r, w) for r in range(w)]
+                continue
             seen = []
             for r in range(w):
                 b, e = shard_batch(n, r, w)
-                assert 0 <= b <= e <= n
+                assert 0 <= b < e <= n
                 seen += list(range(b, e))
             assert seen == list(range(n)), (n, w)
-            # same chunk sizes as torch.chunk (what DataParallel's scatter uses)
-            if n:
-                want = [c.numel() for c in torch.arange(n).chunk(w)]
-                got = [shard_batch(n, r, w)[1] - shard_batch(n, r, w)[0] for r in range(w)]
-                assert [g for g in got if g] == want
+            assert [shard_batch(n, r, w)[1] - shard_batch(n, r, w)[0] for r in range(w)] == want
     with pytest.raises(ValueError):
         shard_batch(4, 2, 2)
+    with pytest.raises(ValueError, match="without samples"):
+        shard_batch(5, 3, 4)
 
 
 def test_grad_bucket_views_alias_flat_buffers():

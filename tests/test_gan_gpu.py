@@ -6,10 +6,11 @@ marked ``fp32`` (CUDA-core validator).
 Tolerances (normwise relative, viai_test_helpers.relerr):
   * spectrograms / discriminator maps / losses: 1e-3 (the north star's bound for fp32 spectrograms);
   * mask application: bit exact;
-  * gradients, PER PARAMETER TENSOR: err vs the fp64 oracle <= max(1e-3, 4 x the fp32 oracle's own error vs fp64)
-    (viai_test_helpers.grad_table; the table of a B200 run is committed as profiles/r02_parity_table.csv).  The L1 loss
-    gradient is sign(fake - real)/n and the ReLU derivatives are step functions, so two fp32 evaluations of the REFERENCE differ
-    by more than 1e-3 on some tensors; the fp32-vs-fp64 distance of the oracle measures exactly that;
+  * gradients, PER PARAMETER TENSOR (viai_test_helpers, "Per-tensor gradient gate"): <= 1e-3 from the exact fp64 gradient of the
+    step taken AT the CUDA path's own ReLU / LeakyReLU / L1-sign decisions, and the CUDA path's decisions differ from the fp64
+    oracle's in no more units than a small multiple of what the fp32 oracle's own do.  (The raw distance to the fp64 oracle is
+    dominated by those ~10 flipped units out of 10^7 -- for the reference's fp32 arithmetic too -- and is tabulated beside it;
+    profiles/r02_parity_table.csv is the table of a B200 run.)
   * post-Adam weights: Adam's first step is lr*sign(g); compared where the sign is well defined.
 """
 import math
@@ -87,11 +88,11 @@ def test_modules_match_reference_golden(name):
     lg, l1 = gl(pred_fake_g, True), L1Loss()(fake, melg)
     assert math.isclose(float(lg), fx["loss_G_GAN"], rel_tol=1e-3) and math.isclose(float(l1), fx["loss_L1"], rel_tol=1e-3)
     ops.lincomb2(lg, 1.0, l1, 100.0).backward()
-    r32, r64 = H.oracle_pair(H.filled(H.encoder_sd(norm)), H.filled(H.decoder_sd(norm)), H.filled(H.discriminator_sd(norm)),
-                             mel, mask, Hh, norm, norm, update=False)
-    H.grad_table({k: p.grad for k, p in E.named_parameters()}, r32["grads_E"], r64["grads_E"], "golden%s/E" % tag)
-    H.grad_table({k: p.grad for k, p in G.named_parameters() if p.grad is not None}, r32["grads_Dec"], r64["grads_Dec"],
-                 "golden%s/Dec" % tag)
+    # (module-by-module run: whole-net sanity criterion here, the per-tensor gate is applied to GanTrainer.train_step below)
+    _, r64 = H.oracle_pair(H.filled(H.encoder_sd(norm)), H.filled(H.decoder_sd(norm)), H.filled(H.discriminator_sd(norm)),
+                           mel, mask, Hh, norm, norm, update=False)
+    H.assert_e2e_grads({k: p.grad for k, p in E.named_parameters()}, r64["grads_E"], "E")
+    H.assert_e2e_grads({k: p.grad for k, p in G.named_parameters() if p.grad is not None}, r64["grads_Dec"], "G")
     for k in fx["dead"]:
         assert dict(G.named_parameters())[k].grad is None              # dead convblock1
     if norm == "bn":
@@ -102,32 +103,41 @@ def test_modules_match_reference_golden(name):
 
 
 def test_smooth_loss_gradients_tight():
-    """Gradient parity through G with a smooth objective (no L1 sign flips): per-tensor gate."""
+    """Gradient parity through E and G with a smooth objective (no L1 sign): per-tensor gate at the CUDA path's decisions."""
     IN, NN, DN, nl, OI = _mods("bn")
     hp = OI.Inpainting_Config(cin_channels=80)
     esd, gsd = H.filled(H.encoder_sd("bn"), 3), H.filled(H.decoder_sd("bn"), 3)
     mel = FX.uniform("smooth", (2, 1, 80, 64))
-    def run(dt):
-        e = {k: v.clone().to(dt).requires_grad_(True) if (v.is_floating_point() and "running" not in k) else
-             (v.clone().to(dt) if v.is_floating_point() else v.clone()) for k, v in esd.items()}
-        g = {k: v.clone().to(dt).requires_grad_(True) if (v.is_floating_point() and "running" not in k) else
-             (v.clone().to(dt) if v.is_floating_point() else v.clone()) for k, v in gsd.items()}
-        fk = O.mel_decoder_forward(g, O.mel_encoder_forward(e, mel.to(dt), 80), mel.shape)
+
+    def run(dt, pattern):
+        leaf = lambda sd: {k: v.clone().to(dt).requires_grad_(True) if (v.is_floating_point() and "running" not in k) else
+                           (v.clone().to(dt) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+        e, g = leaf(esd), leaf(gsd)
+        O._PATTERN = pattern
+        try:
+            fk = O.mel_decoder_forward(g, O.mel_encoder_forward(e, mel.to(dt), 80), mel.shape)
+        finally:
+            O._PATTERN = None
         ((fk - mel.to(dt)) ** 2).mean().backward()
-        return e, g, fk
-    e, g, fake = run(torch.float32)
-    e64, g64, _ = run(torch.float64)
+        grads = lambda sd: {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
+        return grads(e), grads(g), fk
+
     E = _load(IN.MelEncoder(hp), esd)
     G = _load(NN.MelDecoder(hp), gsd)
     from viai_b200 import ops
-    fk = G(E(mel.cuda()), mel.shape)
-    assert H.relerr(fk, fake) < 1e-3
+    with ops.trace_activation_decisions() as trace:
+        fk = G(E(mel.cuda()), mel.shape)
     d = (fk - mel.cuda())
     (d * d).mean().backward()            # scalar glue by torch; the conv/norm/resample backward is the library's
-    for mod, r32, r64 in ((E, e, e64), (G, g, g64)):
-        ref = {k: v.grad for k, v in r64.items() if v.requires_grad and v.grad is not None}
-        ref32 = {k: r32[k].grad for k in ref}
-        H.grad_table({k: p.grad for k, p in mod.named_parameters()}, ref32, ref, "smooth/" + type(mod).__name__)
+    p32, p64 = O.DecisionPattern(), O.DecisionPattern()
+    e32, g32, fake = run(torch.float32, p32)
+    e64, g64, _ = run(torch.float64, p64)
+    pc = O.DecisionPattern([m.permute(0, 3, 1, 2).contiguous().cpu() for m in trace], None)
+    e64m, g64m, _ = run(torch.float64, pc)
+    assert H.relerr(fk, fake) < 1e-3
+    H.assert_flips((sum(pc.flips), sum(int((a != b).sum()) for a, b in zip(p32.masks, p64.masks)), pc.units), "smooth")
+    H.grad_table({k: p.grad for k, p in E.named_parameters()}, e64m, "smooth/MelEncoder", e32, e64)
+    H.grad_table({k: p.grad for k, p in G.named_parameters() if p.grad is not None}, g64m, "smooth/MelDecoder", g32, g64)
 
 
 @pytest.mark.parametrize("variant", ["MelDecoderImage", "MelDecoderImage2", "MelDecoder_old"])
@@ -186,19 +196,23 @@ def test_train_step_matches_oracle(cfg):
     esd, gsd, dsd = cpu(tr.Mel_Encoder), cpu(tr.Mel_Decoder), cpu(tr.netD)
     mel = torch.rand(B, 1, Hh, W)
     mask = O.time_band_mask(mel.shape, W // 4, W // 2)
-    want, want64 = H.oracle_pair(esd, gsd, dsd, mel, mask, Hh, norm, norm)
-    got = tr.train_step(mel.cuda(), mask.cuda())
+    from viai_b200 import ops
+    with ops.trace_activation_decisions() as trace:
+        got = tr.train_step(mel.cuda(), mask.cuda())
+    want, want64, want64m, flips = H.matched_oracle(trace, got, esd, gsd, dsd, mel, mask, Hh, norm, norm)
     assert H.relerr(got["fake"], want["fake"]) < 1e-3
     for k in ("loss_D", "loss_G_GAN", "loss_L1"):
         assert math.isclose(float(got[k]), want[k], rel_tol=1e-3), k
+    case = "step_%s_%dx%dx%d" % (norm, B, Hh, W)
+    H.assert_flips(flips, case)
     # Gradients (read from the flat buckets) by the per-tensor gate; Adam's first moment is linear in them.
     for mod, gk, opt in ((tr.netD, "grads_D", tr.optimizer_D), (tr.Mel_Encoder, "grads_E", tr.optimizer_G),
                          (tr.Mel_Decoder, "grads_Dec", tr.optimizer_G)):
         ps = dict(mod.named_parameters())
-        H.grad_table({k: ps[k]._viai_grad for k in want64[gk]}, want[gk], want64[gk], "step_%s_%dx%dx%d/%s" % (norm, B, Hh, W, gk))
-        H.grad_table({k: opt.state[ps[k]]["exp_avg"] * 2.0 for k in want64[gk]}, want[gk], want64[gk],
-                     "step_%s_%dx%dx%d/%s.exp_avg" % (norm, B, Hh, W, gk))                                    # (1-beta1)=0.5
-    _check_post_adam(tr, want, want64, esd, gsd, dsd)
+        H.grad_table({k: ps[k]._viai_grad for k in want64m[gk]}, want64m[gk], "%s/%s" % (case, gk), want[gk], want64[gk])
+        H.grad_table({k: opt.state[ps[k]]["exp_avg"] * 2.0 for k in want64m[gk]}, want64m[gk], "%s/%s.exp_avg" % (case, gk),
+                     want[gk], want64[gk])                                                                    # (1-beta1)=0.5
+    _check_post_adam(tr, want, want64m, esd, gsd, dsd)
     assert tr.launches_per_step > 100
 
 
@@ -281,15 +295,19 @@ def test_full_size_properties_and_parity(size):
     B = 4
     mel = torch.rand(B, 1, size, size)
     mask = O.time_band_mask(mel.shape, size // 4, size // 2)
-    want, want64 = H.oracle_pair(esd, gsd, dsd, mel, mask, size)
-    got = tr.train_step(mel.cuda(), mask.cuda())
+    from viai_b200 import ops
+    with ops.trace_activation_decisions() as trace:
+        got = tr.train_step(mel.cuda(), mask.cuda())
+    assert ops.f16_overflow() == 0
+    want, want64, want64m, flips = H.matched_oracle(trace, got, esd, gsd, dsd, mel, mask, size)
     assert H.relerr(got["fake"], want["fake"]) < 1e-3
     for k in ("loss_D", "loss_G_GAN", "loss_L1"):
         assert math.isclose(float(got[k]), want[k], rel_tol=1e-3), k
+    H.assert_flips(flips, "c2_B4_%dx%d" % (size, size))
     for mod, gk in ((tr.netD, "grads_D"), (tr.Mel_Encoder, "grads_E"), (tr.Mel_Decoder, "grads_Dec")):
         ps = dict(mod.named_parameters())
-        H.grad_table({k: ps[k]._viai_grad for k in want64[gk]}, want[gk], want64[gk], "c2_B4_%dx%d/%s" % (size, size, gk))
-    _check_post_adam(tr, want, want64, esd, gsd, dsd)
+        H.grad_table({k: ps[k]._viai_grad for k in want64m[gk]}, want64m[gk], "c2_B4_%dx%d/%s" % (size, size, gk), want[gk], want64[gk])
+    _check_post_adam(tr, want, want64m, esd, gsd, dsd)
     # full batch: properties
     melB = torch.rand(32, 1, size, size).cuda()
     maskB = O.time_band_mask(melB.shape, size // 4, size // 2).cuda()
@@ -307,7 +325,6 @@ def test_full_size_properties_and_parity(size):
 
 
 @pytest.mark.parametrize("size,B", [(128, 4), (256, 2), (512, 1)], ids=["128", "256", "512"])
-@pytest.mark.bf16x3
 def test_freeform_masks_mixed_sizes_default_precision(size, B):
     """BASELINE config 5: free-form (seeded random-walk stroke) masks at 128 / 256 / 512 square mels, on the library's
     default tensor-core path.  The mask definition is ours (the reference has none; oracle.freeform_mask is pure integer
@@ -315,7 +332,7 @@ def test_freeform_masks_mixed_sizes_default_precision(size, B):
     IN, NN, DN, nl, OI = _mods("bn")
     from viai_b200 import ops
     from viai_b200.step import GanTrainer
-    assert ops.get_precision() == "bf16x3"
+    assert ops.get_precision() == "fp16x3"
     hp = OI.Inpainting_Config(cin_channels=size)
     torch.manual_seed(7 + size)
     tr = GanTrainer(hp, "cuda")
@@ -334,7 +351,7 @@ def test_freeform_masks_mixed_sizes_default_precision(size, B):
         assert math.isclose(float(got[k]), want[k], rel_tol=2e-3), k
 
 
-@pytest.mark.parametrize("precision", [pytest.param("fp32", marks=pytest.mark.fp32), pytest.param("bf16x3", marks=pytest.mark.bf16x3)])
+@pytest.mark.parametrize("precision", [pytest.param("fp32", marks=pytest.mark.fp32), pytest.param("fp16x3", id="default")])
 def test_vision_infused_step_matches_oracle(precision):
     """BASELINE config 3 at the native 80-bin geometry: ResNet-18 ImageEmbedding (RGB + flow) fused at the generator
     bottleneck through MelDecoderImage, one D + one G update; the video encoder trains with the generator."""
@@ -356,17 +373,25 @@ def test_vision_infused_step_matches_oracle(precision):
     video = FX.normal("c3_video", (B, T, 3, 224, 224)).clamp(-1, 1)
     flow = FX.normal("c3_flow", (B, T, 2, 224, 224)).clamp(-1, 1)
 
-    def oracle(dt):
+    with ops.trace_activation_decisions() as trace:
+        got = tr.train_step(mel.cuda(), mask.cuda(), video.cuda(), flow.cuda())
+    # the GAN part's 33 ReLU / LeakyReLU sites (E 5, MelDecoderImage 16, D 3 x 4); the video encoder's own sites sit between E and
+    # the decoder in call order and only matter for ITS gradients (criterion below)
+    n_video = len(trace) - 33
+    gan_trace = trace[:5] + trace[5 + n_video:]
+    p32, p64 = O.DecisionPattern(), O.DecisionPattern()
+    pc = H.cuda_pattern(gan_trace, got["fake"], mel)
+
+    def oracle(dt, pattern=None):
         to = lambda sd: {k: (v.to(dt) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
         v_leaf = {k: (t.clone().requires_grad_(True) if t.is_floating_point() and "running" not in k else t.clone())
                   for k, t in to(vsd).items()}
         vnet = O.image_embedding_forward(v_leaf, video.to(dt), flow.to(dt))
-        r = O.gan_step(to(esd), to(gsd), to(dsd), mel.to(dt), mask.to(dt), 80, variant="MelDecoderImage", video_net=vnet)
+        r = O.gan_step(to(esd), to(gsd), to(dsd), mel.to(dt), mask.to(dt), 80, variant="MelDecoderImage", video_net=vnet, pattern=pattern)
         r["grads_V"] = {k: t.grad for k, t in v_leaf.items() if t.requires_grad and t.grad is not None}
         return r
 
-    want, want64 = oracle(torch.float32), oracle(torch.float64)
-    got = tr.train_step(mel.cuda(), mask.cuda(), video.cuda(), flow.cuda())
+    want, want64, want64m = oracle(torch.float32, p32), oracle(torch.float64, p64), oracle(torch.float64, pc)
     assert H.relerr(got["fake"], want["fake"]) < 1e-3
     for k in ("loss_D", "loss_G_GAN", "loss_L1"):
         assert math.isclose(float(got[k]), want[k], rel_tol=2e-3), k
@@ -378,9 +403,11 @@ def test_vision_infused_step_matches_oracle(precision):
     l2, cos, _ = H.whole_net_metrics(gotV, want64["grads_V"])
     print("video-encoder grads: cuda vs fp64 L2 %.3e cos %.6f | fp32 oracle vs fp64 L2 %.3e cos %.6f" % (l2, cos, l2_ref, cos_ref))
     assert l2 <= max(5e-2, 4 * l2_ref) and cos >= 0.998
+    flips_ref = sum(int((a != b).sum()) for a, b in zip(p32.masks, p64.masks)) + int((p32.l1_sign != p64.l1_sign).sum())
+    H.assert_flips((sum(pc.flips), flips_ref, pc.units), "c3_%s" % precision)
     for mod, gk in ((tr.Mel_Encoder, "grads_E"), (tr.Mel_Decoder, "grads_Dec"), (tr.netD, "grads_D")):
         p2 = dict(mod.named_parameters())
-        H.grad_table({k: p2[k]._viai_grad for k in want64[gk]}, want[gk], want64[gk], "c3_%s/%s" % (precision, gk))
-    H.grad_table(gotV, want["grads_V"], want64["grads_V"], "c3_%s/grads_V" % precision, check=False)      # table only (criterion above)
+        H.grad_table({k: p2[k]._viai_grad for k in want64m[gk]}, want64m[gk], "c3_%s/%s" % (precision, gk), want[gk], want64[gk])
+    H.grad_table(gotV, want64m["grads_V"], "c3_%s/grads_V" % precision, want["grads_V"], want64["grads_V"], check=False)   # table only
     # bn_1 of the video encoder never reaches the output (reference :123): its gradient slot stays zero
     assert float(ps["bn_1.weight"]._viai_grad.abs().max()) == 0.0

@@ -32,7 +32,7 @@ def test_state_dict_layout_matches_reference():
         assert tuple(got[k].shape) == tuple(want[k].shape), k
 
 
-@pytest.mark.parametrize("precision", [pytest.param("fp32", marks=pytest.mark.fp32), pytest.param("tf32x3", marks=pytest.mark.tf32x3), pytest.param("bf16x3", marks=pytest.mark.bf16x3)])
+@pytest.mark.parametrize("precision", [pytest.param("fp32", marks=pytest.mark.fp32), pytest.param("tf32x3", marks=pytest.mark.tf32x3), pytest.param("bf16x3", marks=pytest.mark.bf16x3), pytest.param("fp16x3", id="default")])
 def test_forward_matches_reference_golden(precision):
     from viai_b200 import ops
     assert ops.get_precision() == precision

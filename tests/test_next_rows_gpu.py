@@ -16,7 +16,7 @@ from oracle import make_golden as MG
 from oracle import viai_oracle as O
 
 pytestmark = pytest.mark.gpu
-PREC = [pytest.param("fp32", marks=pytest.mark.fp32, id="fp32"), pytest.param("bf16x3", marks=pytest.mark.bf16x3, id="bf16x3")]
+PREC = [pytest.param("fp32", marks=pytest.mark.fp32, id="fp32"), pytest.param("fp16x3", id="default")]
 
 
 @pytest.fixture(scope="module")

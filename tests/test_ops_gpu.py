@@ -55,7 +55,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("prec", [pytest.param("bf16x3", id="default"), pytest.param("fp32", marks=pytest.mark.fp32, id="fp32")])
+@pytest.mark.parametrize("prec", [pytest.param("fp16x3", id="default"), pytest.param("fp32", marks=pytest.mark.fp32, id="fp32")])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv2d_forward_backward(ops, case, prec):
     assert ops.get_precision() == prec

@@ -63,7 +63,8 @@ def test_tc_layer_geometry(layer, N):
 
 
 @pytest.mark.parametrize("layer", [l for l in LAYERS if _supported(l)], ids=[l[0] for l in LAYERS if _supported(l)])
-@pytest.mark.parametrize("mode", [pytest.param("tf32x3", marks=pytest.mark.tf32x3), pytest.param("bf16x3", marks=pytest.mark.bf16x3)])
+@pytest.mark.parametrize("mode", [pytest.param("tf32x3", marks=pytest.mark.tf32x3), pytest.param("bf16x3", marks=pytest.mark.bf16x3),
+                                  pytest.param("fp16x3", id="fp16x3-default")])
 def test_x3_forward_is_fp32_accurate(layer, mode):
     """The 3-term products: forward output and fused statistics at fp32-level accuracy."""
     from viai_b200 import ops
@@ -78,8 +79,41 @@ def test_x3_forward_is_fp32_accurate(layer, mode):
     with torch.no_grad():
         yg, stats = ops.conv2d_stats(x.float().permute(0, 2, 3, 1).contiguous().cuda(), w.float().cuda(), b.float().cuda(),
                                      stride, pad, tr, 1)
-    assert H.relerr(yg.permute(0, 3, 1, 2), y) < X3_TOL, name
+    tol = 5e-6 if mode == "fp16x3" else X3_TOL            # fp16 pairs carry 22 significand bits, bf16 pairs 16
+    assert H.relerr(yg.permute(0, 3, 1, 2), y) < tol, name
     assert H.relerr(stats[0], y.sum((0, 2, 3))) < X3_TOL and H.relerr(stats[1], (y * y).sum((0, 2, 3))) < X3_TOL
+    if mode == "fp16x3":
+        assert ops.f16_overflow() == 0
+
+
+@pytest.mark.parametrize("wmag,xmag", [(1e-4, 1.0), (30.0, 1.0), (0.05, 1e-3), (0.05, 500.0)])
+def test_fp16x3_dynamic_range(wmag, xmag):
+    """fp16 pairs have 5 exponent bits: the weights carry a per-tensor power-of-two scale computed on the device, the activations
+    a fixed one (x 8).  Tiny / large weights and activations from 1e-3 to 500 keep the forward at fp32-class accuracy."""
+    from viai_b200 import ops
+    assert ops.get_precision() == "fp16x3"
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(2, 64, 12, 10, generator=g, dtype=torch.float64) * xmag).float().double()
+    w = (torch.randn(48, 64, 3, 3, generator=g, dtype=torch.float64) * wmag).float().double()
+    y = F.conv2d(x, w, None, 1, 1)
+    yg = ops.conv2d(x.float().permute(0, 2, 3, 1).contiguous().cuda(), w.float().cuda(), None, (1, 1), (1, 1), False)
+    assert H.relerr(yg.permute(0, 3, 1, 2), y) < 5e-6
+    assert ops.f16_overflow() == 0
+
+
+def test_fp16x3_saturation_is_finite_and_reported():
+    """|x| >= 8188 cannot be represented by the scaled fp16 pair: the value saturates (no inf / NaN) and the library counts it."""
+    from viai_b200 import ops
+    x = torch.ones(1, 8, 8, 32, device="cuda")
+    x[0, 3, 3, 5] = 1e5
+    w = torch.ones(32, 32, 3, 3, device="cuda") * 0.01
+    ops.f16_overflow()
+    y = ops.conv2d(x, w, None, (1, 1), (1, 1), False)
+    assert bool(torch.isfinite(y).all())
+    assert ops.f16_overflow() > 0 and ops.f16_overflow() == 0
+    with pytest.raises(RuntimeError, match="saturated"):
+        ops.conv2d(x, w, None, (1, 1), (1, 1), False)
+        ops.check_f16_overflow()
 
 
 @pytest.mark.parametrize("shape", [(1, 16, 8), (2, 17, 9), (3, 5, 21), (1, 1, 1), (2, 33, 7)])
@@ -166,13 +200,14 @@ def test_single_tf32_step_is_outside_the_parity_bound():
 
 
 def test_single_tf32_data_gradient_is_outside_the_gradient_gate():
-    """Documents WHY the data gradient runs the 3-term product: with one tf32 product (round-1 default) the encoder's weight
-    gradients sit ~1e-2 from the fp64 oracle at 128 x 128, 10-30x the reference's own fp32 envelope; with the 3-term product they
-    are inside the per-tensor gate (tests/test_gan_gpu.py)."""
+    """Documents WHY the data gradient runs a 3-term product: kind::tf32 truncates both operands, every layer's data gradient
+    comes out ~2^-11 too small and the shrinkage compounds along the ~30-layer chain: at the CUDA path's own decisions (so that
+    no flipped unit blurs the picture) the encoder's gradients are ~1e-2 off with a single tf32 product and inside the 1e-3 gate
+    with the 3-term product."""
     from viai_b200 import Options_inpainting as OI, ops
     from viai_b200.step import GanTrainer
     from oracle import viai_oracle as O
-    assert ops.get_precision() == "bf16x3"
+    assert ops.get_precision() == "fp16x3"
     hp = OI.Inpainting_Config(cin_channels=128)
     mel = torch.rand(2, 1, 128, 128, generator=torch.Generator().manual_seed(3))
     mask = O.time_band_mask(mel.shape, 32, 64)
@@ -184,17 +219,17 @@ def test_single_tf32_data_gradient_is_outside_the_gradient_gate():
             tr = GanTrainer(hp, "cuda")
             cpu = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
             esd, gsd, dsd = cpu(tr.Mel_Encoder), cpu(tr.Mel_Decoder), cpu(tr.netD)
-            if not worst:
-                want, want64 = H.oracle_pair(esd, gsd, dsd, mel, mask, 128, update=False)
-            tr.train_step(mel.cuda(), mask.cuda())
+            with ops.trace_activation_decisions() as trace:
+                got = tr.train_step(mel.cuda(), mask.cuda())
+            want, want64, want64m, _ = H.matched_oracle(trace, got, esd, gsd, dsd, mel, mask, 128, update=False)
             ps = dict(tr.Mel_Encoder.named_parameters())
-            rows = H.grad_table({k: ps[k]._viai_grad for k in want64["grads_E"]}, want["grads_E"], want64["grads_E"],
-                                "dgrad_%s/grads_E" % ("x3" if x3 else "tf32"), check=False)
+            rows = H.grad_table({k: ps[k]._viai_grad for k in want64m["grads_E"]}, want64m["grads_E"],
+                                "dgrad_%s/grads_E" % ("x3" if x3 else "tf32"), want["grads_E"], want64["grads_E"], check=False)
             worst[x3] = max(r[1] for r in rows)
         finally:
             ops.set_dgrad_x3(prev)
-    print("encoder gradients, worst tensor err vs fp64: tf32 dgrad %.3e, 3-term dgrad %.3e" % (worst[False], worst[True]))
-    assert worst[False] > 3e-3 and worst[True] < worst[False] / 3
+    print("encoder gradients, worst tensor err at the CUDA decisions: tf32 dgrad %.3e, 3-term dgrad %.3e" % (worst[False], worst[True]))
+    assert worst[False] > 3e-3 and worst[True] < 1e-3
 
 
 @pytest.mark.parametrize("case", [("block5 32->32", True, 32, 32, (1, 1), 20, 24, "relu"), ("dis 64->128 s2", False, 64, 128, (2, 2), 18, 20, "lrelu"),

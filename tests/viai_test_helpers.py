@@ -241,40 +241,85 @@ def whole_net_metrics(got, ref, skip_below=1e-7):
 
 
 # ------------------------------------------------------------------------------------------------
-# Per-tensor gradient gate of the BENCHED path (bf16x3 forward + data gradient, tf32 weight gradient with rounded operands).
-#   err(cuda, fp64 oracle) <= max(GRAD_FLOOR, GRAD_K * err(fp32 oracle, fp64 oracle))      for EVERY parameter tensor,
-# err = max|a-b| / max|b| (the metric of every other tolerance in tests/).  GRAD_FLOOR is BASELINE.md section 3's 1e-3; K
-# allows the CUDA path a different (equally valid) fp32 summation order / a different set of ReLU- and L1-sign decisions than
-# the CPU oracle took.  Every comparison made through grad_table() is also appended to $VIAI_PARITY_TABLE (CSV) so that the
-# per-tensor table of a B200 run can be committed under profiles/.
+# Per-tensor gradient gate of the BENCHED path (fp16x3 forward, bf16x3 data gradient, tf32 weight gradient on rounded operands).
+#
+# The step's loss is piecewise smooth: every ReLU / LeakyReLU decides the side of zero of its input and the L1 term the sign of
+# fake - real (~10^7 decisions at 128 x 128).  Two roundings of the same forward (the reference in fp32 vs fp64) take ~10 of them
+# differently and EACH flipped unit moves the gradient by a finite amount: measured on the oracle, those 13 flips are the whole
+# fp32-vs-fp64 gradient distance (6e-4 .. 1e-2 per tensor; 1e-5 once the fp64 gradient is taken at the fp32 run's own decisions).
+# The gate therefore has two parts:
+#   (1) DECISIONS: the CUDA step's pattern (ops.trace_activation_decisions + sign(fake - real)) differs from the fp64 oracle's in
+#       at most FLIP_K x as many units as the fp32 oracle's own pattern does (+ FLIP_SLACK): the forward is fp32-class;
+#   (2) GRADIENT AT THOSE DECISIONS: every parameter gradient of the CUDA step is within GRAD_TOL = 1e-3 (BASELINE.md section 3,
+#       max-norm relative) of the EXACT (fp64) gradient of the step evaluated at the CUDA path's decisions
+#       (oracle.DecisionPattern(impose)).
+# The raw distance to the unmatched fp64 oracle and the fp32 oracle's own raw distance (the "envelope") are tabulated next to it.
+# Every comparison is appended to $VIAI_PARITY_TABLE (CSV); the table of a B200 run is committed under profiles/.
 # ------------------------------------------------------------------------------------------------
-GRAD_FLOOR = 1e-3
-GRAD_K = 4.0
+GRAD_TOL = 1e-3
+FLIP_K = 8
+FLIP_SLACK = 64
 
 
-def grad_table(got, r32, r64, what, floor=GRAD_FLOOR, K=GRAD_K, check=True):
-    """got / r32 / r64: {name: tensor}.  Asserts the per-tensor gate for every tensor of ``r64`` whose gradient is not
-    numerically zero relative to the net; returns rows (name, cuda_err, fp32_oracle_err, ratio, bound)."""
-    scale = max(float(v.abs().max()) for v in r64.values())
+def cuda_pattern(trace, fake_gpu, real_cpu):
+    """DecisionPattern (impose mode) from the masks ops.trace_activation_decisions collected (NHWC on the GPU) and the step's
+    own spectrogram."""
+    from oracle import viai_oracle as O
+    masks = [m.permute(0, 3, 1, 2).contiguous().cpu() for m in trace]
+    sign = torch.sign(fake_gpu.detach().cpu().reshape(real_cpu.shape) - real_cpu)
+    return O.DecisionPattern(masks, sign)
+
+
+def matched_oracle(trace, got, esd, gsd, dsd, mel, mask, Hh, norm_g="bn", norm_d="bn", update=True, **kw):
+    """(r32, r64, r64m, flips): the oracle in fp32 and fp64 (each recording its own decisions) and the fp64 oracle evaluated AT
+    the CUDA step's decisions; flips = (CUDA vs fp64, fp32 oracle vs fp64, units)."""
+    from oracle import viai_oracle as O
+    d = torch.float64
+    e64, g64, d64 = to_dtype(esd, d), to_dtype(gsd, d), to_dtype(dsd, d)
+    kw64 = {k: (v.to(d) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in kw.items()}
+    p32, p64 = O.DecisionPattern(), O.DecisionPattern()
+    r32 = O.gan_step(esd, gsd, dsd, mel, mask, Hh, norm_g, norm_d, update=update, pattern=p32, **kw)
+    r64 = O.gan_step(e64, g64, d64, mel.to(d), mask.to(d), Hh, norm_g, norm_d, update=update, pattern=p64, **kw64)
+    pc = cuda_pattern(trace, got["fake"], mel.reshape(got["fake"].shape))
+    assert len(pc.masks) == len(p64.masks), "the CUDA step has %d ReLU sites, the oracle %d" % (len(pc.masks), len(p64.masks))
+    r64m = O.gan_step(e64, g64, d64, mel.to(d), mask.to(d), Hh, norm_g, norm_d, update=update, pattern=pc, **kw64)
+    flips_ref = sum(int((a != b).sum()) for a, b in zip(p32.masks, p64.masks)) + int((p32.l1_sign != p64.l1_sign).sum())
+    return r32, r64, r64m, (sum(pc.flips), flips_ref, pc.units)
+
+
+def assert_flips(flips, what):
+    fc, fr, units = flips
+    path = os.environ.get("VIAI_PARITY_TABLE")
+    if path:
+        with open(path + ".flips", "a") as f:
+            f.write("%s,cuda_vs_fp64=%d,fp32_oracle_vs_fp64=%d,units=%d\n" % (what, fc, fr, units))
+    print("%s: decisions that differ from the fp64 oracle: CUDA %d, fp32 oracle %d (of %d)" % (what, fc, fr, units))
+    assert fc <= FLIP_K * fr + FLIP_SLACK, "%s: the CUDA forward flips %d decisions vs fp64, the fp32 reference only %d" % (what, fc, fr)
+
+
+def grad_table(got, r64m, what, r32=None, r64=None, tol=GRAD_TOL, check=True):
+    """got: {name: CUDA gradient}; r64m: fp64 gradients at the CUDA decisions (the gate); r32 / r64: unmatched fp32 / fp64 oracle
+    gradients (tabulated only).  Tensors whose reference is numerically zero relative to the net must be ~0."""
+    scale = max(float(v.abs().max()) for v in r64m.values())
     rows, bad = [], []
-    for k, ref in r64.items():
+    for k, ref in r64m.items():
         if float(ref.abs().max()) < 1e-7 * scale:
             assert float(got[k].detach().abs().max()) <= 1e-4 * scale, "%s %s: expected ~0" % (what, k)
             continue
-        env = relerr(r32[k], ref)
         err = relerr(got[k], ref)
-        bound = max(floor, K * env)
-        rows.append((k, err, env, err / max(env, 1e-30), bound))
-        if err > bound:
-            bad.append("%s: err %.3e > max(%.0e, %g x fp32 envelope %.3e)" % (k, err, floor, K, env))
+        raw = relerr(got[k], r64[k]) if r64 is not None else float("nan")
+        env = relerr(r32[k], r64[k]) if (r32 is not None and r64 is not None) else float("nan")
+        rows.append((k, err, raw, env))
+        if err > tol:
+            bad.append("%s: err %.3e vs the fp64 gradient at the CUDA decisions > %.0e (raw %.3e, fp32 envelope %.3e)" % (k, err, tol, raw, env))
     path = os.environ.get("VIAI_PARITY_TABLE")
     if path:
         new = not os.path.exists(path)
         with open(path, "a") as f:
             if new:
-                f.write("case,tensor,cuda_err_vs_fp64,fp32_oracle_err_vs_fp64,ratio,bound,ok\n")
-            for k, err, env, ratio, bound in rows:
-                f.write("%s,%s,%.3e,%.3e,%.2f,%.3e,%d\n" % (what, k, err, env, ratio, bound, int(err <= bound)))
+                f.write("case,tensor,cuda_err_vs_fp64_at_cuda_decisions,cuda_err_vs_fp64_raw,fp32_oracle_err_vs_fp64_raw,gate,ok\n")
+            for k, err, raw, env in rows:
+                f.write("%s,%s,%.3e,%.3e,%.3e,%.0e,%d\n" % (what, k, err, raw, env, tol, int(err <= tol)))
     if check:
         assert not bad, "%s: %d of %d tensors outside the gate:\n  %s" % (what, len(bad), len(rows), "\n  ".join(bad))
     return rows

@@ -14,9 +14,14 @@ schedule, loss weights, optimizer settings) is OURS and read from ``hparams`` wi
                      waveform (x_batch, y_batch, input_lengths) conditioned on the inpainted mel (detached) and reports its masked
                      DMoL loss as ``reconstruct_loss_item`` (train_whole_sync.py:105-107); ``hparams.wavenet_kwargs`` overrides the
                      WaveNet constructor defaults
+    cuda_graph     : (``hparams.cuda_graph``, default True) ``optimize_parameters`` captures the whole D + G update as a CUDA
+                     graph on the first batch of a given shape (weights, Adam state and BatchNorm buffers are restored after the
+                     capture's warm-up, so the first replay IS the first step) and replays it afterwards; the mask is a graph
+                     input, so the ``blank_length`` schedule does not force a re-capture; a new batch shape does
     EmbeddingL2    : ``test()`` reports the L2 contrastive loss between the l2-normalised audio bottleneck and visual embedding
                      (``EmbeddingL2_item``, train_whole_sync.py:109) when the two have the same width (native 80-bin mels)
 """
+import contextlib
 import os
 from collections import OrderedDict
 
@@ -28,6 +33,24 @@ from ..loss_functions import L2ContrastiveLoss, sequence_mask
 from ..networks.Image_Embedding import ImageEmbedding
 from ..step import GanTrainer
 from ..utils.util import l2_norm
+
+
+@contextlib.contextmanager
+def _frozen_norm_buffers(modules):
+    """Evaluation forwards use batch statistics like the training forwards (the pix2pix convention the reference borrows,
+    README.md:40) but must not move the BatchNorm running buffers: momentum 0 keeps running_mean / running_var bit-identical,
+    num_batches_tracked is put back afterwards."""
+    bns = [m for mod in modules if mod is not None for m in mod.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+    saved = [(m.momentum, None if m.num_batches_tracked is None else m.num_batches_tracked.clone()) for m in bns]
+    for m in bns:
+        m.momentum = 0.0
+    try:
+        yield
+    finally:
+        for m, (mom, nbt) in zip(bns, saved):
+            m.momentum = mom
+            if nbt is not None:
+                m.num_batches_tracked.copy_(nbt)
 
 
 class AudioModel(object):
@@ -63,6 +86,8 @@ class AudioModel(object):
         self.current_lr = self.optimizer_G.param_groups[0]["lr"]
         self._out = None
         self.mel = self.mask = self.video = self.flow = None
+        self.use_graph = bool(getattr(hparams, "cuda_graph", True))
+        self._graph_key = None
 
     # ---- inputs ------------------------------------------------------------------------------------------------------
     def get_blank_space_length(self, global_step):
@@ -96,7 +121,15 @@ class AudioModel(object):
 
     # ---- one optimisation step / one evaluation forward ----------------------------------------------------------------
     def optimize_parameters(self, global_step):
-        self._out = self.trainer.train_step(self.mel, self.mask, self.video, self.flow)
+        t = self.trainer
+        if self.use_graph:
+            key = tuple(None if x is None else tuple(x.shape) for x in (self.mel, self.video, self.flow))
+            if key != self._graph_key:
+                t.capture(self.mel, self.mask, self.video, self.flow, warmup=1, preserve_state=True)
+                self._graph_key = key
+            self._out = dict(t.replay(self.mel, self.mask, self.video, self.flow))
+        else:
+            self._out = t.train_step(self.mel, self.mask, self.video, self.flow)
         self.fake = self._out["fake"]
         if self.update_wavenet:
             T = self.audio.size(-1)
@@ -108,9 +141,10 @@ class AudioModel(object):
         t = self.trainer
         B, _, Hm, W = self.mel.shape
         masked = ops.mul(self.mel.reshape(B, Hm, W, 1), self.mask.reshape(B, Hm, W, 1)).reshape(self.mel.shape)
-        feats = t.Mel_Encoder(masked)
-        vnet = self.VideoEncoder(self.video, self.flow) if self.use_video else None
-        self.fake = t.Mel_Decoder(feats, self.mel.shape, vnet) if self.use_video else t.Mel_Decoder(feats, self.mel.shape)
+        with _frozen_norm_buffers((t.Mel_Encoder, t.Mel_Decoder, self.VideoEncoder)):
+            feats = t.Mel_Encoder(masked)
+            vnet = self.VideoEncoder(self.video, self.flow) if self.use_video else None
+            self.fake = t.Mel_Decoder(feats, self.mel.shape, vnet) if self.use_video else t.Mel_Decoder(feats, self.mel.shape)
         l1 = t.criterionL1(self.fake, self.mel)
         self._out = dict(fake=self.fake, loss_L1=l1, loss_D=torch.zeros((), device=self.device),
                          loss_G_GAN=torch.zeros((), device=self.device), loss_G=l1 * t.lambda_L1)
@@ -121,6 +155,7 @@ class AudioModel(object):
 
     def get_loss_items(self):
         o = self._out
+        ops.check_f16_overflow()          # the step's only host synchronisation point: also the place to learn about saturation
         self.loss_mel_L1_item = float(o["loss_L1"])
         self.loss_D_item = float(o["loss_D"])
         self.loss_G_GAN_item = float(o["loss_G_GAN"])
@@ -155,11 +190,21 @@ class AudioModel(object):
         hp = hparams if hparams is not None else self.hparams
         path = os.path.join(checkpoint_dir, getattr(hp, "name", "viai") + "_checkpoint_step{:09d}.pth.tar".format(global_step))
         save_opt = getattr(hp, "save_optimizer_state", True)
-        torch.save({"Mel_Encoder": self.Mel_Encoder.state_dict(), "Mel_Decoder": self.Mel_Decoder.state_dict(),
-                    "netD": self.netD.state_dict(),
-                    "optimizer_G": self.optimizer_G.state_dict() if save_opt else None,
-                    "optimizer_D": self.optimizer_D.state_dict() if save_opt else None,
-                    "global_step": global_step, "global_epoch": epoch, "global_test_step": global_test_step}, path)
+        ck = {"Mel_Encoder": self.Mel_Encoder.state_dict(), "Mel_Decoder": self.Mel_Decoder.state_dict(),
+              "netD": self.netD.state_dict(),
+              "optimizer_G": self.optimizer_G.state_dict() if save_opt else None,
+              "optimizer_D": self.optimizer_D.state_dict() if save_opt else None,
+              "global_step": global_step, "global_epoch": epoch, "global_test_step": global_test_step}
+        # Beyond utils/util.py:146-162 (whose VideoEncoder line is commented out): optimizer_G's state covers the visual
+        # encoder's parameters, so a resumed image/flow run needs its weights too; likewise the vocoder when it is trained here.
+        if self.VideoEncoder is not None:
+            ck["VideoEncoder"] = self.VideoEncoder.state_dict()
+        if self.wavenet is not None:
+            ck["wavenet"] = self.wavenet.state_dict()
+            ck["wavenet_optimizer"] = self.wavenet_trainer.optimizer.state_dict() if save_opt else None
+            if self.wavenet_trainer.ema_flat is not None:
+                ck["wavenet_ema"] = self.wavenet_trainer.ema_state_dict()
+        torch.save(ck, path)
         print("Saved checkpoint:", path)
         return path
 
@@ -168,6 +213,14 @@ class AudioModel(object):
         self.Mel_Encoder.load_state_dict(ck["Mel_Encoder"])
         self.Mel_Decoder.load_state_dict(ck["Mel_Decoder"])
         self.netD.load_state_dict(ck["netD"])
+        if self.VideoEncoder is not None and "VideoEncoder" in ck:      # absent from reference-format / older checkpoints
+            self.VideoEncoder.load_state_dict(ck["VideoEncoder"])
+        if self.wavenet is not None and "wavenet" in ck:
+            self.wavenet.load_state_dict(ck["wavenet"])
+            if self.wavenet_trainer.ema_flat is not None and "wavenet_ema" in ck:
+                self.wavenet_trainer.load_ema_state_dict(ck["wavenet_ema"])
+            if not reset_optimizer and ck.get("wavenet_optimizer") is not None:
+                self.wavenet_trainer.optimizer.load_state_dict(ck["wavenet_optimizer"])
         if not reset_optimizer:
             if ck.get("optimizer_G") is not None:
                 self.optimizer_G.load_state_dict(ck["optimizer_G"])

@@ -39,6 +39,7 @@ SIGNATURES = {
     "viai_conv2d_tc": [_GP, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p],
     "viai_conv2d_tc_bwd_reduce": [_GP, c_p, c_p, c_p, ctypes.POINTER(NormBwdCtx), c_p, c_p, c_i, c_p],
     "viai_tc_bn": [c_i],
+    "viai_tc_f16_overflow": [c_i, ctypes.POINTER(ctypes.c_uint)],
     "viai_conv2d_wgrad_tc_supported": [_GP],
     "viai_conv2d_wgrad_tc": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p, c_p],
     "viai_conv2d_thin_supported": [_GP],

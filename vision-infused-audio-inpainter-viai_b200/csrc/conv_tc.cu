@@ -119,11 +119,20 @@ struct TcParams {
   int32_t bx3;           // 1: the same 3-term product on bf16 pairs (x = hi + lo, both bf16): kind::f16 MMAs at twice the tf32
                          //    rate; the fp32 slab is split IN PLACE into [hi: 32 x bf16 | lo: 32 x bf16] per 128-byte pixel row
   int32_t a_sw128;       // 1: activation patch stored as dense 128-byte pixel rows under the 128-byte swizzle (rank-4 TMA)
+  int32_t f16;           // with bx3: the pairs are fp16 (x * a_scale = hi + lo, 22 significand bits: ~2^-21 per product, the accuracy of
+                         //    tf32x3 at the bf16 MMA rate) instead of bf16 (16 bits, ~2^-17); the weights were packed with their own
+                         //    power-of-two scale and the epilogue multiplies the accumulator by *oscale = 1 / (a_scale * w_scale)
+  float a_scale;
+  const float* oscale;
   // Shared-memory matrix descriptors relative to a stage / weight tile, built on the host: they live in the constant bank,
   // so the MMA issuer fetches them with uniform loads and issuing one MMA costs two 64-bit adds.
   uint64_t tabA[MAX_TAP * 4 * 2];   // [tap][K step][part: 0 = hi / only, 1 = lo]
   uint64_t tabB[4 * 2];             // [K step][part]
 };
+
+// Number of split-warp threads that met a value outside the fp16 range (after scaling) in an fp16-pair convolution since the
+// last viai_tc_f16_overflow(reset): such values are saturated (the result stays finite but is inaccurate).
+__device__ unsigned int g_f16_overflow = 0;
 
 __device__ __forceinline__ void transpose_reduce32(float (&v)[32], int lane) {
   // After the call v[0] of lane l holds sum over lanes of the original v[l].
@@ -333,6 +342,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       const int tid = threadIdx.x - XF_WARP0 * 32;
       int sa = 0;
       uint32_t pha = 0;
+      const bool f16 = p.f16 != 0;
+      const float a_scale = p.a_scale;
+      bool ovf = false;
       const uint32_t nrows = p.slab_bytes / 128;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         for (int c = 0; c < p.nchunks; ++c) {
@@ -350,11 +362,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
               // hi and lo are both rounded to nearest (packed cvt.rn.bf16x2): hi + lo represents x to ~2^-17 |x|.  (Truncating hi
               // saves one conversion per pair but doubles the representation error; measured speed difference: none.)
               uint32_t hi[4], lo[4];
+              if (!f16) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                hi[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
-                const float h0 = __uint_as_float(hi[e] << 16), h1 = __uint_as_float(hi[e] & 0xffff0000u);
-                lo[e] = pack_bf16x2(f[2 * e] - h0, f[2 * e + 1] - h1);
+                for (int e = 0; e < 4; ++e) {
+                  hi[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+                  const float h0 = __uint_as_float(hi[e] << 16), h1 = __uint_as_float(hi[e] & 0xffff0000u);
+                  lo[e] = pack_bf16x2(f[2 * e] - h0, f[2 * e + 1] - h1);
+                }
+              } else {
+                // fp16 pairs of the scaled value: hi keeps 11 significand bits, lo = (x - hi) the next 11 (exact subtraction);
+                // values beyond the fp16 range saturate (finite) and raise the library's overflow flag
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a = f[2 * e] * a_scale, b = f[2 * e + 1] * a_scale;
+                  hi[e] = pack_f16x2_sat(a, b);
+                  lo[e] = pack_f16x2_sat(a - f16lo_to_f32(hi[e]), b - f16hi_to_f32(hi[e]));
+                  ovf |= (fabsf(a) > 65504.f) | (fabsf(b) > 65504.f);
+                }
               }
               *reinterpret_cast<uint4*>(row + ((m ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4*>(row + (((4 + m) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -365,6 +389,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
           if (++sa == p.SA) { sa = 0; pha ^= 1u; }
         }
       }
+      if (ovf) atomicAdd(&g_f16_overflow, 1u);
     } else if (MODE == 1) {
       const int tid = threadIdx.x - XF_WARP0 * 32;
       int sa = 0;
@@ -408,6 +433,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc1[i] = acc2[i] = 0.f;
     const float neg_slope = (p.ract == VIAI_ACT_RELU) ? 0.f : (p.ract == VIAI_ACT_LRELU) ? p.rslope : 1.f;   // act'(pre <= 0)
+    const float oscale = (MODE == 2 && p.oscale != nullptr) ? __ldg(p.oscale) : 1.f;      // fp16 pairs: undo the operand scales (a power of two)
     int cur_group = -1, cur_nt = -1;
     auto flush = [&]() {
       if (narrow) {                               // one transposing reduction per group instead of one per tile
@@ -459,6 +485,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
           const int ch0 = nt * p.BN + j * 32;
+          if (MODE == 2 && p.f16) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= oscale;
+          }
           if (p.bias != nullptr) {
             const float4* b4 = reinterpret_cast<const float4*>(bias_s + ch0);      // broadcast reads
 #pragma unroll
@@ -565,6 +595,67 @@ __global__ void pack_weight_bf16x2_kernel(const float* __restrict__ src, uint16_
   }
 }
 
+// fp16-pair packing: the same layout as the bf16 pairs; the weights are first scaled by a per-tensor power of two w_scale that
+// maps max|w| into [2^13, 2^14) (so that hi keeps 11 bits and lo the next 11 for every weight within 2^-17 of the maximum; smaller
+// ones degrade gracefully through fp16 subnormals: absolute error <= 2^-25 / w_scale).  tail = {max|w| bits, w_scale,
+// 1 / (a_scale * w_scale), 0}: written here, read by the convolution's epilogue.
+constexpr float kF16ActScale = 8.0f;     // activations: |x| < 8188 representable; full 22 bits for |x| >= 2^-6
+__device__ __forceinline__ float f16_weight_scale(uint32_t max_bits) {
+  const float mx = __uint_as_float(max_bits);
+  if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
+  int e;
+  frexpf(mx, &e);                       // mx = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.f, 14 - e);
+}
+__global__ void weight_absmax_kernel(const float* __restrict__ src, int O, int I, int R, int S, int64_t so, int64_t si, int64_t sr,
+                                     int64_t ss, uint32_t* __restrict__ tail) {
+  const int64_t total = (int64_t)O * I * R * S;
+  float m = 0.f;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = idx;
+    const int s2 = t % S; t /= S;
+    const int r = t % R; t /= R;
+    const int i = t % I;
+    const int o = (int)(t / I);
+    m = fmaxf(m, fabsf(src[o * so + i * si + r * sr + s2 * ss]));
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(tail, __float_as_uint(m));     // non-negative floats order like their bits
+}
+__global__ void pack_weight_f16x2_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int O, int I, int R, int S,
+                                         int64_t so, int64_t si, int64_t sr, int64_t ss, int flip, int BN, int nchunks, int ntilesN,
+                                         float* __restrict__ tail) {
+  const int64_t total = (int64_t)R * S * nchunks * ntilesN * 2 * (KC / 8) * BN * 8;
+  const float ws = f16_weight_scale(__float_as_uint(tail[0]));
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = idx;
+    const int e = t & 7; t >>= 3;
+    const int row = t % BN; t /= BN;
+    const int j = t % (KC / 8); t /= (KC / 8);
+    const int part = t & 1; t >>= 1;
+    const int nt = t % ntilesN; t /= ntilesN;
+    const int c = t % nchunks; t /= nchunks;
+    const int tap = (int)t;
+    const int r = tap / S, s = tap % S;
+    const int o = nt * BN + row, i = c * KC + j * 8 + e;
+    uint16_t v = 0;
+    if (o < O && i < I) {
+      const int rr = flip ? R - 1 - r : r, sw = flip ? S - 1 - s : s;
+      const float w = src[o * so + i * si + rr * sr + sw * ss] * ws;
+      const uint32_t hi = pack_f16x2_sat(w, 0.f);
+      v = (uint16_t)(part == 0 ? (hi & 0xffffu) : (pack_f16x2_sat(w - f16lo_to_f32(hi), 0.f) & 0xffffu));
+    }
+    dst[idx] = v;
+  }
+  // tail[1], tail[2] are only read by LATER kernels (the convolution), tail[0] only by this one: no ordering issue inside the grid
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    tail[1] = ws;
+    tail[2] = 1.f / (kF16ActScale * ws);
+    tail[3] = 0.f;
+  }
+}
+
 __global__ void pack_weight_tc_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int R, int S,
                                       int64_t so, int64_t si, int64_t sr, int64_t ss, int flip, int BN, int nchunks, int ntilesN,
                                       int parts) {
@@ -619,10 +710,13 @@ inline uint64_t host_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
 }
 
 // Builds and launches one "virtual unit-stride convolution" (see the file header).
+int64_t packed_elems(int O, int I, int R, int S, int split);
+
 int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int inC, int sub_sy, int sub_sx,
                 const TapSpec* taps, int ntap, const float* wp, const float* bias, float* out, int Hv, int Wv, int64_t o_sn,
                 int64_t o_sy, int64_t o_sx, int64_t o_base, int Cout, double* ssum, double* ssq, int stat_groups, int flags,
                 const viai_norm_bwd_ctx* nb, cudaStream_t stream) {
+  const int wR = g.R, wS = g.S;
   TcParams p;
   memset(&p, 0, sizeof(p));
   if (nb != nullptr) {
@@ -635,6 +729,12 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   // TMA); flags & 3 == 3: the same through eight rank-4 copies.  Both alternatives are kept as cross-checks of the layout.
   p.x3 = (flags & 4) ? 1 : 0;
   p.bx3 = (flags & 8) ? 1 : 0;
+  p.f16 = (flags & 32) ? 1 : 0;
+  VIAI_REQUIRE(!p.f16 || p.bx3, "conv2d_tc: the fp16-pair flag (32) goes with the 16-bit pair product (8)");
+  if (p.f16) {
+    p.a_scale = kF16ActScale;
+    p.oscale = wp + packed_elems(Cout, inC, wR, wS, 2) + 2;
+  }
   p.a_sw128 = (flags & 1) ? 0 : 1;
   VIAI_REQUIRE(!(p.x3 && p.bx3), "conv2d_tc: VIAI_TC_X3 and VIAI_TC_BF16X3 are exclusive");
   VIAI_REQUIRE(!(p.x3 | p.bx3) || p.a_sw128, "conv2d_tc: the 3-term products need the swizzled activation layout");
@@ -718,7 +818,7 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   p.Cout = Cout;
   p.o_sn = o_sn; p.o_sy = o_sy; p.o_sx = o_sx; p.o_base = o_base;
   p.btile_bytes = (uint32_t)p.BN * KC * 4 * (p.x3 ? 2u : 1u);      // bf16 pairs: 2 x 2 bytes per element = the fp32 size
-  p.idesc = p.bx3 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
+  p.idesc = p.f16 ? make_idesc_f16(128, p.BN, 0, 0) : p.bx3 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
   // pipeline depths under the 227 KB shared-memory limit
   const size_t fixed = 1024 /*alignment slack*/ + 66 * 8 + 5 * (size_t)(((Cout + 31) / 32) * 32 + 256) * 4;   // barriers + tmem slot + bias + 4 norm constants
   const size_t budget = 227 * 1024;
@@ -787,16 +887,47 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
 
 extern "C" int viai_tc_bn(int Cout) { return tc_bn(Cout); }
 
-extern "C" int64_t viai_tc_packed_size(int O, int I, int R, int S, int split) {
+namespace {
+int64_t packed_elems(int O, int I, int R, int S, int split) {
   const int BN = tc_bn(O);
   return (int64_t)R * S * ((I + KC - 1) / KC) * ((O + BN - 1) / BN) * BN * KC * (split == 1 ? 2 : 1);
+}
+}  // namespace
+
+// split: 0 tf32, 1 tf32 pairs, 2 bf16 pairs, 3 fp16 pairs (+ a 4-float tail holding the weight scale, see pack_weight_f16x2_kernel)
+extern "C" int64_t viai_tc_packed_size(int O, int I, int R, int S, int split) {
+  return packed_elems(O, I, R, S, split) + (split == 3 ? 4 : 0);
+}
+
+// Threads that saturated a value in an fp16-pair convolution since the last reset (synchronises with the device).
+extern "C" int viai_tc_f16_overflow(int reset, unsigned int* count) {
+  VIAI_REQUIRE(count != nullptr, "tc_f16_overflow: null argument");
+  VIAI_CUDA(cudaMemcpyFromSymbol(count, g_f16_overflow, sizeof(unsigned int)));
+  if (reset && *count) {
+    const unsigned int zero = 0;
+    VIAI_CUDA(cudaMemcpyToSymbol(g_f16_overflow, &zero, sizeof(unsigned int)));
+  }
+  return VIAI_OK;
 }
 
 extern "C" int viai_pack_weight_tc(const float* src, float* dst, int O, int I, int R, int S, int64_t so, int64_t si, int64_t sr,
                                    int64_t ss, int flip, int split, viai_stream_t stream) {
   VIAI_REQUIRE(src && dst && O > 0 && I > 0 && R > 0 && S > 0, "pack_weight_tc: bad arguments");
   const int BN = tc_bn(O), nchunks = (I + KC - 1) / KC, ntilesN = (O + BN - 1) / BN;
-  const int64_t total = viai_tc_packed_size(O, I, R, S, split);
+  const int64_t total = packed_elems(O, I, R, S, split);
+  if (split == 3) {
+    float* tail = dst + total;
+    VIAI_CUDA(cudaMemsetAsync(tail, 0, 4 * sizeof(float), STR(stream)));
+    const int64_t nw = (int64_t)O * I * R * S;
+    weight_absmax_kernel<<<(int)imin64(cdiv(nw, 256), 1024), 256, 0, STR(stream)>>>(src, O, I, R, S, so, si, sr, ss,
+                                                                                   reinterpret_cast<uint32_t*>(tail));
+    VIAI_LAUNCHED();
+    const int blocks = (int)imin64(cdiv(total * 2, 256), 4096);
+    pack_weight_f16x2_kernel<<<blocks, 256, 0, STR(stream)>>>(src, reinterpret_cast<uint16_t*>(dst), O, I, R, S, so, si, sr, ss, flip,
+                                                             BN, nchunks, ntilesN, tail);
+    VIAI_LAUNCHED();
+    return VIAI_OK;
+  }
   if (split == 2) {
     const int blocks = (int)imin64(cdiv(total * 2, 256), 4096);
     pack_weight_bf16x2_kernel<<<blocks, 256, 0, STR(stream)>>>(src, reinterpret_cast<uint16_t*>(dst), O, I, R, S, so, si, sr, ss, flip,

@@ -13,7 +13,14 @@ import os
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 
 # Arithmetic of the convolutions (wherever the geometry is tensor-core shaped; CUDA cores otherwise):
-#   "bf16x3" (default): tcgen05 tensor cores; forward convolutions AND data gradients split both operands into bf16 pairs
+#   "fp16x3" (default): tcgen05 tensor cores; FORWARD convolutions split both operands into fp16 pairs of the scaled value
+#            (x * 8 = hi + lo, w * 2^k = hi + lo: 22 significand bits) and accumulate hi*hi + hi*lo + lo*hi in fp32: product
+#            error ~2^-21 -- fp32-class activations (spectrogram ~1e-5 from the fp32 reference), which matters beyond the
+#            spectrogram bound because every ReLU / LeakyReLU / L1-sign decision of the backward pass is taken on them: a
+#            forward that is 30x less accurate (bf16 pairs) flips ~30x more of those decisions and the gradients land
+#            ~sqrt(30)x further from the exact ones (measured).  Same MMA rate as bf16 pairs.  Data
+#            gradients: bf16 pairs (below); weight gradients: one tf32 product on operands rounded in shared memory;
+#   "bf16x3": tcgen05 tensor cores; forward convolutions AND data gradients split both operands into bf16 pairs
 #            (x = hi + lo) and accumulate hi*hi + hi*lo + lo*hi in fp32 (product error ~2^-17: keeps spectrograms within
 #            the 1e-3 parity bound, and keeps the gradient that is chained through ~30 layers at the reference's own fp32
 #            envelope) at the bf16 MMA rate; weight gradients (one hop off the chain, nothing propagates) use one tf32
@@ -23,8 +30,12 @@ ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 #   "tf32x3": the same 3-term scheme on tf32 pairs (~2^-21 per product, half the MMA rate of bf16x3);
 #   "tf32":  one tf32 product everywhere (what cuDNN does by default on Ampere+; ~1e-2 end to end on this network);
 #   "fp32":  CUDA-core fp32 everywhere (the exact path, also the on-device validator of the other two).
-_PRECISION = os.environ.get("VIAI_PRECISION", "bf16x3")
-_FWD_MODE = {"bf16x3": (2, 8), "tf32x3": (1, 4), "tf32": (0, 0)}   # precision -> (weight packing, viai_conv2d_tc flags)
+_PRECISION = os.environ.get("VIAI_PRECISION", "fp16x3")
+_FWD_MODE = {"fp16x3": (3, 8 | 32), "bf16x3": (2, 8), "tf32x3": (1, 4), "tf32": (0, 0)}   # precision -> (weight packing, viai_conv2d_tc flags)
+# data gradients: the operand is a gradient tensor whose magnitude is not known in advance (1e-8 .. 1e-2), which rules out the
+# fp16 pairs' fixed scale; bf16 pairs have fp32's exponent range, and the backward pass is linear in dy (no activation decisions
+# depend on it), so their 2^-17 per product is ample
+_DGRAD_MODE = {"fp16x3": (2, 8), "bf16x3": (2, 8), "tf32x3": (1, 4), "tf32": (0, 0)}
 _WS = {}
 # Fuse the first pass of a layer's norm backward (sum g, sum g*xhat) into the epilogue of the data-gradient convolution that
 # produces dz (tensor-core path, BatchNorm batch statistics): viai_conv2d_tc_bwd_reduce.  Parity-tested, but OFF by default:
@@ -43,14 +54,47 @@ _FAST_STEM = os.environ.get("VIAI_FAST_STEM", "0") == "1"
 
 def set_precision(p):
     global _PRECISION
-    if p not in ("bf16x3", "tf32x3", "tf32", "fp32"):
-        raise ValueError("precision must be 'bf16x3', 'tf32x3', 'tf32' or 'fp32'")
+    if p not in ("fp16x3", "bf16x3", "tf32x3", "tf32", "fp32"):
+        raise ValueError("precision must be 'fp16x3', 'bf16x3', 'tf32x3', 'tf32' or 'fp32'")
     prev, _PRECISION = _PRECISION, p
     return prev
 
 
 def get_precision():
     return _PRECISION
+
+
+def f16_overflow(reset=True):
+    """Number of split-warp threads that saturated an activation (|x| >= 8188) in an fp16-pair forward convolution since the last
+    reset.  Synchronises with the device: call it where the step's loss is read anyway.  Non-zero means the affected outputs are
+    inaccurate (finite, never inf) -- use VIAI_PRECISION=bf16x3 / tf32x3 for such a model."""
+    n = ctypes.c_uint(0)
+    _lib.check(_lib.lib().viai_tc_f16_overflow(int(reset), ctypes.byref(n)), "tc_f16_overflow")
+    return int(n.value)
+
+
+def check_f16_overflow():
+    n = f16_overflow(True)
+    if n:
+        raise RuntimeError("fp16x3 convolutions saturated activations beyond +-8188 in %d thread(s): results are inaccurate; "
+                           "run with VIAI_PRECISION=bf16x3 (or tf32x3)" % n)
+
+
+# Diagnostic hook of the parity tests: while set to a list, every ReLU / LeakyReLU site of _NormActFn appends the bool tensor
+# (output > 0) == (pre-activation > 0): the decisions the backward pass will take.  None (the default) costs nothing.
+_ACT_TRACE = None
+
+
+class trace_activation_decisions(object):
+    def __enter__(self):
+        global _ACT_TRACE
+        _ACT_TRACE = []
+        return _ACT_TRACE
+
+    def __exit__(self, *exc):
+        global _ACT_TRACE
+        _ACT_TRACE = None
+        return False
 
 
 def set_dgrad_x3(flag):
@@ -164,7 +208,7 @@ def _run_conv(g, x, weight, O_dim, I_dim, bias, y, stats=None, groups=1, forward
                 (L.viai_conv2d_thin_supported(ctypes.byref(g)) and x.data_ptr() % 16 == 0):
             norm_ctx, stats = None, None        # not fusable here: plain data gradient, the caller keeps the standalone pass
     if norm_ctx is not None:
-        split, flags = _FWD_MODE[_PRECISION] if _DGRAD_X3 else (0, 0)
+        split, flags = _DGRAD_MODE[_PRECISION] if _DGRAD_X3 else (0, 0)
         wp = _pack_tc(weight, O_dim, I_dim, split)
         nb = _lib.NormBwdCtx(norm_ctx["y"].data_ptr(), _ptr(norm_ctx["mean"]), _ptr(norm_ctx["invstd"]), _ptr(norm_ctx["gamma"]),
                              _ptr(norm_ctx["beta"]), norm_ctx["act"], norm_ctx["slope"])
@@ -176,7 +220,7 @@ def _run_conv(g, x, weight, O_dim, I_dim, bias, y, stats=None, groups=1, forward
         _lib.check(L.viai_conv2d_thin(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _stream()), "conv2d_thin")
         return False
     if _PRECISION != "fp32" and L.viai_conv2d_tc_supported(ctypes.byref(g)):
-        split, flags = _FWD_MODE[_PRECISION] if (forward or _DGRAD_X3) else (0, 0)
+        split, flags = _FWD_MODE[_PRECISION] if forward else _DGRAD_MODE[_PRECISION] if _DGRAD_X3 else (0, 0)
         wp = _pack_tc(weight, O_dim, I_dim, split)
         _lib.check(L.viai_conv2d_tc(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _p(stats[0]) if stats is not None else None,
                                     _p(stats[1]) if stats is not None else None, groups, flags, _stream()), "conv2d_tc")
@@ -373,6 +417,8 @@ class _NormActFn(torch.autograd.Function):
         out = torch.empty_like(y)
         _lib.check(L.viai_norm_act_fwd(_p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta), act, slope,
                                        _p(out), _stream()), "norm_act_fwd")
+        if _ACT_TRACE is not None and act in (ACT_RELU, ACT_LRELU):
+            _ACT_TRACE.append(out > 0)
         ctx.save_for_backward(y, mean, invstd, gamma, beta)
         ctx.cfg = (norm, groups, rpg, act, slope, training or norm != "bn")
         ctx.targets = (grad_target(gamma), grad_target(beta))

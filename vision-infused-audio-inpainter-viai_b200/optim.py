@@ -80,7 +80,12 @@ def shard_batch(n_items, rank, world_size):
         raise ValueError("rank %d outside world of %d" % (rank, world_size))
     chunk = -(-n_items // world_size)          # torch.chunk semantics: ceil-sized leading chunks
     b = min(rank * chunk, n_items)
-    return b, min(b + chunk, n_items)
+    e = min(b + chunk, n_items)
+    if e <= b:
+        # torch.chunk would hand this rank nothing (e.g. 5 samples over 4 ranks -> 2,2,1,0): the kernels need n > 0 and a rank
+        # that skips its all-reduce would hang the others, so refuse loudly instead
+        raise ValueError("shard_batch: a global batch of %d leaves rank %d of %d without samples" % (n_items, rank, world_size))
+    return b, e
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -122,13 +127,20 @@ class FusedAdam(torch.optim.Optimizer):
         """One NCCL all-reduce (sum) over the whole bucket; the 1/world_size is folded into the Adam kernel."""
         self.bucket.all_reduce()
 
+    def sync_lr(self):
+        """Copies ``param_groups[0]['lr']`` into the device scalar the Adam kernel reads.  ``step()`` does it itself; a captured
+        step never runs ``step()`` again, so ``GanTrainer.replay`` / ``WaveNetTrainer.replay`` call this before launching their
+        graphs (LR schedules, ``load_state_dict`` after capture)."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_host:
+            self.lr_dev.fill_(lr)
+            self._lr_host = lr
+
     @torch.no_grad()
     def step(self, closure=None):
         g = self.param_groups[0]
-        lr = float(g["lr"])
-        if lr != self._lr_host:           # LR schedules: refresh the device scalar (outside any captured graph)
-            self.lr_dev.fill_(lr)
-            self._lr_host = lr
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()                # LR schedules: refresh the device scalar (outside any captured graph)
         L = _lib.lib()
         b1, b2 = g["betas"]
         _lib.check(L.viai_adam_step(_p(self.flat_param), _p(self.flat_grad), _p(self.flat_m), _p(self.flat_v),

@@ -41,9 +41,26 @@ class GanTrainer(object):
         self.optimizer_D = FusedAdam(self.netD.parameters(), lr=lr, betas=(b1, 0.999), world_size=world_size,
                                      process_group=process_group)
         self.lambda_L1 = float(getattr(hparams, "lambda_L1", 100.0))
+        self.process_group = process_group
+        self.sync_replicas()
         self._graphs = None
         self._static = None
         self.launches_per_step = None
+
+    def sync_replicas(self, src=0):
+        """Identical weights AND buffers (BatchNorm running statistics) on every rank, from rank ``src`` -- what
+        nn.DataParallel's replicate does every step in the reference (utils/model_util.py:137).  No-op for one rank."""
+        if self.world_size <= 1:
+            return
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("GanTrainer(world_size=%d) needs an initialised torch.distributed process group" % self.world_size)
+        for opt in (self.optimizer_G, self.optimizer_D):
+            opt.bucket.broadcast_params(src)
+        mods = [self.Mel_Encoder, self.Mel_Decoder, self.netD] + ([self.VideoEncoder] if self.VideoEncoder is not None else [])
+        for m in mods:
+            for b in m.buffers():
+                dist.broadcast(b, src, group=self.process_group)
 
     # ---- the three segments of a step; NCCL all-reduces sit between them -------------------------------------
     def _seg_forward_and_d_backward(self, mel, mask, video=None, flow=None):
@@ -108,12 +125,31 @@ class GanTrainer(object):
         return self._outputs()
 
     # ---- CUDA-graph step --------------------------------------------------------------------------------------
-    def capture(self, mel, mask, video=None, flow=None, warmup=2):
+    def _modules(self):
+        return [self.Mel_Encoder, self.Mel_Decoder, self.netD] + ([self.VideoEncoder] if self.VideoEncoder is not None else [])
+
+    def _snapshot(self):
+        opts = [(o.flat_param.clone(), o.flat_m.clone(), o.flat_v.clone(), o.step_dev.clone()) for o in (self.optimizer_G, self.optimizer_D)]
+        return opts, [b.clone() for m in self._modules() for b in m.buffers()]
+
+    def _restore(self, snap):
+        opts, bufs = snap
+        for o, (p, m, v, s) in zip((self.optimizer_G, self.optimizer_D), opts):
+            o.flat_param.copy_(p); o.flat_m.copy_(m); o.flat_v.copy_(v); o.step_dev.copy_(s)
+        for b, saved in zip([b for m in self._modules() for b in m.buffers()], bufs):
+            b.copy_(saved)
+        ops.weights_updated()
+
+    def capture(self, mel, mask, video=None, flow=None, warmup=2, preserve_state=False):
         """Captures the step into CUDA graphs (one graph per segment so that the NCCL all-reduces stay eager when
-        world_size > 1; a single graph otherwise).  ``mel``/``mask`` become the static input buffers."""
+        world_size > 1; a single graph otherwise).  ``mel``/``mask`` become the static input buffers.  The warm-up steps are
+        real optimisation steps; ``preserve_state`` puts weights, Adam moments / step counters and BatchNorm buffers back
+        afterwards, so that the first ``replay()`` is the first step (what ``AudioModel.optimize_parameters`` needs)."""
+        self._graphs = None                  # release a previous capture's memory pool before allocating the new one
         self._static = dict(mel=mel.clone(), mask=mask.clone(),
                             video=None if video is None else video.clone(), flow=None if flow is None else flow.clone())
         st = self._static
+        snap = self._snapshot() if preserve_state else None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -124,6 +160,9 @@ class GanTrainer(object):
         # Drop every autograd graph built during warm-up: the AccumulateGrad nodes they keep alive are bound to the
         # warm-up stream, and a backward inside the capture would then wait on that (uncaptured) stream.
         self._drop_step_state()
+        if snap is not None:
+            self._restore(snap)
+            torch.cuda.synchronize()
         n0 = _lib.launch_count()
         ops.pack_cache_begin()
         if self.world_size == 1:
@@ -188,6 +227,8 @@ class GanTrainer(object):
             st["video"].copy_(video, non_blocking=True)
         if flow is not None:
             st["flow"].copy_(flow, non_blocking=True)
+        self.optimizer_D.sync_lr()          # a changed param_groups[0]['lr'] reaches the captured Adam kernels
+        self.optimizer_G.sync_lr()
         if len(self._graphs) == 1:
             self._graphs[0].replay()
         else:

@@ -58,6 +58,13 @@ class WaveNetTrainer(object):
             out[names[id(p)]] = self.ema_flat[o:o + p.numel()].view(p.shape).clone()
         return out
 
+    def load_ema_state_dict(self, sd):
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        for p, o in zip(self.optimizer._plist, self.optimizer.bucket.offsets):
+            n = names[id(p)]
+            if n in sd:
+                self.ema_flat[o:o + p.numel()].copy_(sd[n].reshape(-1))
+
     # ---- eager / captured step -----------------------------------------------------------------------------------------
     def train_step(self, x, y, c, mask):
         """x (B,1,T) input, y (B,T,1) target (the same signal for raw audio), c (B,cin,T/hop), mask (B,T,1) or (B,T) of {0,1}.
@@ -108,6 +115,7 @@ class WaveNetTrainer(object):
         for k, v in (("x", x), ("y", y), ("c", c), ("mask", mask)):
             if v is not None:
                 st[k].copy_(v.reshape(st[k].shape), non_blocking=True)
+        self.optimizer.sync_lr()
         self._graphs[0].replay()
         if len(self._graphs) > 1:
             self.optimizer.all_reduce_grads()

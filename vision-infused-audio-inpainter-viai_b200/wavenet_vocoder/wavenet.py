@@ -203,9 +203,10 @@ class WaveNet(nn.Module):
         if nC <= 0:
             raise RuntimeError("unsupported WaveNet configuration for the synthesis kernel (R=%d G=%d S=%d C=%d K=%d O=%d B=%d)"
                                % (R, G, S, C, K, O, B))
-        if self._packed is None or self._packed["nC"] != nC:
-            self._packed = self.pack_for_synthesis(nC)
-        pk = self._packed
+        # Re-linearised on every call, like the reference (clear_buffer() on entry, wavenet.py:263 -> conv.py:48-62): the weights
+        # may have been changed by an optimizer step, load_state_dict or make_generation_fast_ since the last synthesis, and
+        # packing 99 MB costs ~1 ms against seconds of synthesis.
+        pk = self._packed = self.pack_for_synthesis(nC)
         nm = O // 3
         if uniforms is None:
             uniforms = torch.empty((T, B, nm + 1), device=dev).uniform_(1e-5, 1.0 - 1e-5)
