@@ -1,16 +1,20 @@
-"""Import the UNMODIFIED reference modules from /root/reference (this container only).
+"""Import the UNMODIFIED reference modules: from /root/reference (this container) or, where that does not exist (the GPU
+box), from the byte-identical copy ``oracle/build_ref.py`` vendored into ``oracle/_ref/``.
 
-TEST INFRASTRUCTURE ONLY -- used by ``oracle/make_golden.py`` and by the ``not gpu`` tests that pin
-the oracle restatement against the real reference classes.  /root/reference does not exist on the
-GPU box; nothing reachable from ``-m gpu`` tests, ``smoke()`` or ``bench.py`` may call this.
+TEST / BASELINE INFRASTRUCTURE ONLY -- used by ``oracle/make_golden.py``, by the ``not gpu`` tests that pin the oracle
+restatement against the real reference classes, and by the CPU-baseline legs of ``bench.py`` (``oracle/ref_step.py``).  Nothing
+under the product package imports it; ``-m gpu`` tests, ``smoke()`` and bench.py's GPU arm never read /root/reference.
 """
 import importlib
 import os
 import sys
 import types
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("VIAI_REFERENCE_ROOT", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "networks")) and os.path.isdir(os.path.join(_HERE, "_ref", "networks")):
+    REFERENCE_ROOT = os.path.join(_HERE, "_ref")
+_SHIMS = os.path.join(_HERE, "shims")
 
 
 def available():

@@ -193,6 +193,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       rbe_s[i] = (p.rbeta != nullptr && in) ? __ldg(&p.rbeta[i]) : 0.f;
     }
   }
+  if (MODE == 2 && p.f16) {
+    // The split warps rewrite whole stages, including the alignment gaps between sub-patches that no TMA copy ever fills:
+    // zero them once so that uninitialised shared memory cannot trip the fp16 saturation counter.
+    const uint32_t n16 = (uint32_t)p.SA * a_stage / 16u;
+    for (uint32_t i = threadIdx.x; i < n16; i += NTHREADS) reinterpret_cast<uint4*>(slabA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy zeros before the async-proxy (TMA) writes
+  }
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();

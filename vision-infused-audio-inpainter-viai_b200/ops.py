@@ -36,6 +36,9 @@ _FWD_MODE = {"fp16x3": (3, 8 | 32), "bf16x3": (2, 8), "tf32x3": (1, 4), "tf32": 
 # fp16 pairs' fixed scale; bf16 pairs have fp32's exponent range, and the backward pass is linear in dy (no activation decisions
 # depend on it), so their 2^-17 per product is ample
 _DGRAD_MODE = {"fp16x3": (2, 8), "bf16x3": (2, 8), "tf32x3": (1, 4), "tf32": (0, 0)}
+if os.environ.get("VIAI_DGRAD") == "tf32x3":          # experiment knob: 2^-21 data gradients at half the MMA rate
+    _DGRAD_MODE = {k: (1, 4) for k in _DGRAD_MODE}
+_WGRAD_FP32 = os.environ.get("VIAI_WGRAD") == "fp32"  # experiment knob: CUDA-core fp32 weight gradients
 _WS = {}
 # Fuse the first pass of a layer's norm backward (sum g, sum g*xhat) into the epilogue of the data-gradient convolution that
 # produces dz (tensor-core path, BatchNorm batch statistics): viai_conv2d_tc_bwd_reduce.  Parity-tested, but OFF by default:
@@ -315,7 +318,7 @@ class _ConvFn(torch.autograd.Function):
                 ws = _workspace(dy.device, L.viai_wgrad_thin_workspace(ctypes.byref(g)))
                 _lib.check(L.viai_conv2d_wgrad_thin(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1), dw.stride(2),
                                                     dw.stride(3), int(wt is not None), _p(ws), _stream()), "conv2d wgrad_thin")
-            elif _PRECISION != "fp32" and L.viai_conv2d_wgrad_tc_supported(ctypes.byref(g)):
+            elif _PRECISION != "fp32" and not _WGRAD_FP32 and L.viai_conv2d_wgrad_tc_supported(ctypes.byref(g)):
                 ws = _workspace(dy.device, L.viai_wgrad_tc_workspace(ctypes.byref(g)))
                 _lib.check(L.viai_conv2d_wgrad_tc(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1), dw.stride(2),
                                                   dw.stride(3), int(wt is not None), _p(ws), _stream()), "conv2d wgrad_tc")
