@@ -83,6 +83,64 @@ def check_f16_overflow():
                            "run with VIAI_PRECISION=bf16x3 (or tf32x3)" % n)
 
 
+# Measurement hook of bench.py: while set to a list, every convolution / normalisation / resampling operator brackets its launches
+# with CUDA events on the launching stream and appends (family, geometry key, algorithmic flops, algorithmic bytes, start, end).
+# None (the default) costs one comparison per op.
+_OP_LOG = None
+
+
+class time_ops(object):
+    """``with ops.time_ops() as log: step()`` -> after a device synchronise, ``summarize_ops(log)`` gives per-(family, geometry)
+    launch counts, total device time, algorithmic FLOPs and bytes of one eager step."""
+
+    def __enter__(self):
+        global _OP_LOG
+        _OP_LOG = []
+        return _OP_LOG
+
+    def __exit__(self, *exc):
+        global _OP_LOG
+        _OP_LOG = None
+        return False
+
+
+class _op_timer(object):
+    __slots__ = ("fam", "key", "flops", "nbytes", "e0")
+
+    def __init__(self, fam, key, flops, nbytes):
+        self.fam, self.key, self.flops, self.nbytes = fam, key, flops, nbytes
+
+    def __enter__(self):
+        if _OP_LOG is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _OP_LOG is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _OP_LOG.append((self.fam, self.key, self.flops, self.nbytes, self.e0, e1))
+        return False
+
+
+def summarize_ops(log):
+    """{(family, key): dict(launches, ms, flops, bytes)} from a ``time_ops`` log (call after torch.cuda.synchronize())."""
+    out = {}
+    for fam, key, flops, nbytes, e0, e1 in log:
+        d = out.setdefault((fam, key), dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        d["launches"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += flops
+        d["bytes"] += nbytes
+    return out
+
+
+def _conv_key(N, H, W, C, Ho, Wo, Cout, R, S, stride, transposed):
+    return "%s%d->%d %dx%d s%d,%d in %dx%dx%d out %dx%d" % ("convT " if transposed else "conv ", C, Cout, R, S, stride[0], stride[1],
+                                                           N, H, W, Ho, Wo)
+
+
 # Diagnostic hook of the parity tests: while set to a list, every ReLU / LeakyReLU site of _NormActFn appends the bool tensor
 # (output > 0) == (pre-activation > 0): the decisions the backward pass will take.  None (the default) costs nothing.
 _ACT_TRACE = None
@@ -262,9 +320,13 @@ class _ConvFn(torch.autograd.Function):
         stats = None
         if stat_groups > 0:
             stats = torch.empty((2, stat_groups * Cout), device=x.device, dtype=torch.float64)
-        if not _run_conv(g, x, weight, od, idim, bias, y, stats, stat_groups, forward=True) and stats is not None:
-            _lib.check(L.viai_channel_stats(_p(y), (N * Ho * Wo) // stat_groups, stat_groups, Cout, _p(stats[0]), _p(stats[1]),
-                                            _stream()), "channel_stats")
+        macs = (N * Ho * Wo * Cout * C * R * S) if not transposed else (N * H * W * C * Cout * R * S)
+        key = _conv_key(N, H, W, C, Ho, Wo, Cout, R, S, stride, transposed)
+        with _op_timer("conv_fwd", key, 2.0 * macs, 4.0 * (x.numel() + y.numel() + weight.numel())):
+            if not _run_conv(g, x, weight, od, idim, bias, y, stats, stat_groups, forward=True) and stats is not None:
+                _lib.check(L.viai_channel_stats(_p(y), (N * Ho * Wo) // stat_groups, stat_groups, Cout, _p(stats[0]), _p(stats[1]),
+                                                _stream()), "channel_stats")
+        ctx.op = (key, 2.0 * macs)
         ctx.save_for_backward(x, weight)
         ctx.cfg = (stride, padding, transposed, bias is not None)
         ctx.targets = (grad_target(weight), grad_target(bias))
@@ -295,12 +357,13 @@ class _ConvFn(torch.autograd.Function):
             if nc is not None and (nc["y"].shape != x.shape or not nc["y"].is_contiguous() or tuple(stride) != (1, 1)):
                 nc = None
             bst = torch.empty((2, C), device=x.device, dtype=torch.float64) if nc is not None else None
-            if not transposed:       # dgrad of Conv2d: transposed gather with wp[o=ci][r][s][i=co]
-                fused = _run_conv(_geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 1), dy, weight, 1, 0, None, dx, bst,
-                                  norm_ctx=nc)
-            else:                    # dgrad of ConvTranspose2d: forward gather with wp[o=ci][r][s][i=co]
-                fused = _run_conv(_geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0), dy, weight, 0, 1, None, dx, bst,
-                                  norm_ctx=nc)
+            with _op_timer("conv_dgrad", ctx.op[0], ctx.op[1], 4.0 * (x.numel() + dy.numel() + weight.numel())):
+                if not transposed:       # dgrad of Conv2d: transposed gather with wp[o=ci][r][s][i=co]
+                    fused = _run_conv(_geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 1), dy, weight, 1, 0, None, dx, bst,
+                                      norm_ctx=nc)
+                else:                    # dgrad of ConvTranspose2d: forward gather with wp[o=ci][r][s][i=co]
+                    fused = _run_conv(_geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0), dy, weight, 0, 1, None, dx, bst,
+                                      norm_ctx=nc)
             if nc is not None and fused:
                 dx._viai_bwd_stats = (bst, nc["token"])      # consumed by the producing layer's _NormActFn.backward
         wt, bt = ctx.targets
@@ -312,19 +375,20 @@ class _ConvFn(torch.autograd.Function):
             else:                    # U = x (A = Cin_t), G = dOut (B = Cout_t)
                 g = _geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0)
                 U, G = x, dy
-            if _FAST_STEM and not transposed and C <= 4 and _PRECISION != "fp32" and Cout % 4 == 0 and Cout >= 16 and R * S > 1:
-                _stem_wgrad(g, x, dy, dw, wt is not None)
-            elif L.viai_conv2d_wgrad_thin_supported(ctypes.byref(g)) and U.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0:
-                ws = _workspace(dy.device, L.viai_wgrad_thin_workspace(ctypes.byref(g)))
-                _lib.check(L.viai_conv2d_wgrad_thin(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1), dw.stride(2),
-                                                    dw.stride(3), int(wt is not None), _p(ws), _stream()), "conv2d wgrad_thin")
-            elif _PRECISION != "fp32" and not _WGRAD_FP32 and L.viai_conv2d_wgrad_tc_supported(ctypes.byref(g)):
-                ws = _workspace(dy.device, L.viai_wgrad_tc_workspace(ctypes.byref(g)))
-                _lib.check(L.viai_conv2d_wgrad_tc(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1), dw.stride(2),
-                                                  dw.stride(3), int(wt is not None), _p(ws), _stream()), "conv2d wgrad_tc")
-            else:
-                _lib.check(L.viai_conv2d_wgrad_simt(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1),
-                                                    dw.stride(2), dw.stride(3), int(wt is not None), _stream()), "conv2d wgrad")
+            with _op_timer("conv_wgrad", ctx.op[0], ctx.op[1], 4.0 * (x.numel() + dy.numel() + weight.numel())):
+                if _FAST_STEM and not transposed and C <= 4 and _PRECISION != "fp32" and Cout % 4 == 0 and Cout >= 16 and R * S > 1:
+                    _stem_wgrad(g, x, dy, dw, wt is not None)
+                elif L.viai_conv2d_wgrad_thin_supported(ctypes.byref(g)) and U.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0:
+                    ws = _workspace(dy.device, L.viai_wgrad_thin_workspace(ctypes.byref(g)))
+                    _lib.check(L.viai_conv2d_wgrad_thin(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1), dw.stride(2),
+                                                        dw.stride(3), int(wt is not None), _p(ws), _stream()), "conv2d wgrad_thin")
+                elif _PRECISION != "fp32" and not _WGRAD_FP32 and L.viai_conv2d_wgrad_tc_supported(ctypes.byref(g)):
+                    ws = _workspace(dy.device, L.viai_wgrad_tc_workspace(ctypes.byref(g)))
+                    _lib.check(L.viai_conv2d_wgrad_tc(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1), dw.stride(2),
+                                                      dw.stride(3), int(wt is not None), _p(ws), _stream()), "conv2d wgrad_tc")
+                else:
+                    _lib.check(L.viai_conv2d_wgrad_simt(ctypes.byref(g), _p(U), _p(G), _p(dw), dw.stride(0), dw.stride(1),
+                                                        dw.stride(2), dw.stride(3), int(wt is not None), _stream()), "conv2d wgrad")
             if wt is not None:
                 dw = None            # accumulated straight into the gradient bucket
         if has_bias and ctx.needs_input_grad[2]:
@@ -418,8 +482,9 @@ class _NormActFn(torch.autograd.Function):
                 invstd = torch.empty(C, device=dev, dtype=torch.float32)
                 _lib.check(L.viai_rsqrt_eps(_p(running_var), C, eps, _p(invstd), _stream()), "rsqrt_eps")
         out = torch.empty_like(y)
-        _lib.check(L.viai_norm_act_fwd(_p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta), act, slope,
-                                       _p(out), _stream()), "norm_act_fwd")
+        with _op_timer("norm_act_fwd", "%dx%dx%dx%d" % (N, H, W, C), 0.0, 8.0 * y.numel()):
+            _lib.check(L.viai_norm_act_fwd(_p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta), act, slope,
+                                           _p(out), _stream()), "norm_act_fwd")
         if _ACT_TRACE is not None and act in (ACT_RELU, ACT_LRELU):
             _ACT_TRACE.append(out > 0)
         ctx.save_for_backward(y, mean, invstd, gamma, beta)
@@ -444,15 +509,16 @@ class _NormActFn(torch.autograd.Function):
         gt, bt = ctx.targets
         s = None
         pre = getattr(dz, "_viai_bwd_stats", None)
-        if pre is not None and ctx.token is not None and pre[1] is ctx.token:
-            s = pre[0]               # (sum g, sum g*xhat) came out of the epilogue of the convolution that produced dz
-        elif mean is not None:
-            s = torch.empty((2, groups * C), device=y.device, dtype=torch.float64)
-            _lib.check(L.viai_norm_act_bwd_reduce(_p(dz), _p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta),
-                                                  act, slope, _p(s[0]), _p(s[1]), _stream()), "norm_act_bwd_reduce")
-        _lib.check(L.viai_norm_act_bwd_apply(_p(dz), _p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta), act,
-                                             slope, _p(s[0]) if s is not None else None, _p(s[1]) if s is not None else None,
-                                             _p(dy), None, None, _stream()), "norm_act_bwd_apply")
+        with _op_timer("norm_act_bwd", "x".join(str(d) for d in y.shape), 0.0, 12.0 * y.numel()):
+            if pre is not None and ctx.token is not None and pre[1] is ctx.token:
+                s = pre[0]               # (sum g, sum g*xhat) came out of the epilogue of the convolution that produced dz
+            elif mean is not None:
+                s = torch.empty((2, groups * C), device=y.device, dtype=torch.float64)
+                _lib.check(L.viai_norm_act_bwd_reduce(_p(dz), _p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta),
+                                                      act, slope, _p(s[0]), _p(s[1]), _stream()), "norm_act_bwd_reduce")
+            _lib.check(L.viai_norm_act_bwd_apply(_p(dz), _p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta), act,
+                                                 slope, _p(s[0]) if s is not None else None, _p(s[1]) if s is not None else None,
+                                                 _p(dy), None, None, _stream()), "norm_act_bwd_apply")
         dgamma = dbeta = None
         if s is not None and gamma is not None and ctx.needs_input_grad[1]:
             dgamma = gt if gt is not None else torch.empty_like(gamma)

@@ -46,6 +46,22 @@ class GanTrainer(object):
         self._graphs = None
         self._static = None
         self.launches_per_step = None
+        # Measurement aid (bench.py): set to {} before an EAGER step and the step fills it with CUDA events bracketing the
+        # generator's kernels -- "g_fwd" (encoder [+ visual encoder] + decoder forward) and "g_bwd" (from the moment d loss / d fake
+        # is complete to the end of the generator's backward), "v_fwd" / "v_bwd" for the visual encoder alone.
+        self.segment_events = None
+
+    def segment_ms(self):
+        """{segment: milliseconds} of the last eager step run with ``segment_events = {}`` (synchronises)."""
+        torch.cuda.synchronize()
+        ev = self.segment_events or {}
+        return {k[:-2]: ev[k].elapsed_time(ev[k[:-2] + "_1"]) for k in ev if k.endswith("_0") and (k[:-2] + "_1") in ev}
+
+    def _mark(self, name):
+        if self.segment_events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.segment_events[name] = e
 
     def sync_replicas(self, src=0):
         """Identical weights AND buffers (BatchNorm running statistics) on every rank, from rank ``src`` -- what
@@ -68,13 +84,19 @@ class GanTrainer(object):
         H = self.hparams.cin_channels
         real = mel.reshape(B, 1, H, -1)
         self.real = real
+        self._mark("g_fwd_0")
         masked = ops.mul(real.reshape(B, H, -1, 1), mask.reshape(B, H, -1, 1)).reshape(real.shape)
         feats = self.Mel_Encoder(masked)
         if self.uses_video:
+            self._mark("v_fwd_0")
             vnet = self.VideoEncoder(video, flow)
+            self._mark("v_fwd_1")
+            if self.segment_events is not None and vnet.requires_grad:
+                vnet.register_hook(lambda g: self._mark("v_bwd_0"))
             self.fake = self.Mel_Decoder(feats, real.shape, vnet)
         else:
             self.fake = self.Mel_Decoder(feats, real.shape)
+        self._mark("g_fwd_1")
         set_requires_grad(self.netD, True)
         self.optimizer_D.zero_grad()
         pred_fake = self.netD(self.fake.detach())
@@ -92,7 +114,12 @@ class GanTrainer(object):
         self.loss_G_GAN = self.criterionGAN(pred_fake, True)
         self.loss_L1 = self.criterionL1(self.fake, self.real)
         self.loss_G = ops.lincomb2(self.loss_G_GAN, 1.0, self.loss_L1, self.lambda_L1)
+        if self.segment_events is not None:
+            self.fake.register_hook(lambda g: self._mark("g_bwd_0"))     # fires once d loss / d fake is complete (D's part is done)
         self.loss_G.backward()
+        self._mark("g_bwd_1")
+        if self.segment_events is not None and "v_bwd_0" in self.segment_events:
+            self.segment_events["v_bwd_1"] = self.segment_events["g_bwd_1"]
         set_requires_grad(self.netD, True)
 
     def _seg_g_update(self):
