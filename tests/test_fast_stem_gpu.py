@@ -1,6 +1,5 @@
-"""Opt-in fast paths of the ResNet stem (VIAI_FAST_STEM=1): viai_im2col, the im2col + tensor-core 1x1 weight gradient of the
-7x7 stem convolution, and the max-pool backward that reads the forward output.  Skipped unless the flag is set (the flag is read
-when viai_b200.ops is imported):   VIAI_FAST_STEM=1 python -m pytest tests/test_fast_stem_gpu.py -m gpu"""
+"""Fast paths of the ResNet stem (default on; VIAI_FAST_STEM=0 disables them and skips this file): viai_im2col, the im2col +
+tensor-core 1x1 weight gradient of the 7x7 stem convolution, and the max-pool backward that reads the forward output."""
 import ctypes
 import math
 import os
@@ -12,8 +11,8 @@ import torch.nn.functional as F
 import viai_test_helpers as H
 
 pytestmark = pytest.mark.gpu
-if os.environ.get("VIAI_FAST_STEM", "0") != "1":
-    pytest.skip("opt-in paths: set VIAI_FAST_STEM=1", allow_module_level=True)
+if os.environ.get("VIAI_FAST_STEM", "1") != "1":
+    pytest.skip("the stem fast paths are disabled (VIAI_FAST_STEM=0)", allow_module_level=True)
 
 
 @pytest.mark.parametrize("cfg", [(2, 3, 7, 7, 2, 3, 30, 26), (3, 2, 7, 7, 2, 3, 224, 224), (2, 4, 3, 3, 1, 1, 9, 8), (1, 3, 5, 3, 2, 1, 11, 13)])

@@ -48,11 +48,10 @@ _FUSE_BWD_REDUCE = os.environ.get("VIAI_FUSE_BWD_REDUCE", "0") == "1"
 _DGRAD_X3 = os.environ.get("VIAI_DGRAD", "x3") != "tf32"
 
 
-# Opt-in fast paths of the ResNet stem (VIAI_FAST_STEM=1; see include/viai_b200.h): the 7x7 / Cin <= 4 weight gradient as im2col +
-# the tensor-core 1x1 weight gradient, and the max-pool backward that reads the forward output.  OFF by default: written from the
-# C3 per-kernel table after this round's GPU budget was spent, validated on the CPU only (host logic) -- to be switched on after a
-# B200 run of tests/test_fast_stem_gpu.py.
-_FAST_STEM = os.environ.get("VIAI_FAST_STEM", "0") == "1"
+# Fast paths of the ResNet stem (see include/viai_b200.h): the 7x7 / Cin <= 4 weight gradient as im2col + the tensor-core 1x1 weight
+# gradient, and the max-pool backward that reads the forward output.  Validated on B200 (tests/test_fast_stem_gpu.py, round 2) and
+# ON by default; VIAI_FAST_STEM=0 restores the CUDA-core stem weight gradient / gather-form max-pool backward.
+_FAST_STEM = os.environ.get("VIAI_FAST_STEM", "1") == "1"
 
 
 def set_precision(p):
