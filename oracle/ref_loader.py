@@ -30,10 +30,18 @@ def load(normlayer=None, cin_channels=None):
     for p in (_SHIMS, REFERENCE_ROOT):
         if p not in sys.path:
             sys.path.insert(0, p)
-    # the reference imports two loader modules it never uses on this path
-    for name in ("Data_loaders.mel_loader", "Data_loaders.AV_loader"):
+    # the reference imports two loader modules it never uses on this path (``from Data_loaders import mel_loader``): stand-ins
+    # for them and for their parent package (the vendored copy has no Data_loaders directory at all)
+    pkg = sys.modules.get("Data_loaders")
+    if pkg is None or not hasattr(pkg, "__path__"):
+        pkg = types.ModuleType("Data_loaders")
+        pkg.__path__ = []
+        sys.modules["Data_loaders"] = pkg
+    for short in ("mel_loader", "AV_loader"):
+        name = "Data_loaders." + short
         if name not in sys.modules:
             sys.modules[name] = types.ModuleType(name)
+        setattr(pkg, short, sys.modules[name])
     import Options_inpainting
     if normlayer is not None:
         Options_inpainting.Inpainting_Config.normlayer = normlayer
