@@ -335,6 +335,34 @@ def run_c4(ctx, pk, T=160000):
     return res
 
 
+def run_stft(ctx, pk, seconds=3600):
+    """STFT -> mel front end (utils/audio.py:70-75): one launch over an hour of 16 kHz audio (T = 57.6 M samples, 230 MB: larger than
+    L2), frames/s and algorithmic HBM bytes (hop * 4 bytes of new samples read + n_mels * 4 bytes written per frame)."""
+    torch = ctx.torch
+    from viai_b200.utils import audio
+    T = 16000 * seconds
+    y = torch.rand(T, device="cuda") * 2 - 1
+    for _ in range(2):
+        mel = audio.melspectrogram_cuda(y)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        mel = audio.melspectrogram_cuda(y)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    M = mel.size(1)
+    nbytes = 4.0 * (T + mel.numel())
+    return {"metric": "STFT->mel frames/sec", "value": M / (ms * 1e-3), "unit": "frames/s", "frames": M, "ms": ms,
+            "config": "fft 1024 / hop 160 / 80 mels, one waveform of %d s at 16 kHz, fused frame + window + rFFT + |.| + mel + dB + normalise" % seconds,
+            "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": nbytes / (ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
+                         "algorithmic_bytes_per_frame": nbytes / M, "flops_per_frame": 35e3,
+                         "note": "35 kFLOP per ~1 kB frame: the kernel is fp32-issue / shared-memory bound (one warp per frame, three "
+                                 "radix-8 passes), not HBM bound"}}
+
+
 def run_c5(ctx, steps=8):
     """Free-form (seeded random-walk stroke) masks at 128 / 256 / 512 square mels, B=32 per GPU, one captured step per size."""
     torch = ctx.torch
@@ -473,6 +501,13 @@ def main():
             c3 = run_c3(ctx, pk)
         except Exception as e:
             c3 = {"error": repr(e)}
+    stft = None
+    if rank == 0 and world == 1 and extra:
+        try:
+            stft = run_stft(ctx, pk)
+        except Exception as e:
+            stft = {"error": repr(e)}
+        ctx.free()
     if rank == 0 and world == 1 and not args.no_wavenet:
         try:
             c4 = run_c4(ctx, pk)
@@ -505,7 +540,7 @@ def main():
                         "h2d_bytes_per_step": 2 * mel_h.numel() * 4, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches) * args.steps, "launches_per_step": int(launches), "f16_saturations": overflow,
                 "clocks": clocks, "sustained": sustained, "roofline": roof, "generator_stack": gen, "whole_step": whole, "top_ops": top,
-                "strong": strong, "cpu_baseline": cpu, "c3": c3, "c4": c4, "c5": c5, "wavenet": c4}
+                "strong": strong, "cpu_baseline": cpu, "c3": c3, "c4": c4, "c5": c5, "stft": stft, "wavenet": c4}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -7,6 +7,7 @@
 // factors staged once per CTA in shared memory; magnitudes stay in shared memory; each warp then owns n_mels/8 filterbank
 // rows and walks only the non-zero span of its triangular filters.  The FR x n_mels results are staged in shared memory so
 // that every global store is a full 32-byte sector of one output row.
+#include <stdlib.h>
 #include "common.cuh"
 using namespace viai;
 
@@ -94,6 +95,200 @@ stft_mel_kernel(const float* __restrict__ y, int64_t T, int pad_left, int N, int
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Fast path for fft_size = 1024: ONE WARP PER FRAME, no block-wide barrier in the frame loop.
+//   * the real frame x[0..1023] is transformed as the 512-point complex sequence z[n] = x[2n] + i x[2n+1] (a float2 load per
+//     element, straight from global memory with the window applied: consecutive lanes read consecutive float2s), followed by the
+//     real-input split  F[k] = (Z[k] + conj Z[512-k]) / 2 - i W_1024^k (Z[k] - conj Z[512-k]) / 2;
+//   * 512 = 8 x 8 x 8: three Stockham radix-8 passes; every lane owns two butterflies per pass (b = lane, lane + 32) whose 8 inputs
+//     are z[b + 64 r] in EVERY pass, so each pass is 16 conflict-free reads of the warp's private 4 KB buffer, two 8-point DFTs in
+//     registers, and 16 writes (pass 0: 8b + q, pass 1: 64 (b >> 3) + (b & 7) + 8q, pass 2: b + 64q) made almost conflict-free by
+//     the skew i + (i >> 3); twiddles of passes 1 and 2 depend on the lane only and stay in registers for the kernel's lifetime;
+//   * magnitudes go to a per-warp buffer, the triangular mel filters are walked filter-per-lane over their non-zero span, and the
+//     80 x 8 results of 8 consecutive frames are staged so that every global store is a full 32-byte sector of an output row.
+// Per frame: ~24 KB of shared-memory traffic and ~35 kFLOP on one warp; HBM sees the samples once (hop * 4 bytes new per frame,
+// the 1024 - hop overlap comes from L1 / L2) and the n_mels results.
+constexpr int FW = 8;                 // warps (= frames in flight) per CTA
+constexpr int FG = 8;                 // consecutive frames per warp between two flushes of its output staging
+constexpr int FBUF = 576;             // 512 + skew
+__device__ __forceinline__ int sk(int i) { return i + (i >> 3); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 negi(float2 a) { return make_float2(a.y, -a.x); }      // a * (-i)
+
+// in-place forward 8-point DFT, natural order
+__device__ __forceinline__ void fft8(float2 (&v)[8]) {
+  const float h = 0.70710678118654752f;
+  const float2 a0 = cadd(v[0], v[4]), a1 = csub(v[0], v[4]), a2 = cadd(v[2], v[6]), a3 = negi(csub(v[2], v[6]));
+  const float2 b0 = cadd(v[1], v[5]), b1 = csub(v[1], v[5]), b2 = cadd(v[3], v[7]), b3 = negi(csub(v[3], v[7]));
+  const float2 E0 = cadd(a0, a2), E1 = cadd(a1, a3), E2 = csub(a0, a2), E3 = csub(a1, a3);
+  const float2 O0 = cadd(b0, b2), O1 = cadd(b1, b3), O2 = csub(b0, b2), O3 = csub(b1, b3);
+  const float2 t1 = make_float2((O1.x + O1.y) * h, (O1.y - O1.x) * h);
+  const float2 t2 = negi(O2);
+  const float2 t3 = make_float2((O3.y - O3.x) * h, -(O3.x + O3.y) * h);
+  v[0] = cadd(E0, O0); v[4] = csub(E0, O0);
+  v[1] = cadd(E1, t1); v[5] = csub(E1, t1);
+  v[2] = cadd(E2, t2); v[6] = csub(E2, t2);
+  v[3] = cadd(E3, t3); v[7] = csub(E3, t3);
+}
+
+__global__ void __launch_bounds__(FW * 32, 2)
+stft_mel_fast_kernel(const float* __restrict__ y, int64_t T, int pad_left, int hop, const float* __restrict__ window,
+                     const float* __restrict__ basis, const int* __restrict__ span, int n_mels, float min_level, float ref_db,
+                     float min_db, int M, float* __restrict__ out, float* __restrict__ mag_out) {
+  constexpr int N = 1024, N2 = 512, NB = 513;
+  extern __shared__ float sm[];
+  float2* win2 = reinterpret_cast<float2*>(sm);              // [512] window pairs
+  float2* tws = win2 + N2;                                   // [257] W_1024^k
+  int* spn = reinterpret_cast<int*>(tws + 258);              // [2 * n_mels]
+  float* per_warp = reinterpret_cast<float*>(spn + 2 * n_mels + (n_mels & 1) * 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wfloats = 2 * FBUF + 520 + n_mels * FG;
+  float* re = per_warp + (size_t)warp * wfloats;
+  float* im = re + FBUF;
+  float* mag = im + FBUF;                                    // [513] (+ pad)
+  float* stage = mag + 520;                                  // [n_mels][FG]
+  for (int i = threadIdx.x; i < N2; i += FW * 32) win2[i] = make_float2(__ldg(window + 2 * i), __ldg(window + 2 * i + 1));
+  for (int i = threadIdx.x; i <= 256; i += FW * 32) {
+    float sn, cs;
+    sincospif(-2.0f * (float)i / (float)N, &sn, &cs);
+    tws[i] = make_float2(cs, sn);
+  }
+  for (int i = threadIdx.x; i < 2 * n_mels; i += FW * 32) spn[i] = __ldg(span + i);
+  __syncthreads();
+  // lane-constant twiddles: pass 1 uses W_64^{(b & 7) r} (the same for both butterflies of a lane), pass 2 W_512^{b r}
+  float2 tw1[7], tw2[2][7];
+#pragma unroll
+  for (int r = 1; r < 8; ++r) {
+    float sn, cs;
+    sincospif(-2.0f * (float)((lane & 7) * r) / 64.0f, &sn, &cs);
+    tw1[r - 1] = make_float2(cs, sn);
+    sincospif(-2.0f * (float)(lane * r) / 512.0f, &sn, &cs);
+    tw2[0][r - 1] = make_float2(cs, sn);
+    sincospif(-2.0f * (float)((lane + 32) * r) / 512.0f, &sn, &cs);
+    tw2[1][r - 1] = make_float2(cs, sn);
+  }
+  const bool aligned = ((hop | pad_left) & 1) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0;
+  const int ngroups = (M + FG - 1) / FG;
+  for (int g = blockIdx.x * FW + warp; g < ngroups; g += gridDim.x * FW) {
+    const int m0 = g * FG;
+    const int nf = min(FG, M - m0);
+    for (int f = 0; f < nf; ++f) {
+      const int m = m0 + f;
+      const int64_t base = (int64_t)m * hop - pad_left;
+      const bool interior = base >= 0 && base + N <= T;
+      float2 v[2][8];
+      // ---- pass 0: inputs from global memory, windowed
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int n = lane + 32 * half + 64 * r;
+          float2 x;
+          if (interior && aligned) {
+            x = __ldg(reinterpret_cast<const float2*>(y + base) + n);
+          } else {
+            const int64_t j = base + 2 * n;
+            x.x = (j >= 0 && j < T) ? __ldg(y + j) : 0.f;
+            x.y = (j + 1 >= 0 && j + 1 < T) ? __ldg(y + j + 1) : 0.f;
+          }
+          const float2 w = win2[n];
+          v[half][r] = make_float2(x.x * w.x, x.y * w.y);
+        }
+        fft8(v[half]);
+      }
+      __syncwarp();                                          // the previous frame's readers of re / im are done
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int b = lane + 32 * half;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int i = sk(8 * b + q); re[i] = v[half][q].x; im[i] = v[half][q].y; }
+      }
+      __syncwarp();
+      // ---- pass 1
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int b = lane + 32 * half;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int i = sk(b + 64 * r);
+          const float2 x = make_float2(re[i], im[i]);
+          v[half][r] = r ? cmul(x, tw1[r - 1]) : x;
+        }
+        fft8(v[half]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int b = lane + 32 * half;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int i = sk((b >> 3) * 64 + (b & 7) + 8 * q); re[i] = v[half][q].x; im[i] = v[half][q].y; }
+      }
+      __syncwarp();
+      // ---- pass 2
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int b = lane + 32 * half;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int i = sk(b + 64 * r);
+          const float2 x = make_float2(re[i], im[i]);
+          v[half][r] = r ? cmul(x, tw2[half][r - 1]) : x;
+        }
+        fft8(v[half]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int b = lane + 32 * half;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int i = sk(b + 64 * q); re[i] = v[half][q].x; im[i] = v[half][q].y; }
+      }
+      __syncwarp();
+      // ---- real-input split + magnitude: bins k and 512 - k together
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int k = lane + 32 * t;
+        if (k == 0) {
+          const float xr = re[0], xi = im[0];
+          mag[0] = fabsf(xr + xi);
+          mag[N2] = fabsf(xr - xi);
+          const int i = sk(256);
+          mag[256] = sqrtf(re[i] * re[i] + im[i] * im[i]);
+        } else {
+          const int i0 = sk(k), i1 = sk(N2 - k);
+          const float ar = 0.5f * (re[i0] + re[i1]), ai = 0.5f * (im[i0] - im[i1]);
+          const float br = 0.5f * (re[i0] - re[i1]), bi = 0.5f * (im[i0] + im[i1]);
+          const float2 tt = cmul(tws[k], make_float2(br, bi));
+          const float pr = ar + tt.y, pi = ai - tt.x, qr = ar - tt.y, qi = ai + tt.x;
+          mag[k] = sqrtf(pr * pr + pi * pi);
+          mag[N2 - k] = sqrtf(qr * qr + qi * qi);
+        }
+      }
+      __syncwarp();
+      if (mag_out)
+        for (int k = lane; k < NB; k += 32) mag_out[(int64_t)k * M + m] = mag[k];
+      // ---- mel filterbank (one filter per lane at a time) + dB + normalise
+      for (int r = lane; r < n_mels; r += 32) {
+        const int lo = spn[2 * r], hi = spn[2 * r + 1];
+        const float* brow = basis + (int64_t)r * NB;
+        float acc = 0.f;
+        for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(brow + k), mag[k], acc);
+        const float db = 20.f * log10f(fmaxf(min_level, acc)) - ref_db;
+        const float val = (db - min_db) / (-min_db);
+        stage[r * FG + f] = fminf(fmaxf(val, 0.f), 1.f);
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < n_mels * FG; i += 32) {
+      const int r = i / FG, f = i - r * FG;
+      if (f < nf) out[(int64_t)r * M + m0 + f] = stage[i];
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 extern "C" int viai_stft_mel(const float* y, int64_t T, int fft_size, int hop, int pad_left, int num_frames, const float* window,
@@ -103,6 +298,24 @@ extern "C" int viai_stft_mel(const float* y, int64_t T, int fft_size, int hop, i
   VIAI_REQUIRE(fft_size >= 64 && fft_size <= 4096 && (fft_size & (fft_size - 1)) == 0, "stft_mel: fft_size must be a power of two in [64, 4096]");
   VIAI_REQUIRE(hop > 0 && n_mels > 0 && num_frames >= 0 && T >= 0, "stft_mel: bad sizes");
   if (num_frames == 0) return VIAI_OK;
+  const float min_level_f = expf(min_level_db / 20.f * logf(10.f));
+  static const bool fast_off = [] { const char* e = getenv("VIAI_STFT_FAST"); return e && e[0] == '0'; }();
+  if (fft_size == 1024 && n_mels <= 128 && !fast_off) {
+    const size_t smem_f = sizeof(float) * (2 * 512 + 2 * 258 + 2 * n_mels + 2 + (size_t)FW * (2 * FBUF + 520 + n_mels * FG));
+    static bool attr_f = false;
+    if (!attr_f) {
+      VIAI_CUDA(cudaFuncSetAttribute(stft_mel_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+      attr_f = true;
+    }
+    VIAI_REQUIRE(smem_f <= 110 * 1024, "stft_mel: shared memory");
+    const int groups = (num_frames + FG - 1) / FG;
+    int blocks = (groups + FW - 1) / FW;
+    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;          // persistent: two CTAs per SM, warps stride over the frame groups
+    stft_mel_fast_kernel<<<blocks, FW * 32, smem_f, STR(stream)>>>(y, T, pad_left, hop, window, mel_basis, mel_span, n_mels,
+                                                                  min_level_f, ref_level_db, min_level_db, num_frames, out, mag_out);
+    VIAI_LAUNCHED();
+    return VIAI_OK;
+  }
   int logN = 0;
   while ((1 << logN) < fft_size) ++logN;
   const size_t smem = sizeof(float) * ((size_t)5 * fft_size + (size_t)n_mels * FR);
