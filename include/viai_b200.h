@@ -74,12 +74,11 @@ int viai_conv2d_simt(const viai_conv_geom* g, const float* in, const float* wp, 
  * VIAI_TC_BF16X3 (8) = the same 3-term scheme on bf16 pairs (hi = bf16(.), lo = bf16(. - hi); kind::f16 MMAs, K = 16, at
  * twice the tf32 rate; product error ~2^-17).  The kernel splits each fp32 activation slab in shared memory in place into
  * [32 x hi | 32 x lo] per 128-byte pixel row; weights are packed with split = 2 (same size as split = 0).
- * VIAI_TC_F16 (32, together with VIAI_TC_BF16X3) = the pairs are fp16 instead of bf16: x * 8 = hi + lo keeps 22 significand
- * bits (product error ~2^-21, the accuracy of VIAI_TC_X3 at the bf16 MMA rate); weights are packed with split = 3, which scales
- * them by a per-tensor power of two (computed on the device from max|w|) and appends 4 floats {max|w| bits, w_scale,
- * 1 / (8 * w_scale), 0} that the epilogue reads to undo the scales (exact: powers of two).  |x| >= 8188 saturates (the result
- * stays finite) and is counted: viai_tc_f16_overflow(reset, &count) returns the number of saturating threads since the last
- * reset (synchronises with the device; the host side checks it where it already reads the loss).
+ * VIAI_TC_F16 (32, together with VIAI_TC_BF16X3) = the pairs are fp16 instead of bf16: activations are scaled by 2^3 and weights
+ * (packed with split = 3) by 2^10 before the split, x = hi + lo keeps 22 significand bits (product error ~2^-21, the accuracy of
+ * VIAI_TC_X3 at the bf16 MMA rate) and the epilogue multiplies the accumulator by 2^-13 (exact).  |x| >= 8188 or |w| >= 64
+ * saturates (the result stays finite) and is counted: viai_tc_f16_overflow(reset, &count) returns the number of saturating threads
+ * since the last reset (synchronises with the device; the host side checks it where it already reads the loss).
  * Other bits select alternative shared-memory layouts used as cross-checks. */
 #define VIAI_TC_X3 4
 #define VIAI_TC_BF16X3 8
@@ -169,6 +168,19 @@ int viai_norm_act_bwd_apply(const float* dz, const float* y, int64_t rows_per_gr
                             const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
                             float slope, const double* s1, const double* s2, float* dy, float* dgamma, float* dbeta,
                             viai_stream_t stream);
+/* The same with the two viai_fold_groups launches folded into the kernel (its first block writes dgamma / dbeta; accumulate != 0
+ * adds into them, which is how they land in a gradient bucket).  Needs the statistics path (mean != NULL). */
+int viai_norm_act_bwd_apply_fold(const float* dz, const float* y, int64_t rows_per_group, int groups, int C,
+                                 const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
+                                 float slope, const double* s1, const double* s2, float* dy, float* dgamma, float* dbeta,
+                                 int accumulate, viai_stream_t stream);
+/* viai_norm_finalize + viai_norm_act_fwd in ONE launch: every thread derives its channels' mean / invstd from the double sums
+ * (same arithmetic), the first block also publishes them (mean / invstd: float[groups*C], for the backward pass) and updates the
+ * running buffers / num_batches_tracked (groups == 1 only; may be NULL). */
+int viai_norm_finalize_act_fwd(const float* y, int64_t rows_per_group, int groups, int C, const double* sum, const double* sumsq,
+                               float eps, const float* gamma, const float* beta, int act, float slope, float* out, float* mean,
+                               float* invstd, float* running_mean, float* running_var, float momentum,
+                               int64_t* num_batches_tracked, viai_stream_t stream);
 /* out[c] (+)= sum_g sums[g*C+c]  -- double -> float fold used for bias gradients. */
 int viai_fold_groups(const double* sums, int groups, int C, float* out, int accumulate, viai_stream_t stream);
 

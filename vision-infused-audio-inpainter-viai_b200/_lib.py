@@ -52,6 +52,8 @@ SIGNATURES = {
     "viai_norm_act_fwd": [c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_f, c_p, c_p],
     "viai_norm_act_bwd_reduce": [c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_f, c_p, c_p, c_p],
     "viai_norm_act_bwd_apply": [c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p],
+    "viai_norm_act_bwd_apply_fold": [c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
+    "viai_norm_finalize_act_fwd": [c_p, c_l, c_i, c_i, c_p, c_p, c_f, c_p, c_p, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
     "viai_fold_groups": [c_p, c_i, c_i, c_p, c_i, c_p],
     "viai_rsqrt_eps": [c_p, c_i, c_f, c_p, c_p],
     "viai_bilinear_fwd": [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p],

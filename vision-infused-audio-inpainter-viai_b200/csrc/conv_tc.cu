@@ -120,10 +120,9 @@ struct TcParams {
                          //    rate; the fp32 slab is split IN PLACE into [hi: 32 x bf16 | lo: 32 x bf16] per 128-byte pixel row
   int32_t a_sw128;       // 1: activation patch stored as dense 128-byte pixel rows under the 128-byte swizzle (rank-4 TMA)
   int32_t f16;           // with bx3: the pairs are fp16 (x * a_scale = hi + lo, 22 significand bits: ~2^-21 per product, the accuracy of
-                         //    tf32x3 at the bf16 MMA rate) instead of bf16 (16 bits, ~2^-17); the weights were packed with their own
-                         //    power-of-two scale and the epilogue multiplies the accumulator by *oscale = 1 / (a_scale * w_scale)
-  float a_scale;
-  const float* oscale;
+                         //    tf32x3 at the bf16 MMA rate) instead of bf16 (16 bits, ~2^-17); the weights were packed scaled by 2^10
+                         //    and the epilogue multiplies the accumulator by oscale = 1 / (a_scale * 2^10)
+  float a_scale, oscale;
   // Shared-memory matrix descriptors relative to a stage / weight tile, built on the host: they live in the constant bank,
   // so the MMA issuer fetches them with uniform loads and issuing one MMA costs two 64-bit adds.
   uint64_t tabA[MAX_TAP * 4 * 2];   // [tap][K step][part: 0 = hi / only, 1 = lo]
@@ -440,7 +439,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc1[i] = acc2[i] = 0.f;
     const float neg_slope = (p.ract == VIAI_ACT_RELU) ? 0.f : (p.ract == VIAI_ACT_LRELU) ? p.rslope : 1.f;   // act'(pre <= 0)
-    const float oscale = (MODE == 2 && p.oscale != nullptr) ? __ldg(p.oscale) : 1.f;      // fp16 pairs: undo the operand scales (a power of two)
+    const float oscale = p.oscale;                    // fp16 pairs: undoes the operand scales (a power of two)
     int cur_group = -1, cur_nt = -1;
     auto flush = [&]() {
       if (narrow) {                               // one transposing reduction per group instead of one per tile
@@ -602,39 +601,20 @@ __global__ void pack_weight_bf16x2_kernel(const float* __restrict__ src, uint16_
   }
 }
 
-// fp16-pair packing: the same layout as the bf16 pairs; the weights are first scaled by a per-tensor power of two w_scale that
-// maps max|w| into [2^13, 2^14) (so that hi keeps 11 bits and lo the next 11 for every weight within 2^-17 of the maximum; smaller
-// ones degrade gracefully through fp16 subnormals: absolute error <= 2^-25 / w_scale).  tail = {max|w| bits, w_scale,
-// 1 / (a_scale * w_scale), 0}: written here, read by the convolution's epilogue.
-constexpr float kF16ActScale = 8.0f;     // activations: |x| < 8188 representable; full 22 bits for |x| >= 2^-6
-__device__ __forceinline__ float f16_weight_scale(uint32_t max_bits) {
-  const float mx = __uint_as_float(max_bits);
-  if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
-  int e;
-  frexpf(mx, &e);                       // mx = m * 2^e, m in [0.5, 1)
-  return ldexpf(1.f, 14 - e);
-}
-__global__ void weight_absmax_kernel(const float* __restrict__ src, int O, int I, int R, int S, int64_t so, int64_t si, int64_t sr,
-                                     int64_t ss, uint32_t* __restrict__ tail) {
-  const int64_t total = (int64_t)O * I * R * S;
-  float m = 0.f;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = idx;
-    const int s2 = t % S; t /= S;
-    const int r = t % R; t /= R;
-    const int i = t % I;
-    const int o = (int)(t / I);
-    m = fmaxf(m, fabsf(src[o * so + i * si + r * sr + s2 * ss]));
-  }
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(tail, __float_as_uint(m));     // non-negative floats order like their bits
-}
+// fp16-pair packing: the same layout as the bf16 pairs.  Operands are scaled by FIXED powers of two before the split so that
+// hi keeps 11 significand bits and lo = (x - hi) the next 11 as a NORMAL fp16 number for every value that matters:
+//   weights     w * 2^10:  |w| < 64 representable; full 22 bits for |w| >= 2^-13 (1.2e-4); below that lo is an fp16 subnormal
+//                          and the absolute error is <= 2^-25 / 2^10 = 2.9e-11 -- against typical weights of 1e-2 .. 1e-1 that
+//                          is still ~2^-28 relative to the tensor;
+//   activations x * 2^3:   |x| < 8188 representable; full 22 bits for |x| >= 2^-6; absolute error below that <= 3.7e-9.
+// The epilogue multiplies the accumulator by 2^-13 (exact).  Values beyond the range saturate (finite) and are counted in
+// g_f16_overflow; the host side turns a non-zero count into an error where it already synchronises.
+constexpr float kF16ActScale = 8.0f;
+constexpr float kF16WeightScale = 1024.0f;
 __global__ void pack_weight_f16x2_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int O, int I, int R, int S,
-                                         int64_t so, int64_t si, int64_t sr, int64_t ss, int flip, int BN, int nchunks, int ntilesN,
-                                         float* __restrict__ tail) {
+                                         int64_t so, int64_t si, int64_t sr, int64_t ss, int flip, int BN, int nchunks, int ntilesN) {
   const int64_t total = (int64_t)R * S * nchunks * ntilesN * 2 * (KC / 8) * BN * 8;
-  const float ws = f16_weight_scale(__float_as_uint(tail[0]));
+  bool ovf = false;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t t = idx;
     const int e = t & 7; t >>= 3;
@@ -649,18 +629,14 @@ __global__ void pack_weight_f16x2_kernel(const float* __restrict__ src, uint16_t
     uint16_t v = 0;
     if (o < O && i < I) {
       const int rr = flip ? R - 1 - r : r, sw = flip ? S - 1 - s : s;
-      const float w = src[o * so + i * si + rr * sr + sw * ss] * ws;
+      const float w = src[o * so + i * si + rr * sr + sw * ss] * kF16WeightScale;
       const uint32_t hi = pack_f16x2_sat(w, 0.f);
       v = (uint16_t)(part == 0 ? (hi & 0xffffu) : (pack_f16x2_sat(w - f16lo_to_f32(hi), 0.f) & 0xffffu));
+      ovf |= fabsf(w) > 65504.f;
     }
     dst[idx] = v;
   }
-  // tail[1], tail[2] are only read by LATER kernels (the convolution), tail[0] only by this one: no ordering issue inside the grid
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    tail[1] = ws;
-    tail[2] = 1.f / (kF16ActScale * ws);
-    tail[3] = 0.f;
-  }
+  if (ovf) atomicAdd(&g_f16_overflow, 1u);
 }
 
 __global__ void pack_weight_tc_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int R, int S,
@@ -717,13 +693,10 @@ inline uint64_t host_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
 }
 
 // Builds and launches one "virtual unit-stride convolution" (see the file header).
-int64_t packed_elems(int O, int I, int R, int S, int split);
-
 int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int inC, int sub_sy, int sub_sx,
                 const TapSpec* taps, int ntap, const float* wp, const float* bias, float* out, int Hv, int Wv, int64_t o_sn,
                 int64_t o_sy, int64_t o_sx, int64_t o_base, int Cout, double* ssum, double* ssq, int stat_groups, int flags,
                 const viai_norm_bwd_ctx* nb, cudaStream_t stream) {
-  const int wR = g.R, wS = g.S;
   TcParams p;
   memset(&p, 0, sizeof(p));
   if (nb != nullptr) {
@@ -740,7 +713,7 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   VIAI_REQUIRE(!p.f16 || p.bx3, "conv2d_tc: the fp16-pair flag (32) goes with the 16-bit pair product (8)");
   if (p.f16) {
     p.a_scale = kF16ActScale;
-    p.oscale = wp + packed_elems(Cout, inC, wR, wS, 2) + 2;
+    p.oscale = 1.0f / (kF16ActScale * kF16WeightScale);
   }
   p.a_sw128 = (flags & 1) ? 0 : 1;
   VIAI_REQUIRE(!(p.x3 && p.bx3), "conv2d_tc: VIAI_TC_X3 and VIAI_TC_BF16X3 are exclusive");
@@ -901,10 +874,8 @@ int64_t packed_elems(int O, int I, int R, int S, int split) {
 }
 }  // namespace
 
-// split: 0 tf32, 1 tf32 pairs, 2 bf16 pairs, 3 fp16 pairs (+ a 4-float tail holding the weight scale, see pack_weight_f16x2_kernel)
-extern "C" int64_t viai_tc_packed_size(int O, int I, int R, int S, int split) {
-  return packed_elems(O, I, R, S, split) + (split == 3 ? 4 : 0);
-}
+// split: 0 tf32, 1 tf32 pairs, 2 bf16 pairs, 3 fp16 pairs (same size as 2)
+extern "C" int64_t viai_tc_packed_size(int O, int I, int R, int S, int split) { return packed_elems(O, I, R, S, split); }
 
 // Threads that saturated a value in an fp16-pair convolution since the last reset (synchronises with the device).
 extern "C" int viai_tc_f16_overflow(int reset, unsigned int* count) {
@@ -923,15 +894,9 @@ extern "C" int viai_pack_weight_tc(const float* src, float* dst, int O, int I, i
   const int BN = tc_bn(O), nchunks = (I + KC - 1) / KC, ntilesN = (O + BN - 1) / BN;
   const int64_t total = packed_elems(O, I, R, S, split);
   if (split == 3) {
-    float* tail = dst + total;
-    VIAI_CUDA(cudaMemsetAsync(tail, 0, 4 * sizeof(float), STR(stream)));
-    const int64_t nw = (int64_t)O * I * R * S;
-    weight_absmax_kernel<<<(int)imin64(cdiv(nw, 256), 1024), 256, 0, STR(stream)>>>(src, O, I, R, S, so, si, sr, ss,
-                                                                                   reinterpret_cast<uint32_t*>(tail));
-    VIAI_LAUNCHED();
     const int blocks = (int)imin64(cdiv(total * 2, 256), 4096);
     pack_weight_f16x2_kernel<<<blocks, 256, 0, STR(stream)>>>(src, reinterpret_cast<uint16_t*>(dst), O, I, R, S, so, si, sr, ss, flip,
-                                                             BN, nchunks, ntilesN, tail);
+                                                             BN, nchunks, ntilesN);
     VIAI_LAUNCHED();
     return VIAI_OK;
   }

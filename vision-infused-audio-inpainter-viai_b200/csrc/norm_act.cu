@@ -110,6 +110,12 @@ __global__ void finalize_kernel(const double* sum, const double* sumsq, int64_t 
   }
 }
 
+// Optional fusion of viai_norm_finalize into the forward apply pass (sum == nullptr: statistics come in as mean / invstd)
+struct FusedFinalize {
+  const double* sum; const double* sumsq; int64_t cnt; float eps;
+  float* mean_out; float* invstd_out; float* running_mean; float* running_var; float momentum; int64_t* nbt;
+};
+
 // Elementwise kernels: a thread owns one channel vector (its per-channel constants live in registers) and walks rows of one
 // statistics group -- no integer division and no parameter loads inside the loop; UNR rows are in flight per thread.
 constexpr int UNR = 4;
@@ -118,7 +124,7 @@ template <int VEC>
 __global__ void __launch_bounds__(THREADS)
 apply_kernel(const float* __restrict__ y, int64_t rows_per_group, int C, const float* __restrict__ mean,
              const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act,
-             float slope, float* __restrict__ out, int64_t rows_per_block) {
+             float slope, float* __restrict__ out, int64_t rows_per_block, FusedFinalize ff) {
   const Lanes L = make_lanes(C, VEC);
   const int cv = threadIdx.x % L.cvec, rl = threadIdx.x / L.cvec;
   if (rl >= L.lanes) return;
@@ -131,8 +137,29 @@ apply_kernel(const float* __restrict__ y, int64_t rows_per_group, int C, const f
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
     const int c = cv * VEC + k;
-    mu[k] = mean ? mean[(int64_t)g * C + c] : 0.f;
-    is[k] = mean ? invstd[(int64_t)g * C + c] : 1.f;
+    if (ff.sum != nullptr) {
+      // viai_norm_finalize fused in: every thread derives its channels' statistics from the double sums (the arithmetic of
+      // finalize_kernel); the first row lane of block x = 0 publishes them for the backward pass and moves the running buffers
+      const int64_t i = (int64_t)g * C + c;
+      const double m = ff.sum[i] / (double)ff.cnt;
+      double var = ff.sumsq[i] / (double)ff.cnt - m * m;
+      if (var < 0.0) var = 0.0;
+      mu[k] = (float)m;
+      is[k] = (float)(1.0 / sqrt(var + (double)ff.eps));
+      if (blockIdx.x == 0 && rl == 0) {
+        ff.mean_out[i] = mu[k];
+        ff.invstd_out[i] = is[k];
+        if (ff.running_mean && gridDim.y == 1) {
+          const double unb = ff.cnt > 1 ? var * (double)ff.cnt / (double)(ff.cnt - 1) : var;
+          ff.running_mean[i] = (1.f - ff.momentum) * ff.running_mean[i] + ff.momentum * (float)m;
+          ff.running_var[i] = (1.f - ff.momentum) * ff.running_var[i] + ff.momentum * (float)unb;
+        }
+        if (ff.nbt && i == 0) *ff.nbt += 1;
+      }
+    } else {
+      mu[k] = mean ? mean[(int64_t)g * C + c] : 0.f;
+      is[k] = mean ? invstd[(int64_t)g * C + c] : 1.f;
+    }
     ga[k] = gamma ? gamma[c] : 1.f;
     be[k] = beta ? beta[c] : 0.f;
   }
@@ -258,7 +285,17 @@ __global__ void __launch_bounds__(THREADS)
 bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, int64_t rows_per_group, int C,
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int act, float slope, const double* __restrict__ s1,
-                 const double* __restrict__ s2, float* __restrict__ dy, int64_t rows_per_block) {
+                 const double* __restrict__ s2, float* __restrict__ dy, int64_t rows_per_block, float* __restrict__ dgamma,
+                 float* __restrict__ dbeta, int accumulate) {
+  if ((dgamma || dbeta) && blockIdx.x == 0 && blockIdx.y == 0) {
+    // viai_fold_groups fused in: dgamma = sum over groups of s2, dbeta = of s1 (written or accumulated into the gradient bucket)
+    for (int c = threadIdx.x; c < C; c += THREADS) {
+      double t1 = 0.0, t2 = 0.0;
+      for (int gg = 0; gg < (int)gridDim.y; ++gg) { t1 += s1[(int64_t)gg * C + c]; t2 += s2[(int64_t)gg * C + c]; }
+      if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)t2;
+      if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)t1;
+    }
+  }
   const Lanes L = make_lanes(C, VEC);
   const int cv = threadIdx.x % L.cvec, rl = threadIdx.x / L.cvec;
   if (rl >= L.lanes) return;
@@ -405,8 +442,28 @@ extern "C" int viai_norm_act_fwd(const float* y, int64_t rows_per_group, int gro
   const int ngr = mean ? groups : 1;
   const int64_t rpb = pick_rows_per_block_elem(rpg, ngr, C, VEC);
   dim3 grid((unsigned)cdiv(rpg, rpb), (unsigned)ngr);
-  if (VEC == 4) apply_kernel<4><<<grid, THREADS, 0, STR(stream)>>>(y, rpg, C, mean, invstd, gamma, beta, act, slope, out, rpb);
-  else apply_kernel<1><<<grid, THREADS, 0, STR(stream)>>>(y, rpg, C, mean, invstd, gamma, beta, act, slope, out, rpb);
+  FusedFinalize ff;
+  memset(&ff, 0, sizeof(ff));
+  if (VEC == 4) apply_kernel<4><<<grid, THREADS, 0, STR(stream)>>>(y, rpg, C, mean, invstd, gamma, beta, act, slope, out, rpb, ff);
+  else apply_kernel<1><<<grid, THREADS, 0, STR(stream)>>>(y, rpg, C, mean, invstd, gamma, beta, act, slope, out, rpb, ff);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_norm_finalize_act_fwd(const float* y, int64_t rows_per_group, int groups, int C, const double* sum,
+                                          const double* sumsq, float eps, const float* gamma, const float* beta, int act,
+                                          float slope, float* out, float* mean, float* invstd, float* running_mean,
+                                          float* running_var, float momentum, int64_t* num_batches_tracked, viai_stream_t stream) {
+  VIAI_REQUIRE(y && out && sum && sumsq && mean && invstd && rows_per_group > 0 && groups > 0 && C > 0,
+               "viai_norm_finalize_act_fwd: bad arguments");
+  VIAI_REQUIRE(running_mean == nullptr || groups == 1, "viai_norm_finalize_act_fwd: running statistics need groups == 1");
+  int VEC = pick_vec(C, y, out);
+  VIAI_REQUIRE(C / VEC <= THREADS, "viai_norm_finalize_act_fwd: C=%d too large", C);
+  const int64_t rpb = pick_rows_per_block_elem(rows_per_group, groups, C, VEC);
+  dim3 grid((unsigned)cdiv(rows_per_group, rpb), (unsigned)groups);
+  FusedFinalize ff = {sum, sumsq, rows_per_group, eps, mean, invstd, running_mean, running_var, momentum, num_batches_tracked};
+  if (VEC == 4) apply_kernel<4><<<grid, THREADS, 0, STR(stream)>>>(y, rows_per_group, C, nullptr, nullptr, gamma, beta, act, slope, out, rpb, ff);
+  else apply_kernel<1><<<grid, THREADS, 0, STR(stream)>>>(y, rows_per_group, C, nullptr, nullptr, gamma, beta, act, slope, out, rpb, ff);
   VIAI_LAUNCHED();
   return VIAI_OK;
 }
@@ -433,10 +490,10 @@ extern "C" int viai_norm_act_bwd_reduce(const float* dz, const float* y, int64_t
   return VIAI_OK;
 }
 
-extern "C" int viai_norm_act_bwd_apply(const float* dz, const float* y, int64_t rows_per_group, int groups, int C,
-                                       const float* mean, const float* invstd, const float* gamma, const float* beta,
-                                       int act, float slope, const double* s1, const double* s2, float* dy, float* dgamma,
-                                       float* dbeta, viai_stream_t stream) {
+static int norm_act_bwd_apply_impl(const float* dz, const float* y, int64_t rows_per_group, int groups, int C,
+                                   const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                   int act, float slope, const double* s1, const double* s2, float* dy, float* dgamma,
+                                   float* dbeta, int fused_fold, int accumulate, viai_stream_t stream) {
   VIAI_REQUIRE(dz && y && dy && rows_per_group > 0 && groups > 0 && C > 0, "viai_norm_act_bwd_apply: bad arguments");
   VIAI_REQUIRE(mean == nullptr || (s1 && s2 && invstd), "viai_norm_act_bwd_apply: statistics missing");
   cudaStream_t st = STR(stream);
@@ -446,9 +503,14 @@ extern "C" int viai_norm_act_bwd_apply(const float* dz, const float* y, int64_t 
   const int ngr = mean ? groups : 1;
   const int64_t rpb = pick_rows_per_block_elem(rpg, ngr, C, VEC);
   dim3 grid((unsigned)cdiv(rpg, rpb), (unsigned)ngr);
-  if (VEC == 4) bwd_apply_kernel<4><<<grid, THREADS, 0, st>>>(dz, y, rpg, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy, rpb);
-  else bwd_apply_kernel<1><<<grid, THREADS, 0, st>>>(dz, y, rpg, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy, rpb);
+  const bool in_kernel = fused_fold && mean != nullptr && s1 && s2;      // (with statistics grid.y == groups: the kernel can fold)
+  float* kg = in_kernel ? dgamma : nullptr;
+  float* kb = in_kernel ? dbeta : nullptr;
+  if (VEC == 4) bwd_apply_kernel<4><<<grid, THREADS, 0, st>>>(dz, y, rpg, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy, rpb, kg, kb, accumulate);
+  else bwd_apply_kernel<1><<<grid, THREADS, 0, st>>>(dz, y, rpg, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy, rpb, kg, kb, accumulate);
   VIAI_LAUNCHED();
+  if (in_kernel) return VIAI_OK;
+  VIAI_REQUIRE(!fused_fold || (!dgamma && !dbeta), "viai_norm_act_bwd_apply_fold: dgamma / dbeta need the statistics path");
   if (dgamma && s2) {
     fold_kernel<<<(C + 255) / 256, 256, 0, st>>>(s2, groups, C, dgamma, 0);
     VIAI_LAUNCHED();
@@ -458,6 +520,22 @@ extern "C" int viai_norm_act_bwd_apply(const float* dz, const float* y, int64_t 
     VIAI_LAUNCHED();
   }
   return VIAI_OK;
+}
+
+extern "C" int viai_norm_act_bwd_apply(const float* dz, const float* y, int64_t rows_per_group, int groups, int C,
+                                       const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                       int act, float slope, const double* s1, const double* s2, float* dy, float* dgamma,
+                                       float* dbeta, viai_stream_t stream) {
+  return norm_act_bwd_apply_impl(dz, y, rows_per_group, groups, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy, dgamma, dbeta,
+                                 0, 0, stream);
+}
+
+extern "C" int viai_norm_act_bwd_apply_fold(const float* dz, const float* y, int64_t rows_per_group, int groups, int C,
+                                            const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                            int act, float slope, const double* s1, const double* s2, float* dy, float* dgamma,
+                                            float* dbeta, int accumulate, viai_stream_t stream) {
+  return norm_act_bwd_apply_impl(dz, y, rows_per_group, groups, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy, dgamma, dbeta,
+                                 1, accumulate, stream);
 }
 
 extern "C" int viai_fold_groups(const double* sums, int groups, int C, float* out, int accumulate, viai_stream_t stream) {

@@ -375,7 +375,9 @@ class _ConvFn(torch.autograd.Function):
                 g = _geom(N, Ho, Wo, Cout, H, W, C, R, S, stride, padding, 0)
                 U, G = x, dy
             with _op_timer("conv_wgrad", ctx.op[0], ctx.op[1], 4.0 * (x.numel() + dy.numel() + weight.numel())):
-                if _FAST_STEM and not transposed and C <= 4 and _PRECISION != "fp32" and Cout % 4 == 0 and Cout >= 16 and R * S > 1:
+                # (the im2col route is for many-tap few-channel stems -- 7x7, Cin 2 / 3; the 1-channel 3x3 / 1x4 first layers of the
+                # encoder / discriminator stay on the wide-tensor-stationary thin kernel, which is 3x faster there: measured)
+                if _FAST_STEM and not transposed and C <= 4 and _PRECISION != "fp32" and Cout % 4 == 0 and Cout >= 16 and R * S >= 25:
                     _stem_wgrad(g, x, dy, dw, wt is not None)
                 elif L.viai_conv2d_wgrad_thin_supported(ctypes.byref(g)) and U.data_ptr() % 16 == 0 and G.data_ptr() % 16 == 0:
                     ws = _workspace(dy.device, L.viai_wgrad_thin_workspace(ctypes.byref(g)))
@@ -458,7 +460,7 @@ class _NormActFn(torch.autograd.Function):
         y = y.contiguous()
         N, H, W, C = y.shape
         dev = y.device
-        mean = invstd = None
+        mean = invstd = fused_stats = None
         groups, rpg = 1, N * H * W
         if norm == "in":
             groups, rpg = N, H * W
@@ -473,17 +475,22 @@ class _NormActFn(torch.autograd.Function):
                     s = torch.empty((2, groups * C), device=dev, dtype=torch.float64)
                     _lib.check(L.viai_channel_stats(_p(y), rpg, groups, C, _p(s[0]), _p(s[1]), _stream()), "channel_stats")
                 upd = norm == "bn" and training and running_mean is not None
-                _lib.check(L.viai_norm_finalize(_p(s[0]), _p(s[1]), rpg, groups, C, eps, _p(mean), _p(invstd),
-                                                _p(running_mean) if upd else None, _p(running_var) if upd else None,
-                                                momentum, _p(nbt) if upd else None, _stream()), "norm_finalize")
+                fused_stats = (s, upd)     # statistics are finalised inside the apply kernel (one launch instead of two)
             else:
                 mean = running_mean
                 invstd = torch.empty(C, device=dev, dtype=torch.float32)
                 _lib.check(L.viai_rsqrt_eps(_p(running_var), C, eps, _p(invstd), _stream()), "rsqrt_eps")
         out = torch.empty_like(y)
         with _op_timer("norm_act_fwd", "%dx%dx%dx%d" % (N, H, W, C), 0.0, 8.0 * y.numel()):
-            _lib.check(L.viai_norm_act_fwd(_p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta), act, slope,
-                                           _p(out), _stream()), "norm_act_fwd")
+            if fused_stats is not None:
+                s, upd = fused_stats
+                _lib.check(L.viai_norm_finalize_act_fwd(_p(y), rpg, groups, C, _p(s[0]), _p(s[1]), eps, _p(gamma), _p(beta), act, slope,
+                                                        _p(out), _p(mean), _p(invstd), _p(running_mean) if upd else None,
+                                                        _p(running_var) if upd else None, momentum, _p(nbt) if upd else None,
+                                                        _stream()), "norm_finalize_act_fwd")
+            else:
+                _lib.check(L.viai_norm_act_fwd(_p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta), act, slope,
+                                               _p(out), _stream()), "norm_act_fwd")
         if _ACT_TRACE is not None and act in (ACT_RELU, ACT_LRELU):
             _ACT_TRACE.append(out > 0)
         ctx.save_for_backward(y, mean, invstd, gamma, beta)
@@ -515,18 +522,30 @@ class _NormActFn(torch.autograd.Function):
                 s = torch.empty((2, groups * C), device=y.device, dtype=torch.float64)
                 _lib.check(L.viai_norm_act_bwd_reduce(_p(dz), _p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta),
                                                       act, slope, _p(s[0]), _p(s[1]), _stream()), "norm_act_bwd_reduce")
-            _lib.check(L.viai_norm_act_bwd_apply(_p(dz), _p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta), act,
-                                                 slope, _p(s[0]) if s is not None else None, _p(s[1]) if s is not None else None,
-                                                 _p(dy), None, None, _stream()), "norm_act_bwd_apply")
-        dgamma = dbeta = None
-        if s is not None and gamma is not None and ctx.needs_input_grad[1]:
-            dgamma = gt if gt is not None else torch.empty_like(gamma)
-            _lib.check(L.viai_fold_groups(_p(s[1]), groups, C, _p(dgamma), int(gt is not None), _stream()), "dgamma")
-            dgamma = None if gt is not None else dgamma
-        if s is not None and beta is not None and ctx.needs_input_grad[2]:
-            dbeta = bt if bt is not None else torch.empty_like(beta)
-            _lib.check(L.viai_fold_groups(_p(s[0]), groups, C, _p(dbeta), int(bt is not None), _stream()), "dbeta")
-            dbeta = None if bt is not None else dbeta
+            want_g = s is not None and gamma is not None and ctx.needs_input_grad[1]
+            want_b = s is not None and beta is not None and ctx.needs_input_grad[2]
+            dgamma = (gt if gt is not None else torch.empty_like(gamma)) if want_g else None
+            dbeta = (bt if bt is not None else torch.empty_like(beta)) if want_b else None
+            # dgamma / dbeta = the group sums of s2 / s1, written (or accumulated into the gradient bucket) by the apply kernel's
+            # first block when both go the same way; otherwise by viai_fold_groups
+            in_kernel = mean is not None and (want_g or want_b) and (not (want_g and want_b) or (gt is None) == (bt is None))
+            if in_kernel:
+                acc = int((gt is not None) if want_g else (bt is not None))
+                _lib.check(L.viai_norm_act_bwd_apply_fold(_p(dz), _p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta), act,
+                                                          slope, _p(s[0]), _p(s[1]), _p(dy), _p(dgamma), _p(dbeta), acc, _stream()),
+                           "norm_act_bwd_apply_fold")
+            else:
+                _lib.check(L.viai_norm_act_bwd_apply(_p(dz), _p(y), rpg, groups, C, _p(mean), _p(invstd), _p(gamma), _p(beta), act,
+                                                     slope, _p(s[0]) if s is not None else None, _p(s[1]) if s is not None else None,
+                                                     _p(dy), None, None, _stream()), "norm_act_bwd_apply")
+                if want_g:
+                    _lib.check(L.viai_fold_groups(_p(s[1]), groups, C, _p(dgamma), int(gt is not None), _stream()), "dgamma")
+                if want_b:
+                    _lib.check(L.viai_fold_groups(_p(s[0]), groups, C, _p(dbeta), int(bt is not None), _stream()), "dbeta")
+        if gt is not None:
+            dgamma = None            # accumulated straight into the gradient bucket
+        if bt is not None:
+            dbeta = None
         return dy, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None, None
 
 
