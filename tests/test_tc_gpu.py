@@ -308,6 +308,7 @@ def test_fused_reduction_is_taken_in_a_layer_chain_and_changes_nothing():
 
     def run(fuse):
         prev, ops._FUSE_BWD_REDUCE = ops._FUSE_BWD_REDUCE, fuse
+        prev_c, ops._FUSE_MAX_C = ops._FUSE_MAX_C, 1 << 30
         try:
             torch.manual_seed(5)
             c1, b1 = nn.Conv2d(32, 64, 3, 1, 1, bias=False).cuda(), nn.BatchNorm2d(64).cuda()
@@ -318,7 +319,7 @@ def test_fused_reduction_is_taken_in_a_layer_chain_and_changes_nothing():
             z.backward(torch.ones_like(z) * 0.01 + z.detach() * 0.1)
             return _lib.launch_count() - n0, [x.grad] + [p.grad for m in (c1, b1, c2, b2) for p in m.parameters()]
         finally:
-            ops._FUSE_BWD_REDUCE = prev
+            ops._FUSE_BWD_REDUCE, ops._FUSE_MAX_C = prev, prev_c
 
     n_fused, g_fused = run(True)
     n_plain, g_plain = run(False)

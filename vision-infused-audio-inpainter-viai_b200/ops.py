@@ -41,10 +41,14 @@ if os.environ.get("VIAI_DGRAD") == "tf32x3":          # experiment knob: 2^-21 d
 _WGRAD_FP32 = os.environ.get("VIAI_WGRAD") == "fp32"  # experiment knob: CUDA-core fp32 weight gradients
 _WS = {}
 # Fuse the first pass of a layer's norm backward (sum g, sum g*xhat) into the epilogue of the data-gradient convolution that
-# produces dz (tensor-core path, BatchNorm batch statistics): viai_conv2d_tc_bwd_reduce.  Parity-tested, but OFF by default:
-# measured on B200 at C2 the four epilogue warps cannot hide the extra y read + arithmetic (step 15.5 ms fused vs 14.8 ms
-# with the standalone viai_norm_act_bwd_reduce pass, which already runs at 4.7 TB/s).  VIAI_FUSE_BWD_REDUCE=1 enables it.
-_FUSE_BWD_REDUCE = os.environ.get("VIAI_FUSE_BWD_REDUCE", "0") == "1"
+# produces dz (tensor-core path, BatchNorm batch statistics): viai_conv2d_tc_bwd_reduce.  Round 1 measured it on every layer
+# and it lost (15.5 ms vs 14.8 ms: on WIDE layers the epilogue warps are busy and cannot hide the extra y read).  On layers with
+# <= _FUSE_MAX_C input channels the kernel is bound by its operand-split stage and the epilogue warps idle ~90 % of the time
+# (profiles/r02_thin_conv_ncu.txt), so there the reduction rides for free and the standalone bwd_reduce pass (a read of dz and y)
+# disappears.  VIAI_FUSE_BWD_REDUCE = 0: never, 1: every unit-stride layer, thin (default): only thin layers.
+_FUSE_MODE = os.environ.get("VIAI_FUSE_BWD_REDUCE", "thin")
+_FUSE_BWD_REDUCE = _FUSE_MODE != "0"
+_FUSE_MAX_C = 32 if _FUSE_MODE == "thin" else 1 << 30
 _DGRAD_X3 = os.environ.get("VIAI_DGRAD", "x3") != "tf32"
 
 
@@ -353,7 +357,7 @@ class _ConvFn(torch.autograd.Function):
             nc = ctx.in_norm
             # fused only for unit-stride layers: a strided convolution's data gradient is four low-K parity-class launches
             # whose short main loops cannot hide the epilogue's extra work
-            if nc is not None and (nc["y"].shape != x.shape or not nc["y"].is_contiguous() or tuple(stride) != (1, 1)):
+            if nc is not None and (nc["y"].shape != x.shape or not nc["y"].is_contiguous() or tuple(stride) != (1, 1) or C > _FUSE_MAX_C):
                 nc = None
             bst = torch.empty((2, C), device=x.device, dtype=torch.float64) if nc is not None else None
             with _op_timer("conv_dgrad", ctx.op[0], ctx.op[1], 4.0 * (x.numel() + dy.numel() + weight.numel())):
