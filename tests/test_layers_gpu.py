@@ -4,11 +4,12 @@ multi-block grids and split-K.
 
 Tolerances (max-norm relative): the CUDA-core validator (``fp32``) 2e-5 everywhere; the library default (the benched path) 2e-5
 for the forward (3-term fp16-pair products, ~2^-21 per product; the rest is the tensor core's truncating fp32 accumulation), 5e-5 for the data gradient (3-term bf16-pair products, ~2^-17
-per product) and 5e-4 for the weight gradient (one tf32
+per product) and 1e-3 for the weight gradient (one tf32
 product on operands ROUNDED to tf32: zero-mean 2^-12 per operand; with the random-sign inputs used here the sum and its error
-are both random walks, ~2e-4 of the tensor's rms.  Without the rounding the hardware's truncation adds a one-sided ~1e-3
+are both random walks, ~2e-4 of the tensor's rms (3-5e-4 at the worst element of 10^5-10^6).  Without the rounding the hardware's truncation adds a one-sided ~1e-3
 bias, see test_wgrad_rounding_removes_the_truncation_bias)."""
 import math
+import zlib
 
 import pytest
 import torch
@@ -51,14 +52,14 @@ LAYERS_C2 = [
     ("D.conv2_2@c2", False, 128, 256, 3, 3, (2, 2), (1, 1), 128, 64),
     ("D.conv3@c2", False, 256, 512, 3, 3, (1, 1), (1, 1), 64, 32),
 ]
-TOL = {"fp32": dict(fwd=2e-5, dgrad=2e-5, wgrad=2e-5, bgrad=2e-5), "fp16x3": dict(fwd=2e-5, dgrad=5e-5, wgrad=5e-4, bgrad=2e-5)}
+TOL = {"fp32": dict(fwd=2e-5, dgrad=2e-5, wgrad=2e-5, bgrad=2e-5), "fp16x3": dict(fwd=2e-5, dgrad=5e-5, wgrad=1e-3, bgrad=2e-5)}
 PREC = [pytest.param("fp16x3", id="default"), pytest.param("fp32", marks=pytest.mark.fp32, id="fp32")]
 
 
 def _run_layer(layer, N=2):
     from viai_b200 import ops
     name, tr, Cin, Cout, kh, kw, stride, pad, Hh, W = layer
-    g = torch.Generator().manual_seed(abs(hash(name)) % 100000)
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 100000)
     x = torch.randn(N, Cin, Hh, W, generator=g, dtype=torch.float64).float().double().requires_grad_(True)
     wshape = (Cin, Cout, kh, kw) if tr else (Cout, Cin, kh, kw)
     w = (torch.randn(wshape, generator=g, dtype=torch.float64) / math.sqrt(Cin * kh * kw)).float().double().requires_grad_(True)

@@ -12,6 +12,7 @@ The DATA gradient runs the same 3-term product (a single tf32 data gradient trun
 gradient keeps one tf32 product on operands rounded in shared memory (tests/test_layers_gpu.py)."""
 import ctypes
 import math
+import zlib
 
 import pytest
 import torch
@@ -37,7 +38,7 @@ def test_tc_layer_geometry(layer, N):
     from viai_b200 import ops, _lib
     assert ops.get_precision() == "tf32"
     name, tr, Cin, Cout, kh, kw, stride, pad, Hh, W = layer
-    g = torch.Generator().manual_seed(abs(hash(name)) % 100000 + N)
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 100000 + N)
     x = torch.randn(N, Cin, Hh, W, generator=g, dtype=torch.float64).float().double().requires_grad_(True)
     wshape = (Cin, Cout, kh, kw) if tr else (Cout, Cin, kh, kw)
     w = (torch.randn(wshape, generator=g, dtype=torch.float64) / math.sqrt(Cin * kh * kw)).float().double().requires_grad_(True)
@@ -70,7 +71,7 @@ def test_x3_forward_is_fp32_accurate(layer, mode):
     from viai_b200 import ops
     assert ops.get_precision() == mode
     name, tr, Cin, Cout, kh, kw, stride, pad, Hh, W = layer
-    g = torch.Generator().manual_seed(abs(hash(name)) % 100000)
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 100000)
     x = torch.randn(2, Cin, Hh, W, generator=g, dtype=torch.float64).float().double()
     wshape = (Cin, Cout, kh, kw) if tr else (Cout, Cin, kh, kw)
     w = (torch.randn(wshape, generator=g, dtype=torch.float64) / math.sqrt(Cin * kh * kw)).float().double()

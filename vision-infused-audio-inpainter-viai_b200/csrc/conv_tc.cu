@@ -73,6 +73,7 @@ constexpr int MAX_SUB = 4, MAX_TAP = 16;
 // Registers are rebalanced with setmaxnreg after the prologue: the producers and the split warps give theirs to the epilogue.
 constexpr int NTHREADS = 512;
 constexpr int XF_WARP0 = 12;
+constexpr int XF2_WARP0 = 8;            // warpgroup 2: second epilogue set, or (TcParams::xf2) second operand-split group
 constexpr int EPI_WARP0 = 4;
 
 struct TcSub {
@@ -123,6 +124,7 @@ struct TcParams {
                          //    tf32x3 at the bf16 MMA rate) instead of bf16 (16 bits, ~2^-17); the weights were packed scaled by 2^10
                          //    and the epilogue multiplies the accumulator by oscale = 1 / (a_scale * 2^10)
   float a_scale, oscale;
+  int32_t xf2;           // 1: warpgroup 2 splits operands instead of running the second epilogue set (thin layers)
   // Shared-memory matrix descriptors relative to a stage / weight tile, built on the host: they live in the constant bank,
   // so the MMA issuer fetches them with uniform loads and issuing one MMA costs two 64-bit adds.
   uint64_t tabA[MAX_TAP * 4 * 2];   // [tap][K step][part: 0 = hi / only, 1 = lo]
@@ -339,21 +341,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       if (leader) mma_commit(&tfull[acc]);
     }
    }
-  } else if (warp >= XF_WARP0) {
+  } else if (warp >= XF_WARP0 || (MODE == 2 && p.xf2 && warp >= XF2_WARP0)) {
     reg_dealloc<80>();
     // ===== tf32x3: split every landed slab into hi = trunc_tf32(x) (in place) and lo = x - hi (second slab) =====
     if (MODE == 2) {
       // bf16 pair split, one thread per 128-byte pixel row (private to the thread, so the rewrite is in place): logical
       // 16-byte chunk j of row r sits at physical chunk j ^ (r & 7) under the 128-byte swizzle, before and after.
-      const int tid = threadIdx.x - XF_WARP0 * 32;
-      int sa = 0;
+      // With p.xf2 (layers of <= 64 output channels, where this stage and not the tensor pipe bounds the kernel and one epilogue
+      // set is idle) warpgroup 2 is a SECOND split group: the two groups take alternate slabs.
+      const int tid = threadIdx.x & 127;
+      const int xg = (warp >= XF_WARP0) ? 0 : 1, nxg = p.xf2 ? 2 : 1;
+      int sa = 0, slab = 0;
       uint32_t pha = 0;
       const bool f16 = p.f16 != 0;
       const float a_scale = p.a_scale;
       float amax = 0.f;
       const uint32_t nrows = p.slab_bytes / 128;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        for (int c = 0; c < p.nchunks; ++c) {
+        for (int c = 0; c < p.nchunks; ++c, ++slab) {
+          if (nxg == 2 && (slab & 1) != xg) {               // the other group's slab
+            if (++sa == p.SA) { sa = 0; pha ^= 1u; }
+            continue;
+          }
           mbar_wait(&fullA[sa], pha);
           uint8_t* base = slabA + (size_t)sa * a_stage;
           for (uint32_t r = tid; r < nrows; r += 128) {
@@ -463,15 +472,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         rs[j] = rq[j] = 0.f;
       }
     };
-    const int eset = (warp - EPI_WARP0) >> 2;       // epilogue set = accumulator set = parity of the CTA's tile counter
-    for (int it = eset, tile = blockIdx.x + eset * gridDim.x; tile < p.ntiles; tile += 2 * gridDim.x, it += 2) {
+    // two epilogue sets, one per accumulator set (= parity of the CTA's tile counter); with p.xf2 warpgroup 1 alone serves both
+    const int nset = (MODE == 2 && p.xf2) ? 1 : 2;
+    const int eset = (nset == 1) ? 0 : (warp - EPI_WARP0) >> 2;
+    for (int it = eset, tile = blockIdx.x + eset * gridDim.x; tile < p.ntiles; tile += nset * gridDim.x, it += nset) {
       const int nt = tile % p.ntilesN;
       int rest = tile / p.ntilesN;
       const int tx = rest % p.tilesX; rest /= p.tilesX;
       const int ty = rest % p.tilesY;
       const int n = rest / p.tilesY;
       const int y = ty * TH + ly;
-      const int acc = eset;
+      const int acc = it & 1;
       if (do_stats) {
         const int grp = (p.stat_groups > 1) ? n : 0;
         if ((grp != cur_group || nt != cur_nt) && cur_group >= 0) flush();   // finished (group, cout tile)
@@ -802,6 +813,8 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   p.Cout = Cout;
   p.o_sn = o_sn; p.o_sy = o_sy; p.o_sx = o_sx; p.o_base = o_base;
   p.btile_bytes = (uint32_t)p.BN * KC * 4 * (p.x3 ? 2u : 1u);      // bf16 pairs: 2 x 2 bytes per element = the fp32 size
+  static const int xf2_env = env_int("VIAI_TC_XF2", 1);
+  p.xf2 = (p.bx3 && xf2_env && p.BN <= 64) ? 1 : 0;
   p.idesc = p.f16 ? make_idesc_f16(128, p.BN, 0, 0) : p.bx3 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
   // pipeline depths under the 227 KB shared-memory limit
   const size_t fixed = 1024 /*alignment slack*/ + 66 * 8 + 5 * (size_t)(((Cout + 31) / 32) * 32 + 256) * 4;   // barriers + tmem slot + bias + 4 norm constants
