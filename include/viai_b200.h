@@ -334,6 +334,13 @@ int viai_im2col(const viai_conv_geom* g, const float* in, int Kpad, float* out, 
 /* nn.MaxPool2d(3, 2, 1) backward that also reads the forward output (rejects non-maximal elements after one load); C % 4 == 0 */
 int viai_maxpool3s2_bwd_out(const float* in, const float* out, const float* dout, int N, int H, int W, int C, float* din, int Ho,
                             int Wo, viai_stream_t stream);
+/* Max-pool with a saved argmax (1 byte per output element: the window position 0..8 of the FIRST maximum, row-major, ATen's
+ * tie-breaking rule): the backward pass gathers dout through it and reads neither the forward input nor output.  C % 4 == 0.
+ * Replaces F.max_pool2d / max_pool2d_with_indices_backward at networks/Image_Embedding.py:21. */
+int viai_maxpool3s2_fwd_idx(const float* in, int N, int H, int W, int C, float* out, unsigned char* idx, int Ho, int Wo,
+                            viai_stream_t stream);
+int viai_maxpool3s2_bwd_idx(const unsigned char* idx, const float* dout, int N, int H, int W, int C, float* din, int Ho, int Wo,
+                            viai_stream_t stream);
 
 #ifdef __cplusplus
 }

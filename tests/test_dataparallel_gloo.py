@@ -84,8 +84,21 @@ def _worker(rank, port, out_dir):
         _fill((dis,), (gD,))
         bG.all_reduce()
         bD.all_reduce()
-        torch.save(dict(G=bG.flat_grad / WORLD, D=bD.flat_grad / WORLD, Gp=bG.flat_param.clone(), Dp=bD.flat_param.clone(),
-                        shard=(b, e)), os.path.join(out_dir, "rank%d.pt" % rank))
+        full_G = bG.flat_grad.clone()
+        # the overlapped form (ranges reduced asynchronously as the backward pass completes them, the remainder at the end, the
+        # all-zero convblock1 slice skipped) must leave exactly the same bucket
+        _fill((enc, dec), (gE, gDec))
+        dec_params = list(dec.parameters())
+        dec_start = bG.offset_of(dec_params[0])
+        blk1 = bG.offset_of(next(dec.convblock1.parameters()))
+        blk2 = bG.offset_of(next(dec.convblock2.parameters()))
+        bG.begin_overlap()
+        bG.reduce_range_async(blk2, bG.numel)
+        bG.reduce_range_async(dec_start, blk1)
+        bG.finish_overlap(skip=[(blk1, blk2)])
+        overlap_equal = bool(torch.equal(bG.flat_grad, full_G))
+        torch.save(dict(G=full_G / WORLD, D=bD.flat_grad / WORLD, Gp=bG.flat_param.clone(), Dp=bD.flat_param.clone(),
+                        shard=(b, e), overlap_equal=overlap_equal), os.path.join(out_dir, "rank%d.pt" % rank))
     finally:
         dist.destroy_process_group()
 
@@ -101,6 +114,7 @@ def test_two_rank_bucket_allreduce_matches_mean_of_replica_grads(tmp_path):
     # broadcast made the replicas identical; all-reduce left identical buckets on both ranks
     for k in ("G", "D", "Gp", "Dp"):
         assert torch.equal(r0[k], r1[k]), k
+    assert r0["overlap_equal"] and r1["overlap_equal"]        # GradBucket.reduce_range_async / finish_overlap == one all-reduce
     # expected: mean over replicas of the per-replica gradients (BatchNorm statistics are per replica, as in DataParallel)
     from viai_b200.optim import GradBucket
     enc, dec, dis = _modules()

@@ -318,7 +318,8 @@ def test_full_size_properties_and_parity(size):
     maskB = O.time_band_mask(melB.shape, size // 4, size // 2).cuda()
     r = tr.train_step(melB, maskB)
     f = r["fake"]
-    assert tuple(f.shape) == (32, 1, size, size) and bool(torch.isfinite(f).all()) and float(f.min()) > 0 and float(f.max()) < 1
+    # (the sigmoid may saturate to exactly 1.0f on this random data after one optimizer step: closed interval)
+    assert tuple(f.shape) == (32, 1, size, size) and bool(torch.isfinite(f).all()) and float(f.min()) >= 0 and float(f.max()) <= 1
     assert all(math.isfinite(float(r[k])) for k in ("loss_D", "loss_G", "loss_L1"))
     # per-sample independence under InstanceNorm-free BN is not available; check permutation equivariance of the batch
     perm = torch.randperm(32, device="cuda")

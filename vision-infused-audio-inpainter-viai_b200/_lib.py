@@ -64,6 +64,8 @@ SIGNATURES = {
     "viai_maxpool3s2_fwd": [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p],
     "viai_maxpool3s2_bwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p],
     "viai_maxpool3s2_bwd_out": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p],
+    "viai_maxpool3s2_fwd_idx": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p],
+    "viai_maxpool3s2_bwd_idx": [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p],
     "viai_im2col": [_GP, c_p, c_i, c_p, c_p],
     "viai_mul": [c_p, c_p, c_p, c_l, c_p],
     "viai_add_act": [c_p, c_p, c_p, c_l, c_i, c_p],

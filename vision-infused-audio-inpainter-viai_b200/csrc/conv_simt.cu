@@ -272,26 +272,40 @@ wgrad_c1_kernel(viai_conv_geom g, const float* __restrict__ U, const float* __re
 // 1x1 weight gradient on the tensor-core kernel instead of a CUDA-core loop over 49 taps with Cin padded to 16.
 __global__ void __launch_bounds__(256)
 im2col_kernel(viai_conv_geom g, const float* __restrict__ in, int Kpad, float* __restrict__ out) {
-  const int K4 = Kpad / 4, RS = g.R * g.S, K = g.Cin * RS;
-  const int64_t M = (int64_t)g.N * g.Hout * g.Wout, total = M * K4;
+  // per-k tap table (input offset relative to the patch origin, and the tap's (r, q) for the bounds test), built once per block:
+  // the element loop then has no integer division by a runtime constant
+  extern __shared__ int tab[];                       // [Kpad][3]: dy, dx, channel  (dy = -1: padding column)
+  const int RS = g.R * g.S, K = g.Cin * RS;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    int dy = -1, dx = 0, c = 0;
+    if (k < K) {
+      c = k / RS;
+      const int t = k - c * RS;
+      dy = t / g.S;
+      dx = t - dy * g.S;
+    }
+    tab[3 * k] = dy; tab[3 * k + 1] = dx; tab[3 * k + 2] = c;
+  }
+  __syncthreads();
+  const int K4 = Kpad / 4;
+  const int64_t M = (int64_t)g.N * g.Hout * g.Wout;
   const int HWo = g.Hout * g.Wout;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k0 = (int)(i % K4) * 4;
+  // a thread walks the K4 float4s of a patch row in steps of the block's lanes-per-row: rows are assigned so that a warp writes
+  // consecutive float4s of consecutive rows (full 128-byte lines)
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M * K4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i / K4;
+    const int k0 = (int)(i - p * K4) * 4;
     const int n = (int)(p / HWo);
     const int rem = (int)(p - (int64_t)n * HWo);
     const int y = rem / g.Wout, x = rem - y * g.Wout;
+    const int Y0 = y * g.stride_h - g.pad_h, X0 = x * g.stride_w - g.pad_w;
+    const float* img = in + (int64_t)n * g.Hin * g.Win * g.Cin;
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int k = k0 + j;
-      v[j] = 0.f;
-      if (k < K) {
-        const int c = k / RS, t = k - c * RS;
-        const int r = t / g.S, q = t - r * g.S;
-        const int Y = y * g.stride_h - g.pad_h + r, X = x * g.stride_w - g.pad_w + q;
-        if (Y >= 0 && Y < g.Hin && X >= 0 && X < g.Win) v[j] = __ldg(in + (((int64_t)n * g.Hin + Y) * g.Win + X) * g.Cin + c);
-      }
+      const int dy = tab[3 * (k0 + j)], dx = tab[3 * (k0 + j) + 1], c = tab[3 * (k0 + j) + 2];
+      const int Y = Y0 + dy, X = X0 + dx;
+      v[j] = (dy >= 0 && Y >= 0 && Y < g.Hin && X >= 0 && X < g.Win) ? __ldg(img + ((int64_t)Y * g.Win + X) * g.Cin + c) : 0.f;
     }
     reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -392,7 +406,8 @@ extern "C" int viai_im2col(const viai_conv_geom* g, const float* in, int Kpad, f
   VIAI_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "viai_im2col: out must be 16-byte aligned");
   const int64_t total = (int64_t)g->N * g->Hout * g->Wout * (Kpad / 4);
   VIAI_REQUIRE(total > 0, "viai_im2col: empty tensor");
-  im2col_kernel<<<(int)imin64(cdiv(total, 256), 32 * kNumSMs), 256, 0, STR(stream)>>>(*g, in, Kpad, out);
+  VIAI_REQUIRE(Kpad <= 4096, "viai_im2col: Kpad %d too large", Kpad);
+  im2col_kernel<<<(int)imin64(cdiv(total, 256), 32 * kNumSMs), 256, (size_t)Kpad * 3 * sizeof(int), STR(stream)>>>(*g, in, Kpad, out);
   VIAI_LAUNCHED();
   return VIAI_OK;
 }

@@ -813,7 +813,11 @@ int launch_plan(const viai_conv_geom& g, const float* in, int inH, int inW, int 
   p.Cout = Cout;
   p.o_sn = o_sn; p.o_sy = o_sy; p.o_sx = o_sx; p.o_base = o_base;
   p.btile_bytes = (uint32_t)p.BN * KC * 4 * (p.x3 ? 2u : 1u);      // bf16 pairs: 2 x 2 bytes per element = the fp32 size
-  static const int xf2_env = env_int("VIAI_TC_XF2", 1);
+  // Second split group on thin layers: measured on B200 (round 2) it changes nothing (15.49 vs 15.34 ms per C2 step) -- the
+  // 32-channel layers are bound by the tensor core's OPERAND FETCH from shared memory (every M=128, K=16 MMA re-reads a 4 KB A
+  // tile whatever N is: 54 MMAs x 5 KB = 270 KB per 128-pixel tile, ~2 100 cycles at 128 B/clk), not by the split stage.  Kept
+  // as an option (VIAI_TC_XF2=1), off by default.
+  static const int xf2_env = env_int("VIAI_TC_XF2", 0);
   p.xf2 = (p.bx3 && xf2_env && p.BN <= 64) ? 1 : 0;
   p.idesc = p.f16 ? make_idesc_f16(128, p.BN, 0, 0) : p.bx3 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
   // pipeline depths under the 227 KB shared-memory limit

@@ -41,12 +41,11 @@ if os.environ.get("VIAI_DGRAD") == "tf32x3":          # experiment knob: 2^-21 d
 _WGRAD_FP32 = os.environ.get("VIAI_WGRAD") == "fp32"  # experiment knob: CUDA-core fp32 weight gradients
 _WS = {}
 # Fuse the first pass of a layer's norm backward (sum g, sum g*xhat) into the epilogue of the data-gradient convolution that
-# produces dz (tensor-core path, BatchNorm batch statistics): viai_conv2d_tc_bwd_reduce.  Round 1 measured it on every layer
-# and it lost (15.5 ms vs 14.8 ms: on WIDE layers the epilogue warps are busy and cannot hide the extra y read).  On layers with
-# <= _FUSE_MAX_C input channels the kernel is bound by its operand-split stage and the epilogue warps idle ~90 % of the time
-# (profiles/r02_thin_conv_ncu.txt), so there the reduction rides for free and the standalone bwd_reduce pass (a read of dz and y)
-# disappears.  VIAI_FUSE_BWD_REDUCE = 0: never, 1: every unit-stride layer, thin (default): only thin layers.
-_FUSE_MODE = os.environ.get("VIAI_FUSE_BWD_REDUCE", "thin")
+# produces dz (tensor-core path, BatchNorm batch statistics): viai_conv2d_tc_bwd_reduce.  Parity-tested, OFF by default: round 1
+# measured it on every layer (15.5 ms vs 14.8 ms: on wide layers the epilogue warps are busy), round 2 on thin layers only, where
+# the epilogue warps idle (15.49 ms vs 15.27 ms: the fused epilogue still has to read y, so only the dz read is saved, and the
+# data gradient itself gets slower).  VIAI_FUSE_BWD_REDUCE = 0 (default): never, 1: every unit-stride layer, thin: <= 32 channels.
+_FUSE_MODE = os.environ.get("VIAI_FUSE_BWD_REDUCE", "0")
 _FUSE_BWD_REDUCE = _FUSE_MODE != "0"
 _FUSE_MAX_C = 32 if _FUSE_MODE == "thin" else 1 << 30
 _DGRAD_X3 = os.environ.get("VIAI_DGRAD", "x3") != "tf32"
@@ -333,6 +332,7 @@ class _ConvFn(torch.autograd.Function):
         ctx.save_for_backward(x, weight)
         ctx.cfg = (stride, padding, transposed, bias is not None)
         ctx.targets = (grad_target(weight), grad_target(bias))
+        ctx.after_grad = getattr(weight, "_viai_after_grad", None)     # data-parallel overlap trigger (step.GanTrainer)
         ctx.in_norm = getattr(x, "_viai_norm_ctx", None) if _FUSE_BWD_REDUCE else None
         if stats is None:
             stats = torch.empty(0, device=x.device, dtype=torch.float64)
@@ -396,6 +396,8 @@ class _ConvFn(torch.autograd.Function):
                                                         dw.stride(2), dw.stride(3), int(wt is not None), _stream()), "conv2d wgrad")
             if wt is not None:
                 dw = None            # accumulated straight into the gradient bucket
+            if ctx.after_grad is not None:
+                ctx.after_grad()     # everything the trigger's bucket range holds has been launched: start its all-reduce
         if has_bias and ctx.needs_input_grad[2]:
             rows = N * Ho * Wo
             acc = torch.empty(Cout, device=dy.device, dtype=torch.float64)
@@ -687,7 +689,9 @@ def avgpool_h(x, kh):
 
 
 class _MaxPoolFn(torch.autograd.Function):
-    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (networks/Image_Embedding.py:21)."""
+    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (networks/Image_Embedding.py:21).  With C % 4 == 0 the forward pass saves a
+    one-byte argmax per output element and the backward pass gathers through it (viai_maxpool3s2_*_idx): neither the input nor the
+    output of the pooling stays alive for the backward pass."""
 
     @staticmethod
     def forward(ctx, x):
@@ -697,25 +701,29 @@ class _MaxPoolFn(torch.autograd.Function):
         N, H, W, C = x.shape
         Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         out = torch.empty((N, Ho, Wo, C), device=x.device, dtype=torch.float32)
-        _lib.check(L.viai_maxpool3s2_fwd(_p(x), N, H, W, C, _p(out), Ho, Wo, _stream()), "maxpool fwd")
+        ctx.shape = (N, H, W, C)
         if _FAST_STEM and C % 4 == 0:
-            ctx.save_for_backward(x, out)
+            idx = torch.empty((N, Ho, Wo, C), device=x.device, dtype=torch.uint8)
+            _lib.check(L.viai_maxpool3s2_fwd_idx(_p(x), N, H, W, C, _p(out), _p(idx), Ho, Wo, _stream()), "maxpool fwd (argmax)")
+            ctx.save_for_backward(idx)
+            ctx.mark_non_differentiable(idx)
         else:
+            _lib.check(L.viai_maxpool3s2_fwd(_p(x), N, H, W, C, _p(out), Ho, Wo, _stream()), "maxpool fwd")
             ctx.save_for_backward(x)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x = ctx.saved_tensors[0]
+        saved = ctx.saved_tensors[0]
         L = _lib.lib()
         dout = dout.contiguous()
-        N, H, W, C = x.shape
-        dx = torch.empty_like(x)
-        if len(ctx.saved_tensors) == 2:
-            _lib.check(L.viai_maxpool3s2_bwd_out(_p(x), _p(ctx.saved_tensors[1]), _p(dout), N, H, W, C, _p(dx), dout.size(1),
-                                                 dout.size(2), _stream()), "maxpool bwd (with output)")
+        N, H, W, C = ctx.shape
+        dx = torch.empty((N, H, W, C), device=dout.device, dtype=torch.float32)
+        if saved.dtype == torch.uint8:
+            _lib.check(L.viai_maxpool3s2_bwd_idx(_p(saved), _p(dout), N, H, W, C, _p(dx), dout.size(1), dout.size(2), _stream()),
+                       "maxpool bwd (argmax)")
         else:
-            _lib.check(L.viai_maxpool3s2_bwd(_p(x), _p(dout), N, H, W, C, _p(dx), dout.size(1), dout.size(2), _stream()), "maxpool bwd")
+            _lib.check(L.viai_maxpool3s2_bwd(_p(saved), _p(dout), N, H, W, C, _p(dx), dout.size(1), dout.size(2), _stream()), "maxpool bwd")
         return dx
 
 

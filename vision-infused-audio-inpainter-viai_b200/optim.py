@@ -66,6 +66,39 @@ class GradBucket(object):
             import torch.distributed as dist
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.process_group)
 
+    # ---- overlapped reduction: ranges of the bucket are all-reduced asynchronously (NCCL's own stream) as soon as the backward
+    # pass has finished writing them; finish_overlap() reduces whatever is left and joins.  Capturable in a CUDA graph.
+    def begin_overlap(self):
+        self._works, self._reduced = [], []
+
+    def reduce_range_async(self, start, end):
+        if self.world_size > 1 and end > start:
+            import torch.distributed as dist
+            self._works.append(dist.all_reduce(self.flat_grad[start:end], op=dist.ReduceOp.SUM, group=self.process_group, async_op=True))
+            self._reduced.append((start, end))
+
+    def finish_overlap(self, skip=()):
+        """All-reduces every range not yet reduced (and not in ``skip``: slices that are zero on every rank, e.g. the reference's
+        never-called convblock1), then waits for the asynchronous ones."""
+        if self.world_size <= 1:
+            return
+        import torch.distributed as dist
+        covered = sorted(list(getattr(self, "_reduced", [])) + [tuple(r) for r in skip])
+        pos = 0
+        for s, e in covered + [(self.numel, self.numel)]:
+            if s > pos:
+                dist.all_reduce(self.flat_grad[pos:s], op=dist.ReduceOp.SUM, group=self.process_group)
+            pos = max(pos, e)
+        for w in getattr(self, "_works", []):
+            w.wait()
+        self._works, self._reduced = [], []
+
+    def offset_of(self, param):
+        for p, off in zip(self.params, self.offsets):
+            if p is param:
+                return off
+        raise KeyError("parameter is not in this bucket")
+
     def broadcast_params(self, src=0):
         """Identical initial weights on every rank (what nn.DataParallel's replicate does each step in the reference)."""
         if self.world_size > 1:

@@ -43,6 +43,11 @@ class GanTrainer(object):
         self.lambda_L1 = float(getattr(hparams, "lambda_L1", 100.0))
         self.process_group = process_group
         self.sync_replicas()
+        import os
+        self.overlap = world_size > 1 and os.environ.get("VIAI_DDP_OVERLAP", "1") != "0"
+        self._triggers = []
+        if self.overlap:
+            self._plan_overlap()
         self._graphs = None
         self._static = None
         self.launches_per_step = None
@@ -62,6 +67,47 @@ class GanTrainer(object):
             e = torch.cuda.Event(enable_timing=True)
             e.record()
             self.segment_events[name] = e
+
+    # ---- data-parallel overlap -----------------------------------------------------------------------------------------
+    def _plan_overlap(self):
+        """Bucket ranges whose gradients are complete before the backward pass ends, with the parameter whose weight gradient is the
+        LAST one written into the range (backward runs in reverse forward order, the bucket is in registration order):
+          D: [conv3.weight, end)  after conv3's weight gradient of the second discriminator pass of the D phase (76 % of D's bytes;
+             the three large-image layers conv2_2 / conv2_1 / conv1 are still to come);
+          G: [convblock2, decoder end) after convblock2's first layer; [decoder start, convblock2) after the decoder's first layer
+             (the encoder's backward is still to come).  What is left (D: 24 %, G: the encoder [+ the visual encoder]) is reduced at
+             the end of the backward pass; ranges that are zero on every rank are part of a range anyway or skipped."""
+        bD, bG = self.optimizer_D.bucket, self.optimizer_G.bucket
+        D, dec = self.netD, self.Mel_Decoder
+        dec_params = list(dec.parameters())
+        dec_start = bG.offset_of(dec_params[0])
+        dec_end = bG.offset_of(dec_params[-1]) + dec_params[-1].numel()
+        blk2 = bG.offset_of(next(dec.convblock2.parameters()))
+        first = dec.deconv1_1_1 if self.uses_video else dec.deconv1_1
+        self._add_trigger(D.conv3.weight, 2, bD, bD.offset_of(D.conv3.weight), bD.numel)
+        self._add_trigger(next(dec.convblock2.parameters()), 1, bG, blk2, dec_end)
+        self._add_trigger(first.weight, 1, bG, dec_start, blk2)
+
+    def _add_trigger(self, param, count, bucket, start, end):
+        st = {"n": 0}
+
+        def fire():
+            st["n"] += 1
+            if st["n"] == count:
+                bucket.reduce_range_async(start, end)
+        param._viai_after_grad = fire
+        self._triggers.append(st)
+
+    def _reduce_begin(self, opt):
+        for st in self._triggers:
+            st["n"] = 0
+        opt.bucket.begin_overlap()
+
+    def _reduce_finish(self, opt):
+        if self.overlap:
+            opt.bucket.finish_overlap()
+        else:
+            opt.all_reduce_grads()
 
     def sync_replicas(self, src=0):
         """Identical weights AND buffers (BatchNorm running statistics) on every rank, from rank ``src`` -- what
@@ -135,17 +181,27 @@ class GanTrainer(object):
         return dict(fake=self.fake.detach(), loss_D=self.loss_D.detach(), loss_G_GAN=self.loss_G_GAN.detach(),
                     loss_L1=self.loss_L1.detach(), loss_G=self.loss_G.detach())
 
+    def _step_body(self, mel, mask, video=None, flow=None):
+        """The whole step with its collectives (world_size > 1): the bucket ranges of _plan_overlap are all-reduced while the rest
+        of the backward pass runs, the remainder right after it."""
+        if self.world_size > 1:
+            self._reduce_begin(self.optimizer_D)
+        self._seg_forward_and_d_backward(mel, mask, video, flow)
+        if self.world_size > 1:
+            self._reduce_finish(self.optimizer_D)
+            self._reduce_begin(self.optimizer_G)
+        self._seg_d_update_and_g_backward()
+        if self.world_size > 1:
+            self._reduce_finish(self.optimizer_G)
+        self._seg_g_update()
+
     # ---- eager step -------------------------------------------------------------------------------------------
     def train_step(self, mel, mask, video=None, flow=None):
         """mel (B,1,H,W) or (B,H,W) fp32 in [0,1]; mask same shape, {0,1}.  Returns dict of device tensors."""
         n0 = _lib.launch_count()
         ops.pack_cache_begin()
         try:
-            self._seg_forward_and_d_backward(mel, mask, video, flow)
-            self.optimizer_D.all_reduce_grads()
-            self._seg_d_update_and_g_backward()
-            self.optimizer_G.all_reduce_grads()
-            self._seg_g_update()
+            self._step_body(mel, mask, video, flow)
         finally:
             ops.pack_cache_end()
         self.launches_per_step = _lib.launch_count() - n0
@@ -192,15 +248,17 @@ class GanTrainer(object):
             torch.cuda.synchronize()
         n0 = _lib.launch_count()
         ops.pack_cache_begin()
-        if self.world_size == 1:
+        if self.world_size == 1 or self.overlap:
+            # ONE graph for the whole step; with world_size > 1 the NCCL all-reduces are captured inside it (on NCCL's own stream,
+            # forked from / joined to the capture stream by events), overlapping the backward pass
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._seg_forward_and_d_backward(st["mel"], st["mask"], st["video"], st["flow"])
-                self._seg_d_update_and_g_backward()
-                self._seg_g_update()
+                self._step_body(st["mel"], st["mask"], st["video"], st["flow"])
                 self._static_out = self._outputs()
             self._graphs = [g]
+            self._segmented = False
         else:
+            self._segmented = True
             pool = torch.cuda.graph_pool_handle()
             g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1, pool=pool):
@@ -256,7 +314,7 @@ class GanTrainer(object):
             st["flow"].copy_(flow, non_blocking=True)
         self.optimizer_D.sync_lr()          # a changed param_groups[0]['lr'] reaches the captured Adam kernels
         self.optimizer_G.sync_lr()
-        if len(self._graphs) == 1:
+        if not getattr(self, "_segmented", False):
             self._graphs[0].replay()
         else:
             self._graphs[0].replay()
