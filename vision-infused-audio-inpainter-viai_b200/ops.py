@@ -324,8 +324,25 @@ class _ConvFn(torch.autograd.Function):
             stats = torch.empty((2, stat_groups * Cout), device=x.device, dtype=torch.float64)
         macs = (N * Ho * Wo * Cout * C * R * S) if not transposed else (N * H * W * C * Cout * R * S)
         key = _conv_key(N, H, W, C, Ho, Wo, Cout, R, S, stride, transposed)
+        # Many-tap few-channel stem (the ResNet 7x7, Cin 3 / 2): too few channels for the implicit-GEMM kernel, 49 taps too many for
+        # CUDA cores (11 % of the C3 step).  Forward = im2col (channel-major K = Cin*kh*kw padded to a multiple of 32) + a 1x1
+        # tensor-core convolution over the patch rows, statistics epilogue included; the weight gradient re-forms the patches
+        # (_stem_wgrad) instead of keeping gigabytes of them alive.  Only when the input needs no gradient (it is the video).
+        stem = (_FAST_STEM and not transposed and C <= 4 and R * S >= 25 and Cout % 4 == 0 and Cout >= 16 and _PRECISION != "fp32"
+                and not ctx.needs_input_grad[0])
         with _op_timer("conv_fwd", key, 2.0 * macs, 4.0 * (x.numel() + y.numel() + weight.numel())):
-            if not _run_conv(g, x, weight, od, idim, bias, y, stats, stat_groups, forward=True) and stats is not None:
+            if stem:
+                K = C * R * S
+                Kpad = (K + 31) // 32 * 32
+                cols = im2col(g, x, Kpad)
+                w2 = torch.zeros((Cout, Kpad, 1, 1), device=x.device, dtype=torch.float32)
+                w2.view(Cout, Kpad)[:, :K] = weight.detach().reshape(Cout, K)
+                g1 = _geom(N, Ho, Wo, Kpad, Ho, Wo, Cout, 1, 1, (1, 1), (0, 0), 0)
+                fused = _run_conv(g1, cols, w2, 0, 1, bias, y, stats, stat_groups, forward=True)
+                del cols
+            else:
+                fused = _run_conv(g, x, weight, od, idim, bias, y, stats, stat_groups, forward=True)
+            if not fused and stats is not None:
                 _lib.check(L.viai_channel_stats(_p(y), (N * Ho * Wo) // stat_groups, stat_groups, Cout, _p(stats[0]), _p(stats[1]),
                                                 _stream()), "channel_stats")
         ctx.op = (key, 2.0 * macs)
