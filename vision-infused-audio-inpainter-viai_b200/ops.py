@@ -413,8 +413,6 @@ class _ConvFn(torch.autograd.Function):
                                                         dw.stride(2), dw.stride(3), int(wt is not None), _stream()), "conv2d wgrad")
             if wt is not None:
                 dw = None            # accumulated straight into the gradient bucket
-            if ctx.after_grad is not None:
-                ctx.after_grad()     # everything the trigger's bucket range holds has been launched: start its all-reduce
         if has_bias and ctx.needs_input_grad[2]:
             rows = N * Ho * Wo
             acc = torch.empty(Cout, device=dy.device, dtype=torch.float64)
@@ -423,6 +421,8 @@ class _ConvFn(torch.autograd.Function):
             _lib.check(L.viai_fold_groups(_p(acc), 1, Cout, _p(db), int(bt is not None), _stream()), "bias grad fold")
             if bt is not None:
                 db = None
+        if ctx.after_grad is not None and ctx.needs_input_grad[1]:
+            ctx.after_grad()         # weight AND bias gradient of the trigger layer are launched: its bucket range is complete
         return dx, dw, db, None, None, None, None
 
 
