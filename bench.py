@@ -264,12 +264,10 @@ def run_c3(ctx, pk):
             for _ in range(2):
                 step()
             ms = ctx.timed(step, 3)
-            seg = {}
-            if ctx.rank == 0:
-                tr.segment_events = {}
-                step()
-                seg = tr.segment_ms()
-                tr.segment_events = None
+            tr.segment_events = {}                 # one more step on EVERY rank (it contains collectives), with segment events
+            step()
+            seg = tr.segment_ms()
+            tr.segment_events = None
             peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
             v_ms = (seg.get("v_fwd") or 0.0) + (seg.get("v_bwd") or 0.0)
             v_flops = 3 * 2 * 3.63e9 * bs * T                           # fwd + dgrad + wgrad, two streams, 3.63 GFLOP per 224^2 frame
@@ -415,7 +413,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # (a short collective timeout: a rank that falls out of step must abort the run in minutes, not hang the box)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=240))
     ctx = Ctx(torch, dist, rank, world)
     from viai_b200 import ops
     pk = peaks()

@@ -27,7 +27,8 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    import datetime
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])), timeout=datetime.timedelta(seconds=120))
     from viai_b200 import Options_inpainting as OI
     from viai_b200.step import GanTrainer
     hp = OI.Inpainting_Config(cin_channels=80)
