@@ -311,6 +311,10 @@ int viai_l2norm_bwd(const float* y, const float* norms, const float* dy, int row
 int viai_pairdist_fwd(const float* f1, const float* f2, int n1, int n2, int F, float* scores, viai_stream_t stream);
 int viai_pairdist_bwd(const float* f1, const float* f2, const float* scores, const float* dscores, int n1, int n2, int F, float* df1,
                       float* df2, viai_stream_t stream);
+/* utils/util.py:99-121 L2retrieval on the (captions x clips) distance matrix of viai_pairdist_fwd: rank[i] = position of clip i in
+ * row i sorted ascending (ties: lower index first), top1[i] = index of the closest clip; int64[n1] each.  Replaces np.argsort +
+ * np.where of the reference without sorting. */
+int viai_retrieval_ranks(const float* dist, int n1, int n2, long long* rank, long long* top1, viai_stream_t stream);
 /* loss_functions.py:111-148 L2ContrastiveLoss on a (B,B) score matrix: loss (float[1], may be NULL) and, with gout/dscores,
  * dscores = gout * d loss / d scores */
 int viai_l2_contrastive(const float* scores, int B, float margin, int max_violation, float* loss, const float* gout, float* dscores,

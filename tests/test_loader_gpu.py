@@ -17,7 +17,7 @@ cv2 = pytest.importorskip("cv2")
 
 @pytest.mark.parametrize("cfg", [(5, 256, 256, 3, 256, 224, 1, 17, 30), (3, 97, 131, 3, 256, 224, 0, 0, 32), (4, 128, 128, 1, 256, 224, 1, 32, 0),
                                  (2, 480, 640, 1, 224, 224, 0, 0, 0), (3, 224, 224, 3, 224, 224, 1, 0, 0), (6, 24, 20, 3, 16, 12, 1, 3, 1),
-                                 (2, 10, 13, 1, 16, 12, 0, 2, 4)], ids=lambda c: "n%d_%dx%dx%d_to%d_crop%d" % c[:6])
+                                 (2, 10, 13, 1, 16, 12, 0, 2, 4), (2, 512, 512, 3, 256, 224, 1, 5, 9), (3, 448, 448, 1, 224, 224, 0, 0, 0)], ids=lambda c: "n%d_%dx%dx%d_to%d_crop%d" % c[:6])
 def test_frames_kernel_bit_exact_with_cv2(cfg):
     from viai_b200 import ops
     n, sh, sw, cn, R, S, flip, cr, cc = cfg

@@ -136,6 +136,15 @@ def pairdist(f1, f2):
     return torch.norm(f1.unsqueeze(1) - f2.unsqueeze(0), p=2, dim=2)
 
 
+def retrieval_ranks(dist):
+    n1 = dist.size(0)
+    own = dist.diagonal()[:n1].unsqueeze(1)
+    j = torch.arange(dist.size(1)).unsqueeze(0)
+    i = torch.arange(n1).unsqueeze(1)
+    ranks = ((dist < own) | ((dist == own) & (j < i))).sum(1)
+    return ranks.to(torch.int64), dist.argmin(1)
+
+
 def l2_contrastive(scores, margin=0.0, max_violation=False):
     cost = (margin - scores).clamp(min=0).masked_fill(torch.eye(scores.size(0)) > 0.5, 0)
     if max_violation:
@@ -170,7 +179,7 @@ def pointwise_wgrad(U, G):
 
 _NAMES = ["conv2d", "conv2d_stats", "norm_act", "cat_channels", "mul", "avgpool_h", "maxpool3s2", "add_act", "shiftcat", "weight_norm",
           "glu_tanh_sigmoid", "axpby", "axpby_", "dmol_nll", "dmol_sample", "masked_sum", "sequence_mask", "l2_normalize", "pairdist",
-          "l2_contrastive", "frames_preprocess", "im2col", "pointwise_wgrad"]
+          "l2_contrastive", "frames_preprocess", "im2col", "pointwise_wgrad", "retrieval_ranks"]
 
 
 @contextlib.contextmanager

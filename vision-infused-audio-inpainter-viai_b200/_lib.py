@@ -97,6 +97,7 @@ SIGNATURES = {
     "viai_l2norm_bwd": [c_p, c_p, c_p, c_i, c_i, c_f, c_p, c_p],
     "viai_pairdist_fwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_p],
     "viai_pairdist_bwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
+    "viai_retrieval_ranks": [c_p, c_i, c_i, c_p, c_p, c_p],
     "viai_l2_contrastive": [c_p, c_i, c_f, c_i, c_p, c_p, c_p, c_p],
 }
 

@@ -153,6 +153,45 @@ extern "C" int viai_pairdist_fwd(const float* f1, const float* f2, int n1, int n
   return VIAI_OK;
 }
 
+// utils/util.py:99-121 L2retrieval, the index work: for caption i the rank of its own clip = the number of clips that are closer
+// (ties: lower index first, the order a stable sort of the row would give) and the index of the closest clip.  One block per row;
+// no sort of the distance matrix is needed.
+__global__ void __launch_bounds__(256) retrieval_rank_kernel(const float* __restrict__ d, int n1, int n2, long long* __restrict__ rank,
+                                                              long long* __restrict__ top1) {
+  __shared__ int s_cnt[256];
+  __shared__ float s_min[256];
+  __shared__ int s_arg[256];
+  const int i = blockIdx.x;
+  const float* row = d + (size_t)i * n2;
+  const float own = row[i];
+  int cnt = 0, arg = n2;
+  float mn = INFINITY;
+  for (int j = threadIdx.x; j < n2; j += blockDim.x) {
+    const float v = row[j];
+    cnt += (v < own) || (v == own && j < i);
+    if (v < mn || (v == mn && j < arg)) { mn = v; arg = j; }
+  }
+  s_cnt[threadIdx.x] = cnt; s_min[threadIdx.x] = mn; s_arg[threadIdx.x] = arg;
+  __syncthreads();
+  for (int off = blockDim.x / 2; off >= 1; off >>= 1) {
+    if (threadIdx.x < off) {
+      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + off];
+      const float v = s_min[threadIdx.x + off];
+      const int a = s_arg[threadIdx.x + off];
+      if (v < s_min[threadIdx.x] || (v == s_min[threadIdx.x] && a < s_arg[threadIdx.x])) { s_min[threadIdx.x] = v; s_arg[threadIdx.x] = a; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { rank[i] = s_cnt[0]; top1[i] = s_arg[0]; }
+}
+
+extern "C" int viai_retrieval_ranks(const float* dist, int n1, int n2, long long* rank, long long* top1, viai_stream_t stream) {
+  VIAI_REQUIRE(dist && rank && top1 && n1 > 0 && n2 >= n1, "retrieval_ranks: bad arguments (every caption needs its own clip: n2 >= n1)");
+  retrieval_rank_kernel<<<n1, 256, 0, STR(stream)>>>(dist, n1, n2, rank, top1);
+  VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
 extern "C" int viai_pairdist_bwd(const float* f1, const float* f2, const float* scores, const float* dscores, int n1, int n2, int F,
                                  float* df1, float* df2, viai_stream_t stream) {
   VIAI_REQUIRE(f1 && f2 && scores && dscores && (df1 || df2) && n1 > 0 && n2 > 0 && F > 0 && (int64_t)(n1 + n2) * F < (1 << 30),

@@ -2,6 +2,9 @@
 // decoded uint8 frames -> cv2.resize (INTER_LINEAR, uint8 fixed point) -> BGR->RGB -> fliplr -> (v - 127) / 128 -> crop ->
 // float NHWC block that the ResNet stem reads without a layout pass.  HBM-bound byte work: one thread per output pixel,
 // 4 source pixels per channel, coefficients recomputed per thread in exactly OpenCV's arithmetic (bit-exact output).
+// (For an exact 2x down-scale in both directions OpenCV takes its INTER_AREA fast path, (a + b + c + d + 2) >> 2: the fixed-point
+// bilinear formula below yields the same bytes there -- both coefficient pairs are exactly (1024, 1024) -- so it needs no special
+// case; tests/test_loader_{cpu,gpu}.py pin 512 -> 256 and 448 -> 224 against cv2.)
 #include "common.cuh"
 #include <math.h>
 using namespace viai;

@@ -1194,6 +1194,17 @@ def pairdist(f1, f2):
     return _PairDistFn.apply(f1, f2)
 
 
+def retrieval_ranks(dist):
+    """(ranks, top1) int64 (n1,) of a (n1 captions x n2 clips) distance matrix: see viai_retrieval_ranks."""
+    _require_cuda(dist)
+    d = dist.detach().contiguous()
+    n1, n2 = d.shape
+    ranks = torch.empty(n1, device=d.device, dtype=torch.int64)
+    top1 = torch.empty(n1, device=d.device, dtype=torch.int64)
+    _lib.check(_lib.lib().viai_retrieval_ranks(_p(d), n1, n2, _p(ranks), _p(top1), _stream()), "retrieval_ranks")
+    return ranks, top1
+
+
 class _L2ContrastiveFn(torch.autograd.Function):
     """The hinge / diagonal reduction of L2ContrastiveLoss on a (B, B) score matrix (loss_functions.py:127-148)."""
 

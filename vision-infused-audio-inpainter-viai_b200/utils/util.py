@@ -12,28 +12,19 @@ def l2_norm(x):
 
 
 def L2retrieval(clips_embed, captions_embed, return_ranks=False):
-    """Recall@{1,5,10,50}, median and mean rank of the matching clip for every caption.  Embeddings are CUDA tensors (or numpy
-    arrays, moved to the device); the (captions x clips) Euclidean distance matrix comes from viai_pairdist_fwd, the ranking
-    itself is index work on the host, as in the reference."""
+    """Recall@{1,5,10,50} (percent), median and mean rank (1-based) of the matching clip of every caption (utils/util.py:99-121).
+    Embeddings are CUDA tensors (or numpy arrays, moved to the device).  The (captions x clips) Euclidean distances come from
+    viai_pairdist_fwd and the rank of caption i's own clip is COUNTED on the device (viai_retrieval_ranks: how many clips are
+    closer) -- the reference's argsort of the whole matrix is not needed; only the n ranks travel to the host."""
     import torch
     to_dev = lambda a: a if torch.is_tensor(a) else torch.as_tensor(np.asarray(a), dtype=torch.float32).cuda()
     clips, caps = to_dev(clips_embed).float(), to_dev(captions_embed).float()
-    captions_num = caps.shape[0]
     with torch.no_grad():
-        d = ops.pairdist(caps, clips).cpu().numpy()
-    inds = np.argsort(d)
-    num = np.arange(captions_num).reshape(captions_num, 1)
-    ranks = np.where(inds == num)[1]
-    top1 = inds[:, 0]
-    r1 = 100.0 * len(np.where(ranks < 1)[0]) / len(ranks)
-    r5 = 100.0 * len(np.where(ranks < 5)[0]) / len(ranks)
-    r10 = 100.0 * len(np.where(ranks < 10)[0]) / len(ranks)
-    r50 = 100.0 * len(np.where(ranks < 50)[0]) / len(ranks)
-    medr = np.floor(np.median(ranks)) + 1
-    meanr = ranks.mean() + 1
-    if return_ranks:
-        return (r1, r5, r10, r50, medr, meanr), (ranks, top1)
-    return (r1, r5, r10, r50, medr, meanr)
+        ranks_t, top1_t = ops.retrieval_ranks(ops.pairdist(caps, clips))
+    ranks, top1 = ranks_t.cpu().numpy(), top1_t.cpu().numpy()
+    recall = lambda k: 100.0 * float((ranks < k).mean())
+    metrics = (recall(1), recall(5), recall(10), recall(50), float(np.floor(np.median(ranks)) + 1), float(ranks.mean() + 1))
+    return (metrics, (ranks, top1)) if return_ranks else metrics
 
 
 def copy_state_dict(state_dict, model, strip=None):
