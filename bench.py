@@ -333,6 +333,45 @@ def run_c4(ctx, pk, T=160000):
     return res
 
 
+def time_wavenet_train(torch, B=4, T=8000, steps=5, warmup=3, graph=True):
+    """WaveNet teacher-forced training step (full C4 network) through ``WaveNetTrainer``: forward over B*T samples
+    in parallel, masked DMoL loss on the shifted targets, backward, fused Adam + EMA, captured as one CUDA graph.  The timed
+    region includes the host->device copy of each step's audio / conditioning from pinned memory and the read-back of the
+    loss.  samples/s = B*T / step time; algorithmic FLOPs 3 x 49.3 MFLOP/sample."""
+    from viai_b200.wavenet_step import WaveNetTrainer
+    from viai_b200.wavenet_vocoder import WaveNet
+    torch.manual_seed(0)
+    m = WaveNet().cuda().train()
+    tr = WaveNetTrainer(m)
+    x_h = (torch.rand(B, 1, T) * 2 - 1).pin_memory()
+    c_h = torch.rand(B, 80, T // 160).pin_memory()
+    mask = torch.ones(B, T, 1).cuda()
+    x, c = x_h.cuda(), c_h.cuda()
+    y = x.transpose(1, 2).contiguous()
+    if graph:
+        tr.capture(x, y, c, mask, warmup=2)
+        step = lambda: tr.replay(x_h, x_h, c_h)          # y is the same signal as x for raw audio: (B,1,T) and (B,T,1) share memory
+    else:
+        def step():
+            xd = x_h.cuda(non_blocking=True)
+            return tr.train_step(xd, xd.transpose(1, 2), c_h.cuda(non_blocking=True), mask)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = float(step())
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"metric": "WaveNet teacher-forced training samples/sec", "value": B * T / ms * 1e3, "unit": "samples/s", "B": B, "T": T,
+            "ms_per_step": ms, "algorithmic_tflops": 3 * 49.30e6 * B * T / (ms * 1e-3) / 1e12, "loss": loss,
+            "launches_per_step": int(tr.launches_per_step), "cuda_graph": bool(graph),
+            "config": "24 layers / 4 stacks, 512/512/256 channels, 80-bin local conditioning, dropout 0.05, masked DMoL loss, "
+                      "Adam + EMA; inputs from pinned host memory and loss read back every step"}
+
+
 def run_stft(ctx, pk, seconds=3600):
     """STFT -> mel front end (utils/audio.py:70-75): one launch over an hour of 16 kHz audio (T = 57.6 M samples, 230 MB: larger than
     L2), frames/s and algorithmic HBM bytes (hop * 4 bytes of new samples read + n_mels * 4 bytes written per frame)."""
@@ -501,7 +540,13 @@ def main():
             c3 = run_c3(ctx, pk)
         except Exception as e:
             c3 = {"error": repr(e)}
-    stft = None
+    stft = wn_train = None
+    if rank == 0 and world == 1 and extra:
+        try:
+            wn_train = time_wavenet_train(torch)
+        except Exception as e:
+            wn_train = {"error": repr(e)}
+        ctx.free()
     if rank == 0 and world == 1 and extra:
         try:
             stft = run_stft(ctx, pk)
@@ -540,7 +585,7 @@ def main():
                         "h2d_bytes_per_step": 2 * mel_h.numel() * 4, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches) * args.steps, "launches_per_step": int(launches), "f16_saturations": overflow,
                 "clocks": clocks, "sustained": sustained, "roofline": roof, "generator_stack": gen, "whole_step": whole, "top_ops": top,
-                "strong": strong, "cpu_baseline": cpu, "c3": c3, "c4": c4, "c5": c5, "stft": stft, "wavenet": c4}
+                "strong": strong, "cpu_baseline": cpu, "c3": c3, "c4": c4, "c5": c5, "stft": stft, "wavenet": c4, "wavenet_train": wn_train}
         print(json.dumps(line), flush=True)
     if world > 1:
         # No barrier / destroy_process_group here: tearing down the NCCL communicator after its all-reduces were captured in CUDA

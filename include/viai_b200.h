@@ -88,6 +88,16 @@ int viai_tc_f16_overflow(int reset, unsigned int* count);
 int64_t viai_tc_packed_size(int O, int I, int R, int S, int split);
 int viai_pack_weight_tc(const float* src, float* dst, int O, int I, int R, int S, int64_t so, int64_t si, int64_t sr,
                         int64_t ss, int flip, int split, viai_stream_t stream);
+/* Every operand re-layout a training-step segment needs in ONE launch (per 24 tensors): kind 0 = viai_pack_weight (fp32
+ * [O][R][S][I]), 1 / 2 / 3 / 4 = viai_pack_weight_tc with split 0 / 1 / 2 / 3; dst sized by O*I*R*S floats resp.
+ * viai_tc_packed_size.  descs is a HOST array, copied into the kernel's parameters. */
+typedef struct viai_pack_desc {
+  const float* src; void* dst;
+  int32_t O, I, R, S;
+  int64_t so, si, sr, ss;     /* element strides of src along O, I, kh, kw */
+  int32_t flip, kind;
+} viai_pack_desc;
+int viai_pack_weights_batched(const viai_pack_desc* descs, int n, viai_stream_t stream);
 int viai_conv2d_tc_supported(const viai_conv_geom* g);
 int viai_conv2d_tc(const viai_conv_geom* g, const float* in, const float* wp_tc, const float* bias, float* out,
                    double* stat_sum, double* stat_sumsq, int stat_groups, int flags, viai_stream_t stream);

@@ -28,6 +28,13 @@ class NormBwdCtx(ctypes.Structure):
                 ("beta", ctypes.c_void_p), ("act", ctypes.c_int32), ("slope", ctypes.c_float)]
 
 
+class PackDesc(ctypes.Structure):
+    """Mirror of ``viai_pack_desc``."""
+    _fields_ = [("src", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("O", ctypes.c_int32), ("I", ctypes.c_int32), ("R", ctypes.c_int32),
+                ("S", ctypes.c_int32), ("so", ctypes.c_int64), ("si", ctypes.c_int64), ("sr", ctypes.c_int64), ("ss", ctypes.c_int64),
+                ("flip", ctypes.c_int32), ("kind", ctypes.c_int32)]
+
+
 _GP = ctypes.POINTER(ConvGeom)
 
 # name -> argtypes (return type is always int)
@@ -35,6 +42,7 @@ SIGNATURES = {
     "viai_pack_weight": [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_l, c_l, c_i, c_p],
     "viai_conv2d_simt": [_GP, c_p, c_p, c_p, c_p, c_p],
     "viai_pack_weight_tc": [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_l, c_l, c_i, c_i, c_p],
+    "viai_pack_weights_batched": [ctypes.POINTER(PackDesc), c_i, c_p],
     "viai_conv2d_tc_supported": [_GP],
     "viai_conv2d_tc": [_GP, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p],
     "viai_conv2d_tc_bwd_reduce": [_GP, c_p, c_p, c_p, ctypes.POINTER(NormBwdCtx), c_p, c_p, c_i, c_p],

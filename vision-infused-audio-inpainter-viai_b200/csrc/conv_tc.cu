@@ -680,6 +680,94 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ src, float* __re
   }
 }
 
+// ---- batched weight packing: every operand re-layout a training-step segment needs in ONE launch ------------------------------
+// (a C2 step re-lays ~95 weight tensors between two optimizer updates: as separate ~3 us launches that is ~2 % of the step and a
+// fifth of its launches).  blockIdx.y selects the tensor, blockIdx.x strides over its packed elements; descriptors travel by value.
+constexpr int kMaxBatchPack = 24;
+struct PackBatch {
+  viai_pack_desc d[kMaxBatchPack];
+  int32_t bn[kMaxBatchPack];
+  int32_t n;
+};
+
+__device__ __forceinline__ float pack_src(const viai_pack_desc& q, int o, int i, int r, int s) {
+  const int rr = q.flip ? q.R - 1 - r : r, sw = q.flip ? q.S - 1 - s : s;
+  return q.src[o * q.so + i * q.si + rr * q.sr + sw * q.ss];
+}
+
+__global__ void __launch_bounds__(256) pack_batched_kernel(const __grid_constant__ PackBatch pb) {
+  const viai_pack_desc& q = pb.d[blockIdx.y];
+  const int O = q.O, I = q.I, R = q.R, S = q.S;
+  if (q.kind == 0) {                                   // thin / CUDA-core operand: fp32 [O][R][S][I]
+    const int64_t total = (int64_t)O * R * S * I;
+    float* dst = reinterpret_cast<float*>(q.dst);
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+      const int i = idx % I;
+      int64_t t = idx / I;
+      const int s = t % S; t /= S;
+      const int r = t % R;
+      const int o = (int)(t / R);
+      dst[idx] = pack_src(q, o, i, r, s);
+    }
+    return;
+  }
+  const int BN = pb.bn[blockIdx.y], nchunks = (I + KC - 1) / KC, ntilesN = (O + BN - 1) / BN;
+  if (q.kind == 1 || q.kind == 2) {                    // tf32 / tf32 pairs: the layout of pack_weight_tc_kernel
+    const int parts = q.kind == 2 ? 2 : 1;
+    const int64_t total = (int64_t)R * S * nchunks * ntilesN * parts * (KC / 4) * BN * 4;
+    float* dst = reinterpret_cast<float*>(q.dst);
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+      int64_t t = idx;
+      const int e = t & 3; t >>= 2;
+      const int row = t % BN; t /= BN;
+      const int j = t % (KC / 4); t /= (KC / 4);
+      const int part = t % parts; t /= parts;
+      const int nt = t % ntilesN; t /= ntilesN;
+      const int c = t % nchunks; t /= nchunks;
+      const int tap = (int)t;
+      const int o = nt * BN + row, i = c * KC + j * 4 + e;
+      float v = 0.f;
+      if (o < O && i < I) {
+        const float w = pack_src(q, o, i, tap / S, tap % S);
+        const float hi = to_tf32(w);
+        v = part == 0 ? hi : to_tf32(w - hi);
+      }
+      dst[idx] = v;
+    }
+    return;
+  }
+  // 16-bit pairs (3: bf16, 4: fp16 of the scaled weight): the layout of pack_weight_bf16x2_kernel / pack_weight_f16x2_kernel
+  const int64_t total = (int64_t)R * S * nchunks * ntilesN * 2 * (KC / 8) * BN * 8;
+  uint16_t* dst = reinterpret_cast<uint16_t*>(q.dst);
+  bool ovf = false;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = idx;
+    const int e = t & 7; t >>= 3;
+    const int row = t % BN; t /= BN;
+    const int j = t % (KC / 8); t /= (KC / 8);
+    const int part = t & 1; t >>= 1;
+    const int nt = t % ntilesN; t /= ntilesN;
+    const int c = t % nchunks; t /= nchunks;
+    const int tap = (int)t;
+    const int o = nt * BN + row, i = c * KC + j * 8 + e;
+    uint16_t v = 0;
+    if (o < O && i < I) {
+      const float w0 = pack_src(q, o, i, tap / S, tap % S);
+      if (q.kind == 3) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w0);
+        v = __bfloat16_as_ushort(part == 0 ? hi : __float2bfloat16_rn(w0 - __bfloat162float(hi)));
+      } else {
+        const float w = w0 * kF16WeightScale;
+        const uint32_t hi = pack_f16x2_sat(w, 0.f);
+        v = (uint16_t)(part == 0 ? (hi & 0xffffu) : (pack_f16x2_sat(w - f16lo_to_f32(hi), 0.f) & 0xffffu));
+        ovf |= fabsf(w) > 65504.f;
+      }
+    }
+    dst[idx] = v;
+  }
+  if (ovf) atomicAdd(&g_f16_overflow, 1u);
+}
+
 // Cout tile.  Capped at 128 so that two M tiles x two accumulator sets fit the 512 TMEM columns: the weight traffic of a layer
 // does not depend on this width (it is K * Cout * pixels / M), only on the number of pixels that share a weight tile.
 inline int env_int(const char* name, int dflt) {
@@ -931,6 +1019,25 @@ extern "C" int viai_pack_weight_tc(const float* src, float* dst, int O, int I, i
   const int blocks = (int)imin64(cdiv(total, 256), 4096);
   pack_weight_tc_kernel<<<blocks, 256, 0, STR(stream)>>>(src, dst, O, I, R, S, so, si, sr, ss, flip, BN, nchunks, ntilesN, split ? 2 : 1);
   VIAI_LAUNCHED();
+  return VIAI_OK;
+}
+
+extern "C" int viai_pack_weights_batched(const viai_pack_desc* descs, int n, viai_stream_t stream) {
+  VIAI_REQUIRE(descs != nullptr && n > 0, "pack_weights_batched: bad arguments");
+  for (int base = 0; base < n; base += kMaxBatchPack) {
+    PackBatch pb;
+    memset(&pb, 0, sizeof(pb));
+    pb.n = n - base < kMaxBatchPack ? n - base : kMaxBatchPack;
+    for (int k = 0; k < pb.n; ++k) {
+      const viai_pack_desc& q = descs[base + k];
+      VIAI_REQUIRE(q.src && q.dst && q.O > 0 && q.I > 0 && q.R > 0 && q.S > 0 && q.kind >= 0 && q.kind <= 4,
+                   "pack_weights_batched: bad descriptor %d", base + k);
+      pb.d[k] = q;
+      pb.bn[k] = tc_bn(q.O);
+    }
+    pack_batched_kernel<<<dim3(48, pb.n), 256, 0, STR(stream)>>>(pb);
+    VIAI_LAUNCHED();
+  }
   return VIAI_OK;
 }
 

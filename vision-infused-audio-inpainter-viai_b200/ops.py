@@ -205,6 +205,19 @@ def _geom(N, Hin, Win, Cin, Hout, Wout, Cout, R, S, stride, pad, mode):
 
 def _pack(weight, O_dim, I_dim, flip=False):
     """[O][R][S][I] operand from a (d0, d1, kh, kw) parameter; O_dim/I_dim say which of d0/d1 is O/I."""
+    if _PACK_STATE["on"]:
+        key = _pack_key(weight, O_dim, I_dim, -1 - int(flip))
+        if _PACK_REC is not None:
+            _PACK_REC.append((weight, O_dim, I_dim, -1 - int(flip)))
+        hit = _PACK_CACHE.get(key)
+        if hit is not None:
+            return hit
+        out = _PACK_CACHE[key] = _pack_uncached(weight, O_dim, I_dim, flip)
+        return out
+    return _pack_uncached(weight, O_dim, I_dim, flip)
+
+
+def _pack_uncached(weight, O_dim, I_dim, flip=False):
     L = _lib.lib()
     O, I = weight.size(O_dim), weight.size(I_dim)
     R, S = weight.size(2), weight.size(3)
@@ -239,16 +252,78 @@ def pack_cache_end():
 def weights_updated():
     _PACK_STATE["epoch"] += 1
     _PACK_CACHE.clear()
+    if _PACK_REC is not None:
+        _PACK_REC.append(None)           # segment boundary: what follows needs the updated weights
+
+
+def _pack_key(weight, O_dim, I_dim, split):
+    return (weight.data_ptr(), weight._version, _PACK_STATE["epoch"], O_dim, I_dim, split, tuple(weight.shape), tuple(weight.stride()))
 
 
 def _pack_tc(weight, O_dim, I_dim, split):
     if not _PACK_STATE["on"]:
         return _pack_tc_uncached(weight, O_dim, I_dim, split)
-    key = (weight.data_ptr(), weight._version, _PACK_STATE["epoch"], O_dim, I_dim, split, tuple(weight.shape), tuple(weight.stride()))
+    if _PACK_REC is not None:
+        _PACK_REC.append((weight, O_dim, I_dim, split))
+    key = _pack_key(weight, O_dim, I_dim, split)
     hit = _PACK_CACHE.get(key)
     if hit is None:
         hit = _PACK_CACHE[key] = _pack_tc_uncached(weight, O_dim, I_dim, split)
     return hit
+
+
+# ---- batched packing: a captured training step re-lays every weight a segment needs (between two optimizer updates) in one launch
+_PACK_REC = None
+
+
+def pack_record_begin():
+    """Starts recording the (weight, layout) requests of a bracketed step; weights_updated() marks the segment boundaries."""
+    global _PACK_REC
+    _PACK_REC = []
+
+
+def pack_record_end():
+    """-> list of segments, each a list of unique (parameter, O_dim, I_dim, split) requests (split < 0: the fp32 thin layout,
+    -1 plain / -2 flipped).  Only nn.Parameters are kept: their storage is stable across replays of a captured step; derived
+    tensors (weight-normed weights, the padded stem matrix) are packed where they are used, as before."""
+    global _PACK_REC
+    rec, _PACK_REC = _PACK_REC, None
+    segs, seen = [[]], set()
+    for r in rec or []:
+        if r is None:
+            segs.append([])
+            seen = set()
+            continue
+        w, od, idim, split = r
+        k = (id(w), od, idim, split)
+        if isinstance(w, torch.nn.Parameter) and k not in seen:
+            seen.add(k)
+            segs[-1].append(r)
+    return segs
+
+
+def prepack(requests):
+    """Packs every request of one segment with ONE viai_pack_weights_batched launch (per 24 tensors) and puts the results into the
+    step's pack cache, where the convolutions find them."""
+    if not requests or not _PACK_STATE["on"]:
+        return
+    L = _lib.lib()
+    descs = (_lib.PackDesc * len(requests))()
+    outs = []
+    for d, (w, od, idim, split) in zip(descs, requests):
+        O, I, R, S = w.size(od), w.size(idim), w.size(2), w.size(3)
+        if split < 0:
+            out = torch.empty((O, R, S, I), device=w.device, dtype=torch.float32)
+            kind, flip = 0, int(split == -2)
+        else:
+            out = torch.empty(L.viai_tc_packed_size(O, I, R, S, split), device=w.device, dtype=torch.float32)
+            kind, flip = 1 + split, 0
+        d.src, d.dst, d.O, d.I, d.R, d.S = w.data_ptr(), out.data_ptr(), O, I, R, S
+        d.so, d.si, d.sr, d.ss, d.flip, d.kind = w.stride(od), w.stride(idim), w.stride(2), w.stride(3), flip, kind
+        outs.append(out)
+    _lib.check(L.viai_pack_weights_batched(descs, len(requests), _stream()), "pack_weights_batched")
+    for (w, od, idim, split), out in zip(requests, outs):
+        _PACK_CACHE[_pack_key(w, od, idim, split)] = out
 
 
 def _pack_tc_uncached(weight, O_dim, I_dim, split):

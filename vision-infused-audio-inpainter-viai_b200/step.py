@@ -55,6 +55,7 @@ class GanTrainer(object):
         # generator's kernels -- "g_fwd" (encoder [+ visual encoder] + decoder forward) and "g_bwd" (from the moment d loss / d fake
         # is complete to the end of the generator's backward), "v_fwd" / "v_bwd" for the visual encoder alone.
         self.segment_events = None
+        self._pack_plan = None                   # set by capture(): batched weight packing per step segment
 
     def segment_ms(self):
         """{segment: milliseconds} of the last eager step run with ``segment_events = {}`` (synchronises)."""
@@ -130,6 +131,8 @@ class GanTrainer(object):
         H = self.hparams.cin_channels
         real = mel.reshape(B, 1, H, -1)
         self.real = real
+        if self._pack_plan:
+            ops.prepack(self._pack_plan[0])          # every weight re-layout up to the discriminator's update: one launch
         self._mark("g_fwd_0")
         masked = ops.mul(real.reshape(B, H, -1, 1), mask.reshape(B, H, -1, 1)).reshape(real.shape)
         feats = self.Mel_Encoder(masked)
@@ -154,6 +157,8 @@ class GanTrainer(object):
 
     def _seg_d_update_and_g_backward(self):
         self.optimizer_D.step()
+        if self._pack_plan and len(self._pack_plan) > 1:
+            ops.prepack(self._pack_plan[1])          # ... and from there (the updated discriminator) to the generator's update
         set_requires_grad(self.netD, False)
         self.optimizer_G.zero_grad()
         pred_fake = self.netD(self.fake)
@@ -204,6 +209,7 @@ class GanTrainer(object):
             self._step_body(mel, mask, video, flow)
         finally:
             ops.pack_cache_end()
+        self._pack_plan = None                   # the plan is baked into the graph; eager steps pack on demand
         self.launches_per_step = _lib.launch_count() - n0
         return self._outputs()
 
@@ -236,8 +242,12 @@ class GanTrainer(object):
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(warmup):
+            self._pack_plan = None
+            for i in range(warmup):
+                if i == warmup - 1:
+                    ops.pack_record_begin()          # learn which operand layouts each segment of the step asks for
                 self.train_step(st["mel"], st["mask"], st["video"], st["flow"])
+            plan = ops.pack_record_end() if warmup > 0 else None
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         # Drop every autograd graph built during warm-up: the AccumulateGrad nodes they keep alive are bound to the
@@ -246,6 +256,8 @@ class GanTrainer(object):
         if snap is not None:
             self._restore(snap)
             torch.cuda.synchronize()
+        import os
+        self._pack_plan = plan if (plan and os.environ.get("VIAI_BATCHED_PACK", "1") != "0") else None
         n0 = _lib.launch_count()
         ops.pack_cache_begin()
         if self.world_size == 1 or self.overlap:
