@@ -1035,7 +1035,7 @@ extern "C" int viai_pack_weights_batched(const viai_pack_desc* descs, int n, via
       pb.d[k] = q;
       pb.bn[k] = tc_bn(q.O);
     }
-    pack_batched_kernel<<<dim3(48, pb.n), 256, 0, STR(stream)>>>(pb);
+    pack_batched_kernel<<<dim3(2 * kNumSMs, pb.n), 256, 0, STR(stream)>>>(pb);   // the largest tensor sets the duration: give it the whole GPU
     VIAI_LAUNCHED();
   }
   return VIAI_OK;
