@@ -253,6 +253,29 @@ def test_cuda_graph_step_equals_eager_step():
     assert float(b.optimizer_G.step_dev) == 2.0 and int(b.netD.bn1.num_batches_tracked) == 6
 
 
+def test_batched_weight_packing_option_equals_on_demand_packing(monkeypatch):
+    """VIAI_BATCHED_PACK=1: the captured step re-lays every weight of a segment in one launch (ops.prepack); same result, fewer
+    launches (off by default: measured slower at C2, see step.py)."""
+    IN, NN, DN, nl, OI = _mods("bn")
+    from viai_b200.step import GanTrainer
+    hp = OI.Inpainting_Config(cin_channels=80)
+    mel = torch.rand(2, 1, 80, 64).cuda()
+    mask = O.time_band_mask(mel.shape, 16, 32).cuda()
+    outs, launches = [], []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VIAI_BATCHED_PACK", flag)
+        torch.manual_seed(7)
+        tr = GanTrainer(hp, "cuda")
+        tr.capture(mel, mask, warmup=1, preserve_state=True)
+        r = tr.replay(mel, mask)
+        torch.cuda.synchronize()
+        outs.append((r["fake"].clone(), tr.optimizer_G.flat_grad.clone(), tr.optimizer_D.flat_param.clone()))
+        launches.append(tr.launches_per_step)
+    assert launches[1] < launches[0] - 20
+    assert H.relerr(outs[1][0], outs[0][0]) < 1e-5 and H.relerr_l2(outs[1][1], outs[0][1]) < 1e-3
+    assert H.relerr_l2(outs[1][2], outs[0][2]) < 1e-3
+
+
 def test_illegal_64x64_mel_raises_like_reference():
     """BASELINE config 1 names a 64x64 mel; the reference's MelEncoder raises for mel height < 65."""
     IN, NN, DN, nl, OI = _mods("bn")
