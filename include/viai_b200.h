@@ -253,6 +253,22 @@ int viai_wavenet_synth_cluster(int L, int layers_per_stack, int R, int G, int S,
                                float log_scale_min, float* ring, const int64_t* ring_off, float* out, float* logits,
                                viai_stream_t stream);
 
+/* Folded schedule of the same synthesis (csrc/wavenet_synth2.cu): one dependent cross-CTA exchange per layer instead of two
+ * (the current-time tap of layer l is folded through layer l-1's residual 1x1 when the parameters are packed).  Same contract
+ * and arguments as viai_wavenet_synth except: packed_layers / last come from WaveNet.pack_for_synthesis_folded;  gbuf holds
+ * 2 * B * (G/2) and xchg 3 * B * R 64-bit words (zeroed, 8-byte aligned).  viai_wavenet2_num_ctas returns 0 when the
+ * configuration is unsupported (L < 3, or it does not fit) -- use viai_wavenet_synth then. */
+int viai_wavenet2_num_ctas(int L, int R, int G, int S, int C, int K, int O, int B);
+int viai_wavenet_synth2(int L, int layers_per_stack, int R, int G, int S, int C, int K, int O, int B, int T, int nC,
+                        const float* packed_layers, const float* last, const float* first, const float* head1,
+                        const float* head2, const float* cond, const float* uniforms, const float* test_inputs, int Ttest,
+                        float log_scale_min, float* ring, const int64_t* ring_off, float* gbuf, float* sbuf, float* hbuf,
+                        unsigned* xchg, float* out, float* logits, viai_stream_t stream);
+
+/* Debug aid: with VIAI_WN2_PROF=1 in the environment, clocks CTA 0 spent per phase of the last viai_wavenet_synth2 launch
+ * (phase list in csrc/wavenet_synth2.cu); synchronises the device. */
+int viai_wavenet2_profile(long long* out16);
+
 /* Losses (loss_functions.py:79-104 GANLoss = MSELoss / BCELoss against an expanded scalar; nn.L1Loss).
  * kind 0: mean (p-t)^2   1: BCE(p, t)   2: mean |p - q|  (q = other tensor).  acc: double[1] workspace.
  * loss_out: float[1] on device. */

@@ -147,6 +147,90 @@ class WaveNet(nn.Module):
         h2 = torch.cat((effective_weight(self.last_conv_layers[3]).float().reshape(-1), self.last_conv_layers[3].bias.float()))
         return dict(layers=out.contiguous(), first=first.contiguous(), head1=h1.contiguous(), head2=h2.contiguous(), nC=nC)
 
+    @torch.no_grad()
+    def pack_for_synthesis_folded(self, nC):
+        """Parameter blocks of the FOLDED synthesis kernel (csrc/wavenet_synth2.cu), which needs one dependent cross-CTA exchange
+        per layer instead of two.  With A_l the current-time tap of layer l's dilated convolution, Wo/bo its residual 1x1 and
+        x_l = r (Wo_{l-1} h_{l-1} + bo_{l-1} + x_{l-1}), r = sqrt(0.5) (modules.py:196-207), the gate pre-activation is
+
+            z_l = [old taps + conditioning + bias]_l + A_l x_l
+                = P'_l + M_l h_{l-1},      M_l = r A_l Wo_{l-1}
+            P'_l = [old taps + conditioning]_l + N_l h_{l-2} + T_l x_{l-2} + const_l,   N_l = r^2 A_l Wo_{l-2},  T_l = r^2 A_l
+
+        P'_l only needs vectors that were exchanged one slot earlier, so it is evaluated off the critical path while h_{l-1} is
+        in flight; only M_l h_{l-1} (fused with the skip / residual rows of layer l-1, which read the same h_{l-1}) is dependent.
+        Layers 0 and 1 use x_0 = fw * sample + fb directly (T_1 = r A_1, N_1 = 0; layer 0: rank-1 term uc = A_0 fw).
+        Block l (per CTA):  [skip rows l-1 | residual rows l-1 | M_l gate rows][G/2]  [their biases, padded to 4]
+                            [gate rows of layer nl = (l+1) % L: N | T | old taps | conditioning]  [const, padded]  [uc, padded]
+        The products are formed in fp64 and rounded once to fp32."""
+        L, R, G, S, C, K, O = self._dims()
+        dev = self.first_conv.bias.device
+        pairs, srows, orows = (G // 2) // nC, S // nC, R // nC
+        pad4 = lambda n: (n + 3) // 4 * 4
+        K2 = G // 2
+        Kn = K2 + R + (K - 1) * R + C
+        rows1, rowsC = 2 * pairs, srows + orows + 2 * pairs
+        stride = rowsC * K2 + pad4(rowsC) + rows1 * Kn + 2 * pad4(rows1)
+        out = torch.zeros((L, nC, stride), device=dev, dtype=torch.float32)
+        i1 = torch.arange(nC * pairs, device=dev).view(nC, pairs)
+        idx1 = torch.stack((i1, i1 + G // 2), dim=2).reshape(nC, rows1)
+        idx_s = torch.arange(S, device=dev).view(nC, srows)
+        idx_o = torch.arange(R, device=dev).view(nC, orows)
+        r2 = math.sqrt(0.5)
+        A, Wt, Wc, b, Wo, bo, Ws, bs = [], [], [], [], [], [], [], []
+        for f in self.conv_layers:
+            w = effective_weight(f.conv).double()                                         # (G, R, K)
+            lin = w.permute(0, 2, 1).reshape(G, K * R)                                    # tap-major (conv.py:56-61)
+            A.append(lin[:, (K - 1) * R:])
+            Wt.append(lin[:, :(K - 1) * R])
+            b1 = f.conv.bias.double().clone()
+            if f.conv1x1c is not None:
+                Wc.append(effective_weight(f.conv1x1c).double().reshape(G, C))
+                b1 += f.conv1x1c.bias.double()
+            else:
+                Wc.append(torch.zeros((G, C), device=dev, dtype=torch.float64))
+            b.append(b1)
+            Ws.append(effective_weight(f.conv1x1_skip).double().reshape(S, K2)); bs.append(f.conv1x1_skip.bias.double())
+            Wo.append(effective_weight(f.conv1x1_out).double().reshape(R, K2)); bo.append(f.conv1x1_out.bias.double())
+        fw, fb = effective_weight(self.first_conv).double().reshape(-1), self.first_conv.bias.double()
+        for l in range(L):
+            if l >= 1:
+                M = r2 * (A[l] @ Wo[l - 1])
+                blk = torch.cat((Ws[l - 1][idx_s], Wo[l - 1][idx_o], M[idx1]), 1)          # (nC, rowsC, K2)
+                out[l, :, :rowsC * K2] = blk.reshape(nC, -1).float()
+                out[l, :, rowsC * K2:rowsC * K2 + srows + orows] = torch.cat((bs[l - 1][idx_s], bo[l - 1][idx_o]), 1).float()
+            o = rowsC * K2 + pad4(rowsC)
+            nl = (l + 1) % L
+            N = torch.zeros((G, K2), device=dev, dtype=torch.float64)
+            Tm = torch.zeros((G, R), device=dev, dtype=torch.float64)
+            cN = b[nl].clone()
+            if nl == 0:
+                cN += A[0] @ fb
+            elif nl == 1:
+                Tm = r2 * A[1]
+                cN += r2 * (A[1] @ bo[0])
+            else:
+                N = 0.5 * (A[nl] @ Wo[nl - 2])
+                Tm = 0.5 * A[nl]
+                cN += r2 * (A[nl] @ bo[nl - 1]) + 0.5 * (A[nl] @ bo[nl - 2])
+            Wn = torch.cat((N, Tm, Wt[nl], Wc[nl]), 1)                                     # (G, Kn)
+            out[l, :, o:o + rows1 * Kn] = Wn[idx1].reshape(nC, -1).float(); o += rows1 * Kn
+            out[l, :, o:o + rows1] = cN[idx1].float(); o += pad4(rows1)
+            if l == 0:
+                out[0, :, o:o + rows1] = (A[0] @ fw)[idx1].float()
+        last = torch.zeros((nC, srows * K2 + pad4(srows)), device=dev)
+        last[:, :srows * K2] = Ws[L - 1][idx_s].reshape(nC, -1).float()
+        last[:, srows * K2:srows * K2 + srows] = bs[L - 1][idx_s].float()
+        first = torch.cat((fw, fb)).float()
+        hrows = S // nC
+        h1 = torch.zeros((nC, hrows * S + pad4(hrows)), device=dev)
+        w1 = effective_weight(self.last_conv_layers[1]).float().reshape(S, S)
+        h1[:, :hrows * S] = w1.view(nC, hrows * S)
+        h1[:, hrows * S:hrows * S + hrows] = self.last_conv_layers[1].bias.float().view(nC, hrows)
+        h2 = torch.cat((effective_weight(self.last_conv_layers[3]).float().reshape(-1), self.last_conv_layers[3].bias.float()))
+        return dict(layers=out.contiguous(), last=last.contiguous(), first=first.contiguous(), head1=h1.contiguous(),
+                    head2=h2.contiguous(), nC=nC, Kn=Kn, rowsC=rowsC, rows1=rows1, stride=stride)
+
     def _upsample(self, c):
         """(B, cin, Tc) -> (B, T, cin): ConvTranspose2d(1,1,(f,s), stride (1,s)) + ReLU per scale (reference :294-304)."""
         if self.upsample_conv is None:
@@ -199,14 +283,18 @@ class WaveNet(nn.Module):
         cluster = want == "cluster" and Lh.viai_wavenet_cluster_supported(R, G, S, C, K, O, B) > 0
         if want == "cluster" and not cluster:
             raise RuntimeError("the cluster synthesis kernel does not support this configuration")
-        nC = 16 if cluster else Lh.viai_wavenet_num_ctas(R, G, S, C, K, O, B)
+        folded = want == "folded" and Lh.viai_wavenet2_num_ctas(L, R, G, S, C, K, O, B) > 0
+        if want == "folded" and not folded:
+            raise RuntimeError("the folded synthesis kernel does not support this configuration")
+        nC = 16 if cluster else (Lh.viai_wavenet2_num_ctas(L, R, G, S, C, K, O, B) if folded else
+                                 Lh.viai_wavenet_num_ctas(R, G, S, C, K, O, B))
         if nC <= 0:
             raise RuntimeError("unsupported WaveNet configuration for the synthesis kernel (R=%d G=%d S=%d C=%d K=%d O=%d B=%d)"
                                % (R, G, S, C, K, O, B))
         # Re-linearised on every call, like the reference (clear_buffer() on entry, wavenet.py:263 -> conv.py:48-62): the weights
         # may have been changed by an optimizer step, load_state_dict or make_generation_fast_ since the last synthesis, and
         # packing 99 MB costs ~1 ms against seconds of synthesis.
-        pk = self._packed = self.pack_for_synthesis(nC)
+        pk = self._packed = self.pack_for_synthesis_folded(nC) if folded else self.pack_for_synthesis(nC)
         nm = O // 3
         if uniforms is None:
             uniforms = torch.empty((T, B, nm + 1), device=dev).uniform_(1e-5, 1.0 - 1e-5)
@@ -220,9 +308,9 @@ class WaveNet(nn.Module):
         ring = torch.zeros(tot, device=dev)
         ring_off = torch.tensor(offs, device=dev, dtype=torch.int64)
         # exchange buffers of 64-bit {value, stage tag} words, zero = "never written"
-        gbuf, sbuf, hbuf = (torch.zeros(2 * B * (G // 2), device=dev), torch.zeros(2 * B * S, device=dev),
+        gbuf, sbuf, hbuf = (torch.zeros((4 if folded else 2) * B * (G // 2), device=dev), torch.zeros(2 * B * S, device=dev),
                             torch.zeros(2 * B * S, device=dev))
-        bar = torch.zeros(2 * B * R, device=dev, dtype=torch.int32)
+        bar = torch.zeros((6 if folded else 2) * B * R, device=dev, dtype=torch.int32)
         out = torch.empty((B, T), device=dev)
         logits = torch.empty((B, T, O), device=dev) if return_logits else None
         ti = None
@@ -234,6 +322,14 @@ class WaveNet(nn.Module):
                                                      0 if ti is None else ti.size(1), float(log_scale_min), _p(ring), _p(ring_off),
                                                      _p(out), _p(logits),
                                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "wavenet_synth_cluster")
+            out = out.view(B, 1, T)
+            return (out, logits) if return_logits else out
+        if folded:
+            _lib.check(Lh.viai_wavenet_synth2(L, self.layers_per_stack, R, G, S, C, K, O, B, T, nC, _p(pk["layers"]), _p(pk["last"]),
+                                              _p(pk["first"]), _p(pk["head1"]), _p(pk["head2"]), _p(cond), _p(uniforms), _p(ti),
+                                              0 if ti is None else ti.size(1), float(log_scale_min), _p(ring), _p(ring_off),
+                                              _p(gbuf), _p(sbuf), _p(hbuf), _p(bar), _p(out), _p(logits),
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "wavenet_synth2")
             out = out.view(B, 1, T)
             return (out, logits) if return_logits else out
         _lib.check(Lh.viai_wavenet_synth(L, self.layers_per_stack, R, G, S, C, K, O, B, T, nC, _p(pk["layers"]), _p(pk["first"]),
