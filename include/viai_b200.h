@@ -265,6 +265,25 @@ int viai_wavenet_synth2(int L, int layers_per_stack, int R, int G, int S, int C,
                         float log_scale_min, float* ring, const int64_t* ring_off, float* gbuf, float* sbuf, float* hbuf,
                         unsigned* xchg, float* out, float* logits, viai_stream_t stream);
 
+/* Warp-specialised variant of the folded schedule (csrc/wavenet_synth3.cu): 8 warps run the dependent chain (one warp per
+ * gate-row pair / residual row / skip row, no CTA-wide barrier), 8 warps evaluate the next layer's independent part, one
+ * producer lane streams the weight blocks through a shared-memory ring with bulk copies.  Same arguments as
+ * viai_wavenet_synth2 except for the exchange buffers, which hold NREP = viai_wavenet3_replicas() copies of every vector
+ * (a CTA reads copy cta % NREP; one copy made 128 CTAs poll the same 8 L2 slices): gbuf 3 * NREP * B * (G/2), xchg
+ * 3 * NREP * B * R, sbuf / hbuf NREP * B * S 64-bit words.  viai_wavenet3_num_ctas returns 0 when the configuration is
+ * unsupported (use viai_wavenet_synth2 / viai_wavenet_synth then). */
+int viai_wavenet3_replicas(void);
+int viai_wavenet3_num_ctas(int L, int R, int G, int S, int C, int K, int O, int B);
+int viai_wavenet_synth3(int L, int layers_per_stack, int R, int G, int S, int C, int K, int O, int B, int T, int nC,
+                        const float* packed_layers, const float* last, const float* first, const float* head1,
+                        const float* head2, const float* cond, const float* uniforms, const float* test_inputs, int Ttest,
+                        float log_scale_min, float* ring, const int64_t* ring_off, float* gbuf, float* sbuf, float* hbuf,
+                        unsigned* xchg, float* out, float* logits, viai_stream_t stream);
+
+/* Debug aid: VIAI_WN3_PROF=1 selects a profiling instantiation of viai_wavenet_synth3; per-phase clocks of CTA 0 (phase list
+ * in csrc/wavenet_synth3.cu); synchronises the device. */
+int viai_wavenet3_profile(long long* out32);
+
 /* Debug aid: with VIAI_WN2_PROF=1 in the environment, clocks CTA 0 spent per phase of the last viai_wavenet_synth2 launch
  * (phase list in csrc/wavenet_synth2.cu); synchronises the device. */
 int viai_wavenet2_profile(long long* out16);

@@ -31,7 +31,7 @@ def main():
     c = torch.rand(B, 80, T // 8)
     u = torch.rand(T, B, 11) * (1 - 2e-5) + 1e-5
     want, wlg = O.wavenet_incremental(sd, c, T, 4, [2, 4], uniforms=u, return_logits=True)
-    for kern in ("grid", "folded"):
+    for kern in ("grid", "folded", "ws"):
         out, lg = run(m, kern, c=c.cuda(), T=T, uniforms=u.cuda(), return_logits=True)
         torch.cuda.synchronize()
         print("small %-6s logits relerr %.2e samples relerr %.2e" % (kern, H.relerr(lg, wlg), H.relerr(out, want)), flush=True)
@@ -43,14 +43,18 @@ def main():
     u = torch.empty((T, 1, 11), device="cuda").uniform_(1e-5, 1 - 1e-5)
     ti = torch.rand(1, T, 1).cuda() * 2 - 1
     res = {}
-    for kern in ("grid", "folded"):
+    for kern in ("grid", "folded", "ws"):
         res[kern] = run(m, kern, c=c, T=T, uniforms=u, test_inputs=ti, return_logits=True)
         torch.cuda.synchronize()
-    print("full teacher-forced T=%d: folded vs grid logits relerr %.2e" % (T, H.relerr(res["folded"][1], res["grid"][1])), flush=True)
+    print("full teacher-forced T=%d: folded vs grid logits relerr %.2e, ws vs grid %.2e" % (
+        T, H.relerr(res["folded"][1], res["grid"][1]), H.relerr(res["ws"][1], res["grid"][1])), flush=True)
+    o1 = run(m, "grid", c=c, T=T, uniforms=u)
+    o2 = run(m, "ws", c=c, T=T, uniforms=u)
+    print("full free-running T=%d: ws vs grid samples relerr %.2e" % (T, H.relerr(o2, o1)), flush=True)
     for Bn in (1, 4):
         T = 8000
         c = torch.rand(Bn, 80, T // 160).cuda()
-        for kern in ("grid", "folded"):
+        for kern in ("grid", "folded", "ws"):
             run(m, kern, c=c[:, :, :10].contiguous(), T=1600)
             torch.cuda.synchronize()
             t0 = time.perf_counter()

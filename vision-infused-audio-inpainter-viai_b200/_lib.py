@@ -81,6 +81,10 @@ SIGNATURES = {
     "viai_stft_mel": [c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_i, c_f, c_f, c_p, c_p, c_p],
     "viai_wavenet_num_ctas": [c_i] * 7,
     "viai_wavenet_synth": [c_i] * 11 + [c_p] * 7 + [c_i, c_f] + [c_p] * 9,
+    "viai_wavenet3_num_ctas": [c_i] * 8,
+    "viai_wavenet3_replicas": [],
+    "viai_wavenet3_profile": [c_p],
+    "viai_wavenet_synth3": [c_i] * 11 + [c_p] * 8 + [c_i, c_f] + [c_p] * 9,
     "viai_wavenet2_num_ctas": [c_i] * 8,
     "viai_wavenet2_profile": [c_p],
     "viai_wavenet_synth2": [c_i] * 11 + [c_p] * 8 + [c_i, c_f] + [c_p] * 9,

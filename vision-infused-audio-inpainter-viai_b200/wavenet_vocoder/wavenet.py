@@ -275,18 +275,29 @@ class WaveNet(nn.Module):
         else:
             cond = self._upsample(c.to(dev).float())
             assert cond.size(1) == T, "upsampled conditioning covers %d steps, T = %d" % (cond.size(1), T)
-        # kernel choice: the grid-wide kernel (128 CTAs exchanging tagged words through global memory; 7.6 k samples/s on B200) is
-        # the default; VIAI_WAVENET_KERNEL=cluster selects the single 16-CTA cluster variant that exchanges through distributed
-        # shared memory (exchange latency 0.1-0.3 us instead of ~1.3 us, but 8x more rows per CTA: 5.4 k samples/s so far).
+        # Kernel choice (VIAI_WAVENET_KERNEL; default "auto" = the fastest one that supports the configuration).  Samples/s of the
+        # C4 network on one B200 at B = 1, T = 8000 (scripts/r02_wavenet_folded.py):
+        #   ws      14.0 k  csrc/wavenet_synth3.cu  folded schedule (one dependent exchange per layer), warp-specialised
+        #   folded   9.5 k  csrc/wavenet_synth2.cu  folded schedule, one instruction stream
+        #   grid     7.1 k  csrc/wavenet_synth.cu   two exchanges per layer (round 1)
+        #   cluster  5.4 k  csrc/wavenet_synth_cluster.cu  one 16-CTA cluster over distributed shared memory
         import os
-        want = os.environ.get("VIAI_WAVENET_KERNEL", "grid")
+        want = os.environ.get("VIAI_WAVENET_KERNEL", "auto")
+        if want not in ("auto", "ws", "folded", "grid", "cluster"):
+            raise RuntimeError("VIAI_WAVENET_KERNEL must be one of auto, ws, folded, grid, cluster (got %r)" % want)
+        if want == "auto":
+            want = ("ws" if Lh.viai_wavenet3_num_ctas(L, R, G, S, C, K, O, B) > 0 else
+                    "folded" if Lh.viai_wavenet2_num_ctas(L, R, G, S, C, K, O, B) > 0 else "grid")
         cluster = want == "cluster" and Lh.viai_wavenet_cluster_supported(R, G, S, C, K, O, B) > 0
         if want == "cluster" and not cluster:
             raise RuntimeError("the cluster synthesis kernel does not support this configuration")
-        folded = want == "folded" and Lh.viai_wavenet2_num_ctas(L, R, G, S, C, K, O, B) > 0
-        if want == "folded" and not folded:
-            raise RuntimeError("the folded synthesis kernel does not support this configuration")
-        nC = 16 if cluster else (Lh.viai_wavenet2_num_ctas(L, R, G, S, C, K, O, B) if folded else
+        ws = want == "ws" and Lh.viai_wavenet3_num_ctas(L, R, G, S, C, K, O, B) > 0
+        folded = ws or (want == "folded" and Lh.viai_wavenet2_num_ctas(L, R, G, S, C, K, O, B) > 0)
+        if want in ("folded", "ws") and not folded:
+            raise RuntimeError("the %s synthesis kernel does not support this configuration" % want)
+        self.last_synthesis_kernel = want
+        nC = 16 if cluster else (Lh.viai_wavenet3_num_ctas(L, R, G, S, C, K, O, B) if ws else
+                                 Lh.viai_wavenet2_num_ctas(L, R, G, S, C, K, O, B) if folded else
                                  Lh.viai_wavenet_num_ctas(R, G, S, C, K, O, B))
         if nC <= 0:
             raise RuntimeError("unsupported WaveNet configuration for the synthesis kernel (R=%d G=%d S=%d C=%d K=%d O=%d B=%d)"
@@ -308,9 +319,11 @@ class WaveNet(nn.Module):
         ring = torch.zeros(tot, device=dev)
         ring_off = torch.tensor(offs, device=dev, dtype=torch.int64)
         # exchange buffers of 64-bit {value, stage tag} words, zero = "never written"
-        gbuf, sbuf, hbuf = (torch.zeros((4 if folded else 2) * B * (G // 2), device=dev), torch.zeros(2 * B * S, device=dev),
-                            torch.zeros(2 * B * S, device=dev))
-        bar = torch.zeros((6 if folded else 2) * B * R, device=dev, dtype=torch.int32)
+        nrep = Lh.viai_wavenet3_replicas() if ws else 1        # copies of every exchanged vector (spreads the polling over L2 slices)
+        nbuf = 3 if folded else 1                                # h / x vectors in flight
+        gbuf, sbuf, hbuf = (torch.zeros(2 * nbuf * nrep * B * (G // 2), device=dev), torch.zeros(2 * nrep * B * S, device=dev),
+                            torch.zeros(2 * nrep * B * S, device=dev))
+        bar = torch.zeros(2 * nbuf * nrep * B * R, device=dev, dtype=torch.int32)
         out = torch.empty((B, T), device=dev)
         logits = torch.empty((B, T, O), device=dev) if return_logits else None
         ti = None
@@ -325,11 +338,11 @@ class WaveNet(nn.Module):
             out = out.view(B, 1, T)
             return (out, logits) if return_logits else out
         if folded:
-            _lib.check(Lh.viai_wavenet_synth2(L, self.layers_per_stack, R, G, S, C, K, O, B, T, nC, _p(pk["layers"]), _p(pk["last"]),
-                                              _p(pk["first"]), _p(pk["head1"]), _p(pk["head2"]), _p(cond), _p(uniforms), _p(ti),
-                                              0 if ti is None else ti.size(1), float(log_scale_min), _p(ring), _p(ring_off),
-                                              _p(gbuf), _p(sbuf), _p(hbuf), _p(bar), _p(out), _p(logits),
-                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "wavenet_synth2")
+            fn = Lh.viai_wavenet_synth3 if ws else Lh.viai_wavenet_synth2
+            _lib.check(fn(L, self.layers_per_stack, R, G, S, C, K, O, B, T, nC, _p(pk["layers"]), _p(pk["last"]), _p(pk["first"]),
+                          _p(pk["head1"]), _p(pk["head2"]), _p(cond), _p(uniforms), _p(ti), 0 if ti is None else ti.size(1),
+                          float(log_scale_min), _p(ring), _p(ring_off), _p(gbuf), _p(sbuf), _p(hbuf), _p(bar), _p(out), _p(logits),
+                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "wavenet_synth3" if ws else "wavenet_synth2")
             out = out.view(B, 1, T)
             return (out, logits) if return_logits else out
         _lib.check(Lh.viai_wavenet_synth(L, self.layers_per_stack, R, G, S, C, K, O, B, T, nC, _p(pk["layers"]), _p(pk["first"]),
