@@ -309,14 +309,30 @@ def run_c4(ctx, pk, T=160000):
         e1.synchronize()
     ms = e0.elapsed_time(e1)
     rate = T / ms * 1e3
-    wbytes = 24.74e6 * 4
+    kern = getattr(m, "last_synthesis_kernel", "grid")
+    wbytes = float(m._packed["layers"].numel() + m._packed["head1"].numel() + m._packed["head2"].numel()) * 4
+    # four utterances at once (the reference's incremental_forward takes a batch; the dependent chain is shared)
+    T4 = 16000
+    c4 = torch.rand(4, 80, T4 // 160).cuda()
+    with torch.no_grad():
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        out4 = m.incremental_forward(c=c4, T=T4)
+        e3.record()
+        e3.synchronize()
+    ms4 = e2.elapsed_time(e3)
     res = {"metric": "WaveNet samples/sec", "value": rate, "unit": "samples/s", "T": T, "seconds_of_audio": T / 16000.0, "ms": ms,
            "real_time_factor": (T / 16000.0) / (ms * 1e-3), "finite": bool(torch.isfinite(out).all()),
-           "in_range": bool((out.abs() <= 1).all()),
+           "in_range": bool((out.abs() <= 1).all()), "kernel": kern,
            "config": "C4: 24 layers / 4 stacks, 512/512/256 channels, 80-bin local conditioning, B=1, scalar (DMoL) output, 16 kHz",
+           "batch4": {"value": 4 * T4 / ms4 * 1e3, "unit": "samples/s", "B": 4, "T": T4, "ms": ms4,
+                      "finite": bool(torch.isfinite(out4).all())},
            "roofline": {"bound": "hbm", "achieved": wbytes * rate / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": wbytes * rate / 1e9 / pk["hbm"],
-                        "traffic": None, "note": "algorithmic bytes = the 98.9 MB of fp32 weights every sample touches; they are L2-resident, "
-                                                 "the loop is bound by the 2*24+2 dependent mat-vec stages per sample (latency), not by HBM"}}
+                        "traffic": 119.3e6 if kern == "ws" else None,
+                        "note": "algorithmic bytes = the %.1f MB of packed fp32 parameters every sample touches; the per-sample sweep is cyclic "
+                                "and larger than what the 126 MB L2 keeps, so they stream from HBM every sample (ncu: 119 MB of DRAM reads per "
+                                "sample, profiles/r02_wavenet_folded_ncu_summary.txt); the loop is bound by the %d dependent cross-CTA "
+                                "exchanges per sample (latency), not by HBM" % (wbytes / 1e6, 26 if kern in ("ws", "folded") else 50)}}
     del m
     ctx.free()
     try:

@@ -13,7 +13,7 @@ from viai_b200.wavenet_vocoder import WaveNet  # noqa: E402
 
 D = ["rest", "stage h", "group barrier", "weight wait", "dots", "P' wait", "gate+publish", "last skip+fence", "barrier A", "head",
      "barrier B", "sampler+barrier C"]
-I = ["rest", "gathers", "group barrier 1", "weight wait", "operand wait", "dot", "group barrier 2", "P' hand-over", "barrier A",
+I = ["rest", "B: x + h gather", "B: group barrier", "A: weight wait", "A: operand wait", "A: taps dot", "B: dot + barrier", "P hand-over", "barrier A",
      "head..C"]
 
 

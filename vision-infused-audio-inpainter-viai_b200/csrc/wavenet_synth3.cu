@@ -33,7 +33,7 @@ constexpr int NT3 = NWORK + 32;                    // + the producer warp
 constexpr int NW16 = NWORK / 32;
 constexpr int MAXSTAGE = 3;           // weight stages in flight (2 when the operand buffers of a large batch need the room)
 constexpr int MAXB = 4;
-constexpr int NREP = 4;               // replicas of every cross-CTA vector (see put_lane)
+constexpr int NREP = 8;               // replicas of every cross-CTA vector (see put_lane)
 constexpr int kSmemLimit = 226 * 1024;
 __host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
 
@@ -88,6 +88,19 @@ __device__ __forceinline__ float get_tagged(const unsigned long long* p, unsigne
   if ((unsigned)(w >> 32) == tag) return __uint_as_float((unsigned)w);
   return get_tagged_spin(p, tag);
 }
+// two adjacent tagged words with one 16-byte load (each 8-byte half is written atomically and carries its own tag)
+__device__ __forceinline__ float2 get_tagged2(const unsigned long long* p, unsigned tag) {
+  unsigned long long w0, w1;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+  if ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag) {
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+      if (clock64() - t0 > 4000000000LL) __trap();
+    } while ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag);
+  }
+  return make_float2(__uint_as_float((unsigned)w0), __uint_as_float((unsigned)w1));
+}
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -132,6 +145,21 @@ __device__ __forceinline__ void row_dot(uint32_t wr, uint32_t xs, int xstride, i
   }
 #pragma unroll
   for (int b = 0; b < B; ++b) acc[b] = warp_sum_f(acc[b]);
+}
+
+// this lane's share of one row over the float4 range [k0, k1), accumulated into acc (no reduction)
+template <int B>
+__device__ __forceinline__ void row_acc(uint32_t wr, uint32_t xs, int xstride, int k0, int k1, float* acc) {
+#pragma unroll 2
+  for (int k = k0 + (int)(threadIdx.x & 31); k < k1; k += 32) {
+    const float4 w = lds128(wr + 16u * (uint32_t)k);
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const float4 v = lds128(xs + (uint32_t)(b * xstride + 4 * k) * 4u);
+      acc[b] = fmaf(w.x, v.x, acc[b]); acc[b] = fmaf(w.y, v.y, acc[b]);
+      acc[b] = fmaf(w.z, v.z, acc[b]); acc[b] = fmaf(w.w, v.w, acc[b]);
+    }
+  }
 }
 
 // two adjacent rows (the tanh / sigmoid pair) against the same columns: the x loads are shared and the reductions interleave
@@ -204,7 +232,7 @@ __host__ __device__ inline Smem3 smem3_layout(int R, int G, int S, int C, int K,
   int o = 0;
   m.wst = o; o += nstage * m.wpad;
   m.xin = o; o += 2 * B * m.xlen;
-  m.hD = o; o += 2 * B * K2;
+  m.hD = o; o += 3 * B * K2;
   m.Pn = o; o += 2 * pad4(m.rows1) * MAXB;
   m.partI = o; o += pad4(m.rows1 * m.ksN) * MAXB;
   m.first = o; o += 2 * R;
@@ -261,8 +289,8 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
   uint64_t* const xempty = xfull + 2;              // [2] the I warps are done with the operand buffer
   uint64_t* const pnfull = xempty + 2;             // [2] P' of a slot written
   uint64_t* const pnempty = pnfull + 2;            // [2] ... and consumed by the gate lanes
-  uint64_t* const dbar = pnempty + 2;              // [2] h_{l-1} staged in hD[n & 1] by the 256 D threads (n-th staging)
-  uint64_t* const ibar = dbar + 2;                 // I group barrier
+  uint64_t* const dbar = pnempty + 2;              // [3] h_{l-1} staged in hD[n % 3] by the 256 D threads (n-th staging)
+  uint64_t* const ibar = dbar + 3;                 // I group barrier
   uint64_t* const hbar = ibar + 1;                 // D group barrier of the head
   long long* const profs = reinterpret_cast<long long*>(sm + m.prof);
   long long tprev = 0;
@@ -303,8 +331,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
       mbar_init(&xfull[i], 1); mbar_init(&xempty[i], NI);
       mbar_init(&pnfull[i], rows1 * B); mbar_init(&pnempty[i], p.pairs * B);   // (replica-0 lanes arrive on pnempty)
     }
-    mbar_init(&dbar[0], NDT);
-    mbar_init(&dbar[1], NDT);
+    for (int i = 0; i < 3; ++i) mbar_init(&dbar[i], NDT);
     mbar_init(ibar, NIT);
     mbar_init(hbar, NDT);
     fence_barrier_init();
@@ -357,43 +384,21 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
     const int wI = warp - ND, tI = tid - NDT;
     uint32_t iparity = 0;
     const int rowN = wI % rows1, sliceN = wI / rows1;
-    const int chunkN = (K4n + ksN - 1) / ksN;
-    const int kN0 = sliceN * chunkN, kN1 = sliceN < ksN ? min(K4n, kN0 + chunkN) : kN0;
     // I slot v: P' of layer v % L at step v / L, from stream item v (block (v - 1) mod L), h / x of the D slot before
+    // The mat-vec is split at float4 index KA0 = (K2 + R) / 4: columns [KA0, K4n) (old taps, conditioning) are known long
+    // before the slot and are accumulated FIRST; columns [0, KA0) (h_{lp-1}, x_{lp-1}) arrive together with the D group's own
+    // input, so only that part -- 41 % of the row -- sits between their arrival and the gate warps' P'.
+    const int KA0 = (p.K2 + p.R) >> 2;
+    const int chunkA = (K4n - KA0 + ksN - 1) / ksN, chunkB = (KA0 + ksN - 1) / ksN;
+    const bool has_slice = (wI / rows1) < ksN;
+    const int kA0 = KA0 + sliceN * chunkA, kA1 = has_slice ? min(K4n, kA0 + chunkA) : kA0;
+    const int kB0 = sliceN * chunkB, kB1 = has_slice ? min(KA0, kB0 + chunkB) : kB0;
     auto islot = [&](uint32_t v) {
       const int nl = (int)(v % (uint32_t)p.L), nt = (int)(v / (uint32_t)p.L);
       const uint32_t xb = v & 1u, st = v % NSTAGE;
       float* x = xin + xb * B * xlen;
       WN3_MARK(tI == 0, 16);
-      if (v >= 1u) {
-        const int tq = (int)((v - 1u) / (uint32_t)p.L), lp = (int)((v - 1u) % (uint32_t)p.L);
-        const unsigned tagq = 1u + (unsigned)tq * per_sample;
-        if (lp >= 1 && lp + 1 < p.L) {             // N_{nl} h_{lp-1}: staged by this CTA's D group for its own slot lp
-          const uint32_t n = (uint32_t)tq * (uint32_t)p.L + (uint32_t)lp - 1u;
-          mbar_wait(&dbar[n & 1u], (n >> 1) & 1u);
-          const float* h = hD + (n & 1u) * B * p.K2;
-#pragma unroll 1
-          for (int i = tI; i < B * p.K2; i += NIT) {
-            const int b = i / p.K2, k = i - b * p.K2;
-            x[b * xlen + k] = h[i];
-          }
-        }
-        if (lp <= 1) {                             // layers 1 and 2 see x_0 = fw * sample + fb
-#pragma unroll
-          for (int b = 0; b < B; ++b) {
-            const float c = cur[b];
-#pragma unroll 1
-            for (int r = tI; r < p.R; r += NIT) x[b * xlen + p.K2 + r] = fmaf(first[r], c, first[p.R + r]);
-          }
-        } else if (lp + 1 < p.L) {                 // T_{nl} x_{lp-1}
-          const unsigned long long* xs = p.xnew + ((size_t)((lp - 1) % 3) * NREP + rep) * xstride;
-#pragma unroll 1
-          for (int i = tI; i < B * p.R; i += NIT) {
-            const int b = i / p.R, r = i - b * p.R;
-            x[b * xlen + p.K2 + r] = get_tagged(xs + i, tagq + 2u * (unsigned)(lp - 1) + 1u);
-          }
-        }
-      }
+      // ---- part A: old taps and conditioning ----
       if (nl == 0) {                               // layer 0's old taps are rebuilt from the last input samples
 #pragma unroll 1
         for (int j = 0; j < p.K - 1; ++j) {
@@ -407,20 +412,63 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
           }
         }
         fence_proxy_async();                       // these generic writes precede the bulk copies that reuse the tail later
+        group_sync(ibar, iparity);
       }
-      WN3_MARK(tI == 0, 17);
-      group_sync(ibar, iparity);
-      WN3_MARK(tI == 0, 18);
       mbar_wait(&full[st], (v / NSTAGE) & 1u);
       WN3_MARK(tI == 0, 19);
       mbar_wait(&xfull[xb], (v >> 1) & 1u);
       WN3_MARK(tI == 0, 20);
       const float* Wn = wst + st * wpad + offN;
+      const uint32_t wrow = smem_u32(Wn) + (uint32_t)(rowN * K4n) * 16u;
       float cn = 0.f;
       if (tI < rows1 * B) cn = Wn[rows1 * xlen + tI / B];
-      if (kN1 > kN0) {
-        float acc[B];
-        row_dot<B>(smem_u32(Wn) + (uint32_t)(rowN * K4n) * 16u, smem_u32(x), xlen, kN0, kN1, acc);
+      float acc[B];
+#pragma unroll
+      for (int b = 0; b < B; ++b) acc[b] = 0.f;
+      row_acc<B>(wrow, smem_u32(x), xlen, kA0, kA1, acc);
+      WN3_MARK(tI == 0, 21);
+      // ---- part B: h_{lp-1} (staged by this CTA's D group for its own slot lp) and x_{lp-1} ----
+      if (v >= 1u) {
+        const int tq = (int)((v - 1u) / (uint32_t)p.L), lp = (int)((v - 1u) % (uint32_t)p.L);
+        const unsigned tagq = 1u + (unsigned)tq * per_sample;
+        if (lp <= 1) {                             // layers 1 and 2 see x_0 = fw * sample + fb
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            const float c = cur[b];
+#pragma unroll 1
+            for (int r = tI; r < p.R; r += NIT) x[b * xlen + p.K2 + r] = fmaf(first[r], c, first[p.R + r]);
+          }
+        } else if (lp + 1 < p.L) {                 // T_{nl} x_{lp-1}: published a slot ago, two words per 16-byte load
+          const unsigned long long* xs = p.xnew + ((size_t)((lp - 1) % 3) * NREP + rep) * xstride;
+          const int half = p.R >> 1;
+#pragma unroll 1
+          for (int i = tI; i < B * half; i += NIT) {
+            const int b = i / half, r2i = i - b * half;
+            const float2 v2 = get_tagged2(xs + (size_t)b * p.R + 2 * r2i, tagq + 2u * (unsigned)(lp - 1) + 1u);
+            *reinterpret_cast<float2*>(x + b * xlen + p.K2 + 2 * r2i) = v2;
+          }
+        }
+        if (lp >= 1 && lp + 1 < p.L) {             // N_{nl} h_{lp-1}
+          // hD is a ring of THREE: the D group's residual / skip warps do not wait for P', so they start staging h_{lp+1}
+          // (two stagings later) as soon as faster CTAs publish it, possibly before this copy; three stagings later they
+          // cannot (that needs this CTA's own gate of slot lp+1, i.e. the P' this slot produces)
+          const uint32_t n = (uint32_t)tq * (uint32_t)p.L + (uint32_t)lp - 1u;
+          mbar_wait(&dbar[n % 3u], (n / 3u) & 1u);
+          const float* h = hD + (n % 3u) * B * p.K2;
+#pragma unroll 1
+          for (int i = tI; i < B * p.K2; i += NIT) {
+            const int b = i / p.K2, k = i - b * p.K2;
+            x[b * xlen + k] = h[i];
+          }
+        }
+      }
+      WN3_MARK(tI == 0, 17);
+      group_sync(ibar, iparity);
+      WN3_MARK(tI == 0, 18);
+      row_acc<B>(wrow, smem_u32(x), xlen, kB0, kB1, acc);
+      if (has_slice) {
+#pragma unroll
+        for (int b = 0; b < B; ++b) acc[b] = warp_sum_f(acc[b]);
         float sv = acc[0];
 #pragma unroll
         for (int b = 1; b < B; ++b) sv = lane == b ? acc[b] : sv;
@@ -431,16 +479,15 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
         mbar_arrive(&empty[st]);
         mbar_arrive(&xempty[xb]);
       }
-      WN3_MARK(tI == 0, 21);
       group_sync(ibar, iparity);
       WN3_MARK(tI == 0, 22);
       if (tI < rows1 * B) {
         const int row = tI / B, b = tI - row * B;
         if (v >= 2u) mbar_wait(&pnempty[v & 1u], ((v >> 1) - 1u) & 1u);
-        float s = cn;
+        float sum = cn;
 #pragma unroll 4
-        for (int ks = 0; ks < ksN; ++ks) s += partI[(row * ksN + ks) * MAXB + b];
-        Pn[(v & 1u) * pad4(rows1) * MAXB + row * MAXB + b] = s;
+        for (int ks = 0; ks < ksN; ++ks) sum += partI[(row * ksN + ks) * MAXB + b];
+        Pn[(v & 1u) * pad4(rows1) * MAXB + row * MAXB + b] = sum;
         mbar_arrive(&pnfull[v & 1u]);
       }
       WN3_MARK(tI == 0, 23);
@@ -513,18 +560,19 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
 #pragma unroll
         for (int b = 0; b < B; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
         WN3_MARK(tid == 0, 0);
+        // the weight stage (asked for three slots ago) does not depend on h_{l-1}: wait for it first
+        if (l > 0) mbar_wait(&full[st], (s / NSTAGE) & 1u);
+        WN3_MARK(tid == 0, 3);
         if (l > 0) {
           const uint32_t n = g - 1u;               // n-th staging of this CTA: t * L + (l - 1)
-          float* h = hD + (n & 1u) * B * p.K2;
+          float* h = hD + (n % 3u) * B * p.K2;
           const unsigned long long* gb = p.gbuf + ((size_t)((l - 1) % 3) * NREP + rep) * gstride;
 #pragma unroll 1
           for (int i = tid; i < B * p.K2; i += NDT) h[i] = get_tagged(gb + i, tag_h - 2u);
           WN3_MARK(tid == 0, 1);
-          mbar_arrive(&dbar[n & 1u]);
-          mbar_wait(&dbar[n & 1u], (n >> 1) & 1u);
+          mbar_arrive(&dbar[n % 3u]);
+          mbar_wait(&dbar[n % 3u], (n / 3u) & 1u);
           WN3_MARK(tid == 0, 2);
-          mbar_wait(&full[st], (s / NSTAGE) & 1u);
-          WN3_MARK(tid == 0, 3);
           const float* Wc = wst + st * wpad;
           if (utype != UNIT_NONE) {
             if (utype == UNIT_PAIR) {
@@ -575,12 +623,12 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
       // ---- skip rows of the last layer, relu(skips) ----
       {
         const uint32_t n = (uint32_t)t * (uint32_t)p.L + (uint32_t)p.L - 1u;
-        float* h = hD + (n & 1u) * B * p.K2;
+        float* h = hD + (n % 3u) * B * p.K2;
         const unsigned long long* gb = p.gbuf + ((size_t)((p.L - 1) % 3) * NREP + rep) * gstride;
 #pragma unroll 1
         for (int i = tid; i < B * p.K2; i += NDT) h[i] = get_tagged(gb + i, tag0 + 2u * (unsigned)(p.L - 1));
-        mbar_arrive(&dbar[n & 1u]);
-        mbar_wait(&dbar[n & 1u], (n >> 1) & 1u);
+        mbar_arrive(&dbar[n % 3u]);
+        mbar_wait(&dbar[n % 3u], (n / 3u) & 1u);
         if (utype == UNIT_SKIP) {
           float acc[B];
           row_dot<B>(smem_u32(wlast) + (uint32_t)(uidx * K4c) * 16u, smem_u32(h), p.K2, 0, K4c, acc);
