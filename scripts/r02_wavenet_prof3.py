@@ -23,7 +23,7 @@ def main():
     torch.manual_seed(0)
     m = WaveNet().cuda().eval()
     m.make_generation_fast_()
-    for B in (1, 4):
+    for B in (1,):
         T = 3200
         c = torch.rand(B, 80, T // 160).cuda()
         m.incremental_forward(c=c, T=T)
@@ -32,6 +32,8 @@ def main():
         print("B=%d T=%d  gate warp: %.0f clocks/step" % (B, T, sum(buf[:12]) / T))
         for n, v in zip(D, buf[:12]):
             print("   D %-18s %8.0f clocks/step" % (n, v / T))
+        for n, v in zip(["dots only (12)", "select (13)", "P' loads + add (14)"], buf[12:15]):
+            print("   D   %-18s %8.0f clocks/step" % (n, v / T))
         print("   independent group: %.0f clocks/step" % (sum(buf[16:26]) / T))
         for n, v in zip(I, buf[16:26]):
             print("   I %-18s %8.0f clocks/step" % (n, v / T))

@@ -379,181 +379,166 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
     return;
   }
 
-  // ============================================ independent group (I) ============================================
-  if (warp >= ND) {
-    const int wI = warp - ND, tI = tid - NDT;
-    uint32_t iparity = 0;
-    const int rowN = wI % rows1, sliceN = wI / rows1;
-    // I slot v: P' of layer v % L at step v / L, from stream item v (block (v - 1) mod L), h / x of the D slot before
-    // The mat-vec is split at float4 index KA0 = (K2 + R) / 4: columns [KA0, K4n) (old taps, conditioning) are known long
-    // before the slot and are accumulated FIRST; columns [0, KA0) (h_{lp-1}, x_{lp-1}) arrive together with the D group's own
-    // input, so only that part -- 41 % of the row -- sits between their arrival and the gate warps' P'.
-    const int KA0 = (p.K2 + p.R) >> 2;
-    const int chunkA = (K4n - KA0 + ksN - 1) / ksN, chunkB = (KA0 + ksN - 1) / ksN;
-    const bool has_slice = (wI / rows1) < ksN;
-    const int kA0 = KA0 + sliceN * chunkA, kA1 = has_slice ? min(K4n, kA0 + chunkA) : kA0;
-    const int kB0 = sliceN * chunkB, kB1 = has_slice ? min(KA0, kB0 + chunkB) : kB0;
-    auto islot = [&](uint32_t v) {
-      const int nl = (int)(v % (uint32_t)p.L), nt = (int)(v / (uint32_t)p.L);
-      const uint32_t xb = v & 1u, st = v % NSTAGE;
-      float* x = xin + xb * B * xlen;
-      WN3_MARK(tI == 0, 16);
-      // ---- part A: old taps and conditioning ----
-      if (nl == 0) {                               // layer 0's old taps are rebuilt from the last input samples
+  // ========================================== worker warps: D and I ==============================================
+  // One loop over the samples for both groups (the head is common code); inside, a warp runs either the D slots or the I
+  // slots of the sample.  All per-slot indices are counters: run-time divisions (v % L, s % stages, ...) cost 100+ clocks each
+  // and sat on the dependent chain.
+  const bool isD = warp < ND;
+  uint32_t iparity = 0, dparity = 0;
+  // ---- I group: slot v computes P' of layer nl = v % L at step nt = v / L from stream item v (block (v - 1) mod L) ----
+  const int wI = isD ? 0 : warp - ND, tI = tid - NDT;
+  const int rowN = wI % rows1, sliceN = wI / rows1;
+  // The row is split at float4 index KA0 = (K2 + R) / 4: columns [KA0, K4n) (old taps, conditioning) are known long before
+  // the slot and are accumulated first; columns [0, KA0) (h_{lp-1}, x_{lp-1}) arrive together with the D group's own input.
+  const int KA0 = (p.K2 + p.R) >> 2;
+  const int chunkA = (K4n - KA0 + ksN - 1) / ksN, chunkB = (KA0 + ksN - 1) / ksN;
+  const bool has_slice = sliceN < ksN;
+  const int kA0 = KA0 + sliceN * chunkA, kA1 = has_slice ? min(K4n, kA0 + chunkA) : kA0;
+  const int kB0 = sliceN * chunkB, kB1 = has_slice ? min(KA0, kB0 + chunkB) : kB0;
+  uint32_t iv = 0, ist = 0, iph = 0;               // slot, its weight stage and that stage's phase
+  int inl = 0, int_t = 0, ilp = -1, itq = 0;       // (layer, step) of the slot; (layer, step) of the D slot it runs beside
+  unsigned itag = 1u;                              // tag0 of step itq
+  uint32_t in3 = 0, inph = 0;                      // staging v - 2 of the D group: ring index and phase (valid from v = 2)
+  auto islot = [&]() {
+    const uint32_t v = iv, xb = v & 1u, st = ist;
+    const int nl = inl, nt = int_t, lp = ilp;
+    float* x = xin + xb * B * xlen;
+    WN3_MARK(tI == 0, 16);
+    // ---- part A: old taps and conditioning ----
+    if (nl == 0) {                                 // layer 0's old taps are rebuilt from the last input samples
 #pragma unroll 1
-        for (int j = 0; j < p.K - 1; ++j) {
-          const int tau = nt - (p.K - 1 - j);
+      for (int j = 0; j < p.K - 1; ++j) {
+        const int tau = nt - (p.K - 1 - j);
 #pragma unroll
-          for (int b = 0; b < B; ++b) {
-            const float c = tau >= 0 ? curh[(tau % Hc) * MAXB + b] : 0.f;
-            float* xt = x + b * xlen + p.K2 + p.R + j * p.R;
+        for (int b = 0; b < B; ++b) {
+          const float c = tau >= 0 ? curh[(tau % Hc) * MAXB + b] : 0.f;
+          float* xt = x + b * xlen + p.K2 + p.R + j * p.R;
 #pragma unroll 1
-            for (int r = tI; r < p.R; r += NIT) xt[r] = tau >= 0 ? fmaf(first[r], c, first[p.R + r]) : 0.f;
-          }
+          for (int r = tI; r < p.R; r += NIT) xt[r] = tau >= 0 ? fmaf(first[r], c, first[p.R + r]) : 0.f;
         }
-        fence_proxy_async();                       // these generic writes precede the bulk copies that reuse the tail later
-        group_sync(ibar, iparity);
       }
-      mbar_wait(&full[st], (v / NSTAGE) & 1u);
-      WN3_MARK(tI == 0, 19);
-      mbar_wait(&xfull[xb], (v >> 1) & 1u);
-      WN3_MARK(tI == 0, 20);
-      const float* Wn = wst + st * wpad + offN;
-      const uint32_t wrow = smem_u32(Wn) + (uint32_t)(rowN * K4n) * 16u;
-      float cn = 0.f;
-      if (tI < rows1 * B) cn = Wn[rows1 * xlen + tI / B];
-      float acc[B];
+      fence_proxy_async();                         // these generic writes precede the bulk copies that reuse the tail later
+      group_sync(ibar, iparity);
+    }
+    mbar_wait(&full[st], iph);
+    WN3_MARK(tI == 0, 19);
+    mbar_wait(&xfull[xb], (v >> 1) & 1u);
+    WN3_MARK(tI == 0, 20);
+    const float* Wn = wst + st * wpad + offN;
+    const uint32_t wrow = smem_u32(Wn) + (uint32_t)(rowN * K4n) * 16u;
+    float cn = 0.f;
+    if (tI < rows1 * B) cn = Wn[rows1 * xlen + tI / B];
+    float acc[B];
 #pragma unroll
-      for (int b = 0; b < B; ++b) acc[b] = 0.f;
-      row_acc<B>(wrow, smem_u32(x), xlen, kA0, kA1, acc);
-      WN3_MARK(tI == 0, 21);
-      // ---- part B: h_{lp-1} (staged by this CTA's D group for its own slot lp) and x_{lp-1} ----
-      if (v >= 1u) {
-        const int tq = (int)((v - 1u) / (uint32_t)p.L), lp = (int)((v - 1u) % (uint32_t)p.L);
-        const unsigned tagq = 1u + (unsigned)tq * per_sample;
-        if (lp <= 1) {                             // layers 1 and 2 see x_0 = fw * sample + fb
+    for (int b = 0; b < B; ++b) acc[b] = 0.f;
+    row_acc<B>(wrow, smem_u32(x), xlen, kA0, kA1, acc);
+    WN3_MARK(tI == 0, 21);
+    // ---- part B: h_{lp-1} (staged by this CTA's D group for its own slot lp) and x_{lp-1} ----
+    if (v >= 1u) {
+      if (lp <= 1) {                               // layers 1 and 2 see x_0 = fw * sample + fb
 #pragma unroll
-          for (int b = 0; b < B; ++b) {
-            const float c = cur[b];
+        for (int b = 0; b < B; ++b) {
+          const float c = cur[b];
 #pragma unroll 1
-            for (int r = tI; r < p.R; r += NIT) x[b * xlen + p.K2 + r] = fmaf(first[r], c, first[p.R + r]);
-          }
-        } else if (lp + 1 < p.L) {                 // T_{nl} x_{lp-1}: published a slot ago, two words per 16-byte load
-          const unsigned long long* xs = p.xnew + ((size_t)((lp - 1) % 3) * NREP + rep) * xstride;
-          const int half = p.R >> 1;
+          for (int r = tI; r < p.R; r += NIT) x[b * xlen + p.K2 + r] = fmaf(first[r], c, first[p.R + r]);
+        }
+      } else if (lp + 1 < p.L) {                   // T_{nl} x_{lp-1}: published a slot ago, two words per 16-byte load
+        const unsigned long long* xs = p.xnew + ((size_t)((lp - 1) % 3) * NREP + rep) * xstride;
+        const int half = p.R >> 1;
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
 #pragma unroll 1
-          for (int i = tI; i < B * half; i += NIT) {
-            const int b = i / half, r2i = i - b * half;
-            const float2 v2 = get_tagged2(xs + (size_t)b * p.R + 2 * r2i, tagq + 2u * (unsigned)(lp - 1) + 1u);
+          for (int r2i = tI; r2i < half; r2i += NIT) {
+            const float2 v2 = get_tagged2(xs + (size_t)b * p.R + 2 * r2i, itag + 2u * (unsigned)(lp - 1) + 1u);
             *reinterpret_cast<float2*>(x + b * xlen + p.K2 + 2 * r2i) = v2;
           }
         }
-        if (lp >= 1 && lp + 1 < p.L) {             // N_{nl} h_{lp-1}
-          // hD is a ring of THREE: the D group's residual / skip warps do not wait for P', so they start staging h_{lp+1}
-          // (two stagings later) as soon as faster CTAs publish it, possibly before this copy; three stagings later they
-          // cannot (that needs this CTA's own gate of slot lp+1, i.e. the P' this slot produces)
-          const uint32_t n = (uint32_t)tq * (uint32_t)p.L + (uint32_t)lp - 1u;
-          mbar_wait(&dbar[n % 3u], (n / 3u) & 1u);
-          const float* h = hD + (n % 3u) * B * p.K2;
+      }
+      if (lp >= 1 && lp + 1 < p.L) {               // N_{nl} h_{lp-1}
+        // hD is a ring of THREE: the D group's residual / skip warps do not wait for P', so they start staging h_{lp+1}
+        // (two stagings later) as soon as faster CTAs publish it, possibly before this copy; three stagings later they
+        // cannot (that needs this CTA's own gate of slot lp+1, i.e. the P' this slot produces)
+        mbar_wait(&dbar[in3], inph);
+        const float* h = hD + in3 * B * p.K2;
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
 #pragma unroll 1
-          for (int i = tI; i < B * p.K2; i += NIT) {
-            const int b = i / p.K2, k = i - b * p.K2;
-            x[b * xlen + k] = h[i];
-          }
+          for (int k = tI; k < p.K2; k += NIT) x[b * xlen + k] = h[b * p.K2 + k];
         }
       }
-      WN3_MARK(tI == 0, 17);
-      group_sync(ibar, iparity);
-      WN3_MARK(tI == 0, 18);
-      row_acc<B>(wrow, smem_u32(x), xlen, kB0, kB1, acc);
-      if (has_slice) {
-#pragma unroll
-        for (int b = 0; b < B; ++b) acc[b] = warp_sum_f(acc[b]);
-        float sv = acc[0];
-#pragma unroll
-        for (int b = 1; b < B; ++b) sv = lane == b ? acc[b] : sv;
-        if (lane < B) partI[(rowN * ksN + sliceN) * MAXB + lane] = sv;
-      }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&empty[st]);
-        mbar_arrive(&xempty[xb]);
-      }
-      group_sync(ibar, iparity);
-      WN3_MARK(tI == 0, 22);
-      if (tI < rows1 * B) {
-        const int row = tI / B, b = tI - row * B;
-        if (v >= 2u) mbar_wait(&pnempty[v & 1u], ((v >> 1) - 1u) & 1u);
-        float sum = cn;
-#pragma unroll 4
-        for (int ks = 0; ks < ksN; ++ks) sum += partI[(row * ksN + ks) * MAXB + b];
-        Pn[(v & 1u) * pad4(rows1) * MAXB + row * MAXB + b] = sum;
-        mbar_arrive(&pnfull[v & 1u]);
-      }
-      WN3_MARK(tI == 0, 23);
-    };
-    islot(0);
-#pragma unroll 1
-    for (int t = 0; t < p.T; ++t) {
-#pragma unroll 1
-      for (int l = 0; l < p.L; ++l) {
-        const uint32_t v = (uint32_t)t * (uint32_t)p.L + (uint32_t)l + 1u;
-        if (v < total_items) islot(v);
-      }
-      // ---- head (with the D group) ----
-      WN3_MARK(tI == 0, 16);
-      bar_work();                                  // (A) relu(skips) of this CTA published, ring stores fenced
-      WN3_MARK(tI == 0, 24);
-      {
-        const unsigned tag0 = 1u + (unsigned)t * per_sample;
-        const unsigned long long* hb = p.hbuf + (size_t)rep * sstride;
-#pragma unroll 1
-        for (int i = tI; i < B * p.S; i += NIT) vecH[i] = get_tagged(hb + i, tag0 + per_sample - 1u);
-      }
-      __threadfence();                             // acquire: every CTA's ring stores of this sample precede the next bulk reads
-      bar_work();                                  // (A2) relu(head 1) of every CTA staged
-#pragma unroll 1
-      for (int o = warp; o < p.O; o += NW16) {
-        float acc[B];
-        row_dot<B>(smem_u32(h2w) + (uint32_t)(o * (p.S >> 2)) * 16u, smem_u32(vecH), p.S, 0, p.S >> 2, acc);
-        if (lane < B) {
-          float sv = acc[0];
-#pragma unroll
-          for (int b = 1; b < B; ++b) sv = lane == b ? acc[b] : sv;
-          res[o * MAXB + lane] = sv + h2w[p.O * p.S + o];
-        }
-      }
-      bar_work();                                  // (B)
-      bar_work();                                  // (C) next input sample in place
-      WN3_MARK(tI == 0, 25);
     }
-    if (PROF && cta == 0 && tI < 16) g_wn3_prof[16 + tI] = profs[16 + tI];
-    return;
-  }
+    WN3_MARK(tI == 0, 17);
+    group_sync(ibar, iparity);
+    WN3_MARK(tI == 0, 18);
+    row_acc<B>(wrow, smem_u32(x), xlen, kB0, kB1, acc);
+    if (has_slice) {
+#pragma unroll
+      for (int b = 0; b < B; ++b) acc[b] = warp_sum_f(acc[b]);
+      float sv = acc[0];
+#pragma unroll
+      for (int b = 1; b < B; ++b) sv = lane == b ? acc[b] : sv;
+      if (lane < B) partI[(rowN * ksN + sliceN) * MAXB + lane] = sv;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&empty[st]);
+      mbar_arrive(&xempty[xb]);
+    }
+    group_sync(ibar, iparity);
+    WN3_MARK(tI == 0, 22);
+    if (tI < rows1 * B) {
+      const int row = tI / B, b = tI - row * B;
+      if (v >= 2u) mbar_wait(&pnempty[v & 1u], ((v >> 1) - 1u) & 1u);
+      float sum = cn;
+#pragma unroll 4
+      for (int ks = 0; ks < ksN; ++ks) sum += partI[(row * ksN + ks) * MAXB + b];
+      Pn[(v & 1u) * pad4(rows1) * MAXB + row * MAXB + b] = sum;
+      mbar_arrive(&pnfull[v & 1u]);
+    }
+    WN3_MARK(tI == 0, 23);
+    // ---- counters of the next slot ----
+    if (v >= 2u) { if (++in3 == 3u) { in3 = 0; inph ^= 1u; } }
+    if (v >= 1u && nl == 0) itag += per_sample;    // (lp, tq) <- (nl, nt): tq advances when the slot's layer was 0
+    ilp = nl; itq = nt;
+    if (++inl == p.L) { inl = 0; ++int_t; }
+    if (++ist == NSTAGE) { ist = 0; iph ^= 1u; }
+    ++iv;
+  };
 
-  // ============================================= dependent group (D) =============================================
-  {
-    uint32_t dparity = 0;
-    int utype = UNIT_NONE, uidx = 0;
+  // ---- D group: one warp per output unit ----
+  int utype = UNIT_NONE, uidx = 0;
+  if (isD) {
     if (warp < p.pairs) { utype = UNIT_PAIR; uidx = warp; }
     else if (warp < p.pairs + p.orows) { utype = UNIT_OUT; uidx = warp - p.pairs; }
     else if (warp < p.pairs + p.orows + p.srows) { utype = UNIT_SKIP; uidx = warp - p.pairs - p.orows; }
-    // block row order: [skip rows | residual rows | gate rows (a, g adjacent)]
-    const int row0 = utype == UNIT_PAIR ? rows2 + 2 * uidx : utype == UNIT_OUT ? p.srows + uidx : uidx;
-    float uc_a = 0.f, uc_g = 0.f;                  // layer 0's rank-one coefficients A_0 fw (block 0)
-    if (utype == UNIT_PAIR) {
-      const float* uc = blk0 + offN + rows1 * xlen + pad4(rows1);
-      uc_a = __ldg(uc + 2 * uidx);
-      uc_g = __ldg(uc + 2 * uidx + 1);
-    }
-    float state = 0.f;                             // lane b: x_{l-1}[own row] (residual unit) / running skip sum (skip unit)
-    if (lane == 0) mbar_arrive(&empty[0]);         // stream item 0 (the prologue's block) has no dependent part
+  }
+  // block row order: [skip rows | residual rows | gate rows (a, g adjacent)]
+  const int row0 = utype == UNIT_PAIR ? rows2 + 2 * uidx : utype == UNIT_OUT ? p.srows + uidx : uidx;
+  float uc_a = 0.f, uc_g = 0.f;                    // layer 0's rank-one coefficients A_0 fw (block 0)
+  if (utype == UNIT_PAIR) {
+    const float* uc = blk0 + offN + rows1 * xlen + pad4(rows1);
+    uc_a = __ldg(uc + 2 * uidx);
+    uc_g = __ldg(uc + 2 * uidx + 1);
+  }
+  float state = 0.f;                               // lane (copy, b): x_{l-1}[own row] (residual unit) / running skip sum (skip unit)
+  uint32_t dst = 1u % NSTAGE, dph = 1u / NSTAGE;   // stream item g + 1 of the current slot: stage and phase
+  uint32_t dn3 = 0, dnph = 0;                      // staging counter n: ring index n % 3 and phase (n / 3) & 1
+  if (isD && lane == 0) mbar_arrive(&empty[0]);    // stream item 0 (the prologue's block) has no dependent part
+
 #pragma unroll 1
-    for (int t = 0; t < p.T; ++t) {
-      const unsigned tag0 = 1u + (unsigned)t * per_sample;
+  for (int t = 0; t < p.T; ++t) {
+    const unsigned tag0 = 1u + (unsigned)t * per_sample;
+    if (!isD) {
+#pragma unroll 1
+      for (int l = (t == 0 ? -1 : 0); l < p.L; ++l) {   // (step 0 starts with the extra slot 0: P' of layer 0 at step 0)
+        if (iv < total_items) islot();
+      }
+      WN3_MARK(tI == 0, 16);
+    } else {
+      int lm = 0;                                  // l % layers_per_stack
 #pragma unroll 1
       for (int l = 0; l < p.L; ++l) {
-        const uint32_t g = (uint32_t)t * (uint32_t)p.L + (uint32_t)l, s = g + 1u, st = s % NSTAGE;
+        const uint32_t g = (uint32_t)t * (uint32_t)p.L + (uint32_t)l, st = dst;
         const unsigned tag_h = tag0 + 2u * (unsigned)l, tag_x = tag_h + 1u;
         float acc0[B], acc1[B];
         float bias = 0.f;
@@ -561,37 +546,38 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
         for (int b = 0; b < B; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
         WN3_MARK(tid == 0, 0);
         // the weight stage (asked for three slots ago) does not depend on h_{l-1}: wait for it first
-        if (l > 0) mbar_wait(&full[st], (s / NSTAGE) & 1u);
+        if (l > 0) mbar_wait(&full[st], dph);
         WN3_MARK(tid == 0, 3);
         if (l > 0) {
-          const uint32_t n = g - 1u;               // n-th staging of this CTA: t * L + (l - 1)
-          float* h = hD + (n % 3u) * B * p.K2;
+          float* h = hD + dn3 * B * p.K2;          // n-th staging of this CTA, n = t * L + (l - 1)
           const unsigned long long* gb = p.gbuf + ((size_t)((l - 1) % 3) * NREP + rep) * gstride;
 #pragma unroll 1
           for (int i = tid; i < B * p.K2; i += NDT) h[i] = get_tagged(gb + i, tag_h - 2u);
           WN3_MARK(tid == 0, 1);
-          mbar_arrive(&dbar[n % 3u]);
-          mbar_wait(&dbar[n % 3u], (n / 3u) & 1u);
+          mbar_arrive(&dbar[dn3]);
+          mbar_wait(&dbar[dn3], dnph);
+          if (++dn3 == 3u) { dn3 = 0; dnph ^= 1u; }
           WN3_MARK(tid == 0, 2);
           const float* Wc = wst + st * wpad;
-          if (utype != UNIT_NONE) {
-            if (utype == UNIT_PAIR) {
-              row_dot2<B>(smem_u32(Wc) + (uint32_t)(row0 * K4c) * 16u, (uint32_t)K4c * 16u, smem_u32(h), p.K2, K4c, acc0, acc1);
-            } else {
-              row_dot<B>(smem_u32(Wc) + (uint32_t)(row0 * K4c) * 16u, smem_u32(h), p.K2, 0, K4c, acc0);
-              bias = Wc[rowsC * p.K2 + row0];
-            }
+          if (utype == UNIT_PAIR) {
+            row_dot2<B>(smem_u32(Wc) + (uint32_t)(row0 * K4c) * 16u, (uint32_t)K4c * 16u, smem_u32(h), p.K2, K4c, acc0, acc1);
+          } else if (utype != UNIT_NONE) {
+            row_dot<B>(smem_u32(Wc) + (uint32_t)(row0 * K4c) * 16u, smem_u32(h), p.K2, 0, K4c, acc0);
+            bias = Wc[rowsC * p.K2 + row0];
           }
         }
+        WN3_MARK(tid == 0, 12);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
+        if (++dst == NSTAGE) { dst = 0; dph ^= 1u; }
         WN3_MARK(tid == 0, 4);
-        if (lane < NREP * B) {                     // lane = (replica r, column b): every replica lane repeats the column's arithmetic
+        if (lane < NREP * B) {                     // lane = (copy r_, column b): every copy lane repeats the column's arithmetic
           const int b = lane % B, r_ = lane / B;
           float a0 = acc0[0], a1 = acc1[0];
 #pragma unroll
           for (int bb = 1; bb < B; ++bb) { a0 = b == bb ? acc0[bb] : a0; a1 = b == bb ? acc1[bb] : a1; }
           if (utype == UNIT_PAIR) {
+            WN3_MARK(tid == 0, 13);
             mbar_wait(&pnfull[g & 1u], (g >> 1) & 1u);
             WN3_MARK(tid == 0, 5);
             const float* P = Pn + (g & 1u) * pad4(rows1) * MAXB;
@@ -599,6 +585,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
             if (r_ == 0) mbar_arrive(&pnempty[g & 1u]);
             if (l > 0) { a += a0; gg += a1; }
             else { a = fmaf(uc_a, cur[b], a); gg = fmaf(uc_g, cur[b], gg); }
+            WN3_MARK(tid == 0, 14);
             put_max(p.gbuf + ((size_t)(l % 3) * NREP + r_) * gstride + (size_t)b * p.K2 + cta * p.pairs + uidx,
                     tanhf(a) * (1.f / (1.f + expf(-gg))), tag_h);
             WN3_MARK(tid == 0, 6);
@@ -608,8 +595,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
             const float xo = (a0 + bias + xprev) * r2;
             state = xo;
             if (r_ == 0) {
-              const int d = 1 << (l % p.layers_per_stack);
-              const int rl = (p.K - 1) * d + 1;
+              const int rl = (p.K - 1) * (1 << lm) + 1;
               p.ring[p.ring_off[l] + ((size_t)(t % rl) * B + b) * p.R + r] = xo;          // taps of later samples
             }
             if (l + 2 < p.L) put_max(p.xnew + ((size_t)(l % 3) * NREP + r_) * xstride + (size_t)b * p.R + r, xo, tag_x);
@@ -618,17 +604,18 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
             state = (l == 1) ? v : (state + v) * r2;
           }
         }
+        if (++lm == p.layers_per_stack) lm = 0;
       }
       WN3_MARK(tid == 0, 0);
       // ---- skip rows of the last layer, relu(skips) ----
       {
-        const uint32_t n = (uint32_t)t * (uint32_t)p.L + (uint32_t)p.L - 1u;
-        float* h = hD + (n % 3u) * B * p.K2;
+        float* h = hD + dn3 * B * p.K2;
         const unsigned long long* gb = p.gbuf + ((size_t)((p.L - 1) % 3) * NREP + rep) * gstride;
 #pragma unroll 1
         for (int i = tid; i < B * p.K2; i += NDT) h[i] = get_tagged(gb + i, tag0 + 2u * (unsigned)(p.L - 1));
-        mbar_arrive(&dbar[n % 3u]);
-        mbar_wait(&dbar[n % 3u], (n / 3u) & 1u);
+        mbar_arrive(&dbar[dn3]);
+        mbar_wait(&dbar[dn3], dnph);
+        if (++dn3 == 3u) { dn3 = 0; dnph ^= 1u; }
         if (utype == UNIT_SKIP) {
           float acc[B];
           row_dot<B>(smem_u32(wlast) + (uint32_t)(uidx * K4c) * 16u, smem_u32(h), p.K2, 0, K4c, acc);
@@ -645,77 +632,84 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
       }
       __threadfence();                             // release: this sample's ring stores precede the head-1 words below
       WN3_MARK(tid == 0, 7);
-      bar_work();                                  // (A)
-      WN3_MARK(tid == 0, 8);
-      // ---- head 1: relu(skips) of every CTA staged once, one warp per row of this CTA ----
-      {
-        const unsigned long long* sb = p.sbuf + (size_t)rep * sstride;
+    }
+    // ================================================ output head ==================================================
+    bar_work();                                    // (A) relu(skips) of this CTA published, ring stores fenced
+    WN3_MARK(tid == 0, 8);
+    WN3_MARK(!isD && tI == 0, 24);
+    if (isD) {                                     // head 1: relu(skips) of every CTA staged once, one warp per row of this CTA
+      const unsigned long long* sb = p.sbuf + (size_t)rep * sstride;
 #pragma unroll 1
-        for (int i = tid; i < B * p.S; i += NDT) vecS[i] = get_tagged(sb + i, tag0 + per_sample - 2u);
-        group_sync(hbar, dparity);
-        if (warp < p.hrows) {
-          float acc[B];
-          row_dot<B>(smem_u32(h1w) + (uint32_t)(warp * (p.S >> 2)) * 16u, smem_u32(vecS), p.S, 0, p.S >> 2, acc);
-          if (lane < NREP * B) {
-            const int b = lane % B, r_ = lane / B;
-            float sv = acc[0];
-#pragma unroll
-            for (int bb = 1; bb < B; ++bb) sv = b == bb ? acc[bb] : sv;
-            put_max(p.hbuf + (size_t)r_ * sstride + (size_t)b * p.S + cta * p.hrows + warp, fmaxf(sv + h1w[p.hrows * p.S + warp], 0.f),
-                    tag0 + per_sample - 1u);
-          }
-        }
-      }
-      bar_work();                                  // (A2) the I group staged relu(head 1) of every CTA
-      // ---- head 2 (every CTA, all 16 worker warps) ----
-#pragma unroll 1
-      for (int o = warp; o < p.O; o += NW16) {
+      for (int i = tid; i < B * p.S; i += NDT) vecS[i] = get_tagged(sb + i, tag0 + per_sample - 2u);
+      group_sync(hbar, dparity);
+      if (warp < p.hrows) {
         float acc[B];
-        row_dot<B>(smem_u32(h2w) + (uint32_t)(o * (p.S >> 2)) * 16u, smem_u32(vecH), p.S, 0, p.S >> 2, acc);
-        if (lane < B) {
+        row_dot<B>(smem_u32(h1w) + (uint32_t)(warp * (p.S >> 2)) * 16u, smem_u32(vecS), p.S, 0, p.S >> 2, acc);
+        if (lane < NREP * B) {
+          const int b = lane % B, r_ = lane / B;
           float sv = acc[0];
 #pragma unroll
-          for (int b = 1; b < B; ++b) sv = lane == b ? acc[b] : sv;
-          res[o * MAXB + lane] = sv + h2w[p.O * p.S + o];
+          for (int bb = 1; bb < B; ++bb) sv = b == bb ? acc[bb] : sv;
+          put_max(p.hbuf + (size_t)r_ * sstride + (size_t)b * p.S + cta * p.hrows + warp, fmaxf(sv + h1w[p.hrows * p.S + warp], 0.f),
+                  tag0 + per_sample - 1u);
         }
       }
-      WN3_MARK(tid == 0, 9);
-      bar_work();                                  // (B)
-      WN3_MARK(tid == 0, 10);
-      // ---- sample from the discretised mixture of logistics (every CTA computes the same value) ----
-      if (tid < B) {
-        const int b = tid, nm = p.O / 3;
-        const float* u = p.uniforms + ((size_t)t * B + b) * (nm + 1);
-        int arg = 0;
-        float best = -INFINITY;
+    } else {                                       // the I group stages relu(head 1) of every CTA
+      const unsigned long long* hb = p.hbuf + (size_t)rep * sstride;
 #pragma unroll 1
-        for (int mm = 0; mm < nm; ++mm) {
-          const float v = res[mm * MAXB + b] - logf(-logf(u[mm]));
-          if (v > best) { best = v; arg = mm; }
-        }
-        const float mean = res[(nm + arg) * MAXB + b];
-        const float ls = fmaxf(res[(2 * nm + arg) * MAXB + b], p.log_scale_min);
-        const float ul = u[nm];
-        float xs = mean + expf(ls) * (logf(ul) - logf(1.f - ul));
-        xs = fminf(fmaxf(xs, -1.f), 1.f);
-        if (cta == 0) p.out[(size_t)b * p.T + t] = xs;
-        const float nxt = (p.test_inputs != nullptr && t + 1 < p.Ttest) ? p.test_inputs[(size_t)b * p.Ttest + t + 1] : xs;
-        cur[b] = nxt;
-        curh[((t + 1) % Hc) * MAXB + b] = nxt;
-      }
-      if (tid == 32) st_volatile_s32(released, t + 1);
-      if (cta == 0 && p.logits != nullptr) {
-#pragma unroll 1
-        for (int i = tid; i < p.O * B; i += NDT) {
-          const int o = i / B, b = i - o * B;
-          p.logits[((size_t)b * p.T + t) * p.O + o] = res[o * MAXB + b];
-        }
-      }
-      bar_work();                                  // (C)
-      WN3_MARK(tid == 0, 11);
+      for (int i = tI; i < B * p.S; i += NIT) vecH[i] = get_tagged(hb + i, tag0 + per_sample - 1u);
+      __threadfence();                             // acquire: every CTA's ring stores of this sample precede the next bulk reads
     }
-    if (PROF && cta == 0 && tid < 16) g_wn3_prof[tid] = profs[tid];
+    bar_work();                                    // (A2)
+#pragma unroll 1
+    for (int o = warp; o < p.O; o += NW16) {       // head 2: every CTA, all 16 worker warps
+      float acc[B];
+      row_dot<B>(smem_u32(h2w) + (uint32_t)(o * (p.S >> 2)) * 16u, smem_u32(vecH), p.S, 0, p.S >> 2, acc);
+      if (lane < B) {
+        float sv = acc[0];
+#pragma unroll
+        for (int b = 1; b < B; ++b) sv = lane == b ? acc[b] : sv;
+        res[o * MAXB + lane] = sv + h2w[p.O * p.S + o];
+      }
+    }
+    WN3_MARK(tid == 0, 9);
+    bar_work();                                    // (B)
+    WN3_MARK(tid == 0, 10);
+    // ---- sample from the discretised mixture of logistics (every CTA computes the same value) ----
+    if (tid < B) {
+      const int b = tid, nm = p.O / 3;
+      const float* u = p.uniforms + ((size_t)t * B + b) * (nm + 1);
+      int arg = 0;
+      float best = -INFINITY;
+#pragma unroll 1
+      for (int mm = 0; mm < nm; ++mm) {
+        const float v = res[mm * MAXB + b] - logf(-logf(u[mm]));
+        if (v > best) { best = v; arg = mm; }
+      }
+      const float mean = res[(nm + arg) * MAXB + b];
+      const float ls = fmaxf(res[(2 * nm + arg) * MAXB + b], p.log_scale_min);
+      const float ul = u[nm];
+      float xs = mean + expf(ls) * (logf(ul) - logf(1.f - ul));
+      xs = fminf(fmaxf(xs, -1.f), 1.f);
+      if (cta == 0) p.out[(size_t)b * p.T + t] = xs;
+      const float nxt = (p.test_inputs != nullptr && t + 1 < p.Ttest) ? p.test_inputs[(size_t)b * p.Ttest + t + 1] : xs;
+      cur[b] = nxt;
+      curh[((t + 1) % Hc) * MAXB + b] = nxt;
+    }
+    if (tid == 32) st_volatile_s32(released, t + 1);
+    if (cta == 0 && p.logits != nullptr && isD) {
+#pragma unroll 1
+      for (int i = tid; i < p.O * B; i += NDT) {
+        const int o = i / B, b = i - o * B;
+        p.logits[((size_t)b * p.T + t) * p.O + o] = res[o * MAXB + b];
+      }
+    }
+    bar_work();                                    // (C) next input sample in place
+    WN3_MARK(tid == 0, 11);
+    WN3_MARK(!isD && tI == 0, 25);
   }
+  if (PROF && cta == 0 && tid < 16) g_wn3_prof[tid] = profs[tid];
+  if (PROF && cta == 0 && !isD && tI < 16) g_wn3_prof[16 + tI] = profs[16 + tI];
 #undef WN3_MARK
 }
 
