@@ -65,7 +65,6 @@ struct Wn2Params {
   unsigned long long* hbuf;            // [B][S]       relu(head1)
   float* out;
   float* logits;
-  int exp;                             // VIAI_WN2_EXP (timing experiments only; results are wrong when non-zero)
 };
 
 __device__ long long g_wn2_prof[16];
@@ -226,8 +225,6 @@ __global__ void __launch_bounds__(NT, 1) wavenet_synth2_kernel(const __grid_cons
   float4 wc[NWC], wn[NWN];
   float bias_c = 0.f, const_n = 0.f;                                       // bC[row] of a row thread / cN[row] of a P' thread
   auto load_wc = [&](int layer) {
-    if (p.exp == 1) return;
-    if (p.exp == 2) layer &= 1;
     const float* blk = blk0 + (size_t)layer * p.layer_stride;
 #pragma unroll
     for (int i = 0; i < NWC; ++i) {
@@ -237,8 +234,6 @@ __global__ void __launch_bounds__(NT, 1) wavenet_synth2_kernel(const __grid_cons
     if (row_thread) bias_c = __ldg(blk + rowsC * p.K2 + (tid - row_base) / B);
   };
   auto load_wn = [&](int layer) {
-    if (p.exp == 1) return;
-    if (p.exp == 2) layer &= 1;
     const float* blk = blk0 + (size_t)layer * p.layer_stride + offN;
 #pragma unroll
     for (int i = 0; i < NWN; ++i) {
@@ -612,8 +607,6 @@ extern "C" int viai_wavenet_synth2(int L, int layers_per_stack, int R, int G, in
   p.ring = ring; p.ring_off = ring_off; p.out = out; p.logits = logits;
   p.gbuf = reinterpret_cast<unsigned long long*>(gbuf); p.sbuf = reinterpret_cast<unsigned long long*>(sbuf);
   p.hbuf = reinterpret_cast<unsigned long long*>(hbuf); p.xnew = reinterpret_cast<unsigned long long*>(xchg);
-  const char* px = getenv("VIAI_WN2_EXP");
-  p.exp = px ? atoi(px) : 0;
   const char* pe = getenv("VIAI_WN2_PROF");
   const bool prof = pe && pe[0] == '1';
   const size_t smem = (size_t)wn2_smem_bytes(R, G, S, C, K, O, B, nC);

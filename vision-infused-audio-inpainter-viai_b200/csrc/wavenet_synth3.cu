@@ -73,20 +73,23 @@ __device__ __forceinline__ void put_max(unsigned long long* p, float v, unsigned
   const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
   asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-__device__ __noinline__ float get_tagged_spin(const unsigned long long* p, unsigned tag) {
-  unsigned long long w;
-  const long long t0 = clock64();
-  do {
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-    if (clock64() - t0 > 4000000000LL) __trap();
-  } while ((unsigned)(w >> 32) != tag);
-  return __uint_as_float((unsigned)w);
-}
+// Poll until the word carries `tag`.  The loop is tight (load, compare, branch); the watchdog looks at the clock only every 256
+// polls so that it does not sit between two polls of the dependent chain.
 __device__ __forceinline__ float get_tagged(const unsigned long long* p, unsigned tag) {
   unsigned long long w;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-  if ((unsigned)(w >> 32) == tag) return __uint_as_float((unsigned)w);
-  return get_tagged_spin(p, tag);
+  if ((unsigned)(w >> 32) != tag) {
+    long long t0 = 0;
+    unsigned n = 0;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+      if ((++n & 255u) == 0u) {
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    } while ((unsigned)(w >> 32) != tag);
+  }
+  return __uint_as_float((unsigned)w);
 }
 // two adjacent tagged words with one 16-byte load (each 8-byte half is written atomically and carries its own tag)
 __device__ __forceinline__ float2 get_tagged2(const unsigned long long* p, unsigned tag) {
