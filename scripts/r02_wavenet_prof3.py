@@ -34,6 +34,7 @@ def main():
             print("   D %-18s %8.0f clocks/step" % (n, v / T))
         for n, v in zip(["dots only (12)", "select (13)", "P' loads + add (14)"], buf[12:15]):
             print("   D   %-18s %8.0f clocks/step" % (n, v / T))
+        print("   D   P' not ready at first look: %.2f of 24 slots per step" % (buf[15] / T))
         print("   independent group: %.0f clocks/step" % (sum(buf[16:26]) / T))
         for n, v in zip(I, buf[16:26]):
             print("   I %-18s %8.0f clocks/step" % (n, v / T))

@@ -32,6 +32,7 @@ constexpr int NWORK = NDT + NIT;                   // threads that take part in 
 constexpr int NT3 = NWORK + 32;                    // + the producer warp
 constexpr int NW16 = NWORK / 32;
 constexpr int MAXSTAGE = 3;           // weight stages in flight (2 when the operand buffers of a large batch need the room)
+constexpr int MAXTAIL = 4;           // old-taps / conditioning buffers in flight (fewer when a large batch needs the room)
 constexpr int MAXB = 4;
 constexpr int NREP = 8;               // replicas of every cross-CTA vector (see put_lane)
 constexpr int kSmemLimit = 226 * 1024;
@@ -41,7 +42,7 @@ struct Wn3Params {
   int L, R, G, S, C, K, O, B, T, nC;
   int layers_per_stack;
   int pairs, srows, orows, hrows;
-  int K2, Kn, nstage;
+  int K2, Kn, nstage, ntail;
   const float* wl;
   int64_t layer_stride, cta_stride;
   const float* wlast;
@@ -219,22 +220,26 @@ __device__ __noinline__ void issue_taps(const Wn3Params& p, int layer, int t, fl
 }
 
 struct Smem3 {                                      // offsets in floats, shared by the kernel and the host-side size check
-  int wst, xin, hD, Pn, partI, first, h1w, h2w, wlast, vec, res, cur, curh, flags, bars, prof, total;
-  int wpad, xlen, rows1, rows2, rowsC, ksN, Hc, nstage;
+  int wst, hx, tails, hD, Pn, partI, first, h1w, h2w, wlast, vec, res, cur, curh, flags, bars, prof, total;
+  int wpad, xlen, hxlen, tlen, rows1, rows2, rowsC, ksN, Hc, nstage, ntail;
 };
-__host__ __device__ inline Smem3 smem3_layout(int R, int G, int S, int C, int K, int O, int B, int nC, int nstage) {
+__host__ __device__ inline Smem3 smem3_layout(int R, int G, int S, int C, int K, int O, int B, int nC, int nstage, int ntail) {
   Smem3 m;
   m.nstage = nstage;
+  m.ntail = ntail;
   const int pairs = (G / 2) / nC, srows = S / nC, orows = R / nC, hrows = S / nC;
   const int K2 = G / 2;
   m.xlen = K2 + R + (K - 1) * R + C;
+  m.hxlen = K2 + R;                                 // [h_{l-1} | x_{l-1}]: arrive with the slot
+  m.tlen = (K - 1) * R + C;                         // [old taps | conditioning]: known long before
   m.rows1 = 2 * pairs; m.rows2 = srows + orows; m.rowsC = m.rows2 + m.rows1;
   m.wpad = m.rowsC * K2 + pad4(m.rowsC) + m.rows1 * m.xlen + 2 * pad4(m.rows1);
   m.ksN = m.rows1 <= NI ? NI / m.rows1 : 1;
   m.Hc = K > 1 ? K - 1 : 1;
   int o = 0;
   m.wst = o; o += nstage * m.wpad;
-  m.xin = o; o += 2 * B * m.xlen;
+  m.hx = o; o += 2 * B * m.hxlen;
+  m.tails = o; o += ntail * B * m.tlen;
   m.hD = o; o += 3 * B * K2;
   m.Pn = o; o += 2 * pad4(m.rows1) * MAXB;
   m.partI = o; o += pad4(m.rows1 * m.ksN) * MAXB;
@@ -247,7 +252,7 @@ __host__ __device__ inline Smem3 smem3_layout(int R, int G, int S, int C, int K,
   m.cur = o; o += MAXB;
   m.curh = o; o += pad4(m.Hc * MAXB);
   m.flags = o; o += 4;
-  m.bars = o; o += 2 * 24;                          // up to 24 mbarriers (8 bytes each)
+  m.bars = o; o += 2 * 28;                          // up to 28 mbarriers (8 bytes each)
   m.prof = o; o += 2 * 32;                          // profiling counters (PROF instantiation only)
   m.total = o;
   return m;
@@ -255,7 +260,13 @@ __host__ __device__ inline Smem3 smem3_layout(int R, int G, int S, int C, int K,
 
 __host__ __device__ inline int smem3_stages(int R, int G, int S, int C, int K, int O, int B, int nC) {
   for (int n = MAXSTAGE; n >= 2; --n)
-    if ((long long)smem3_layout(R, G, S, C, K, O, B, nC, n).total * 4 + 64 <= kSmemLimit) return n;
+    if ((long long)smem3_layout(R, G, S, C, K, O, B, nC, n, 2).total * 4 + 64 <= kSmemLimit) return n;
+  return 0;
+}
+// ... and, with that many weight stages, the largest number of tail buffers
+__host__ __device__ inline int smem3_tails(int R, int G, int S, int C, int K, int O, int B, int nC, int nstage) {
+  for (int n = MAXTAIL; n >= 2; --n)
+    if ((long long)smem3_layout(R, G, S, C, K, O, B, nC, nstage, n).total * 4 + 64 <= kSmemLimit) return n;
   return 0;
 }
 
@@ -267,11 +278,12 @@ template <int B, bool PROF>
 __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_constant__ Wn3Params p) {
   extern __shared__ __align__(16) float sm[];
   const int cta = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const Smem3 m = smem3_layout(p.R, p.G, p.S, p.C, p.K, p.O, B, p.nC, p.nstage);
-  const uint32_t NSTAGE = (uint32_t)p.nstage;
-  const int rows1 = m.rows1, rows2 = m.rows2, rowsC = m.rowsC, xlen = m.xlen, wpad = m.wpad, Hc = m.Hc, ksN = m.ksN;
+  const Smem3 m = smem3_layout(p.R, p.G, p.S, p.C, p.K, p.O, B, p.nC, p.nstage, p.ntail);
+  const uint32_t NSTAGE = (uint32_t)p.nstage, NTAIL = (uint32_t)p.ntail;
+  const int rows1 = m.rows1, rows2 = m.rows2, rowsC = m.rowsC, xlen = m.xlen, hxlen = m.hxlen, tlen = m.tlen, wpad = m.wpad, Hc = m.Hc, ksN = m.ksN;
   float* const wst = sm + m.wst;
-  float* const xin = sm + m.xin;
+  float* const hx = sm + m.hx;                     // two [B][h_{l-1} | x_{l-1}]
+  float* const tails = sm + m.tails;               // NTAIL x [B][old taps | conditioning]
   float* const hD = sm + m.hD;
   float* const Pn = sm + m.Pn;
   float* const partI = sm + m.partI;
@@ -288,9 +300,9 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
   uint64_t* const bars = reinterpret_cast<uint64_t*>(sm + m.bars);
   uint64_t* const full = bars;                     // [NSTAGE] weight stage landed (tx)
   uint64_t* const empty = bars + MAXSTAGE;           // [NSTAGE] all 16 consumer warps are done with the stage
-  uint64_t* const xfull = bars + 2 * MAXSTAGE;       // [2] old taps / conditioning landed (tx)
-  uint64_t* const xempty = xfull + 2;              // [2] the I warps are done with the operand buffer
-  uint64_t* const pnfull = xempty + 2;             // [2] P' of a slot written
+  uint64_t* const xfull = bars + 2 * MAXSTAGE;       // [NTAIL] old taps / conditioning landed (tx)
+  uint64_t* const xempty = xfull + MAXTAIL;        // [NTAIL] the I warps are done with the tail buffer
+  uint64_t* const pnfull = xempty + MAXTAIL;             // [2] P' of a slot written
   uint64_t* const pnempty = pnfull + 2;            // [2] ... and consumed by the gate lanes
   uint64_t* const dbar = pnempty + 2;              // [3] h_{l-1} staged in hD[n % 3] by the 256 D threads (n-th staging)
   uint64_t* const ibar = dbar + 3;                 // I group barrier
@@ -323,15 +335,15 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
 #pragma unroll 1
   for (int i = tid; i < p.srows * p.K2 + p.srows; i += NT3) wlast[i] = p.wlast[(size_t)cta * (p.srows * p.K2 + pad4(p.srows)) + i];
 #pragma unroll 1
-  for (int i = tid; i < 2 * B * xlen; i += NT3) xin[i] = 0.f;             // zero weights must not meet NaN bit patterns
+  for (int i = tid; i < 2 * B * hxlen + (int)NTAIL * B * tlen; i += NT3) hx[i] = 0.f;   // (hx and tails are adjacent) zero weights must not meet NaNs
   if (tid < MAXB) cur[tid] = (p.test_inputs != nullptr && p.Ttest > 0 && tid < B) ? p.test_inputs[(size_t)tid * p.Ttest] : 0.f;
   if (tid < Hc * MAXB) curh[tid] = 0.f;
   if (PROF && tid < 32) profs[tid] = 0;
   if (tid == 0) {
     *released = 0;
     for (int i = 0; i < MAXSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], ND + NI); }
+    for (int i = 0; i < MAXTAIL; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], NI); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&xfull[i], 1); mbar_init(&xempty[i], NI);
       mbar_init(&pnfull[i], rows1 * B); mbar_init(&pnempty[i], p.pairs * B);   // (replica-0 lanes arrive on pnempty)
     }
     for (int i = 0; i < 3; ++i) mbar_init(&dbar[i], NDT);
@@ -349,30 +361,34 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
     fence_proxy_async();                           // the generic-proxy initialisation above precedes the bulk writes
     const uint32_t totalW = total_items + 1u, totalX = total_items;
     const uint32_t wbytes = (uint32_t)wpad * 4u;
-    uint32_t sw = 0, sx = 0;
+    uint32_t sw = 0, wstg = 0, wrnd = 0, block = (uint32_t)p.L - 1u;       // weight item, its stage, sw / stages, its block
+    uint32_t sx = 0, tbuf = 0, trnd = 0;                                   // tail item, its buffer, sx / buffers
+    int nl = 0, nt = 0, lm = 0;                                            // ... its layer, step, layer % layers_per_stack
     int fenced = 0;
     long long t0 = clock64();
     while (sw < totalW || sx < totalX) {
       bool progress = false;
-      if (sw < totalW) {
-        const uint32_t st = sw % NSTAGE;
-        if (sw < NSTAGE || mbar_try_wait(&empty[st], ((sw / NSTAGE) - 1u) & 1u)) {
-          const uint32_t block = (sw + (uint32_t)p.L - 1u) % (uint32_t)p.L;        // item s carries block (s - 1) mod L
-          mbar_expect_tx(&full[st], wbytes);
-          bulk_load(wst + st * wpad, blk0 + (size_t)block * p.layer_stride, wbytes, &full[st]);
-          ++sw;
-          progress = true;
-        }
+      if (sw < totalW && (wrnd == 0u || mbar_try_wait(&empty[wstg], (wrnd - 1u) & 1u))) {
+        mbar_expect_tx(&full[wstg], wbytes);                               // item s carries block (s - 1) mod L
+        bulk_load(wst + wstg * wpad, blk0 + (size_t)block * p.layer_stride, wbytes, &full[wstg]);
+        ++sw;
+        if (++wstg == NSTAGE) { wstg = 0; ++wrnd; }
+        if (++block == (uint32_t)p.L) block = 0;
+        progress = true;
       }
       if (sx < totalX) {
-        const int nl = (int)(sx % (uint32_t)p.L), nt = (int)(sx / (uint32_t)p.L);
-        const uint32_t xb = sx & 1u;
-        // ring data of step nt's taps were written during steps < nt: readable once head(nt - 1) has been acquired
-        if ((nl == 0 || ld_volatile_s32(released) >= nt) && (sx < 2 || mbar_try_wait(&xempty[xb], ((sx >> 1) - 1u) & 1u))) {
-          if (nl != 0 && fenced != nt) { fence_proxy_async(); fenced = nt; }
-          mbar_expect_tx(&xfull[xb], tap_bytes(p, nl));
-          issue_taps(p, nl, nt, xin + xb * B * xlen + p.K2 + p.R, xlen, &xfull[xb]);
+        // the taps of layer nl at step nt were written during steps <= nt - d (d = the layer's dilation): readable once the
+        // head of step nt - d has been acquired, i.e. released >= nt - d + 1; they are asked for up to NTAIL slots ahead
+        const int rel = ld_volatile_s32(released);
+        const bool ready = nl == 0 || rel >= nt - (1 << lm) + 1;
+        if (ready && (trnd == 0u || mbar_try_wait(&xempty[tbuf], (trnd - 1u) & 1u))) {
+          if (nl != 0 && fenced != rel) { fence_proxy_async(); fenced = rel; }
+          mbar_expect_tx(&xfull[tbuf], tap_bytes(p, nl));
+          issue_taps(p, nl, nt, tails + tbuf * B * tlen, tlen, &xfull[tbuf]);
           ++sx;
+          if (++tbuf == NTAIL) { tbuf = 0; ++trnd; }
+          if (++lm == p.layers_per_stack) lm = 0;
+          if (++nl == p.L) { nl = 0; lm = 0; ++nt; }
           progress = true;
         }
       }
@@ -399,13 +415,15 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
   const int kA0 = KA0 + sliceN * chunkA, kA1 = has_slice ? min(K4n, kA0 + chunkA) : kA0;
   const int kB0 = sliceN * chunkB, kB1 = has_slice ? min(KA0, kB0 + chunkB) : kB0;
   uint32_t iv = 0, ist = 0, iph = 0;               // slot, its weight stage and that stage's phase
+  uint32_t itb = 0, itph = 0;                      // its tail buffer and that buffer's phase
   int inl = 0, int_t = 0, ilp = -1, itq = 0;       // (layer, step) of the slot; (layer, step) of the D slot it runs beside
   unsigned itag = 1u;                              // tag0 of step itq
   uint32_t in3 = 0, inph = 0;                      // staging v - 2 of the D group: ring index and phase (valid from v = 2)
   auto islot = [&]() {
-    const uint32_t v = iv, xb = v & 1u, st = ist;
+    const uint32_t v = iv, st = ist, tb = itb;
     const int nl = inl, nt = int_t, lp = ilp;
-    float* x = xin + xb * B * xlen;
+    float* x = hx + (v & 1u) * B * hxlen;          // [h | x] of this slot
+    float* tl = tails + tb * B * tlen;             // [old taps | conditioning] of this slot
     WN3_MARK(tI == 0, 16);
     // ---- part A: old taps and conditioning ----
     if (nl == 0) {                                 // layer 0's old taps are rebuilt from the last input samples
@@ -415,7 +433,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
 #pragma unroll
         for (int b = 0; b < B; ++b) {
           const float c = tau >= 0 ? curh[(tau % Hc) * MAXB + b] : 0.f;
-          float* xt = x + b * xlen + p.K2 + p.R + j * p.R;
+          float* xt = tl + b * tlen + j * p.R;
 #pragma unroll 1
           for (int r = tI; r < p.R; r += NIT) xt[r] = tau >= 0 ? fmaf(first[r], c, first[p.R + r]) : 0.f;
         }
@@ -425,7 +443,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
     }
     mbar_wait(&full[st], iph);
     WN3_MARK(tI == 0, 19);
-    mbar_wait(&xfull[xb], (v >> 1) & 1u);
+    mbar_wait(&xfull[tb], itph);
     WN3_MARK(tI == 0, 20);
     const float* Wn = wst + st * wpad + offN;
     const uint32_t wrow = smem_u32(Wn) + (uint32_t)(rowN * K4n) * 16u;
@@ -434,7 +452,9 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
     float acc[B];
 #pragma unroll
     for (int b = 0; b < B; ++b) acc[b] = 0.f;
-    row_acc<B>(wrow, smem_u32(x), xlen, kA0, kA1, acc);
+    row_acc<B>(wrow, smem_u32(tl) - (uint32_t)KA0 * 16u, tlen, kA0, kA1, acc);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&xempty[tb]);       // the tail buffer can be refilled (NTAIL slots ahead)
     WN3_MARK(tI == 0, 21);
     // ---- part B: h_{lp-1} (staged by this CTA's D group for its own slot lp) and x_{lp-1} ----
     if (v >= 1u) {
@@ -443,7 +463,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
         for (int b = 0; b < B; ++b) {
           const float c = cur[b];
 #pragma unroll 1
-          for (int r = tI; r < p.R; r += NIT) x[b * xlen + p.K2 + r] = fmaf(first[r], c, first[p.R + r]);
+          for (int r = tI; r < p.R; r += NIT) x[b * hxlen + p.K2 + r] = fmaf(first[r], c, first[p.R + r]);
         }
       } else if (lp + 1 < p.L) {                   // T_{nl} x_{lp-1}: published a slot ago, two words per 16-byte load
         const unsigned long long* xs = p.xnew + ((size_t)((lp - 1) % 3) * NREP + rep) * xstride;
@@ -453,7 +473,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
 #pragma unroll 1
           for (int r2i = tI; r2i < half; r2i += NIT) {
             const float2 v2 = get_tagged2(xs + (size_t)b * p.R + 2 * r2i, itag + 2u * (unsigned)(lp - 1) + 1u);
-            *reinterpret_cast<float2*>(x + b * xlen + p.K2 + 2 * r2i) = v2;
+            *reinterpret_cast<float2*>(x + b * hxlen + p.K2 + 2 * r2i) = v2;
           }
         }
       }
@@ -466,14 +486,14 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
 #pragma unroll
         for (int b = 0; b < B; ++b) {
 #pragma unroll 1
-          for (int k = tI; k < p.K2; k += NIT) x[b * xlen + k] = h[b * p.K2 + k];
+          for (int k = tI; k < p.K2; k += NIT) x[b * hxlen + k] = h[b * p.K2 + k];
         }
       }
     }
     WN3_MARK(tI == 0, 17);
     group_sync(ibar, iparity);
     WN3_MARK(tI == 0, 18);
-    row_acc<B>(wrow, smem_u32(x), xlen, kB0, kB1, acc);
+    row_acc<B>(wrow, smem_u32(x), hxlen, kB0, kB1, acc);
     if (has_slice) {
 #pragma unroll
       for (int b = 0; b < B; ++b) acc[b] = warp_sum_f(acc[b]);
@@ -483,10 +503,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
       if (lane < B) partI[(rowN * ksN + sliceN) * MAXB + lane] = sv;
     }
     __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(&empty[st]);
-      mbar_arrive(&xempty[xb]);
-    }
+    if (lane == 0) mbar_arrive(&empty[st]);
     group_sync(ibar, iparity);
     WN3_MARK(tI == 0, 22);
     if (tI < rows1 * B) {
@@ -505,6 +522,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
     ilp = nl; itq = nt;
     if (++inl == p.L) { inl = 0; ++int_t; }
     if (++ist == NSTAGE) { ist = 0; iph ^= 1u; }
+    if (++itb == NTAIL) { itb = 0; itph ^= 1u; }
     ++iv;
   };
 
@@ -570,8 +588,6 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
           }
         }
         WN3_MARK(tid == 0, 12);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
         if (++dst == NSTAGE) { dst = 0; dph ^= 1u; }
         WN3_MARK(tid == 0, 4);
         if (lane < NREP * B) {                     // lane = (copy r_, column b): every copy lane repeats the column's arithmetic
@@ -581,16 +597,17 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
           for (int bb = 1; bb < B; ++bb) { a0 = b == bb ? acc0[bb] : a0; a1 = b == bb ? acc1[bb] : a1; }
           if (utype == UNIT_PAIR) {
             WN3_MARK(tid == 0, 13);
+            if (PROF && cta == 0 && tid == 0 && !mbar_try_wait(&pnfull[g & 1u], (g >> 1) & 1u)) profs[15] += 1;   // P' not ready yet
             mbar_wait(&pnfull[g & 1u], (g >> 1) & 1u);
             WN3_MARK(tid == 0, 5);
             const float* P = Pn + (g & 1u) * pad4(rows1) * MAXB;
             float a = P[(2 * uidx) * MAXB + b], gg = P[(2 * uidx + 1) * MAXB + b];
-            if (r_ == 0) mbar_arrive(&pnempty[g & 1u]);
             if (l > 0) { a += a0; gg += a1; }
             else { a = fmaf(uc_a, cur[b], a); gg = fmaf(uc_g, cur[b], gg); }
             WN3_MARK(tid == 0, 14);
             put_max(p.gbuf + ((size_t)(l % 3) * NREP + r_) * gstride + (size_t)b * p.K2 + cta * p.pairs + uidx,
                     tanhf(a) * (1.f / (1.f + expf(-gg))), tag_h);
+            if (r_ == 0) mbar_arrive(&pnempty[g & 1u]);       // (arrivals have release semantics: after the publication)
             WN3_MARK(tid == 0, 6);
           } else if (utype == UNIT_OUT && l > 0) {
             const int r = cta * p.orows + uidx;
@@ -607,6 +624,8 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
             state = (l == 1) ? v : (state + v) * r2;
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);    // the stage is free for the producer (after the publication, off the chain)
         if (++lm == p.layers_per_stack) lm = 0;
       }
       WN3_MARK(tid == 0, 0);
@@ -737,7 +756,8 @@ extern "C" int viai_wavenet3_num_ctas(int L, int R, int G, int S, int C, int K, 
     if ((G / 2) % n || S % n || R % n) continue;
     const int pairs = (G / 2) / n, srows = S / n, orows = R / n, hrows = S / n;
     if (pairs + orows + srows > ND || 2 * pairs > NI || hrows > ND) continue;
-    if (smem3_stages(R, G, S, C, K, O, B, n) >= 2) return n;
+    const int ns = smem3_stages(R, G, S, C, K, O, B, n);
+    if (ns >= 2 && smem3_tails(R, G, S, C, K, O, B, n, ns) >= 2) return n;
   }
   return 0;
 }
@@ -767,7 +787,8 @@ extern "C" int viai_wavenet_synth3(int L, int layers_per_stack, int R, int G, in
   p.pairs = (G / 2) / nC; p.srows = S / nC; p.orows = R / nC; p.hrows = S / nC;
   p.K2 = G / 2; p.Kn = p.K2 + R + (K - 1) * R + C;
   p.nstage = smem3_stages(R, G, S, C, K, O, B, nC);
-  const Smem3 m = smem3_layout(R, G, S, C, K, O, B, nC, p.nstage);
+  p.ntail = smem3_tails(R, G, S, C, K, O, B, nC, p.nstage);
+  const Smem3 m = smem3_layout(R, G, S, C, K, O, B, nC, p.nstage, p.ntail);
   p.cta_stride = m.wpad;
   p.layer_stride = p.cta_stride * nC;
   p.wl = packed_layers; p.wlast = last; p.first = first; p.head1 = head1; p.head2 = head2; p.cond = cond; p.uniforms = uniforms;
