@@ -92,6 +92,16 @@ __device__ __forceinline__ float get_tagged(const unsigned long long* p, unsigne
   }
   return __uint_as_float((unsigned)w);
 }
+// B tagged words `stride` apart (one per batch column): all loads are issued before the first tag is looked at, so the B columns
+// cost one L2 round trip instead of B
+template <int B>
+__device__ __forceinline__ void get_tagged_cols(const unsigned long long* p, size_t stride, unsigned tag, float* out) {
+  unsigned long long w[B];
+#pragma unroll
+  for (int b = 0; b < B; ++b) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w[b]) : "l"(p + (size_t)b * stride) : "memory");
+#pragma unroll
+  for (int b = 0; b < B; ++b) out[b] = ((unsigned)(w[b] >> 32) == tag) ? __uint_as_float((unsigned)w[b]) : get_tagged(p + (size_t)b * stride, tag);
+}
 // two adjacent tagged words with one 16-byte load (each 8-byte half is written atomically and carries its own tag)
 __device__ __forceinline__ float2 get_tagged2(const unsigned long long* p, unsigned tag) {
   unsigned long long w0, w1;
@@ -220,7 +230,7 @@ __device__ __noinline__ void issue_taps(const Wn3Params& p, int layer, int t, fl
 }
 
 struct Smem3 {                                      // offsets in floats, shared by the kernel and the host-side size check
-  int wst, hx, tails, hD, Pn, partI, first, h1w, h2w, wlast, vec, res, cur, curh, flags, bars, prof, total;
+  int wst, hx, tails, hD, Pn, partI, first, h1w, h2w, wlast, vec, res, usm, cur, curh, flags, bars, prof, total;
   int wpad, xlen, hxlen, tlen, rows1, rows2, rowsC, ksN, Hc, nstage, ntail;
 };
 __host__ __device__ inline Smem3 smem3_layout(int R, int G, int S, int C, int K, int O, int B, int nC, int nstage, int ntail) {
@@ -249,6 +259,7 @@ __host__ __device__ inline Smem3 smem3_layout(int R, int G, int S, int C, int K,
   m.wlast = o; o += srows * K2 + pad4(srows);
   m.vec = o; o += 2 * B * S;                        // relu(skips) / relu(head 1) staged for the head
   m.res = o; o += pad4(O) * MAXB;
+  m.usm = o; o += pad4(MAXB * (O / 3 + 1));          // this step's uniform draws
   m.cur = o; o += MAXB;
   m.curh = o; o += pad4(m.Hc * MAXB);
   m.flags = o; o += 4;
@@ -294,6 +305,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
   float* const vecS = sm + m.vec;
   float* const vecH = vecS + B * p.S;
   float* const res = sm + m.res;
+  float* const usm = sm + m.usm;
   float* const cur = sm + m.cur;
   float* const curh = sm + m.curh;
   int* const released = reinterpret_cast<int*>(sm + m.flags);             // samples whose head (ring acquire) is done
@@ -550,6 +562,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
   for (int t = 0; t < p.T; ++t) {
     const unsigned tag0 = 1u + (unsigned)t * per_sample;
     if (!isD) {
+      if (tI < B * (p.O / 3 + 1)) usm[tI] = __ldg(p.uniforms + (size_t)t * B * (p.O / 3 + 1) + tI);   // read by the sampler after (B)
 #pragma unroll 1
       for (int l = (t == 0 ? -1 : 0); l < p.L; ++l) {   // (step 0 starts with the extra slot 0: P' of layer 0 at step 0)
         if (iv < total_items) islot();
@@ -573,7 +586,12 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
           float* h = hD + dn3 * B * p.K2;          // n-th staging of this CTA, n = t * L + (l - 1)
           const unsigned long long* gb = p.gbuf + ((size_t)((l - 1) % 3) * NREP + rep) * gstride;
 #pragma unroll 1
-          for (int i = tid; i < B * p.K2; i += NDT) h[i] = get_tagged(gb + i, tag_h - 2u);
+          for (int k = tid; k < p.K2; k += NDT) {
+            float hv[B];
+            get_tagged_cols<B>(gb + k, (size_t)p.K2, tag_h - 2u, hv);
+#pragma unroll
+            for (int b = 0; b < B; ++b) h[b * p.K2 + k] = hv[b];
+          }
           WN3_MARK(tid == 0, 1);
           mbar_arrive(&dbar[dn3]);
           mbar_wait(&dbar[dn3], dnph);
@@ -634,7 +652,12 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
         float* h = hD + dn3 * B * p.K2;
         const unsigned long long* gb = p.gbuf + ((size_t)((p.L - 1) % 3) * NREP + rep) * gstride;
 #pragma unroll 1
-        for (int i = tid; i < B * p.K2; i += NDT) h[i] = get_tagged(gb + i, tag0 + 2u * (unsigned)(p.L - 1));
+        for (int k = tid; k < p.K2; k += NDT) {
+          float hv[B];
+          get_tagged_cols<B>(gb + k, (size_t)p.K2, tag0 + 2u * (unsigned)(p.L - 1), hv);
+#pragma unroll
+          for (int b = 0; b < B; ++b) h[b * p.K2 + k] = hv[b];
+        }
         mbar_arrive(&dbar[dn3]);
         mbar_wait(&dbar[dn3], dnph);
         if (++dn3 == 3u) { dn3 = 0; dnph ^= 1u; }
@@ -662,7 +685,12 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
     if (isD) {                                     // head 1: relu(skips) of every CTA staged once, one warp per row of this CTA
       const unsigned long long* sb = p.sbuf + (size_t)rep * sstride;
 #pragma unroll 1
-      for (int i = tid; i < B * p.S; i += NDT) vecS[i] = get_tagged(sb + i, tag0 + per_sample - 2u);
+      for (int k = tid; k < p.S; k += NDT) {
+        float sv[B];
+        get_tagged_cols<B>(sb + k, (size_t)p.S, tag0 + per_sample - 2u, sv);
+#pragma unroll
+        for (int b = 0; b < B; ++b) vecS[b * p.S + k] = sv[b];
+      }
       group_sync(hbar, dparity);
       if (warp < p.hrows) {
         float acc[B];
@@ -679,7 +707,12 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
     } else {                                       // the I group stages relu(head 1) of every CTA
       const unsigned long long* hb = p.hbuf + (size_t)rep * sstride;
 #pragma unroll 1
-      for (int i = tI; i < B * p.S; i += NIT) vecH[i] = get_tagged(hb + i, tag0 + per_sample - 1u);
+      for (int k = tI; k < p.S; k += NIT) {
+        float hv[B];
+        get_tagged_cols<B>(hb + k, (size_t)p.S, tag0 + per_sample - 1u, hv);
+#pragma unroll
+        for (int b = 0; b < B; ++b) vecH[b * p.S + k] = hv[b];
+      }
       __threadfence();                             // acquire: every CTA's ring stores of this sample precede the next bulk reads
     }
     bar_work();                                    // (A2)
@@ -697,26 +730,39 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
     WN3_MARK(tid == 0, 9);
     bar_work();                                    // (B)
     WN3_MARK(tid == 0, 10);
-    // ---- sample from the discretised mixture of logistics (every CTA computes the same value) ----
-    if (tid < B) {
-      const int b = tid, nm = p.O / 3;
-      const float* u = p.uniforms + ((size_t)t * B + b) * (nm + 1);
-      int arg = 0;
-      float best = -INFINITY;
+    // ---- sample from the discretised mixture of logistics (every CTA computes the same value): warp 0, lane m = mixture m
+    if (warp == 0) {
+      const int nm = p.O / 3;
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const float* u = usm + b * (nm + 1);
+        float best = -INFINITY;
+        int arg = 0x7fffffff;
 #pragma unroll 1
-      for (int mm = 0; mm < nm; ++mm) {
-        const float v = res[mm * MAXB + b] - logf(-logf(u[mm]));
-        if (v > best) { best = v; arg = mm; }
+        for (int m0 = 0; m0 < nm; m0 += 32) {      // (nm = 10 in every configuration of the reference: one trip)
+          const int mm = m0 + lane;
+          float v = -INFINITY;
+          if (mm < nm) v = res[mm * MAXB + b] - logf(-logf(u[mm]));
+          if (v > best) { best = v; arg = mm; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {         // arg max, the FIRST maximum like the reference's argmax over the mixture axis
+          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+          if (ov > best || (ov == best && oa < arg)) { best = ov; arg = oa; }
+        }
+        if (lane == 0) {
+          const float mean = res[(nm + arg) * MAXB + b];
+          const float ls = fmaxf(res[(2 * nm + arg) * MAXB + b], p.log_scale_min);
+          const float ul = u[nm];
+          float xs = mean + expf(ls) * (logf(ul) - logf(1.f - ul));
+          xs = fminf(fmaxf(xs, -1.f), 1.f);
+          if (cta == 0) p.out[(size_t)b * p.T + t] = xs;
+          const float nxt = (p.test_inputs != nullptr && t + 1 < p.Ttest) ? p.test_inputs[(size_t)b * p.Ttest + t + 1] : xs;
+          cur[b] = nxt;
+          curh[((t + 1) % Hc) * MAXB + b] = nxt;
+        }
       }
-      const float mean = res[(nm + arg) * MAXB + b];
-      const float ls = fmaxf(res[(2 * nm + arg) * MAXB + b], p.log_scale_min);
-      const float ul = u[nm];
-      float xs = mean + expf(ls) * (logf(ul) - logf(1.f - ul));
-      xs = fminf(fmaxf(xs, -1.f), 1.f);
-      if (cta == 0) p.out[(size_t)b * p.T + t] = xs;
-      const float nxt = (p.test_inputs != nullptr && t + 1 < p.Ttest) ? p.test_inputs[(size_t)b * p.Ttest + t + 1] : xs;
-      cur[b] = nxt;
-      curh[((t + 1) % Hc) * MAXB + b] = nxt;
     }
     if (tid == 32) st_volatile_s32(released, t + 1);
     if (cta == 0 && p.logits != nullptr && isD) {
