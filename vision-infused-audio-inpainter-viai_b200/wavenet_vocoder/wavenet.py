@@ -277,7 +277,7 @@ class WaveNet(nn.Module):
             assert cond.size(1) == T, "upsampled conditioning covers %d steps, T = %d" % (cond.size(1), T)
         # Kernel choice (VIAI_WAVENET_KERNEL; default "auto" = the fastest one that supports the configuration).  Samples/s of the
         # C4 network on one B200 at B = 1, T = 8000 (scripts/r02_wavenet_folded.py):
-        #   ws      14.6 k  csrc/wavenet_synth3.cu  folded schedule (one dependent exchange per layer), warp-specialised
+        #   ws      22.4 k  csrc/wavenet_synth3.cu  folded schedule (one dependent exchange per layer), warp-specialised
         #   folded   9.5 k  csrc/wavenet_synth2.cu  folded schedule, one instruction stream
         #   grid     7.1 k  csrc/wavenet_synth.cu   two exchanges per layer (round 1)
         #   cluster  5.4 k  csrc/wavenet_synth_cluster.cu  one 16-CTA cluster over distributed shared memory
