@@ -42,7 +42,7 @@ struct Wn3Params {
   int L, R, G, S, C, K, O, B, T, nC;
   int layers_per_stack;
   int pairs, srows, orows, hrows;
-  int K2, Kn, nstage, ntail;
+  int K2, Kn, nstage, ntail, h2w_smem;
   const float* wl;
   int64_t layer_stride, cta_stride;
   const float* wlast;
@@ -114,6 +114,19 @@ __device__ __forceinline__ float2 get_tagged2(const unsigned long long* p, unsig
     } while ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag);
   }
   return make_float2(__uint_as_float((unsigned)w0), __uint_as_float((unsigned)w1));
+}
+// ... for B columns `stride` words apart, all loads issued before the first tag is looked at
+template <int B>
+__device__ __forceinline__ void get_tagged2_cols(const unsigned long long* p, size_t stride, unsigned tag, float2* out) {
+  unsigned long long w0[B], w1[B];
+#pragma unroll
+  for (int b = 0; b < B; ++b)
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[b]), "=l"(w1[b]) : "l"(p + (size_t)b * stride) : "memory");
+#pragma unroll
+  for (int b = 0; b < B; ++b) {
+    if ((unsigned)(w0[b] >> 32) == tag && (unsigned)(w1[b] >> 32) == tag) out[b] = make_float2(__uint_as_float((unsigned)w0[b]), __uint_as_float((unsigned)w1[b]));
+    else out[b] = get_tagged2(p + (size_t)b * stride, tag);
+  }
 }
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   float4 v;
@@ -203,9 +216,6 @@ __device__ __forceinline__ void row_dot2(uint32_t wr, uint32_t row_bytes, uint32
   }
 }
 
-// largest stage count whose layout fits
-__host__ __device__ inline int smem3_stages(int R, int G, int S, int C, int K, int O, int B, int nC);
-
 __device__ __forceinline__ uint32_t tap_bytes(const Wn3Params& p, int layer) {
   return (uint32_t)p.B * ((layer == 0 ? 0u : (uint32_t)(p.K - 1) * p.R * 4u) + (uint32_t)p.C * 4u);
 }
@@ -231,12 +241,13 @@ __device__ __noinline__ void issue_taps(const Wn3Params& p, int layer, int t, fl
 
 struct Smem3 {                                      // offsets in floats, shared by the kernel and the host-side size check
   int wst, hx, tails, hD, Pn, partI, first, h1w, h2w, wlast, vec, res, usm, cur, curh, flags, bars, prof, total;
-  int wpad, xlen, hxlen, tlen, rows1, rows2, rowsC, ksN, Hc, nstage, ntail;
+  int wpad, xlen, hxlen, tlen, rows1, rows2, rowsC, ksN, Hc, nstage, ntail, h2w_smem;
 };
-__host__ __device__ inline Smem3 smem3_layout(int R, int G, int S, int C, int K, int O, int B, int nC, int nstage, int ntail) {
+__host__ __device__ inline Smem3 smem3_layout(int R, int G, int S, int C, int K, int O, int B, int nC, int nstage, int ntail, int h2w_smem = 1) {
   Smem3 m;
   m.nstage = nstage;
   m.ntail = ntail;
+  m.h2w_smem = h2w_smem;
   const int pairs = (G / 2) / nC, srows = S / nC, orows = R / nC, hrows = S / nC;
   const int K2 = G / 2;
   m.xlen = K2 + R + (K - 1) * R + C;
@@ -255,7 +266,7 @@ __host__ __device__ inline Smem3 smem3_layout(int R, int G, int S, int C, int K,
   m.partI = o; o += pad4(m.rows1 * m.ksN) * MAXB;
   m.first = o; o += 2 * R;
   m.h1w = o; o += hrows * S + pad4(hrows);
-  m.h2w = o; o += O * S + pad4(O);
+  m.h2w = o; o += h2w_smem ? O * S + pad4(O) : 0;   // the last 1x1 (used once per sample) stays in L2 when the room is needed
   m.wlast = o; o += srows * K2 + pad4(srows);
   m.vec = o; o += 2 * B * S;                        // relu(skips) / relu(head 1) staged for the head
   m.res = o; o += pad4(O) * MAXB;
@@ -269,16 +280,15 @@ __host__ __device__ inline Smem3 smem3_layout(int R, int G, int S, int C, int K,
   return m;
 }
 
-__host__ __device__ inline int smem3_stages(int R, int G, int S, int C, int K, int O, int B, int nC) {
-  for (int n = MAXSTAGE; n >= 2; --n)
-    if ((long long)smem3_layout(R, G, S, C, K, O, B, nC, n, 2).total * 4 + 64 <= kSmemLimit) return n;
-  return 0;
-}
-// ... and, with that many weight stages, the largest number of tail buffers
-__host__ __device__ inline int smem3_tails(int R, int G, int S, int C, int K, int O, int B, int nC, int nstage) {
-  for (int n = MAXTAIL; n >= 2; --n)
-    if ((long long)smem3_layout(R, G, S, C, K, O, B, nC, nstage, n).total * 4 + 64 <= kSmemLimit) return n;
-  return 0;
+struct Smem3Config { int nstage, ntail, h2w_smem; };
+// Preference: weight stages first, then tail buffers; the last 1x1 (used once per sample) moves out of shared memory to L2
+// when that buys a stage or a buffer.
+__host__ __device__ inline Smem3Config smem3_config(int R, int G, int S, int C, int K, int O, int B, int nC) {
+  for (int ns = MAXSTAGE; ns >= 2; --ns)
+    for (int nt = MAXTAIL; nt >= 2; --nt)
+      for (int hs = 1; hs >= 0; --hs)
+        if ((long long)smem3_layout(R, G, S, C, K, O, B, nC, ns, nt, hs).total * 4 + 64 <= kSmemLimit) return Smem3Config{ns, nt, hs};
+  return Smem3Config{0, 0, 1};
 }
 
 enum { UNIT_NONE = 0, UNIT_PAIR = 1, UNIT_OUT = 2, UNIT_SKIP = 3 };
@@ -289,7 +299,7 @@ template <int B, bool PROF>
 __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_constant__ Wn3Params p) {
   extern __shared__ __align__(16) float sm[];
   const int cta = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const Smem3 m = smem3_layout(p.R, p.G, p.S, p.C, p.K, p.O, B, p.nC, p.nstage, p.ntail);
+  const Smem3 m = smem3_layout(p.R, p.G, p.S, p.C, p.K, p.O, B, p.nC, p.nstage, p.ntail, p.h2w_smem);
   const uint32_t NSTAGE = (uint32_t)p.nstage, NTAIL = (uint32_t)p.ntail;
   const int rows1 = m.rows1, rows2 = m.rows2, rowsC = m.rowsC, xlen = m.xlen, hxlen = m.hxlen, tlen = m.tlen, wpad = m.wpad, Hc = m.Hc, ksN = m.ksN;
   float* const wst = sm + m.wst;
@@ -342,8 +352,10 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
   for (int i = tid; i < 2 * p.R; i += NT3) first[i] = p.first[i];
 #pragma unroll 1
   for (int i = tid; i < p.hrows * p.S + p.hrows; i += NT3) h1w[i] = p.head1[(size_t)cta * (p.hrows * p.S + pad4(p.hrows)) + i];
+  if (p.h2w_smem) {
 #pragma unroll 1
-  for (int i = tid; i < p.O * p.S + p.O; i += NT3) h2w[i] = p.head2[i];
+    for (int i = tid; i < p.O * p.S + p.O; i += NT3) h2w[i] = p.head2[i];
+  }
 #pragma unroll 1
   for (int i = tid; i < p.srows * p.K2 + p.srows; i += NT3) wlast[i] = p.wlast[(size_t)cta * (p.srows * p.K2 + pad4(p.srows)) + i];
 #pragma unroll 1
@@ -480,13 +492,12 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
       } else if (lp + 1 < p.L) {                   // T_{nl} x_{lp-1}: published a slot ago, two words per 16-byte load
         const unsigned long long* xs = p.xnew + ((size_t)((lp - 1) % 3) * NREP + rep) * xstride;
         const int half = p.R >> 1;
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
 #pragma unroll 1
-          for (int r2i = tI; r2i < half; r2i += NIT) {
-            const float2 v2 = get_tagged2(xs + (size_t)b * p.R + 2 * r2i, itag + 2u * (unsigned)(lp - 1) + 1u);
-            *reinterpret_cast<float2*>(x + b * hxlen + p.K2 + 2 * r2i) = v2;
-          }
+        for (int r2i = tI; r2i < half; r2i += NIT) {
+          float2 v2[B];
+          get_tagged2_cols<B>(xs + 2 * r2i, (size_t)p.R, itag + 2u * (unsigned)(lp - 1) + 1u, v2);
+#pragma unroll
+          for (int b = 0; b < B; ++b) *reinterpret_cast<float2*>(x + b * hxlen + p.K2 + 2 * r2i) = v2[b];
         }
       }
       if (lp >= 1 && lp + 1 < p.L) {               // N_{nl} h_{lp-1}
@@ -719,12 +730,30 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
 #pragma unroll 1
     for (int o = warp; o < p.O; o += NW16) {       // head 2: every CTA, all 16 worker warps
       float acc[B];
-      row_dot<B>(smem_u32(h2w) + (uint32_t)(o * (p.S >> 2)) * 16u, smem_u32(vecH), p.S, 0, p.S >> 2, acc);
+      if (p.h2w_smem) {
+        row_dot<B>(smem_u32(h2w) + (uint32_t)(o * (p.S >> 2)) * 16u, smem_u32(vecH), p.S, 0, p.S >> 2, acc);
+      } else {                                     // weights straight from L2 (once per sample)
+#pragma unroll
+        for (int b = 0; b < B; ++b) acc[b] = 0.f;
+        const float4* wg = reinterpret_cast<const float4*>(p.head2 + (size_t)o * p.S);
+#pragma unroll 2
+        for (int k = lane; k < (p.S >> 2); k += 32) {
+          const float4 w = __ldg(wg + k);
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            const float4 v = *reinterpret_cast<const float4*>(vecH + b * p.S + 4 * k);
+            acc[b] = fmaf(w.x, v.x, acc[b]); acc[b] = fmaf(w.y, v.y, acc[b]);
+            acc[b] = fmaf(w.z, v.z, acc[b]); acc[b] = fmaf(w.w, v.w, acc[b]);
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) acc[b] = warp_sum_f(acc[b]);
+      }
       if (lane < B) {
         float sv = acc[0];
 #pragma unroll
         for (int b = 1; b < B; ++b) sv = lane == b ? acc[b] : sv;
-        res[o * MAXB + lane] = sv + h2w[p.O * p.S + o];
+        res[o * MAXB + lane] = sv + (p.h2w_smem ? h2w[p.O * p.S + o] : __ldg(p.head2 + (size_t)p.O * p.S + o));
       }
     }
     WN3_MARK(tid == 0, 9);
@@ -802,8 +831,8 @@ extern "C" int viai_wavenet3_num_ctas(int L, int R, int G, int S, int C, int K, 
     if ((G / 2) % n || S % n || R % n) continue;
     const int pairs = (G / 2) / n, srows = S / n, orows = R / n, hrows = S / n;
     if (pairs + orows + srows > ND || 2 * pairs > NI || hrows > ND) continue;
-    const int ns = smem3_stages(R, G, S, C, K, O, B, n);
-    if (ns >= 2 && smem3_tails(R, G, S, C, K, O, B, n, ns) >= 2) return n;
+    const Smem3Config c = smem3_config(R, G, S, C, K, O, B, n);
+    if (c.nstage >= 2 && c.ntail >= 2) return n;
   }
   return 0;
 }
@@ -832,9 +861,9 @@ extern "C" int viai_wavenet_synth3(int L, int layers_per_stack, int R, int G, in
   p.layers_per_stack = layers_per_stack;
   p.pairs = (G / 2) / nC; p.srows = S / nC; p.orows = R / nC; p.hrows = S / nC;
   p.K2 = G / 2; p.Kn = p.K2 + R + (K - 1) * R + C;
-  p.nstage = smem3_stages(R, G, S, C, K, O, B, nC);
-  p.ntail = smem3_tails(R, G, S, C, K, O, B, nC, p.nstage);
-  const Smem3 m = smem3_layout(R, G, S, C, K, O, B, nC, p.nstage, p.ntail);
+  const Smem3Config cfg = smem3_config(R, G, S, C, K, O, B, nC);
+  p.nstage = cfg.nstage; p.ntail = cfg.ntail; p.h2w_smem = cfg.h2w_smem;
+  const Smem3 m = smem3_layout(R, G, S, C, K, O, B, nC, p.nstage, p.ntail, p.h2w_smem);
   p.cta_stride = m.wpad;
   p.layer_stride = p.cta_stride * nC;
   p.wl = packed_layers; p.wlast = last; p.first = first; p.head1 = head1; p.head2 = head2; p.cond = cond; p.uniforms = uniforms;
