@@ -23,7 +23,7 @@ def main():
     torch.manual_seed(0)
     m = WaveNet().cuda().eval()
     m.make_generation_fast_()
-    for B in (1,):
+    for B in (1, 4):
         T = 3200
         c = torch.rand(B, 80, T // 160).cuda()
         m.incremental_forward(c=c, T=T)

@@ -102,3 +102,17 @@ def test_lr_schedule_known_answers():
     assert math.isclose(P.noam_learning_rate_decay(1e-3, 1999), 1e-3, rel_tol=1e-9)
     assert math.isclose(P.step_learning_rate_decay(1e-3, 100000), 9.604e-4, rel_tol=1e-9)
     assert math.isclose(P.cyclic_cosine_annealing(1e-3, 1, 1000, 5), 1e-3, rel_tol=1e-12)
+
+
+def test_wavenet_synthesis_kernel_selection_is_host_logic(lib):
+    """viai_wavenet{,2,3}_num_ctas are pure host functions (shared-memory budget, one warp per output unit): the C4 network gets 128
+    cooperating CTAs for every batch the kernels accept, a batch of 5 or a 2-layer network is refused (the host side then falls
+    back to the next kernel), the small test network of tests/test_wavenet_gpu.py gets 16."""
+    for B in (1, 2, 3, 4):
+        assert lib.viai_wavenet_num_ctas(512, 512, 256, 80, 3, 30, B) == 128
+        assert lib.viai_wavenet2_num_ctas(24, 512, 512, 256, 80, 3, 30, B) == 128
+        assert lib.viai_wavenet3_num_ctas(24, 512, 512, 256, 80, 3, 30, B) == 128
+    assert lib.viai_wavenet3_num_ctas(24, 512, 512, 256, 80, 3, 30, 5) == 0 and lib.viai_wavenet2_num_ctas(24, 512, 512, 256, 80, 3, 30, 5) == 0
+    assert lib.viai_wavenet3_num_ctas(2, 512, 512, 256, 80, 3, 30, 1) == 0           # the folded schedule needs >= 3 layers
+    assert lib.viai_wavenet3_num_ctas(8, 32, 32, 32, 80, 3, 30, 3) == 16
+    assert lib.viai_wavenet3_replicas() == 8
