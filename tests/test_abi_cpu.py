@@ -108,6 +108,7 @@ def test_wavenet_synthesis_kernel_selection_is_host_logic(lib):
     """viai_wavenet{,2,3}_num_ctas are pure host functions (shared-memory budget, one warp per output unit): the C4 network gets 128
     cooperating CTAs for every batch the kernels accept, a batch of 5 or a 2-layer network is refused (the host side then falls
     back to the next kernel), the small test network of tests/test_wavenet_gpu.py gets 16."""
+    lib = lib.lib()
     for B in (1, 2, 3, 4):
         assert lib.viai_wavenet_num_ctas(512, 512, 256, 80, 3, 30, B) == 128
         assert lib.viai_wavenet2_num_ctas(24, 512, 512, 256, 80, 3, 30, B) == 128
