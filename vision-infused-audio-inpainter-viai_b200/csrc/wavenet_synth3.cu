@@ -42,7 +42,7 @@ struct Wn3Params {
   int L, R, G, S, C, K, O, B, T, nC;
   int layers_per_stack;
   int pairs, srows, orows, hrows;
-  int K2, Kn, nstage, ntail, h2w_smem;
+  int K2, Kn, nstage, ntail, h2w_smem, nrep_used;
   const float* wl;
   int64_t layer_stride, cta_stride;
   const float* wlast;
@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
   const unsigned per_sample = 2u * (unsigned)p.L + 2u;
   const float r2 = 0.70710678118654752440f;
   const size_t gstride = (size_t)B * p.K2, xstride = (size_t)B * p.R, sstride = (size_t)B * p.S;   // one replica
-  const int rep = cta % NREP;
+  const int NREPB = p.nrep_used;                   // copies actually written / read (<= NREP, the buffers' stride)
+  const int rep = cta % NREPB;
   const int K4c = p.K2 >> 2, K4n = xlen >> 2;
   const int offN = rowsC * p.K2 + pad4(rowsC);
   const float* const blk0 = p.wl + (size_t)cta * p.cta_stride;
@@ -619,7 +620,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
         WN3_MARK(tid == 0, 12);
         if (++dst == NSTAGE) { dst = 0; dph ^= 1u; }
         WN3_MARK(tid == 0, 4);
-        if (lane < NREP * B) {                     // lane = (copy r_, column b): every copy lane repeats the column's arithmetic
+        if (lane < NREPB * B) {                    // lane = (copy r_, column b): every copy lane repeats the column's arithmetic
           const int b = lane % B, r_ = lane / B;
           float a0 = acc0[0], a1 = acc1[0];
 #pragma unroll
@@ -675,7 +676,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
         if (utype == UNIT_SKIP) {
           float acc[B];
           row_dot<B>(smem_u32(wlast) + (uint32_t)(uidx * K4c) * 16u, smem_u32(h), p.K2, 0, K4c, acc);
-          if (lane < NREP * B) {
+          if (lane < NREPB * B) {
             const int b = lane % B, r_ = lane / B;
             float a0 = acc[0];
 #pragma unroll
@@ -706,7 +707,7 @@ __global__ void __launch_bounds__(NT3, 1) wavenet_synth3_kernel(const __grid_con
       if (warp < p.hrows) {
         float acc[B];
         row_dot<B>(smem_u32(h1w) + (uint32_t)(warp * (p.S >> 2)) * 16u, smem_u32(vecS), p.S, 0, p.S >> 2, acc);
-        if (lane < NREP * B) {
+        if (lane < NREPB * B) {
           const int b = lane % B, r_ = lane / B;
           float sv = acc[0];
 #pragma unroll
@@ -873,6 +874,13 @@ extern "C" int viai_wavenet_synth3(int L, int layers_per_stack, int R, int G, in
   p.hbuf = reinterpret_cast<unsigned long long*>(hbuf); p.xnew = reinterpret_cast<unsigned long long*>(xchg);
   const size_t smem = (size_t)m.total * 4 + 64;
   cudaError_t e = cudaErrorInvalidValue;
+  {
+    // copies of the exchanged vectors in use (tuning knob VIAI_WN3_NREP): with red.max publication they matter little -- measured
+    // on B200, 8 / 4 / 2 / 1 copies: B = 1 22.2 / 22.3 / 21.4 / 22.0 k samples/s, B = 4 37.2 / 37.9 / 38.8 / 40.2 k
+    const char* pn = getenv("VIAI_WN3_NREP");
+    p.nrep_used = pn ? atoi(pn) : (B <= 2 ? NREP : 1);
+    if (p.nrep_used < 1 || p.nrep_used > NREP || p.nrep_used * B > 32) p.nrep_used = B <= 2 ? NREP : 1;
+  }
   const char* pe = getenv("VIAI_WN3_PROF");
   const bool prof = pe && pe[0] == '1';
   switch (B * 2 + (prof ? 1 : 0)) {
