@@ -143,6 +143,14 @@ int viai_conv2d_wgrad_simt(const viai_conv_geom* g, const float* U, const float*
 int viai_conv2d_thin_supported(const viai_conv_geom* g);
 int viai_conv2d_thin(const viai_conv_geom* g, const float* in, const float* wp, const float* bias, float* out,
                      viai_stream_t stream);
+/* Cin == 1 convolution followed by BatchNorm (MelEncoder.conv1 -> bn1, networks/Inpainting_Networks.py:54-55,72-73;
+ * MelDiscriminator.conv1 -> bn1, networks/Discriminator_Networks.py:14-15,39): the same kernel also leaves the per-channel
+ * sum / sum of squares of `out` (one statistics group; zeroed here first) in stat_sum / stat_sumsq (Cout doubles each) --
+ * viai_channel_stats's result without its read pass over the wide tensor.  3x3 and 1x4 filters, Cout <= 64
+ * (viai_conv2d_thin_stats_supported; VIAI_CIN1_STATS=0 disables it). */
+int viai_conv2d_thin_stats_supported(const viai_conv_geom* g);
+int viai_conv2d_thin_stats(const viai_conv_geom* g, const float* in, const float* wp, const float* bias, float* out,
+                           double* stat_sum, double* stat_sumsq, viai_stream_t stream);
 int viai_conv2d_wgrad_thin_supported(const viai_conv_geom* g);
 int64_t viai_wgrad_thin_workspace(const viai_conv_geom* g);   /* floats of caller-owned scratch (per-CTA partial sums) */
 int viai_conv2d_wgrad_thin(const viai_conv_geom* g, const float* U, const float* G, float* dw, int64_t sa, int64_t sb,

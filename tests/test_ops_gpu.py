@@ -82,6 +82,45 @@ def test_conv2d_forward_backward(ops, case, prec):
         assert H.relerr(bg.grad, b.grad) < TOL
 
 
+CIN1_STAT_CASES = [c for c in CONV_CASES if c[2] == 1 and c[3] >= 4] + [
+    # more pixel groups than the grid has lane groups (the grid-stride loop runs twice for some lanes), ragged last group
+    ("dis.conv1.large", False, 1, 64, 1, 4, (1, 2), (0, 1), 4, 128, 1278, True),
+    ("enc.conv1.large", False, 1, 32, 3, 3, (2, 2), (1, 1), 3, 250, 1022, False),
+    ("cin1.48ch", False, 1, 48, 3, 3, (1, 1), (1, 1), 2, 17, 23, True),
+]
+
+
+@pytest.mark.parametrize("case", CIN1_STAT_CASES, ids=[c[0] for c in CIN1_STAT_CASES])
+def test_cin1_conv_fused_statistics(ops, case):
+    """MelEncoder.conv1 / MelDiscriminator.conv1 in front of their BatchNorm: the per-channel sum and sum of squares come out of the
+    convolution kernel (viai_conv2d_thin_stats) -- same numbers as viai_channel_stats over the output, and no launch of it."""
+    import ctypes
+    from viai_b200 import _lib
+    name, tr, Cin, Cout, kh, kw, stride, pad, N, Hh, W, has_bias = case
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0xFFFF)
+    x = torch.randn(N, Cin, Hh, W, generator=g)
+    w = torch.randn((Cout, Cin, kh, kw), generator=g) / math.sqrt(Cin * kh * kw)
+    b = torch.randn(Cout, generator=g) * 0.1 if has_bias else None
+    y = F.conv2d(x.double(), w.double(), b.double() if has_bias else None, stride, pad)
+    xg, wg, bg = nhwc(x), w.cuda(), (b.cuda() if has_bias else None)
+    Ho, Wo = y.shape[2], y.shape[3]
+    geom = ops._geom(N, Hh, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad, 0)
+    assert _lib.lib().viai_conv2d_thin_stats_supported(ctypes.byref(geom)) == 1
+    with torch.no_grad():
+        ops.conv2d_stats(xg, wg, bg, stride, pad, False, 1)              # (packs the weight: not counted below)
+        n0 = _lib.launch_count()
+        yg, stats = ops.conv2d_stats(xg, wg, bg, stride, pad, False, 1)
+        launches = _lib.launch_count() - n0
+        yi, stats_in = ops.conv2d_stats(xg, wg, bg, stride, pad, False, N)   # InstanceNorm groups: the separate pass
+    assert launches <= 2, launches                                        # (weight re-layout +) convolution: no statistics pass
+    assert H.relerr(nchw(yg), y) < TOL
+    assert stats.shape == (2, Cout) and stats.dtype == torch.float64
+    assert H.relerr(stats[0], y.sum((0, 2, 3))) < 1e-5
+    assert H.relerr(stats[1], (y * y).sum((0, 2, 3))) < 1e-5
+    assert H.relerr(yi, yg) < 1e-6
+    assert H.relerr(stats_in[0].view(N, Cout).sum(0), stats[0].view(-1)) < 1e-5
+
+
 @pytest.mark.parametrize("norm", ["bn", "in", "none"])
 @pytest.mark.parametrize("act", ["lrelu", "relu", "sigmoid", "none"])
 @pytest.mark.parametrize("C", [1, 32, 6])

@@ -52,6 +52,8 @@ SIGNATURES = {
     "viai_conv2d_wgrad_tc": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p, c_p],
     "viai_conv2d_thin_supported": [_GP],
     "viai_conv2d_thin": [_GP, c_p, c_p, c_p, c_p, c_p],
+    "viai_conv2d_thin_stats_supported": [_GP],
+    "viai_conv2d_thin_stats": [_GP, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "viai_conv2d_wgrad_thin_supported": [_GP],
     "viai_conv2d_wgrad_thin": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p, c_p],
     "viai_conv2d_wgrad_simt": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p],

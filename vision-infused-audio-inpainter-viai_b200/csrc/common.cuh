@@ -12,6 +12,10 @@ namespace viai {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
+// Where the most recent launch's sweep over its tensors ended: 0 = at the tail (a front-to-back sweep: every kernel unless it
+// says otherwise), 1 = at the front.  Read by the normalisation passes (norm_act.cu), which start where the previous kernel
+// ended -- on the lines that are still in L2.  A performance hint only (results do not depend on it).
+extern std::atomic<int> g_sweep_end;
 
 inline cudaStream_t STR(viai_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -36,6 +40,7 @@ inline cudaStream_t STR(viai_stream_t s) { return reinterpret_cast<cudaStream_t>
 #define VIAI_LAUNCHED()                                                            \
   do {                                                                             \
     viai::g_launches.fetch_add(1, std::memory_order_relaxed);                      \
+    viai::g_sweep_end.store(0, std::memory_order_relaxed);                         \
     cudaError_t _e = cudaPeekAtLastError();                                        \
     if (_e != cudaSuccess) {                                                       \
       (void)cudaGetLastError();                                                    \

@@ -14,6 +14,7 @@
 //           block reduction, atomics.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 using namespace viai;
 using namespace viai::tc;
 
@@ -256,12 +257,22 @@ int launch_cout1_tma(const viai_conv_geom& g, const float* in, const float* wp, 
 // ---- Cin == 1 ----------------------------------------------------------------------------------------------------
 // wp: [Cout][R][S].  Eight lanes share CIN1_PX adjacent output pixels: the (tap, pixel) input scalars and their index
 // arithmetic are evaluated once, then the lanes sweep the output channels 32 at a time (128-byte stores per pixel).
+// STATS: the per-channel sum / sum of squares of the output (what the following BatchNorm needs; viai_channel_stats's result)
+// come out of the same kernel: a lane always owns the same <= CIN1_SV channel vectors, keeps fp32 partial sums over the ~16
+// pixels it produces, the partials are reduced over the lanes of a warp by shuffles, over the warps through shared memory in
+// double, and one double atomic per (block, channel, moment) lands in HBM -- the separate read pass over the wide tensor
+// (65 us for MelDiscriminator.conv1's 268 MB at B = 32) disappears.
 constexpr int CIN1_PX = 4;
-template <int R_, int S_>
+constexpr int CIN1_SV = 2;          // channel vectors per lane with STATS: Cout <= 64
+template <int R_, int S_, bool STATS>
 __global__ void __launch_bounds__(256) conv_cin1_kernel(viai_conv_geom g, const float* __restrict__ in, const float* __restrict__ wp,
-                                                        const float* __restrict__ bias, float* __restrict__ out) {
+                                                        const float* __restrict__ bias, float* __restrict__ out,
+                                                        double* __restrict__ stat_sum, double* __restrict__ stat_sumsq) {
   extern __shared__ float wsm[];   // [tap][Cout] + bias[Cout]
   constexpr int taps = R_ * S_;
+  float4 ssum[CIN1_SV], ssq[CIN1_SV];
+#pragma unroll
+  for (int j = 0; j < CIN1_SV; ++j) { ssum[j] = make_float4(0.f, 0.f, 0.f, 0.f); ssq[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
   for (int i = threadIdx.x; i < taps * g.Cout; i += blockDim.x) {
     const int co = i / taps, tap = i - co * taps;
     wsm[tap * g.Cout + co] = wp[i];
@@ -298,7 +309,7 @@ __global__ void __launch_bounds__(256) conv_cin1_kernel(viai_conv_geom g, const 
         for (int k = 0; k < CIN1_PX; ++k) a[r * S_ + s][k] = (rv && Xs[s][k] >= 0) ? __ldg(irow + Xs[s][k]) : 0.f;
     }
     float* obase = out + (((int64_t)n * g.Hout + y) * g.Wout + x0) * g.Cout;
-    for (int cv = l8; cv < c4n; cv += 8) {
+    auto one_vector = [&](int cv, float4& s4, float4& q4) {
       const float4 b4 = *reinterpret_cast<const float4*>(wsm + taps * g.Cout + cv * 4);
       float4 acc[CIN1_PX];
 #pragma unroll
@@ -314,7 +325,57 @@ __global__ void __launch_bounds__(256) conv_cin1_kernel(viai_conv_geom g, const 
       }
 #pragma unroll
       for (int k = 0; k < CIN1_PX; ++k)
-        if (x0 + k < g.Wout) *reinterpret_cast<float4*>(obase + (int64_t)k * g.Cout + cv * 4) = acc[k];
+        if (x0 + k < g.Wout) {
+          *reinterpret_cast<float4*>(obase + (int64_t)k * g.Cout + cv * 4) = acc[k];
+          if (STATS) {
+            s4.x += acc[k].x; s4.y += acc[k].y; s4.z += acc[k].z; s4.w += acc[k].w;
+            q4.x = fmaf(acc[k].x, acc[k].x, q4.x); q4.y = fmaf(acc[k].y, acc[k].y, q4.y);
+            q4.z = fmaf(acc[k].z, acc[k].z, q4.z); q4.w = fmaf(acc[k].w, acc[k].w, q4.w);
+          }
+        }
+    };
+    if (STATS) {
+#pragma unroll
+      for (int j = 0; j < CIN1_SV; ++j)
+        if (l8 + 8 * j < c4n) one_vector(l8 + 8 * j, ssum[j], ssq[j]);
+    } else {
+      float4 dummy_s = make_float4(0.f, 0.f, 0.f, 0.f), dummy_q = dummy_s;
+      for (int cv = l8; cv < c4n; cv += 8) one_vector(cv, dummy_s, dummy_q);
+    }
+  }
+  if (STATS) {
+    // lanes l8, l8+8, l8+16, l8+24 of a warp own the same channels
+    float v[CIN1_SV][8];
+#pragma unroll
+    for (int j = 0; j < CIN1_SV; ++j) {
+      v[j][0] = ssum[j].x; v[j][1] = ssum[j].y; v[j][2] = ssum[j].z; v[j][3] = ssum[j].w;
+      v[j][4] = ssq[j].x; v[j][5] = ssq[j].y; v[j][6] = ssq[j].z; v[j][7] = ssq[j].w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[j][i] += __shfl_xor_sync(0xffffffffu, v[j][i], 8);
+        v[j][i] += __shfl_xor_sync(0xffffffffu, v[j][i], 16);
+      }
+    }
+    __syncthreads();                                     // every thread is done with the weights in wsm: reuse it
+    float* red = wsm;                                    // [warp 8][l8 8][j CIN1_SV][8]  (4 KB <= the weight table? see host)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < 8) {
+#pragma unroll
+      for (int j = 0; j < CIN1_SV; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[((warp * 8 + lane) * CIN1_SV + j) * 8 + i] = v[j][i];
+    }
+    __syncthreads();
+    // thread t < 2*Cout: moment m = t / Cout, channel c = t % Cout;  c = (l8 + 8 j) * 4 + e
+    const int t = threadIdx.x;
+    if (t < 2 * g.Cout) {
+      const int m = t / g.Cout, c = t - m * g.Cout;
+      const int cv = c >> 2, e = c & 3;
+      const int l = cv & 7, j = cv >> 3;
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += (double)red[((w * 8 + l) * CIN1_SV + j) * 8 + m * 4 + e];
+      atomicAdd((m == 0 ? stat_sum : stat_sumsq) + c, tot);
     }
   }
 }
@@ -487,9 +548,32 @@ extern "C" int viai_conv2d_thin_supported(const viai_conv_geom* g) {
   return 0;
 }
 
+extern "C" int viai_conv2d_thin_stats_supported(const viai_conv_geom* g) {
+  static const bool off = [] { const char* e = getenv("VIAI_CIN1_STATS"); return e && e[0] == '0'; }();
+  if (off || viai_conv2d_thin_supported(g) != 2) return 0;
+  const bool shaped = (g->R == 3 && g->S == 3) || (g->R == 1 && g->S == 4);
+  return (shaped && g->Cout <= 32 * CIN1_SV) ? 1 : 0;
+}
+
+static int conv2d_thin_impl(const viai_conv_geom* gp, const float* in, const float* wp, const float* bias, float* out,
+                            double* stat_sum, double* stat_sumsq, viai_stream_t stream);
+
 // Same operands as viai_conv2d_simt: wp is the [O][R][S][I] re-layout produced by viai_pack_weight.
 extern "C" int viai_conv2d_thin(const viai_conv_geom* gp, const float* in, const float* wp, const float* bias, float* out,
                                 viai_stream_t stream) {
+  return conv2d_thin_impl(gp, in, wp, bias, out, nullptr, nullptr, stream);
+}
+
+extern "C" int viai_conv2d_thin_stats(const viai_conv_geom* gp, const float* in, const float* wp, const float* bias, float* out,
+                                      double* stat_sum, double* stat_sumsq, viai_stream_t stream) {
+  VIAI_REQUIRE(gp && stat_sum && stat_sumsq, "conv2d_thin_stats: null argument");
+  VIAI_REQUIRE(viai_conv2d_thin_stats_supported(gp), "conv2d_thin_stats: unsupported geometry (Cin %d, Cout %d, %dx%d)", gp->Cin,
+               gp->Cout, gp->R, gp->S);
+  return conv2d_thin_impl(gp, in, wp, bias, out, stat_sum, stat_sumsq, stream);
+}
+
+static int conv2d_thin_impl(const viai_conv_geom* gp, const float* in, const float* wp, const float* bias, float* out,
+                            double* stat_sum, double* stat_sumsq, viai_stream_t stream) {
   VIAI_REQUIRE(gp && in && wp && out, "conv2d_thin: null argument");
   const viai_conv_geom& g = *gp;
   const int kind = viai_conv2d_thin_supported(gp);
@@ -498,6 +582,14 @@ extern "C" int viai_conv2d_thin(const viai_conv_geom* gp, const float* in, const
                    (reinterpret_cast<uintptr_t>(wp) & 15) == 0,
                "conv2d_thin: pointers must be 16-byte aligned");
   const int64_t M = (int64_t)g.N * g.Hout * g.Wout;
+  if (stat_sum) {
+    if (stat_sumsq == stat_sum + g.Cout) {
+      VIAI_CUDA(cudaMemsetAsync(stat_sum, 0, 2 * sizeof(double) * g.Cout, STR(stream)));
+    } else {
+      VIAI_CUDA(cudaMemsetAsync(stat_sum, 0, sizeof(double) * g.Cout, STR(stream)));
+      VIAI_CUDA(cudaMemsetAsync(stat_sumsq, 0, sizeof(double) * g.Cout, STR(stream)));
+    }
+  }
   if (M == 0) return VIAI_OK;
   if (kind == 1) {
     const int rc = launch_cout1_tma(g, in, wp, bias, out, STR(stream));
@@ -505,12 +597,17 @@ extern "C" int viai_conv2d_thin(const viai_conv_geom* gp, const float* in, const
     const int blocks = (int)imin64(cdiv(M, 8), 16 * kNumSMs);
     conv_cout1_kernel<<<blocks, 256, 0, STR(stream)>>>(g, in, wp, bias, out);
   } else {
-    const size_t smem = sizeof(float) * (size_t)(g.R * g.S * g.Cout + g.Cout);
+    size_t smem = sizeof(float) * (size_t)(g.R * g.S * g.Cout + g.Cout);
     const int64_t total = (int64_t)g.N * g.Hout * ((g.Wout + CIN1_PX - 1) / CIN1_PX) * 8;
     VIAI_REQUIRE(total < (int64_t)1 << 31, "conv2d_thin: tensor too large");
     const int blocks = (int)imin64(cdiv(total, 256), 16 * kNumSMs);
-    if (g.R == 3 && g.S == 3) conv_cin1_kernel<3, 3><<<blocks, 256, smem, STR(stream)>>>(g, in, wp, bias, out);
-    else if (g.R == 1 && g.S == 4) conv_cin1_kernel<1, 4><<<blocks, 256, smem, STR(stream)>>>(g, in, wp, bias, out);
+    if (stat_sum) {
+      const size_t red = sizeof(float) * 8 * 8 * CIN1_SV * 8;       // the block reduction reuses the weight table's space
+      if (smem < red) smem = red;
+      if (g.R == 3 && g.S == 3) conv_cin1_kernel<3, 3, true><<<blocks, 256, smem, STR(stream)>>>(g, in, wp, bias, out, stat_sum, stat_sumsq);
+      else conv_cin1_kernel<1, 4, true><<<blocks, 256, smem, STR(stream)>>>(g, in, wp, bias, out, stat_sum, stat_sumsq);
+    } else if (g.R == 3 && g.S == 3) conv_cin1_kernel<3, 3, false><<<blocks, 256, smem, STR(stream)>>>(g, in, wp, bias, out, nullptr, nullptr);
+    else if (g.R == 1 && g.S == 4) conv_cin1_kernel<1, 4, false><<<blocks, 256, smem, STR(stream)>>>(g, in, wp, bias, out, nullptr, nullptr);
     else {
       const int64_t tot = M * (g.Cout / 4);
       conv_cin1_generic_kernel<<<(int)imin64(cdiv(tot, 256), 16 * kNumSMs), 256, smem, STR(stream)>>>(g, in, wp, bias, out);

@@ -1,10 +1,38 @@
 // Batch / instance normalisation statistics, fused normalise+activation, and its two-pass backward (NHWC fp32).
 #include "common.cuh"
+#include <stdlib.h>
 using namespace viai;
 
 namespace {
 
 constexpr int THREADS = 256;
+
+// Walk direction of the HBM passes.  Consecutive kernels of a normalisation layer sweep the same tensors; when a tensor (pair)
+// is larger than the 126 MB L2, a second front-to-back sweep finds nothing of the first one (a cyclic walk through an LRU-like
+// cache evicts every line just before it is needed).  Each pass here therefore starts where the previous launch ENDED
+// (viai::g_sweep_end), on lines that are still resident:
+//   forward : conv epilogue writes z front to back -> apply walks BACK to front (and ends on the rows the next convolution's
+//             first tiles read); thin convolution -> stats (back to front) -> apply (front to back);
+//   backward: the data-gradient kernel writes dz front to back -> bwd_reduce back to front -> bwd_apply front to back.
+// Block (x, y) of a reversed kernel takes the rows of block (gridDim.x-1-x, gridDim.y-1-y); results are unchanged (every block
+// owns the same row range as before, only WHEN it runs differs).  VIAI_NORM_WALK=0 restores all-forward sweeps (measurement).
+// Measured (B200, C2 step, CUDA-graph replay, one box, ms/step): no alternation 15.33; every tensor 15.18; tensors >= 200 MiB
+// 15.29, >= 100 MiB 15.26, >= 60 MiB 15.05.  Small tensors LOSE from the reversal: they are L2-resident anyway, and block i of
+// consecutive kernels lands on the same SM, hence on the L2 partition (die) that cached its rows the pass before -- the mirrored
+// block order breaks that affinity.  So only tensors of at least VIAI_NORM_WALK_MB MiB (default below) alternate.
+int64_t walk_min_bytes() {
+  static const int64_t mb = [] { const char* e = getenv("VIAI_NORM_WALK_MB"); return e ? (int64_t)atoll(e) : (int64_t)48; }();
+  return mb << 20;
+}
+bool walk_alternate() {
+  static const bool on = [] { const char* e = getenv("VIAI_NORM_WALK"); return !(e && e[0] == '0'); }();
+  return on;
+}
+// -> 1: sweep back to front.  Call BEFORE the launch; after VIAI_LAUNCHED() (which records a forward sweep) call walk_done(rev).
+int walk_pick(int64_t tensor_bytes) {
+  return (walk_alternate() && tensor_bytes >= walk_min_bytes() && g_sweep_end.load(std::memory_order_relaxed) == 0) ? 1 : 0;
+}
+void walk_done(int rev) { g_sweep_end.store(rev, std::memory_order_relaxed); }
 
 // thread -> (channel vector cv, row lane rl).  VEC channels per thread; cvec = C/VEC <= THREADS.
 struct Lanes {
@@ -37,14 +65,14 @@ __device__ __forceinline__ void block_reduce_lanes(double (&v)[NV], int cv, int 
 template <int VEC, bool SQ>
 __global__ void __launch_bounds__(THREADS)
 stats_kernel(const float* __restrict__ y, int64_t rows_per_group, int C, double* __restrict__ sum, double* __restrict__ sumsq,
-             int64_t rows_per_block) {
+             int64_t rows_per_block, int rev) {
   extern __shared__ double sred[];
   const Lanes L = make_lanes(C, VEC);
   const int tid = threadIdx.x;
   const int cv = tid % L.cvec, rl = tid / L.cvec;
-  const int g = blockIdx.y;
+  const int g = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const bool active = rl < L.lanes;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r0 = (int64_t)(rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * rows_per_block;
   const int64_t r1 = imin64(r0 + rows_per_block, rows_per_group);
   // Sums and squares are accumulated in double (the square is formed in double too): the variance is later taken as
   // E[x^2] - E[x]^2, which is only safe for channels whose mean dwarfs their spread (ResNet features after residual adds)
@@ -124,12 +152,12 @@ template <int VEC>
 __global__ void __launch_bounds__(THREADS)
 apply_kernel(const float* __restrict__ y, int64_t rows_per_group, int C, const float* __restrict__ mean,
              const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act,
-             float slope, float* __restrict__ out, int64_t rows_per_block, FusedFinalize ff) {
+             float slope, float* __restrict__ out, int64_t rows_per_block, FusedFinalize ff, int rev) {
   const Lanes L = make_lanes(C, VEC);
   const int cv = threadIdx.x % L.cvec, rl = threadIdx.x / L.cvec;
   if (rl >= L.lanes) return;
-  const int g = blockIdx.y;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int g = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int64_t r0 = (int64_t)(rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * rows_per_block;
   const int64_t r1 = imin64(r0 + rows_per_block, rows_per_group);
   // out = act(((y - mu) * is) * ga + be): the subtraction comes first (as in the reference's batch_norm) so that channels
   // whose mean is large against their spread lose nothing to cancellation
@@ -146,7 +174,7 @@ apply_kernel(const float* __restrict__ y, int64_t rows_per_group, int C, const f
       if (var < 0.0) var = 0.0;
       mu[k] = (float)m;
       is[k] = (float)(1.0 / sqrt(var + (double)ff.eps));
-      if (blockIdx.x == 0 && rl == 0) {
+      if (blockIdx.x == 0 && rl == 0) {            // one block per group (whichever rows it owns)
         ff.mean_out[i] = mu[k];
         ff.invstd_out[i] = is[k];
         if (ff.running_mean && gridDim.y == 1) {
@@ -204,14 +232,14 @@ __global__ void __launch_bounds__(THREADS)
 bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ y, int64_t rows_per_group, int C,
                   const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                   const float* __restrict__ beta, int act, float slope, double* __restrict__ s1, double* __restrict__ s2,
-                  int64_t rows_per_block) {
+                  int64_t rows_per_block, int rev) {
   extern __shared__ double sred[];
   const Lanes L = make_lanes(C, VEC);
   const int tid = threadIdx.x;
   const int cv = tid % L.cvec, rl = tid / L.cvec;
-  const int g = blockIdx.y;
+  const int g = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const bool active = rl < L.lanes;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r0 = (int64_t)(rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * rows_per_block;
   const int64_t r1 = imin64(r0 + rows_per_block, rows_per_group);
   float a1[VEC], a2[VEC], mu[VEC], is[VEC], ga[VEC], be[VEC];
 #pragma unroll
@@ -286,7 +314,7 @@ bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, int6
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int act, float slope, const double* __restrict__ s1,
                  const double* __restrict__ s2, float* __restrict__ dy, int64_t rows_per_block, float* __restrict__ dgamma,
-                 float* __restrict__ dbeta, int accumulate) {
+                 float* __restrict__ dbeta, int accumulate, int rev) {
   if ((dgamma || dbeta) && blockIdx.x == 0 && blockIdx.y == 0) {
     // viai_fold_groups fused in: dgamma = sum over groups of s2, dbeta = of s1 (written or accumulated into the gradient bucket)
     for (int c = threadIdx.x; c < C; c += THREADS) {
@@ -299,8 +327,8 @@ bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, int6
   const Lanes L = make_lanes(C, VEC);
   const int cv = threadIdx.x % L.cvec, rl = threadIdx.x / L.cvec;
   if (rl >= L.lanes) return;
-  const int g = blockIdx.y;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int g = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int64_t r0 = (int64_t)(rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * rows_per_block;
   const int64_t r1 = imin64(r0 + rows_per_block, rows_per_group);
   const float inv_cnt = 1.f / (float)rows_per_group;
   const bool has_norm = mean != nullptr;
@@ -407,14 +435,16 @@ extern "C" int viai_channel_stats(const float* y, int64_t rows_per_group, int gr
   const int64_t rpb = pick_rows_per_block(rows_per_group, groups, C, VEC);
   dim3 grid((unsigned)cdiv(rows_per_group, rpb), (unsigned)groups);
   size_t smem = sizeof(double) * THREADS * 2 * VEC;
+  const int rev = walk_pick(rows_per_group * groups * (int64_t)C * 4);
   if (VEC == 4) {
-    if (sumsq) stats_kernel<4, true><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq, rpb);
-    else stats_kernel<4, false><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq, rpb);
+    if (sumsq) stats_kernel<4, true><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq, rpb, rev);
+    else stats_kernel<4, false><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq, rpb, rev);
   } else {
-    if (sumsq) stats_kernel<1, true><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq, rpb);
-    else stats_kernel<1, false><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq, rpb);
+    if (sumsq) stats_kernel<1, true><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq, rpb, rev);
+    else stats_kernel<1, false><<<grid, THREADS, smem, st>>>(y, rows_per_group, C, sum, sumsq, rpb, rev);
   }
   VIAI_LAUNCHED();
+  walk_done(rev);
   return VIAI_OK;
 }
 
@@ -444,9 +474,11 @@ extern "C" int viai_norm_act_fwd(const float* y, int64_t rows_per_group, int gro
   dim3 grid((unsigned)cdiv(rpg, rpb), (unsigned)ngr);
   FusedFinalize ff;
   memset(&ff, 0, sizeof(ff));
-  if (VEC == 4) apply_kernel<4><<<grid, THREADS, 0, STR(stream)>>>(y, rpg, C, mean, invstd, gamma, beta, act, slope, out, rpb, ff);
-  else apply_kernel<1><<<grid, THREADS, 0, STR(stream)>>>(y, rpg, C, mean, invstd, gamma, beta, act, slope, out, rpb, ff);
+  const int rev = walk_pick(rpg * ngr * (int64_t)C * 4);
+  if (VEC == 4) apply_kernel<4><<<grid, THREADS, 0, STR(stream)>>>(y, rpg, C, mean, invstd, gamma, beta, act, slope, out, rpb, ff, rev);
+  else apply_kernel<1><<<grid, THREADS, 0, STR(stream)>>>(y, rpg, C, mean, invstd, gamma, beta, act, slope, out, rpb, ff, rev);
   VIAI_LAUNCHED();
+  walk_done(rev);
   return VIAI_OK;
 }
 
@@ -462,9 +494,11 @@ extern "C" int viai_norm_finalize_act_fwd(const float* y, int64_t rows_per_group
   const int64_t rpb = pick_rows_per_block_elem(rows_per_group, groups, C, VEC);
   dim3 grid((unsigned)cdiv(rows_per_group, rpb), (unsigned)groups);
   FusedFinalize ff = {sum, sumsq, rows_per_group, eps, mean, invstd, running_mean, running_var, momentum, num_batches_tracked};
-  if (VEC == 4) apply_kernel<4><<<grid, THREADS, 0, STR(stream)>>>(y, rows_per_group, C, nullptr, nullptr, gamma, beta, act, slope, out, rpb, ff);
-  else apply_kernel<1><<<grid, THREADS, 0, STR(stream)>>>(y, rows_per_group, C, nullptr, nullptr, gamma, beta, act, slope, out, rpb, ff);
+  const int rev = walk_pick(rows_per_group * groups * (int64_t)C * 4);
+  if (VEC == 4) apply_kernel<4><<<grid, THREADS, 0, STR(stream)>>>(y, rows_per_group, C, nullptr, nullptr, gamma, beta, act, slope, out, rpb, ff, rev);
+  else apply_kernel<1><<<grid, THREADS, 0, STR(stream)>>>(y, rows_per_group, C, nullptr, nullptr, gamma, beta, act, slope, out, rpb, ff, rev);
   VIAI_LAUNCHED();
+  walk_done(rev);
   return VIAI_OK;
 }
 
@@ -484,9 +518,11 @@ extern "C" int viai_norm_act_bwd_reduce(const float* dz, const float* y, int64_t
   const int64_t rpb = pick_rows_per_block(rows_per_group, groups, C, VEC);
   dim3 grid((unsigned)cdiv(rows_per_group, rpb), (unsigned)groups);
   size_t smem = sizeof(double) * THREADS * 2 * VEC;
-  if (VEC == 4) bwd_reduce_kernel<4><<<grid, THREADS, smem, st>>>(dz, y, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2, rpb);
-  else bwd_reduce_kernel<1><<<grid, THREADS, smem, st>>>(dz, y, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2, rpb);
+  const int rev = walk_pick(rows_per_group * groups * (int64_t)C * 4);
+  if (VEC == 4) bwd_reduce_kernel<4><<<grid, THREADS, smem, st>>>(dz, y, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2, rpb, rev);
+  else bwd_reduce_kernel<1><<<grid, THREADS, smem, st>>>(dz, y, rows_per_group, C, mean, invstd, gamma, beta, act, slope, s1, s2, rpb, rev);
   VIAI_LAUNCHED();
+  walk_done(rev);
   return VIAI_OK;
 }
 
@@ -506,9 +542,11 @@ static int norm_act_bwd_apply_impl(const float* dz, const float* y, int64_t rows
   const bool in_kernel = fused_fold && mean != nullptr && s1 && s2;      // (with statistics grid.y == groups: the kernel can fold)
   float* kg = in_kernel ? dgamma : nullptr;
   float* kb = in_kernel ? dbeta : nullptr;
-  if (VEC == 4) bwd_apply_kernel<4><<<grid, THREADS, 0, st>>>(dz, y, rpg, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy, rpb, kg, kb, accumulate);
-  else bwd_apply_kernel<1><<<grid, THREADS, 0, st>>>(dz, y, rpg, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy, rpb, kg, kb, accumulate);
+  const int rev = walk_pick(rpg * ngr * (int64_t)C * 4);
+  if (VEC == 4) bwd_apply_kernel<4><<<grid, THREADS, 0, st>>>(dz, y, rpg, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy, rpb, kg, kb, accumulate, rev);
+  else bwd_apply_kernel<1><<<grid, THREADS, 0, st>>>(dz, y, rpg, C, mean, invstd, gamma, beta, act, slope, s1, s2, dy, rpb, kg, kb, accumulate, rev);
   VIAI_LAUNCHED();
+  walk_done(rev);
   if (in_kernel) return VIAI_OK;
   VIAI_REQUIRE(!fused_fold || (!dgamma && !dbeta), "viai_norm_act_bwd_apply_fold: dgamma / dbeta need the statistics path");
   if (dgamma && s2) {

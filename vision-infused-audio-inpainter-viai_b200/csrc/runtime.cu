@@ -5,6 +5,7 @@
 namespace viai {
 static thread_local char t_err[512] = "";
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_sweep_end{0};
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

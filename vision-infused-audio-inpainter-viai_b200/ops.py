@@ -355,6 +355,11 @@ def _run_conv(g, x, weight, O_dim, I_dim, bias, y, stats=None, groups=1, forward
         return True
     if L.viai_conv2d_thin_supported(ctypes.byref(g)) and x.data_ptr() % 16 == 0:
         wp = _pack(weight, O_dim, I_dim)
+        if stats is not None and groups == 1 and L.viai_conv2d_thin_stats_supported(ctypes.byref(g)):
+            # Cin == 1 layer in front of a BatchNorm: the statistics come out of the convolution kernel itself
+            _lib.check(L.viai_conv2d_thin_stats(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _p(stats[0]), _p(stats[1]),
+                                                _stream()), "conv2d_thin_stats")
+            return True
         _lib.check(L.viai_conv2d_thin(ctypes.byref(g), _p(x), _p(wp), _p(bias), _p(y), _stream()), "conv2d_thin")
         return False
     if _PRECISION != "fp32" and L.viai_conv2d_tc_supported(ctypes.byref(g)):
