@@ -436,7 +436,7 @@ __global__ void zero_dw_kernel(float* dw, int A, int B, int R, int S, int64_t sa
 // The loop runs over the pixels of the WIDE tensor (each read once, 128-bit); the thin tensor supplies one scalar per tap.
 // R_ x S_ are compile-time (3x3, 1x4; R_ == 0: generic, up to WG_MAXTAP runtime taps) so that the tap loops unroll into
 // straight-line code with the per-tap offsets folded into immediates.
-template <bool WIDE_U, int R_, int S_>
+template <bool WIDE_U, int R_, int S_, int UN>
 __global__ void __launch_bounds__(256) wgrad_thin_kernel(viai_conv_geom g, const float* __restrict__ U, const float* __restrict__ G,
                                                          float* __restrict__ ws, int pix_per_block) {
   extern __shared__ float red[];   // [planes][taps][C]
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(256) wgrad_thin_kernel(viai_conv_geom g, const
     int m = p0 + pl;
     int x = m % Ww, tq = m / Ww;
     int y = tq % Hw, n = tq / Hw;
-    constexpr int UN = 2;                                 // wide pixels in flight per thread
+    // UN wide pixels (16 bytes each) in flight per thread
     while (m < p1) {
       float4 w4[UN];
 #pragma unroll
@@ -667,19 +667,27 @@ extern "C" int viai_conv2d_wgrad_thin(const viai_conv_geom* gp, const float* U, 
   }
   const size_t smem = sizeof(float) * (size_t)planes * taps * C;
   VIAI_REQUIRE(smem <= 64 * 1024, "conv2d_wgrad_thin: reduction buffer too large");
-#define VIAI_WGT_LAUNCH(WU, RR, SS)                                                                                         \
+  // wide pixels in flight per thread: VIAI_WGT_UN selects 2 (default) or 4.  Measured: 4 is SLOWER (C2 step 15.27 vs 15.19 ms):
+  // the extra registers (80 -> 96 for the 3x3 kernels) cost a resident CTA, which outweighs the deeper per-thread queue
+  static const int un_env = [] { const char* e = getenv("VIAI_WGT_UN"); return e ? atoi(e) : 2; }();
+#define VIAI_WGT_LAUNCH_UN(WU, RR, SS, UNV)                                                                                 \
   do {                                                                                                                      \
     static bool attr_done = false;                                                                                          \
     if (!attr_done) {                                                                                                       \
-      VIAI_CUDA(cudaFuncSetAttribute(wgrad_thin_kernel<WU, RR, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
+      VIAI_CUDA(cudaFuncSetAttribute(wgrad_thin_kernel<WU, RR, SS, UNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
       attr_done = true;                                                                                                     \
     }                                                                                                                       \
-    wgrad_thin_kernel<WU, RR, SS><<<(unsigned)blocks, 256, smem, st>>>(g, U, G, workspace, ppb);                            \
+    wgrad_thin_kernel<WU, RR, SS, UNV><<<(unsigned)blocks, 256, smem, st>>>(g, U, G, workspace, ppb);                       \
+  } while (0)
+#define VIAI_WGT_LAUNCH(WU, RR, SS)                                                                                         \
+  do {                                                                                                                      \
+    if (un_env == 4) VIAI_WGT_LAUNCH_UN(WU, RR, SS, 4); else VIAI_WGT_LAUNCH_UN(WU, RR, SS, 2);                             \
   } while (0)
   if (g.R == 3 && g.S == 3) { if (wide_u) VIAI_WGT_LAUNCH(true, 3, 3); else VIAI_WGT_LAUNCH(false, 3, 3); }
   else if (g.R == 1 && g.S == 4) { if (wide_u) VIAI_WGT_LAUNCH(true, 1, 4); else VIAI_WGT_LAUNCH(false, 1, 4); }
   else { if (wide_u) VIAI_WGT_LAUNCH(true, 0, 0); else VIAI_WGT_LAUNCH(false, 0, 0); }
 #undef VIAI_WGT_LAUNCH
+#undef VIAI_WGT_LAUNCH_UN
   VIAI_LAUNCHED();
   wgrad_thin_finish_kernel<<<(taps * C + 31) / 32, 256, 0, st>>>(workspace, (int)blocks, taps, C, g.S, wide_u ? 1 : 0, dw, sa, sb, sr, ss,
                                                                accumulate);

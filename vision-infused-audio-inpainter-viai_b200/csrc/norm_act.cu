@@ -16,12 +16,13 @@ constexpr int THREADS = 256;
 //   backward: the data-gradient kernel writes dz front to back -> bwd_reduce back to front -> bwd_apply front to back.
 // Block (x, y) of a reversed kernel takes the rows of block (gridDim.x-1-x, gridDim.y-1-y); results are unchanged (every block
 // owns the same row range as before, only WHEN it runs differs).  VIAI_NORM_WALK=0 restores all-forward sweeps (measurement).
-// Measured (B200, C2 step, CUDA-graph replay, one box, ms/step): no alternation 15.33; every tensor 15.18; tensors >= 200 MiB
-// 15.29, >= 100 MiB 15.26, >= 60 MiB 15.05.  Small tensors LOSE from the reversal: they are L2-resident anyway, and block i of
+// Measured (B200, C2 step, CUDA-graph replay, ms/step; tensors of the step are 256 / 128 / 64 / 32 / 16 / ... MiB): one box: no
+// alternation 15.33, tensors >= 200 MiB 15.29, >= 100 MiB 15.26, >= 60 MiB 15.05; another box: >= 48 MiB 15.19, >= 30 MiB 15.08,
+// >= 14 MiB 15.19, >= 6 MiB 15.25.  Small tensors LOSE from the reversal: they are L2-resident anyway, and block i of
 // consecutive kernels lands on the same SM, hence on the L2 partition (die) that cached its rows the pass before -- the mirrored
-// block order breaks that affinity.  So only tensors of at least VIAI_NORM_WALK_MB MiB (default below) alternate.
+// block order breaks that affinity.  So only tensors of at least VIAI_NORM_WALK_MB MiB (default 24) alternate.
 int64_t walk_min_bytes() {
-  static const int64_t mb = [] { const char* e = getenv("VIAI_NORM_WALK_MB"); return e ? (int64_t)atoll(e) : (int64_t)48; }();
+  static const int64_t mb = [] { const char* e = getenv("VIAI_NORM_WALK_MB"); return e ? (int64_t)atoll(e) : (int64_t)24; }();
   return mb << 20;
 }
 bool walk_alternate() {
