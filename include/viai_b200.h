@@ -156,6 +156,13 @@ int64_t viai_wgrad_thin_workspace(const viai_conv_geom* g);   /* floats of calle
 int viai_conv2d_wgrad_thin(const viai_conv_geom* g, const float* U, const float* G, float* dw, int64_t sa, int64_t sb,
                            int64_t sr, int64_t ss, int accumulate, float* workspace, viai_stream_t stream);
 
+/* Sweep direction of the normalisation passes below (viai_channel_stats, viai_norm_*_fwd, viai_norm_act_bwd_*).  On tensors of
+ * at least `mb` MiB every pass walks its tensors starting where the previous launch of this library ended (back to front after a
+ * front-to-back kernel and vice versa), so that it begins on lines still resident in L2; smaller tensors always walk front to
+ * back.  Results do not depend on it.  mb >= 0 sets the threshold (0: every tensor), mb < 0 only queries; returns the previous
+ * value.  Initial value: VIAI_NORM_WALK_MB or 24; VIAI_NORM_WALK=0 disables the alternation altogether. */
+int viai_norm_walk_mb(int mb);
+
 /* Per-(group,channel) sum and sum of squares over rows of an NHWC tensor: groups = 1 is BatchNorm2d's
  * batch statistics, groups = N is InstanceNorm2d's (rows_per_group = H*W).  sum/sumsq are double[groups*C],
  * zeroed by the call.  sumsq may be NULL (plain channel sum: the bias gradient). */

@@ -160,6 +160,57 @@ def test_norm_act_forward_backward(ops, norm, act, C):
         assert H.relerr(nchw(zeg), ze) < TOL
 
 
+@pytest.mark.parametrize("norm", ["bn", "in", "none"])
+@pytest.mark.parametrize("C", [32, 6, 512])
+def test_norm_sweep_direction_does_not_change_results(ops, norm, C):
+    """viai_norm_walk_mb: with the threshold at 0 every pass walks its tensors from where the previous launch ended (mirrored
+    block order: apply back to front, bwd_reduce back to front, bwd_apply front to back); with a huge threshold everything walks
+    front to back.  Same row ranges per block either way: the elementwise outputs are bit-identical, the per-channel sums equal
+    up to the order of their double atomics.  Several blocks per group and a ragged last block."""
+    import copy
+    import torch.nn as nn
+    from viai_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(C + len(norm))
+    N, Hh, W = 3, 61, 47 if C < 512 else 13
+    x = (torch.randn(N, Hh, W, C, generator=g) * 2 + 0.5).cuda()
+    dz = torch.randn(N, Hh, W, C, generator=g).cuda()
+    mod = {"bn": nn.BatchNorm2d(C), "in": nn.InstanceNorm2d(C, affine=True), "none": None}[norm]
+    if mod is not None:
+        with torch.no_grad():
+            mod.weight.copy_(torch.rand(C, generator=g) + 0.5)
+            mod.bias.copy_(torch.randn(C, generator=g) * 0.2)
+    prev = L.viai_norm_walk_mb(-1)
+    assert prev >= 0
+    res = {}
+    try:
+        for name, mb in (("alternate", 0), ("forward", 1 << 20)):
+            L.viai_norm_walk_mb(mb)
+            assert L.viai_norm_walk_mb(-1) == mb
+            m = copy.deepcopy(mod).cuda() if mod is not None else None
+            xg = x.clone().requires_grad_(True)
+            # a front-to-back launch first (as the producing convolution would be), then statistics -> apply, backward: reduce -> apply
+            ops.mul(x, x)
+            if norm == "none":
+                z = ops.norm_act(xg, None, "none", ops.ACT_LRELU, 0.2)
+            else:
+                z = ops.norm_act(xg, m, norm, ops.ACT_LRELU, 0.2)
+            ops.mul(x, x)
+            z.backward(dz)
+            res[name] = (z.detach().clone(), xg.grad.clone(), None if m is None else (m.weight.grad.clone(), m.bias.grad.clone()),
+                         None if norm != "bn" else (m.running_mean.clone(), m.running_var.clone()))
+    finally:
+        L.viai_norm_walk_mb(prev)
+    a, f = res["alternate"], res["forward"]
+    if norm == "none":
+        assert torch.equal(a[0], f[0]) and torch.equal(a[1], f[1])
+    else:
+        assert H.relerr(a[0], f[0]) < 1e-6 and H.relerr(a[1], f[1]) < 1e-6
+        assert H.relerr(a[2][0], f[2][0]) < 1e-6 and H.relerr(a[2][1], f[2][1]) < 1e-6
+    if norm == "bn":
+        assert H.relerr(a[3][0], f[3][0]) < 1e-6 and H.relerr(a[3][1], f[3][1]) < 1e-6
+
+
 BILINEAR_CASES = [(3, 16, 5, 32), (5, 32, 10, 64), (4, 16, 16, 32), (40, 128, 80, 256), (7, 9, 7, 9), (8, 8, 3, 5), (1, 4, 2, 8), (3, 3, 1, 1)]
 
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "viai_conv2d_wgrad_thin_supported": [_GP],
     "viai_conv2d_wgrad_thin": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p, c_p],
     "viai_conv2d_wgrad_simt": [_GP, c_p, c_p, c_p, c_l, c_l, c_l, c_l, c_i, c_p],
+    "viai_norm_walk_mb": [c_i],
     "viai_channel_stats": [c_p, c_l, c_i, c_i, c_p, c_p, c_p],
     "viai_norm_finalize": [c_p, c_p, c_l, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
     "viai_norm_act_fwd": [c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_f, c_p, c_p],

@@ -21,8 +21,15 @@ constexpr int THREADS = 256;
 // >= 14 MiB 15.19, >= 6 MiB 15.25.  Small tensors LOSE from the reversal: they are L2-resident anyway, and block i of
 // consecutive kernels lands on the same SM, hence on the L2 partition (die) that cached its rows the pass before -- the mirrored
 // block order breaks that affinity.  So only tensors of at least VIAI_NORM_WALK_MB MiB (default 24) alternate.
+std::atomic<int64_t> g_walk_mb{-1};        // < 0: not initialised yet
 int64_t walk_min_bytes() {
-  static const int64_t mb = [] { const char* e = getenv("VIAI_NORM_WALK_MB"); return e ? (int64_t)atoll(e) : (int64_t)24; }();
+  int64_t mb = g_walk_mb.load(std::memory_order_relaxed);
+  if (mb < 0) {
+    const char* e = getenv("VIAI_NORM_WALK_MB");
+    mb = e ? (int64_t)atoll(e) : (int64_t)24;
+    if (mb < 0) mb = 0;
+    g_walk_mb.store(mb, std::memory_order_relaxed);
+  }
   return mb << 20;
 }
 bool walk_alternate() {
@@ -420,6 +427,12 @@ int pick_vec(int C, const void* p0, const void* p1 = nullptr) {
 }
 
 }  // namespace
+
+extern "C" int viai_norm_walk_mb(int mb) {
+  const int prev = (int)(walk_min_bytes() >> 20);
+  if (mb >= 0) g_walk_mb.store(mb, std::memory_order_relaxed);
+  return prev;
+}
 
 extern "C" int viai_channel_stats(const float* y, int64_t rows_per_group, int groups, int C, double* sum, double* sumsq,
                                   viai_stream_t stream) {
