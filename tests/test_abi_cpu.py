@@ -34,6 +34,30 @@ def test_library_exports_every_declared_symbol(lib):
     assert L.viai_version() >= 100
 
 
+def test_host_side_selectors_need_no_gpu(lib):
+    """Geometry / tuning selectors of the C ABI are plain host functions: which Cin = 1 layers get their BatchNorm statistics from
+    the convolution kernel, and the size threshold of the alternating normalisation sweeps (set, query, restore)."""
+    import ctypes
+    from viai_b200 import ops
+    L = lib.lib()
+    sup = lambda *a: L.viai_conv2d_thin_stats_supported(ctypes.byref(ops._geom(*a)))
+    if os.environ.get("VIAI_CIN1_STATS", "1") != "0":
+        assert sup(32, 256, 256, 1, 256, 128, 64, 1, 4, (1, 2), (0, 1), 0) == 1      # MelDiscriminator.conv1 at C2
+        assert sup(32, 256, 256, 1, 128, 128, 32, 3, 3, (2, 2), (1, 1), 0) == 1      # MelEncoder.conv1 at C2
+    assert sup(2, 16, 16, 1, 16, 16, 128, 3, 3, (1, 1), (1, 1), 0) == 0              # more than 64 output channels
+    assert sup(2, 16, 16, 1, 16, 16, 32, 5, 5, (1, 1), (2, 2), 0) == 0               # other filter shapes: generic kernel
+    assert sup(2, 16, 16, 32, 16, 16, 1, 3, 3, (1, 1), (1, 1), 0) == 0               # Cout == 1 is the other thin kernel
+    assert sup(2, 16, 16, 32, 16, 16, 32, 3, 3, (1, 1), (1, 1), 0) == 0              # tensor-core layer
+    prev = L.viai_norm_walk_mb(-1)
+    assert prev >= 0
+    try:
+        assert L.viai_norm_walk_mb(0) == prev and L.viai_norm_walk_mb(-1) == 0
+        assert L.viai_norm_walk_mb(512) == 0 and L.viai_norm_walk_mb(-5) == 512
+    finally:
+        L.viai_norm_walk_mb(prev)
+    assert L.viai_norm_walk_mb(-1) == prev
+
+
 def test_no_cpu_fallback(lib):
     from viai_b200 import ops
     with pytest.raises(RuntimeError, match="no CPU path"):
