@@ -262,10 +262,11 @@ int launch_cout1_tma(const viai_conv_geom& g, const float* in, const float* wp, 
 // pixels it produces, the partials are reduced over the lanes of a warp by shuffles, over the warps through shared memory in
 // double, and one double atomic per (block, channel, moment) lands in HBM -- the separate read pass over the wide tensor
 // (65 us for MelDiscriminator.conv1's 268 MB at B = 32) disappears.
+// The 1x4 statistics variant is held to 80 registers (3 CTAs per SM instead of 2; 16 bytes of spill): C2 step 15.19 vs 15.26 ms.
 constexpr int CIN1_PX = 4;
 constexpr int CIN1_SV = 2;          // channel vectors per lane with STATS: Cout <= 64
 template <int R_, int S_, bool STATS>
-__global__ void __launch_bounds__(256) conv_cin1_kernel(viai_conv_geom g, const float* __restrict__ in, const float* __restrict__ wp,
+__global__ void __launch_bounds__(256, (STATS && R_ * S_ <= 4) ? 3 : 1) conv_cin1_kernel(viai_conv_geom g, const float* __restrict__ in, const float* __restrict__ wp,
                                                         const float* __restrict__ bias, float* __restrict__ out,
                                                         double* __restrict__ stat_sum, double* __restrict__ stat_sumsq) {
   extern __shared__ float wsm[];   // [tap][Cout] + bias[Cout]
